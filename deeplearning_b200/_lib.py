@@ -1,0 +1,80 @@
+"""ctypes binding of libb200cls.so (the C-ABI boundary declared in include/b200cls.h).
+
+There is no fallback: if the shared library is missing, or a call fails, a RuntimeError is raised.
+Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or ``make -C deeplearning_b200/csrc``.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb200cls.so")
+
+_lib = None
+
+_P = c_void_p
+_I = c_int
+_L = c_longlong
+_F = c_float
+_D = c_double
+
+# name -> (restype, argtypes); must list every symbol of include/b200cls.h (tests/test_abi.py checks this).
+SIGNATURES = {
+    "b200_last_error": (c_char_p, []),
+    "b200_abi_version": (_I, []),
+    "b200_sm_count": (_I, []),
+    "b200_conv2d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
+    "b200_conv2d_fwd_mtiles": (_I, [_I, _I, _I, _I, _I]),
+    "b200_conv2d_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "b200_conv2d_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
+    "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
+    "b200_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
+    "b200_bn_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _P]),
+    "b200_bn_bwd_blocks": (_I, [_L, _I]),
+    "b200_bn_bwd_finalize": (_I, [_P, _I, _I, _D, _P, _P, _I, _P, _P, _P]),
+    "b200_bn_bwd_apply": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P]),
+    "b200_bn_relu_maxpool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "b200_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200_avgpool_bwd": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200_softmax_xent": (_I, [_P, _L, _P, _I, _I, _F, _P, _P, _L, _P, _P]),
+    "b200_mean": (_I, [_P, _I, _P, _P]),
+    "b200_colsum_bf16": (_I, [_P, _L, _L, _I, _P, _I, _P]),
+    "b200_pack_weight": (_I, [_P, _P, _I, _I, _I, _I, _L, _P]),
+    "b200_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
+    "b200_cast_bf16_to_f32": (_I, [_P, _P, _L, _P]),
+    "b200_im2col_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_debug_set_desc": (_I, [_I, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
+    "b200_sgd_momentum": (_I, [_P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
+}
+
+
+def load():
+    """Load (once) and return the ctypes handle; raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the CUDA extension is not built (run __graft_entry__.build()); "
+            "deeplearning_b200 has no CPU / PyTorch fallback for the hot path"
+        )
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error():
+    msg = load().b200_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {last_error()}")

@@ -1,0 +1,434 @@
+// C-ABI entry points for the tcgen05 implicit-GEMM kernels (forward / dgrad / wgrad). Host side only builds tensor maps,
+// tap tables and tile geometry; see conv_gemm.cuh / wgrad_gemm.cuh for the device code.
+#include <string.h>
+#include "../../include/b200cls.h"
+#include "conv_gemm.cuh"
+#include "host_utils.h"
+#include "wgrad_gemm.cuh"
+
+using namespace b200;
+
+namespace {
+
+// Descriptor strides; overridable through b200_debug_set_desc() for bring-up experiments only.
+uint32_t g_fwd_lbo = 16, g_fwd_sbo = 1024;
+uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024, g_wg_kstep = 2048;
+
+struct Box3 {
+  int b1, b2, b3;
+};
+
+// Factor P pixels (power of two) into a (w, h, n) box minimising padded work; ties -> longer w, then longer h.
+Box3 choose_box(long long d1, long long d2, long long d3, int P) {
+  Box3 best{P, 1, 1};
+  double best_cost = -1;
+  for (int b1 = 1; b1 <= P; b1 <<= 1) {
+    for (int b2 = 1; b1 * b2 <= P; b2 <<= 1) {
+      const int b3 = P / (b1 * b2);
+      if (b1 > 256 || b2 > 256 || b3 > 256) continue;
+      const double c1 = double((d1 + b1 - 1) / b1) * b1, c2 = double((d2 + b2 - 1) / b2) * b2,
+                   c3 = double((d3 + b3 - 1) / b3) * b3;
+      const double cost = c1 * c2 * c3;
+      if (best_cost < 0 || cost < best_cost - 0.5 ||
+          (cost < best_cost + 0.5 && (b1 > best.b1 || (b1 == best.b1 && b2 > best.b2)))) {
+        best_cost = cost;
+        best = Box3{b1, b2, b3};
+      }
+    }
+  }
+  return best;
+}
+
+inline int out_dim(int in, int ksize, int stride) { return (in + 2 * (ksize / 2) - ksize) / stride + 1; }
+
+// 4-D activation view descriptor (channels innermost).
+struct View {
+  const void* base;
+  uint64_t dims[4];
+  uint64_t strides[4];  // elements
+};
+
+// NHWC tensor [B][H][W][C] (contiguous) viewed with pixel phase (ph, pw) and step `s` along h/w.
+View make_view(const void* base, int B, int H, int W, int C, int s, int ph, int pw) {
+  View v;
+  v.base = static_cast<const char*>(base) + (static_cast<long long>(ph) * W + pw) * C * 2;
+  v.dims[0] = C;
+  v.dims[1] = (W - pw + s - 1) / s;
+  v.dims[2] = (H - ph + s - 1) / s;
+  v.dims[3] = B;
+  v.strides[0] = 1;
+  v.strides[1] = static_cast<uint64_t>(s) * C;
+  v.strides[2] = static_cast<uint64_t>(s) * W * C;
+  v.strides[3] = static_cast<uint64_t>(H) * W * C;
+  return v;
+}
+// Same tensor flattened to [B*H*W][C] (dims (C, M, 1, 1)).
+View make_flat_view(const void* base, long long M, int C) {
+  View v;
+  v.base = base;
+  v.dims[0] = C;
+  v.dims[1] = M;
+  v.dims[2] = 1;
+  v.dims[3] = 1;
+  v.strides[0] = 1;
+  v.strides[1] = C;
+  v.strides[2] = static_cast<uint64_t>(M) * C;
+  v.strides[3] = static_cast<uint64_t>(M) * C;
+  return v;
+}
+int encode_view(CUtensorMap* m, const View& v, const Box3& bx) {
+  uint32_t box[4] = {64, (uint32_t)bx.b1, (uint32_t)bx.b2, (uint32_t)bx.b3};
+  if (v.dims[1] == 0 || v.dims[2] == 0 || v.dims[3] == 0) {
+    set_error("empty activation view");
+    return EINVAL_;
+  }
+  return encode_tmap_bf16(m, v.base, 4, v.dims, v.strides, box);
+}
+
+template <int BLOCK_N>
+int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
+  using Cfg = ConvGemmCfg<BLOCK_N>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int tiles = p.tiles1 * p.tiles2 * p.tiles3 * p.n_tiles;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  ConvGemmParams q = p;
+  q.desc_lbo = g_fwd_lbo;
+  q.desc_sbo = g_fwd_sbo;
+  conv_gemm_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int dispatch_conv_gemm(ConvGemmParams& p, int N, cudaStream_t st) {
+  if (N <= 64) return launch_conv_gemm<64>(p, st);
+  if (N <= 128) return launch_conv_gemm<128>(p, st);
+  return launch_conv_gemm<256>(p, st);
+}
+int block_n_for(int N) { return N <= 64 ? 64 : (N <= 128 ? 128 : 256); }
+
+template <int BLOCK_NG>
+int launch_wgrad(const WgradParams& p, cudaStream_t st) {
+  using Cfg = WgradCfg<BLOCK_NG>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int items = p.mg_tiles * p.ng_tiles * p.num_taps * p.splits;
+  const int grid = items < device_sm_count() ? items : device_sm_count();
+  WgradParams q = p;
+  q.desc_lbo = g_wg_lbo;
+  q.desc_sbo = g_wg_sbo;
+  q.desc_kstep = g_wg_kstep;
+  wgrad_gemm_kernel<BLOCK_NG><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+struct WgradPlan {
+  int block_ng, mg_tiles, ng_tiles, taps;
+  Box3 box;
+  int tiles1, tiles2, tiles3, kb_total, splits, kb_per_split;
+  int Ho, Wo;
+};
+
+WgradPlan plan_wgrad(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+  WgradPlan pl;
+  pl.taps = ksize * ksize;
+  pl.Ho = out_dim(H, ksize, stride);
+  pl.Wo = out_dim(W, ksize, stride);
+  pl.block_ng = Cin <= 64 ? 64 : 128;
+  pl.mg_tiles = (Cout + 127) / 128;
+  pl.ng_tiles = (Cin + pl.block_ng - 1) / pl.block_ng;
+  const bool flat = (ksize == 1 && stride == 1);
+  const long long d1 = flat ? static_cast<long long>(B) * H * W : pl.Wo;
+  const long long d2 = flat ? 1 : pl.Ho;
+  const long long d3 = flat ? 1 : B;
+  pl.box = choose_box(d1, d2, d3, 64);
+  pl.tiles1 = static_cast<int>((d1 + pl.box.b1 - 1) / pl.box.b1);
+  pl.tiles2 = static_cast<int>((d2 + pl.box.b2 - 1) / pl.box.b2);
+  pl.tiles3 = static_cast<int>((d3 + pl.box.b3 - 1) / pl.box.b3);
+  pl.kb_total = pl.tiles1 * pl.tiles2 * pl.tiles3;
+  const int items_per_split = pl.mg_tiles * pl.ng_tiles * pl.taps;
+  const int target = 2 * device_sm_count();
+  int splits = (target + items_per_split - 1) / items_per_split;
+  const int max_splits = pl.kb_total / 4 > 0 ? pl.kb_total / 4 : 1;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
+  pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
+  return pl;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200_debug_set_desc(int which, unsigned lbo, unsigned sbo, unsigned kstep) {
+  if (which == 0) {
+    g_fwd_lbo = lbo, g_fwd_sbo = sbo;
+  } else {
+    g_wg_lbo = lbo, g_wg_sbo = sbo, g_wg_kstep = kstep;
+  }
+  return OK;
+}
+
+int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride) {
+  const int Ho = out_dim(H, ksize, stride), Wo = out_dim(W, ksize, stride);
+  const bool flat = (ksize == 1 && stride == 1);
+  const long long d1 = flat ? static_cast<long long>(B) * H * W : Wo;
+  const long long d2 = flat ? 1 : Ho;
+  const long long d3 = flat ? 1 : B;
+  const Box3 bx = choose_box(d1, d2, d3, 128);
+  return static_cast<int>(((d1 + bx.b1 - 1) / bx.b1) * ((d2 + bx.b2 - 1) / bx.b2) * ((d3 + bx.b3 - 1) / bx.b3));
+}
+
+int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                    float* stats, const float* bias, int act, const void* residual, float* out_f32, long long ld_out,
+                    void* stream) {
+  B200_REQUIRE(ksize == 1 || ksize == 3, "conv2d_fwd: ksize %d unsupported (1 or 3)", ksize);
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fwd: stride %d unsupported (1 or 2)", stride);
+  B200_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_fwd: Cin=%d / Cout=%d must be multiples of 8", Cin, Cout);
+  B200_REQUIRE(ksize == 1 || Cin % 64 == 0, "conv2d_fwd: 3x3 needs Cin %% 64 == 0 (got %d)", Cin);
+  B200_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_fwd: empty input");
+  B200_REQUIRE(out_f32 == nullptr || (ksize == 1 && stride == 1), "conv2d_fwd: fp32 output only for 1x1/s1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Ho = out_dim(H, ksize, stride), Wo = out_dim(W, ksize, stride);
+  const bool flat = (ksize == 1 && stride == 1);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const long long d1 = flat ? static_cast<long long>(B) * H * W : Wo;
+  const long long d2 = flat ? 1 : Ho;
+  const long long d3 = flat ? 1 : B;
+  const Box3 bx = choose_box(d1, d2, d3, 128);
+  p.box1 = bx.b1, p.box2 = bx.b2, p.box3 = bx.b3;
+  p.dim1 = static_cast<int>(d1), p.dim2 = static_cast<int>(d2), p.dim3 = static_cast<int>(d3);
+  p.tiles1 = static_cast<int>((d1 + bx.b1 - 1) / bx.b1);
+  p.tiles2 = static_cast<int>((d2 + bx.b2 - 1) / bx.b2);
+  p.tiles3 = static_cast<int>((d3 + bx.b3 - 1) / bx.b3);
+  p.N = Cout;
+  const int BN = block_n_for(Cout);
+  p.n_tiles = (Cout + BN - 1) / BN;
+  p.k_per_tap = Cin;
+  p.k_blocks_per_tap = (Cin + 63) / 64;
+  p.num_taps = ksize * ksize;
+  int rc;
+  if (flat) {
+    if ((rc = encode_view(&p.a_maps[0], make_flat_view(x, d1, Cin), bx))) return rc;
+    for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+    p.tap_map[0] = 0, p.tap_o1[0] = 0, p.tap_o2[0] = 0, p.tap_w[0] = 0;
+  } else if (stride == 1) {
+    if ((rc = encode_view(&p.a_maps[0], make_view(x, B, H, W, Cin, 1, 0, 0), bx))) return rc;
+    for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+    for (int kh = 0; kh < ksize; ++kh)
+      for (int kw = 0; kw < ksize; ++kw) {
+        const int t = kh * ksize + kw;
+        p.tap_map[t] = 0;
+        p.tap_o1[t] = static_cast<int8_t>(kw - ksize / 2);
+        p.tap_o2[t] = static_cast<int8_t>(kh - ksize / 2);
+        p.tap_w[t] = static_cast<int8_t>(t);
+      }
+  } else {
+    // stride 2: tap (kh,kw) reads input row 2*oh + kh - pad -> phase ((kh-pad)&1), index oh + floor((kh-pad)/2)
+    B200_REQUIRE(H >= 2 && W >= 2, "conv2d_fwd: stride-2 needs H,W >= 2");
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        if ((rc = encode_view(&p.a_maps[ph * 2 + pw], make_view(x, B, H, W, Cin, 2, ph, pw), bx))) return rc;
+    const int pad = ksize / 2;
+    for (int kh = 0; kh < ksize; ++kh)
+      for (int kw = 0; kw < ksize; ++kw) {
+        const int t = kh * ksize + kw;
+        const int dh = kh - pad, dw = kw - pad;
+        const int ph = dh & 1, pw = dw & 1;
+        p.tap_map[t] = static_cast<int8_t>(ph * 2 + pw);
+        p.tap_o1[t] = static_cast<int8_t>((dw - pw) / 2);
+        p.tap_o2[t] = static_cast<int8_t>((dh - ph) / 2);
+        p.tap_w[t] = static_cast<int8_t>(t);
+      }
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(p.num_taps) * Cin, static_cast<uint64_t>(Cout)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(p.num_taps) * Cin};
+    uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    if ((rc = encode_tmap_bf16(&p.b_map, w, 2, dims, strides, box))) return rc;
+  }
+  {
+    View dv = flat ? make_flat_view(y, d1, Cout) : make_view(y, B, Ho, Wo, Cout, 1, 0, 0);
+    if ((rc = encode_view(&p.d_map, dv, bx))) return rc;
+  }
+  p.stats = stats;
+  p.bias = bias;
+  p.act = act;
+  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.rs1 = Cout;
+  p.rs2 = static_cast<long long>(d1) * Cout;
+  p.rs3 = static_cast<long long>(d1) * d2 * Cout;
+  p.out_f32 = out_f32;
+  p.ld_out = ld_out;
+  return dispatch_conv_gemm(p, Cout, st);
+}
+
+int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, int W, int Cin, int Cout, int ksize,
+                      int stride, const void* residual, void* stream) {
+  B200_REQUIRE(ksize == 1 || ksize == 3, "conv2d_dgrad: ksize %d unsupported", ksize);
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_dgrad: stride %d unsupported", stride);
+  B200_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_dgrad: Cin=%d / Cout=%d must be multiples of 8", Cin, Cout);
+  B200_REQUIRE(ksize == 1 || Cout % 64 == 0, "conv2d_dgrad: 3x3 needs Cout %% 64 == 0 (got %d)", Cout);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Ho = out_dim(H, ksize, stride), Wo = out_dim(W, ksize, stride);
+  const int taps = ksize * ksize;
+  const int BN = block_n_for(Cin);
+  int rc;
+  CUtensorMap b_map;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(taps) * Cout, static_cast<uint64_t>(Cin)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(taps) * Cout};
+    uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    if ((rc = encode_tmap_bf16(&b_map, wd, 2, dims, strides, box))) return rc;
+  }
+  const int nphase = (stride == 2 && ksize == 3) ? 2 : 1;  // phases per spatial dim that need their own launch
+  for (int ph = 0; ph < nphase; ++ph) {
+    for (int pw = 0; pw < nphase; ++pw) {
+      ConvGemmParams p;
+      memset(&p, 0, sizeof(p));
+      p.b_map = b_map;
+      const bool flat = (ksize == 1 && stride == 1);
+      // output (dx) view for this launch
+      View dv = flat ? make_flat_view(dx, static_cast<long long>(B) * H * W, Cin)
+                     : make_view(dx, B, H, W, Cin, stride, ph, pw);
+      const long long d1 = dv.dims[1], d2 = dv.dims[2], d3 = dv.dims[3];
+      const Box3 bx = choose_box(d1, d2, d3, 128);
+      p.box1 = bx.b1, p.box2 = bx.b2, p.box3 = bx.b3;
+      p.dim1 = static_cast<int>(d1), p.dim2 = static_cast<int>(d2), p.dim3 = static_cast<int>(d3);
+      p.tiles1 = static_cast<int>((d1 + bx.b1 - 1) / bx.b1);
+      p.tiles2 = static_cast<int>((d2 + bx.b2 - 1) / bx.b2);
+      p.tiles3 = static_cast<int>((d3 + bx.b3 - 1) / bx.b3);
+      p.N = Cin;
+      p.n_tiles = (Cin + BN - 1) / BN;
+      p.k_per_tap = Cout;
+      p.k_blocks_per_tap = (Cout + 63) / 64;
+      if ((rc = encode_view(&p.d_map, dv, bx))) return rc;
+      View av = flat ? make_flat_view(dy, static_cast<long long>(B) * H * W, Cout)
+                     : make_view(dy, B, Ho, Wo, Cout, 1, 0, 0);
+      if ((rc = encode_view(&p.a_maps[0], av, bx))) return rc;
+      for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+      int nt = 0;
+      if (ksize == 1) {
+        p.tap_map[0] = 0, p.tap_o1[0] = 0, p.tap_o2[0] = 0, p.tap_w[0] = 0;
+        nt = 1;
+      } else if (stride == 1) {
+        // dx[q] = sum_{kh,kw} W[kh,kw]^T dy[q - (kh-1, kw-1)]
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            p.tap_map[nt] = 0;
+            p.tap_o1[nt] = static_cast<int8_t>(1 - kw);
+            p.tap_o2[nt] = static_cast<int8_t>(1 - kh);
+            p.tap_w[nt] = static_cast<int8_t>(kh * 3 + kw);
+            ++nt;
+          }
+      } else {
+        // stride 2, 3x3, pad 1: input row ih = 2j+ph receives taps kh with (ih + 1 - kh) even, from oh = (ih+1-kh)/2
+        for (int kh = 0; kh < 3; ++kh) {
+          if (((ph + 1 - kh) & 1) != 0) continue;
+          for (int kw = 0; kw < 3; ++kw) {
+            if (((pw + 1 - kw) & 1) != 0) continue;
+            p.tap_map[nt] = 0;
+            p.tap_o1[nt] = static_cast<int8_t>((pw + 1 - kw) / 2);
+            p.tap_o2[nt] = static_cast<int8_t>((ph + 1 - kh) / 2);
+            p.tap_w[nt] = static_cast<int8_t>(kh * 3 + kw);
+            ++nt;
+          }
+        }
+      }
+      p.num_taps = nt;
+      if (residual != nullptr) {
+        p.residual = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(residual) +
+                                                            (static_cast<const char*>(dv.base) - static_cast<const char*>(dx)));
+        p.rs1 = static_cast<long long>(dv.strides[1]);
+        p.rs2 = static_cast<long long>(dv.strides[2]);
+        p.rs3 = static_cast<long long>(dv.strides[3]);
+      }
+      if ((rc = dispatch_conv_gemm(p, Cin, st))) return rc;
+    }
+  }
+  return OK;
+}
+
+size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+  const WgradPlan pl = plan_wgrad(B, H, W, Cin, Cout, ksize, stride);
+  return static_cast<size_t>(pl.splits) * Cout * pl.taps * Cin * sizeof(float);
+}
+
+int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
+                      int W, int Cin, int Cout, int ksize, int stride, int accumulate, void* stream) {
+  B200_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize %d unsupported", ksize);
+  B200_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride %d unsupported", stride);
+  B200_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_wgrad: Cin=%d / Cout=%d must be multiples of 8", Cin, Cout);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const WgradPlan pl = plan_wgrad(B, H, W, Cin, Cout, ksize, stride);
+  const size_t need = static_cast<size_t>(pl.splits) * Cout * pl.taps * Cin * sizeof(float);
+  B200_REQUIRE(workspace != nullptr && workspace_bytes >= need, "conv2d_wgrad: workspace too small (%zu < %zu)",
+               workspace_bytes, need);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_taps = pl.taps;
+  p.Cout = Cout, p.Cin = Cin;
+  p.mg_tiles = pl.mg_tiles, p.ng_tiles = pl.ng_tiles;
+  p.tiles1 = pl.tiles1, p.tiles2 = pl.tiles2, p.tiles3 = pl.tiles3;
+  p.box1 = pl.box.b1, p.box2 = pl.box.b2, p.box3 = pl.box.b3;
+  p.splits = pl.splits, p.kb_per_split = pl.kb_per_split, p.kb_total = pl.kb_total;
+  p.ld_partial = static_cast<long long>(pl.taps) * Cin;
+  p.partial = static_cast<float*>(workspace);
+  const bool flat = (ksize == 1 && stride == 1);
+  int rc;
+  View dyv = flat ? make_flat_view(dy, static_cast<long long>(B) * H * W, Cout)
+                  : make_view(dy, B, pl.Ho, pl.Wo, Cout, 1, 0, 0);
+  if ((rc = encode_view(&p.dy_map, dyv, pl.box))) return rc;
+  if (flat) {
+    if ((rc = encode_view(&p.x_maps[0], make_flat_view(x, static_cast<long long>(B) * H * W, Cin), pl.box))) return rc;
+    for (int i = 1; i < 4; ++i) p.x_maps[i] = p.x_maps[0];
+  } else if (stride == 1) {
+    if ((rc = encode_view(&p.x_maps[0], make_view(x, B, H, W, Cin, 1, 0, 0), pl.box))) return rc;
+    for (int i = 1; i < 4; ++i) p.x_maps[i] = p.x_maps[0];
+    for (int kh = 0; kh < ksize; ++kh)
+      for (int kw = 0; kw < ksize; ++kw) {
+        const int t = kh * ksize + kw;
+        p.tap_map[t] = 0;
+        p.tap_o1[t] = static_cast<int8_t>(kw - ksize / 2);
+        p.tap_o2[t] = static_cast<int8_t>(kh - ksize / 2);
+      }
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw)
+        if ((rc = encode_view(&p.x_maps[ph * 2 + pw], make_view(x, B, H, W, Cin, 2, ph, pw), pl.box))) return rc;
+    const int pad = ksize / 2;
+    for (int kh = 0; kh < ksize; ++kh)
+      for (int kw = 0; kw < ksize; ++kw) {
+        const int t = kh * ksize + kw;
+        const int dh = kh - pad, dw_ = kw - pad;
+        const int ph = dh & 1, pw = dw_ & 1;
+        p.tap_map[t] = static_cast<int8_t>(ph * 2 + pw);
+        p.tap_o1[t] = static_cast<int8_t>((dw_ - pw) / 2);
+        p.tap_o2[t] = static_cast<int8_t>((dh - ph) / 2);
+      }
+  }
+  if (pl.block_ng == 64)
+    rc = launch_wgrad<64>(p, st);
+  else
+    rc = launch_wgrad<128>(p, st);
+  if (rc) return rc;
+  const long long total = static_cast<long long>(Cout) * Cin * pl.taps;
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,213 @@
+// C-ABI entry points for the HBM-bound passes (see elementwise.cuh).
+#include <string.h>
+
+#include "../../include/b200cls.h"
+#include "elementwise.cuh"
+#include "host_utils.h"
+
+using namespace b200;
+
+namespace {
+inline int ew_grid(long long work_items, int block = 256) {
+  long long blocks = (work_items + block - 1) / block;
+  const long long cap = static_cast<long long>(device_sm_count()) * 16;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+struct BnBwdPlan {
+  int blocks, rows_per_block;
+};
+BnBwdPlan plan_bn_bwd(long long rows, int C) {
+  const int cvec = C / 8;
+  const int rpi = 256 / cvec;
+  long long blocks = static_cast<long long>(device_sm_count()) * 4;
+  long long rpb = (rows + blocks - 1) / blocks;
+  rpb = ((rpb + rpi - 1) / rpi) * rpi;
+  if (rpb < rpi) rpb = rpi;
+  blocks = (rows + rpb - 1) / rpb;
+  return BnBwdPlan{static_cast<int>(blocks), static_cast<int>(rpb)};
+}
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error(void) { return get_error(); }
+int b200_abi_version(void) { return 1; }
+int b200_sm_count(void) { return device_sm_count(); }
+
+int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream) {
+  B200_REQUIRE(T > 0 && C > 0 && count > 0, "bn_finalize: bad sizes T=%d C=%d", T, C);
+  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partial, T, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, mean, invstd,
+      scale, shift);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  bn_eval_coeffs_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, gamma, beta, running_mean,
+                                                                                       running_var, eps, scale, shift);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_bn_apply(const void* x, const void* residual, void* y, const float* scale, const float* shift, long long rows,
+                  int C, int relu, void* stream) {
+  B200_REQUIRE(C % 8 == 0, "bn_apply: C=%d must be a multiple of 8", C);
+  const long long nvec = rows * (C / 8);
+  bn_apply_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<const uint4*>(residual), static_cast<uint4*>(y), scale, shift, nvec,
+      C / 8, relu);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_bn_bwd_blocks(long long rows, int C) {
+  if (C % 8 != 0 || !pow2(C / 8) || C / 8 > 256) return -1;
+  return plan_bn_bwd(rows, C).blocks;
+}
+
+int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu, long long rows, int C,
+                       float* partial, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_bwd_reduce: C=%d must be 8*2^k <= 2048", C);
+  const BnBwdPlan pl = plan_bn_bwd(rows, C);
+  bn_bwd_reduce_kernel<<<pl.blocks, 256, 256 * 17 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out),
+      static_cast<uint4*>(dz_out), scale, shift, mean, invstd, relu, rows, C / 8, pl.rows_per_block, partial);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
+                         float* m1, float* m2, void* stream) {
+  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, T, C, count, dgamma,
+                                                                                      dbeta, accumulate, m1, m2);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
+                      int relu, long long rows, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0, "bn_bwd_apply: C=%d must be a multiple of 8", C);
+  const long long nvec = rows * (C / 8);
+  bn_bwd_apply_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out), g_is_dz,
+      static_cast<uint4*>(dx), scale, shift, mean, invstd, m1, m2, relu, nvec, C / 8);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_bn_relu_maxpool_fwd(const void* x, void* y, void* idx, const float* scale, const float* shift, int B, int H,
+                             int W, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0, "maxpool: C=%d must be a multiple of 8", C);
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long long nvec = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  bn_relu_maxpool_fwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), static_cast<unsigned long long*>(idx), scale, shift, B, H, W,
+      C / 8);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_maxpool_bwd(const void* g_out, const void* idx, void* g_in, int B, int H, int W, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", C);
+  const long long nvec = static_cast<long long>(B) * H * W * (C / 8);
+  maxpool_bwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(g_out), static_cast<const unsigned long long*>(idx), static_cast<uint4*>(g_in), B, H, W,
+      C / 8);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_avgpool_fwd(const void* x, void* y, int B, int HW, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0, "avgpool: C=%d must be a multiple of 8", C);
+  const long long nvec = static_cast<long long>(B) * (C / 8);
+  avgpool_fwd_kernel<<<ew_grid(nvec, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(y), B, HW, C / 8);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+int b200_avgpool_bwd(const void* gy, void* gx, int B, int HW, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0, "avgpool_bwd: C=%d must be a multiple of 8", C);
+  const long long nvec = static_cast<long long>(B) * HW * (C / 8);
+  avgpool_bwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(gy), static_cast<uint4*>(gx), B, HW, C / 8);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_softmax_xent(const float* logits, long long ld, const long long* labels, int B, int N, float gscale,
+                      float* loss_rows, void* dlogits, long long ld_d, int* correct, void* stream) {
+  B200_REQUIRE(B > 0 && N > 0, "softmax_xent: empty input");
+  softmax_xent_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, ld, labels, N, gscale, loss_rows, static_cast<__nv_bfloat16*>(dlogits), ld_d, correct);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_mean(const float* v, int n, float* out, void* stream) {
+  mean_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, n, out);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, float* out, int accumulate, void* stream) {
+  colsum_kernel<<<(cols + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(m), rows, ld, cols, out, accumulate);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mode, long long ld_dst, void* stream) {
+  B200_REQUIRE(mode == 0 || mode == 1, "pack_weight: mode %d", mode);
+  const long long rows = mode == 0 ? O : I;
+  const long long need = static_cast<long long>(taps) * (mode == 0 ? I : O);
+  B200_REQUIRE(ld_dst >= need, "pack_weight: ld_dst %lld < %lld", ld_dst, need);
+  pack_weight_kernel<<<ew_grid(rows * ld_dst), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, static_cast<__nv_bfloat16*>(dst), O, I, taps, mode, ld_dst);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  cast_f32_bf16_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst),
+                                                                                  n);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
+  cast_bf16_f32_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), dst, n);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int KH, int KW, int stride, int pad,
+                     int ldk, void* stream) {
+  B200_REQUIRE(ldk % 8 == 0 && ldk >= KH * KW * Cin, "im2col: ldk=%d must be a multiple of 8 and >= %d", ldk,
+               KH * KW * Cin);
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const long long nvec = static_cast<long long>(B) * Ho * Wo * (ldk / 8);
+  im2col_nchw_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<uint4*>(a), B, Cin, H, W, KH, KW, stride, pad, Ho, Wo, ldk);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
+                      float gscale, int first_step, void* stream) {
+  sgd_momentum_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, buf, n, lr, momentum,
+                                                                               weight_decay, gscale, first_step);
+  B200_CHECK_CUDA(cudaPeekAtLastError());
+  return OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,584 @@
+// HBM-bound passes of the classification training step (NHWC bf16 activations, fp32 statistics):
+// train/eval BatchNorm finalize + apply(+ReLU)(+residual), BatchNorm backward (reduce / finalize / apply),
+// stem max-pool forward/backward, global average pool, soft-max cross-entropy, layout packing and the fused SGD update.
+// All kernels move 16-byte vectors (8 bf16 channels per thread) and use grid-stride loops over a grid sized from the SM count.
+//
+// Reference semantics: nn.BatchNorm2d defaults (eps 1e-5, momentum 0.1, biased var to normalise, unbiased running_var)
+// as used at classification/resnet/models/networks.py:45,91,134; MaxPool2d(3,2,1) :152; AdaptiveAvgPool2d(1) :160;
+// CrossEntropyLoss (classification/resnet/train.py:104); SGD momentum (classification/resnet/train.py:96).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct bf16x8 {
+  uint4 u;
+};
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x);
+  f[1] = bf16_hi(u.x);
+  f[2] = bf16_lo(u.y);
+  f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z);
+  f[5] = bf16_hi(u.z);
+  f[6] = bf16_lo(u.w);
+  f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]);
+  u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]);
+  u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BatchNorm statistics finalize: partial[T][2][C] (sum, sum of squares per 128-row tile) -> mean/invstd/scale/shift,
+// running-stat update. One block = 32 channels x 8 partial-row groups; accumulation in double.
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int T, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, long long* num_batches,
+                                   float* mean_out, float* invstd_out, float* scale_out, float* shift_out) {
+  __shared__ double sh[2][8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0, ss = 0.0;
+  if (c < C) {
+    for (int t = ry; t < T; t += 8) {
+      s += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
+      ss += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
+    }
+  }
+  sh[0][ry][cx] = s;
+  sh[1][ry][cx] = ss;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) {
+      s += sh[0][i][cx];
+      ss += sh[1][i][cx];
+    }
+    const double mean = s / count;
+    double var = ss / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    mean_out[c] = static_cast<float>(mean);
+    invstd_out[c] = static_cast<float>(invstd);
+    const float sc = static_cast<float>(g * invstd);
+    scale_out[c] = sc;
+    shift_out[c] = static_cast<float>(b - mean * g * invstd);
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
+    }
+  }
+  if (num_batches && blockIdx.x == 0 && threadIdx.x == 0) *num_batches += 1;
+}
+
+// Eval-mode BN: scale/shift from running statistics.
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float eps, float* scale_out, float* shift_out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    const float invstd = 1.0f / sqrtf(running_var[c] + eps);
+    const float sc = gamma[c] * invstd;
+    scale_out[c] = sc;
+    shift_out[c] = beta[c] - running_mean[c] * sc;
+  }
+}
+
+// y = act(x * scale[c] + shift[c] (+ residual)); x,y,residual bf16 [rows][C].
+__global__ void bn_apply_kernel(const uint4* __restrict__ x, const uint4* __restrict__ residual, uint4* __restrict__ y,
+                                const float* __restrict__ scale, const float* __restrict__ shift, long long nvec,
+                                int cvec, int relu) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cvec);
+    float sc[8], sh[8], v[8];
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+    unpack8(__ldg(x + i), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    if (residual) {
+      float r[8];
+      unpack8(__ldg(residual + i), r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += r[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
+    y[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// BatchNorm backward, pass 1: dz = g * relu_mask; per-channel partial sums of dz and dz * xhat.
+//   mask source: y_out (saved post-activation output, used when a residual was added) if given, else recomputed from
+//   x*scale+shift > 0; relu == 0 -> no mask.  Optionally stores dz (bf16) for reuse (identity-branch gradient).
+// Block = 256 threads; each thread owns one 8-channel group and strides over rows. partial[blocks][2][C].
+__global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x,
+                                     const uint4* __restrict__ y_out, uint4* __restrict__ dz_out,
+                                     const float* __restrict__ scale, const float* __restrict__ shift,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                     long long rows, int cvec, int rows_per_block, float* __restrict__ partial) {
+  extern __shared__ float red[];  // [256][17]
+  const int tpr = cvec;                  // threads per row (power of two, <= 256)
+  const int rpi = 256 / tpr;             // rows per iteration
+  const int cg = threadIdx.x % tpr;
+  const int rsub = threadIdx.x / tpr;
+  float sc[8], sh[8], mu[8], is[8];
+  load8f(scale + cg * 8, sc);
+  load8f(shift + cg * 8, sh);
+  load8f(mean + cg * 8, mu);
+  load8f(invstd + cg * 8, is);
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + rsub; r < r1; r += rpi) {
+    const long long i = r * cvec + cg;
+    float gv[8], xv[8];
+    unpack8(__ldg(g + i), gv);
+    unpack8(__ldg(x + i), xv);
+    if (relu) {
+      if (y_out) {
+        float yv[8];
+        unpack8(__ldg(y_out + i), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? gv[j] : 0.f;
+      }
+    }
+    if (dz_out) dz_out[i] = pack8(gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      a1[j] += gv[j];
+      a2[j] = fmaf(gv[j], (xv[j] - mu[j]) * is[j], a2[j]);
+    }
+  }
+  float* my = red + threadIdx.x * 17;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    my[j] = a1[j];
+    my[8 + j] = a2[j];
+  }
+  __syncthreads();
+  if (rsub == 0) {
+    for (int k = 1; k < rpi; ++k) {
+      const float* o = red + (k * tpr + cg) * 17;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += o[j];
+        a2[j] += o[8 + j];
+      }
+    }
+    const int C = cvec * 8;
+    float* p1 = partial + (static_cast<long long>(blockIdx.x) * 2 + 0) * C + cg * 8;
+    float* p2 = partial + (static_cast<long long>(blockIdx.x) * 2 + 1) * C + cg * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p1[j] = a1[j];
+      p2[j] = a2[j];
+    }
+  }
+}
+
+// BN backward finalize: partial[T][2][C] -> dbeta = sum dz, dgamma = sum dz*xhat, and the per-channel means used by
+// the apply pass: m1 = dbeta / count, m2 = dgamma / count.
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int T, int C, double count,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
+                                       float* __restrict__ m1, float* __restrict__ m2) {
+  __shared__ double sh[2][8][32];
+  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
+  double s = 0.0, ss = 0.0;
+  if (c < C) {
+    for (int t = ry; t < T; t += 8) {
+      s += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
+      ss += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
+    }
+  }
+  sh[0][ry][cx] = s;
+  sh[1][ry][cx] = ss;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    for (int i = 1; i < 8; ++i) {
+      s += sh[0][i][cx];
+      ss += sh[1][i][cx];
+    }
+    if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s) : static_cast<float>(s);
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(ss) : static_cast<float>(ss);
+    m1[c] = static_cast<float>(s / count);
+    m2[c] = static_cast<float>(ss / count);
+  }
+}
+
+// BN backward, pass 2: dx = scale * (dz - m1 - xhat * m2), dz recomputed exactly as in pass 1 (or read from dz_in).
+__global__ void bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x,
+                                    const uint4* __restrict__ y_out, int g_is_dz, uint4* __restrict__ dx,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ m1, const float* __restrict__ m2, int relu,
+                                    long long nvec, int cvec) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cvec);
+    float sc[8], sh[8], mu[8], is[8], q1[8], q2[8], gv[8], xv[8];
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+    load8f(mean + cg * 8, mu);
+    load8f(invstd + cg * 8, is);
+    load8f(m1 + cg * 8, q1);
+    load8f(m2 + cg * 8, q2);
+    unpack8(__ldg(g + i), gv);
+    unpack8(__ldg(x + i), xv);
+    if (relu && !g_is_dz) {
+      if (y_out) {
+        float yv[8];
+        unpack8(__ldg(y_out + i), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? gv[j] : 0.f;
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = sc[j] * (gv[j] - q1[j] - (xv[j] - mu[j]) * is[j] * q2[j]);
+    dx[i] = pack8(o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Stem: y = maxpool3x3s2p1(relu(x*scale+shift)); also records the arg-max tap (0..8) for the backward pass.
+__global__ void bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                           unsigned long long* __restrict__ idx, const float* __restrict__ scale,
+                                           const float* __restrict__ shift, int B, int H, int W, int cvec) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long nvec = static_cast<long long>(B) * Ho * Wo * cvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cvec);
+    long long t = i / cvec;
+    const int ow = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float sc[8], sh[8], best[8];
+    int bi[8];
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 - 1 + kh;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 - 1 + kw;
+        if (iw < 0 || iw >= W) continue;
+        float v[8];
+        unpack8(__ldg(x + ((static_cast<long long>(b) * H + ih) * W + iw) * cvec + cg), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // round through bf16 so that the comparison sees exactly the activation a stand-alone pass would store
+          const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f)));
+          if (a > best[j]) {
+            best[j] = a;
+            bi[j] = kh * 3 + kw;
+          }
+        }
+      }
+    }
+    y[i] = pack8(best);
+    unsigned long long packed = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) packed |= static_cast<unsigned long long>(bi[j] & 0xFF) << (8 * j);
+    idx[i] = packed;
+  }
+}
+
+// Max-pool backward: g_in[b,h,w,c] = sum over the (<=4) windows covering (h,w) whose arg-max is this pixel.
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ g_out, const unsigned long long* __restrict__ idx,
+                                   uint4* __restrict__ g_in, int B, int H, int W, int cvec) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long nvec = static_cast<long long>(B) * H * W * cvec;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cvec);
+    long long t = i / cvec;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int b = static_cast<int>(t / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // windows oh with 2*oh-1+kh == h  ->  oh = (h+1-kh)/2 for kh with matching parity
+    for (int kh = 0; kh < 3; ++kh) {
+      const int th = h + 1 - kh;
+      if (th < 0 || (th & 1)) continue;
+      const int oh = th >> 1;
+      if (oh >= Ho) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tw = w + 1 - kw;
+        if (tw < 0 || (tw & 1)) continue;
+        const int ow = tw >> 1;
+        if (ow >= Wo) continue;
+        const long long o = ((static_cast<long long>(b) * Ho + oh) * Wo + ow) * cvec + cg;
+        const unsigned long long pk = __ldg(idx + o);
+        float gv[8];
+        unpack8(__ldg(g_out + o), gv);
+        const int tap = kh * 3 + kw;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (static_cast<int>((pk >> (8 * j)) & 0xFF) == tap) acc[j] += gv[j];
+      }
+    }
+    g_in[i] = pack8(acc);
+  }
+}
+
+// Global average pool over HW: x [B][HW][C] bf16 -> y [B][C] bf16.
+__global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int B, int HW, int cvec) {
+  const long long nvec = static_cast<long long>(B) * cvec;
+  const float inv = 1.0f / HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cvec);
+    const long long b = i / cvec;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      float v[8];
+      unpack8(__ldg(x + (b * HW + p) * cvec + cg), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] *= inv;
+    y[i] = pack8(acc);
+  }
+}
+// Backward: g_x[b][p][c] = g_y[b][c] / HW.
+__global__ void avgpool_bwd_kernel(const uint4* __restrict__ gy, uint4* __restrict__ gx, int B, int HW, int cvec) {
+  const long long nvec = static_cast<long long>(B) * HW * cvec;
+  const float inv = 1.0f / HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int cg = static_cast<int>(i % cvec);
+    const long long b = i / (static_cast<long long>(HW) * cvec);
+    float v[8];
+    unpack8(__ldg(gy + b * cvec + cg), v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= inv;
+    gx[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Soft-max cross-entropy (mean reduction) forward + backward in one pass. One block per row.
+//   logits fp32 [B][ld], labels int64 -> loss_rows[B] (fp32, un-normalised), dlogits bf16 [B][ld_d] = (p - onehot)*gscale
+__global__ void softmax_xent_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
+                                    int N, float gscale, float* __restrict__ loss_rows,
+                                    __nv_bfloat16* __restrict__ dlogits, long long ld_d, int* __restrict__ correct) {
+  __shared__ float sh[32];
+  __shared__ int shi[32];
+  const int b = blockIdx.x;
+  const float* row = logits + b * ld;
+  float mx = -INFINITY;
+  int amax = 0;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    const float v = row[j];
+    if (v > mx) {
+      mx = v;
+      amax = j;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+    const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+    if (om > mx || (om == mx && oa < amax)) {
+      mx = om;
+      amax = oa;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[threadIdx.x >> 5] = mx;
+    shi[threadIdx.x >> 5] = amax;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  mx = sh[0];
+  amax = shi[0];
+  for (int i = 1; i < nw; ++i)
+    if (sh[i] > mx || (sh[i] == mx && shi[i] < amax)) {
+      mx = sh[i];
+      amax = shi[i];
+    }
+  __syncthreads();
+  float s = 0.f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s += __expf(row[j] - mx);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int i = 0; i < nw; ++i) s += sh[i];
+  const int label = static_cast<int>(labels[b]);
+  const float lse = mx + logf(s);
+  if (threadIdx.x == 0) {
+    loss_rows[b] = lse - row[label];
+    if (correct) correct[b] = (amax == label) ? 1 : 0;
+  }
+  if (dlogits) {
+    const float inv = 1.0f / s;
+    for (int j = threadIdx.x; j < ld_d; j += blockDim.x) {
+      float d = 0.f;
+      if (j < N) d = (__expf(row[j] - mx) * inv - (j == label ? 1.f : 0.f)) * gscale;
+      dlogits[b * ld_d + j] = __float2bfloat16_rn(d);
+    }
+  }
+}
+
+// mean of n floats -> out[0] (single block)
+__global__ void mean_kernel(const float* __restrict__ v, int n, float* __restrict__ out) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += v[i];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    out[0] = t / n;
+  }
+}
+
+// Column sums of a bf16 matrix [rows][ld] -> fp32 out[cols] (bias gradients). One block per 64 columns.
+__global__ void colsum_kernel(const __nv_bfloat16* __restrict__ m, long long rows, long long ld, int cols,
+                              float* __restrict__ out, int accumulate) {
+  __shared__ float sh[4][64];
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cx;
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = ry; r < rows; r += 4) s += __bfloat162float(m[r * ld + c]);
+  sh[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    s = sh[0][cx] + sh[1][cx] + sh[2][cx] + sh[3][cx];
+    out[c] = accumulate ? out[c] + s : s;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Weight packing: fp32 OIHW master parameter -> bf16 GEMM operand.
+//   mode 0 (forward / wgrad layout): dst[o][tap*I + i]      (row pitch ld_dst, zero padded)
+//   mode 1 (dgrad layout):           dst[i][tap*O + o]
+__global__ void pack_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int O, int I,
+                                   int taps, int mode, long long ld_dst) {
+  const long long rows = mode == 0 ? O : I;
+  const long long total = rows * ld_dst;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = idx / ld_dst;
+    const long long k = idx % ld_dst;
+    float v = 0.f;
+    if (mode == 0) {
+      if (k < static_cast<long long>(taps) * I) {
+        const int tap = static_cast<int>(k / I), i = static_cast<int>(k % I);
+        v = src[(r * I + i) * taps + tap];
+      }
+    } else {
+      if (k < static_cast<long long>(taps) * O) {
+        const int tap = static_cast<int>(k / O), o = static_cast<int>(k % O);
+        v = src[(static_cast<long long>(o) * I + r) * taps + tap];
+      }
+    }
+    dst[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+// fp32 -> bf16 cast of a flat buffer (n multiple of 1 element; scalar tail-safe).
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __float2bfloat16_rn(src[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+
+// Stem im2col: x fp32 NCHW [B][Cin][H][W] -> A bf16 [B*Ho*Wo][ldk], k = (kh*KW + kw)*Cin + c, zero padded to ldk.
+__global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restrict__ a, int B, int Cin, int H, int W,
+                                   int KH, int KW, int stride, int pad, int Ho, int Wo, int ldk) {
+  const int kvec = ldk / 8;
+  const long long nvec = static_cast<long long>(B) * Ho * Wo * kvec;
+  const int K = KH * KW * Cin;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kv = static_cast<int>(i % kvec);
+    long long t = i / kvec;
+    const int ow = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int oh = static_cast<int>(t % Ho);
+    const int b = static_cast<int>(t / Ho);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kv * 8 + j;
+      float val = 0.f;
+      if (k < K) {
+        const int c = k % Cin;
+        const int tap = k / Cin;
+        const int kw = tap % KW, kh = tap / KW;
+        const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
+        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
+          val = __ldg(x + ((static_cast<long long>(b) * Cin + c) * H + ih) * W + iw);
+      }
+      v[j] = val;
+    }
+    a[i] = pack8(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused SGD with momentum over a flat fp32 arena (torch.optim.SGD semantics, dampening 0, no nesterov):
+//   g' = g*gscale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
+__global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                    long long n, float lr, float momentum, float wd, float gscale, int first_step) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float pv = p[i];
+    const float gg = fmaf(wd, pv, g[i] * gscale);
+    const float bv = first_step ? gg : fmaf(momentum, buf[i], gg);
+    buf[i] = bv;
+    p[i] = pv - lr * bv;
+  }
+}
+
+}  // namespace b200

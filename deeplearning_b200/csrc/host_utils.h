@@ -1,0 +1,41 @@
+// Host-side helpers shared by the C-ABI translation units: error convention, TMA descriptor encoding.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace b200 {
+
+// Thread-local last-error text, read through b200_last_error().
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+// Error codes of the C ABI (negative = failure).
+enum : int { OK = 0, EINVAL_ = -1, EUNSUPPORTED_ = -2, ECUDA_ = -3 };
+
+#define B200_CHECK_CUDA(expr)                                                                      \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      ::b200::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return ::b200::ECUDA_;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define B200_REQUIRE(cond, ...)            \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::b200::set_error(__VA_ARGS__);      \
+      return ::b200::EINVAL_;              \
+    }                                      \
+  } while (0)
+
+// Encode a bf16 tiled tensor map of rank 2..4 with 128B swizzle. dims/strides are in elements
+// (innermost first, stride[0] == 1 implied); box in elements. Returns 0 on success.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box);
+
+int device_sm_count();
+
+}  // namespace b200

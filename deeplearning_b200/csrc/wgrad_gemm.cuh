@@ -1,0 +1,231 @@
+// Weight-gradient GEMM for sm_100a:   dW[cout, tap, cin] = sum_pixels dY[pixel, cout] * X_tap[pixel (+tap offset), cin]
+//
+// The reduction runs over pixels, so both operands are "MN-major" for the tensor core: a TMA box of 64 pixels x 64 channels
+// (64 rows of 128 B, 128B swizzle) is exactly one canonical MN-major SWIZZLE_128B atom column (K = pixel rows). The same
+// NHWC activation tensors and the same tap/phase tensor maps as the forward kernel are used - no transposes, no im2col.
+// The pixel range is split across CTAs (split-K); each CTA writes its fp32 partial tile to a workspace which
+// wgrad_reduce_kernel sums deterministically (no atomics) into the OIHW gradient.
+//
+// Replaces the cuDNN backward-filter / cuBLAS calls autograd issues for nn.Conv2d / nn.Linear in the reference
+// (loss.backward(): classification/resnet/utils.py:43).
+#pragma once
+#include "common.cuh"
+#include "conv_gemm.cuh"
+
+namespace b200 {
+
+struct alignas(64) WgradParams {
+  CUtensorMap dy_map;     // 4-D (Cout, d1, d2, d3), box (64, b1, b2, b3), b1*b2*b3 = 64 pixels
+  CUtensorMap x_maps[4];  // 4-D (Cin, ...), same box
+  int num_taps;
+  int Cout, Cin;
+  int mg_tiles, ng_tiles;
+  int tiles1, tiles2, tiles3;
+  int box1, box2, box3;
+  int splits, kb_per_split, kb_total;
+  long long ld_partial;  // taps * Cin (row pitch of the partial matrix, in floats)
+  int8_t tap_map[kMaxTaps];
+  int8_t tap_o1[kMaxTaps];
+  int8_t tap_o2[kMaxTaps];
+  float* partial;  // [splits][Cout][taps*Cin]
+  uint32_t desc_lbo, desc_sbo, desc_kstep;  // MN-major smem descriptor strides (bytes): 8192 / 1024 / 2048
+};
+
+template <int BLOCK_NG>
+struct WgradCfg {
+  static constexpr int BLOCK_K = 64;                       // pixels per stage
+  static constexpr int A_BYTES = 2 * 64 * 128;             // two 64-channel atoms of dY
+  static constexpr int B_BYTES = (BLOCK_NG / 64) * 64 * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_NG == 128) ? 6 : 8;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
+  static constexpr int TMEM_COLS = (2 * BLOCK_NG <= 128) ? 128 : 256;
+};
+
+template <int BLOCK_NG>
+__global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_NG>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint64_t* tmem_empty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  // work item = (split, mg, ng, tap); tap fastest so CTAs sharing the same pixels run together (L2 reuse)
+  const int items_per_split = p.mg_tiles * p.ng_tiles * p.num_taps;
+  const int num_items = items_per_split * p.splits;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&p.dy_map);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.x_maps[i]);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp_idx == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item / items_per_split;
+        int r = item - split * items_per_split;
+        const int tap = r % p.num_taps;
+        r /= p.num_taps;
+        const int ng = r % p.ng_tiles;
+        const int mg = r / p.ng_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const CUtensorMap* xm = &p.x_maps[p.tap_map[tap]];
+        const int o1 = p.tap_o1[tap], o2 = p.tap_o2[tap];
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int t1 = kb % p.tiles1;
+          const int t2 = (kb / p.tiles1) % p.tiles2;
+          const int t3 = kb / (p.tiles1 * p.tiles2);
+          const int c1 = t1 * p.box1, c2 = t2 * p.box2, c3 = t3 * p.box3;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          tma_load_4d(a_dst, &p.dy_map, &full_bar[stage], mg * 128, c1, c2, c3);
+          tma_load_4d(a_dst + 8192, &p.dy_map, &full_bar[stage], mg * 128 + 64, c1, c2, c3);
+#pragma unroll
+          for (int j = 0; j < BLOCK_NG / 64; ++j)
+            tma_load_4d(b_dst + j * 8192, xm, &full_bar[stage], ng * BLOCK_NG + j * 64, c1 + o1, c2 + o2, c3);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp_idx == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_NG, 1, 1);  // both operands MN-major
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        const int split = item / items_per_split;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_NG;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            // 16 pixel rows per MMA = 2048 B; LBO = next 64-channel atom (8192 B); SBO = next 8 pixel rows (1024 B)
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * p.desc_kstep, p.desc_lbo, p.desc_sbo);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * p.desc_kstep, p.desc_lbo, p.desc_sbo);
+            umma_f16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp_idx & 3;
+    const int row = q * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      const int split = item / items_per_split;
+      int r = item - split * items_per_split;
+      const int tap = r % p.num_taps;
+      r /= p.num_taps;
+      const int ng = r % p.ng_tiles;
+      const int mg = r / p.ng_tiles;
+      const int cout = mg * 128 + row;
+      float* out_row = p.partial + (static_cast<long long>(split) * p.Cout + cout) * p.ld_partial +
+                       static_cast<long long>(tap) * p.Cin + ng * BLOCK_NG;
+      // (the host guarantees every split owns at least one pixel block)
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + acc * BLOCK_NG + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_NG / 32; ++ch) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_acc + ch * 32, v);
+        tmem_ld_wait();
+        if (cout < p.Cout) {
+          const int cin0 = ng * BLOCK_NG + ch * 32;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (cin0 + j * 4 < p.Cin) {  // Cin is a multiple of 8
+              uint4 w = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              *reinterpret_cast<uint4*>(out_row + ch * 32 + j * 4) = w;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp_idx == 1) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+// grad[cout][cin][tap] (OIHW, fp32) (+)= sum_s partial[s][cout][tap*Cin + cin]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
+                                    int Cin, int taps, int accumulate) {
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  const long long slice = total;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    // i indexes the partial layout (coalesced reads): [cout][tap][cin]
+    const int cin = static_cast<int>(i % Cin);
+    const long long t = i / Cin;
+    const int tap = static_cast<int>(t % taps);
+    const int cout = static_cast<int>(t / taps);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[k * slice + i];
+    const long long o = (static_cast<long long>(cout) * Cin + cin) * taps + tap;
+    grad[o] = accumulate ? grad[o] + s : s;
+  }
+}
+
+}  // namespace b200

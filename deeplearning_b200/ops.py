@@ -1,0 +1,287 @@
+"""Tensor-level wrappers over the C ABI (include/b200cls.h).
+
+PyTorch is used for device memory and streams only; every arithmetic op below is a hand-written sm_100a kernel.
+Activations are NHWC bf16 tensors ``[B, H, W, C]`` (``[rows, C]`` for linear layers); parameters and statistics fp32.
+"""
+import torch
+
+from . import _lib
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _chk_act(t, name):
+    if t.dtype != BF16 or not t.is_cuda or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
+
+
+def out_hw(h, ksize, stride):
+    return (h + 2 * (ksize // 2) - ksize) // stride + 1
+
+
+# --------------------------------------------------------------------------------------------------------- packing
+def pack_weight(w, mode=0, ld=None):
+    """fp32 OIHW (or [out,in]) parameter -> bf16 GEMM operand. mode 0: [O][taps*I]; mode 1 (dgrad): [I][taps*O]."""
+    lib = _lib.load()
+    w = w.detach()
+    if w.dtype != F32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    O, I = w.shape[0], w.shape[1]
+    taps = 1
+    for d in w.shape[2:]:
+        taps *= d
+    rows = O if mode == 0 else I
+    cols = taps * (I if mode == 0 else O)
+    ld = cols if ld is None else ld
+    out = torch.empty(rows, ld, dtype=BF16, device=w.device)
+    _lib.check(lib.b200_pack_weight(_p(w), _p(out), O, I, taps, mode, ld, _stream()), "b200_pack_weight")
+    return out
+
+
+def cast_bf16(x):
+    lib = _lib.load()
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    _lib.check(lib.b200_cast_f32_to_bf16(_p(x), _p(out), x.numel(), _stream()), "b200_cast_f32_to_bf16")
+    return out
+
+
+def cast_f32(x):
+    lib = _lib.load()
+    out = torch.empty(x.shape, dtype=F32, device=x.device)
+    _lib.check(lib.b200_cast_bf16_to_f32(_p(x), _p(out), x.numel(), _stream()), "b200_cast_bf16_to_f32")
+    return out
+
+
+def im2col_nchw(x, KH, KW, stride, pad, ldk):
+    """Stem only: fp32 NCHW batch -> bf16 [B*Ho*Wo, ldk] patch matrix (k = (kh*KW+kw)*Cin + c)."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    a = torch.empty(B * Ho * Wo, ldk, dtype=BF16, device=x.device)
+    _lib.check(lib.b200_im2col_nchw(_p(x), _p(a), B, C, H, W, KH, KW, stride, pad, ldk, _stream()), "b200_im2col_nchw")
+    return a, Ho, Wo
+
+
+# --------------------------------------------------------------------------------------------------------- conv / linear
+def conv2d_fwd(x, w_packed, ksize=1, stride=1, want_stats=False, bias=None, act=0, residual=None, out_f32=False):
+    """y = conv(x) (+bias)(act)(+residual). Returns (y, stats) with stats = [T,2,Cout] partial sums or None."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    Ho, Wo = out_hw(H, ksize, stride), out_hw(W, ksize, stride)
+    stats = None
+    if want_stats:
+        T = lib.b200_conv2d_fwd_mtiles(B, H, W, ksize, stride)
+        stats = torch.empty(T, 2, Cout, dtype=F32, device=x.device)
+    if out_f32:
+        y = torch.empty(B, Ho, Wo, Cout, dtype=F32, device=x.device)
+        rc = lib.b200_conv2d_fwd(_p(x), _p(w_packed), None, B, H, W, Cin, Cout, ksize, stride, _p(stats), _p(bias), act,
+                                 _p(residual), _p(y), Cout, _stream())
+    else:
+        y = torch.empty(B, Ho, Wo, Cout, dtype=BF16, device=x.device)
+        rc = lib.b200_conv2d_fwd(_p(x), _p(w_packed), _p(y), B, H, W, Cin, Cout, ksize, stride, _p(stats), _p(bias), act,
+                                 _p(residual), None, 0, _stream())
+    _lib.check(rc, "b200_conv2d_fwd")
+    return y, stats
+
+
+def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=None):
+    """dx[B,H,W,Cin] from dy[B,Ho,Wo,Cout]; wd_packed = pack_weight(w, mode=1). `out` lets 1x1/s2 accumulate in place."""
+    lib = _lib.load()
+    _chk_act(dy, "dy")
+    B, Ho, Wo, Cout = dy.shape
+    H, W = in_hw
+    Cin = wd_packed.shape[0]
+    dx = out if out is not None else torch.empty(B, H, W, Cin, dtype=BF16, device=dy.device)
+    rc = lib.b200_conv2d_dgrad(_p(dy), _p(wd_packed), _p(dx), B, H, W, Cin, Cout, ksize, stride, _p(residual), _stream())
+    _lib.check(rc, "b200_conv2d_dgrad")
+    return dx
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False):
+    """dw fp32 OIHW [Cout, Cin, k, k] = sum over pixels of dy (x) x."""
+    lib = _lib.load()
+    _chk_act(dy, "dy")
+    _chk_act(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    nbytes = lib.b200_conv2d_wgrad_workspace_bytes(B, H, W, Cin, Cout, ksize, stride)
+    ws = _workspace(nbytes, x.device)
+    if out is None:
+        out = torch.empty(Cout, Cin, ksize, ksize, dtype=F32, device=x.device)
+        accumulate = False
+    rc = lib.b200_conv2d_wgrad(_p(dy), _p(x), _p(out), _p(ws), ws.numel(), B, H, W, Cin, Cout, ksize, stride,
+                               1 if accumulate else 0, _stream())
+    _lib.check(rc, "b200_conv2d_wgrad")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------- batch norm
+class BnCoeffs:
+    """Per-channel vectors of one BatchNorm application (all fp32 [C])."""
+    __slots__ = ("mean", "invstd", "scale", "shift")
+
+    def __init__(self, C, device):
+        buf = torch.empty(4, C, dtype=F32, device=device)
+        self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked):
+    lib = _lib.load()
+    T, _, C = stats.shape
+    co = BnCoeffs(C, stats.device)
+    rc = lib.b200_bn_finalize(_p(stats), T, C, float(count), _p(gamma), _p(beta), eps, momentum, _p(running_mean),
+                              _p(running_var), _p(num_batches_tracked), _p(co.mean), _p(co.invstd), _p(co.scale),
+                              _p(co.shift), _stream())
+    _lib.check(rc, "b200_bn_finalize")
+    return co
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps):
+    lib = _lib.load()
+    C = gamma.numel()
+    co = BnCoeffs(C, gamma.device)
+    co.mean.copy_(running_mean)
+    rc = lib.b200_bn_eval_coeffs(C, _p(gamma), _p(beta), _p(running_mean), _p(running_var), eps, _p(co.scale),
+                                 _p(co.shift), _stream())
+    _lib.check(rc, "b200_bn_eval_coeffs")
+    return co
+
+
+def bn_apply(x, co, relu=True, residual=None):
+    lib = _lib.load()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty_like(x)
+    rc = lib.b200_bn_apply(_p(x), _p(residual), _p(y), _p(co.scale), _p(co.shift), rows, C, 1 if relu else 0, _stream())
+    _lib.check(rc, "b200_bn_apply")
+    return y
+
+
+def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbeta=None):
+    """Train-mode BN (+ReLU) backward. g: grad wrt the post-activation output; x: raw conv output.
+    Returns (dx, dgamma, dbeta, dz) with dz only when want_dz (masked upstream gradient, bf16)."""
+    lib = _lib.load()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    nblk = lib.b200_bn_bwd_blocks(rows, C)
+    if nblk <= 0:
+        raise RuntimeError(f"bn_backward: unsupported channel count {C}")
+    partial = torch.empty(nblk, 2, C, dtype=F32, device=x.device)
+    dz = torch.empty_like(x) if want_dz else None
+    rc = lib.b200_bn_bwd_reduce(_p(g), _p(x), _p(y_out), _p(dz), _p(co.scale), _p(co.shift), _p(co.mean),
+                                _p(co.invstd), 1 if relu else 0, rows, C, _p(partial), _stream())
+    _lib.check(rc, "b200_bn_bwd_reduce")
+    acc = 0
+    if dgamma is None:
+        dgamma = torch.empty(C, dtype=F32, device=x.device)
+        dbeta = torch.empty(C, dtype=F32, device=x.device)
+    else:
+        acc = 1
+    m = torch.empty(2, C, dtype=F32, device=x.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, float(rows), _p(dgamma), _p(dbeta), acc, _p(m[0]), _p(m[1]),
+                                  _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    dx = torch.empty_like(x)
+    src = dz if want_dz else g
+    rc = lib.b200_bn_bwd_apply(_p(src), _p(x), _p(y_out), 1 if want_dz else 0, _p(dx), _p(co.scale), _p(co.shift),
+                               _p(co.mean), _p(co.invstd), _p(m[0]), _p(m[1]), 1 if relu else 0, rows, C, _stream())
+    _lib.check(rc, "b200_bn_bwd_apply")
+    return dx, dgamma, dbeta, dz
+
+
+# --------------------------------------------------------------------------------------------------------- pooling
+def bn_relu_maxpool_fwd(x, co):
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty(B, Ho, Wo, C, dtype=BF16, device=x.device)
+    idx = torch.empty(B, Ho, Wo, C // 8, dtype=torch.int64, device=x.device)
+    rc = lib.b200_bn_relu_maxpool_fwd(_p(x), _p(y), _p(idx), _p(co.scale), _p(co.shift), B, H, W, C, _stream())
+    _lib.check(rc, "b200_bn_relu_maxpool_fwd")
+    return y, idx
+
+
+def maxpool_bwd(g_out, idx, in_hw):
+    lib = _lib.load()
+    B, Ho, Wo, C = g_out.shape
+    H, W = in_hw
+    g_in = torch.empty(B, H, W, C, dtype=BF16, device=g_out.device)
+    _lib.check(lib.b200_maxpool_bwd(_p(g_out), _p(idx), _p(g_in), B, H, W, C, _stream()), "b200_maxpool_bwd")
+    return g_in
+
+
+def avgpool_fwd(x):
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    y = torch.empty(B, C, dtype=BF16, device=x.device)
+    _lib.check(lib.b200_avgpool_fwd(_p(x), _p(y), B, H * W, C, _stream()), "b200_avgpool_fwd")
+    return y
+
+
+def avgpool_bwd(gy, hw):
+    lib = _lib.load()
+    B, C = gy.shape
+    H, W = hw
+    gx = torch.empty(B, H, W, C, dtype=BF16, device=gy.device)
+    _lib.check(lib.b200_avgpool_bwd(_p(gy), _p(gx), B, H * W, C, _stream()), "b200_avgpool_bwd")
+    return gx
+
+
+# --------------------------------------------------------------------------------------------------------- loss / optimiser
+def softmax_xent(logits, labels, want_grad=True, ld_d=None):
+    """Mean cross-entropy. Returns (loss scalar tensor, dlogits bf16 [B, ld_d] or None, correct int32 [B])."""
+    lib = _lib.load()
+    B, N = logits.shape
+    ld_d = ld_d or ((N + 7) // 8) * 8
+    rows = torch.empty(B, dtype=F32, device=logits.device)
+    correct = torch.empty(B, dtype=torch.int32, device=logits.device)
+    d = torch.empty(B, ld_d, dtype=BF16, device=logits.device) if want_grad else None
+    rc = lib.b200_softmax_xent(_p(logits), logits.stride(0), _p(labels), B, N, 1.0 / B, _p(rows), _p(d), ld_d,
+                               _p(correct), _stream())
+    _lib.check(rc, "b200_softmax_xent")
+    loss = torch.empty(1, dtype=F32, device=logits.device)
+    _lib.check(lib.b200_mean(_p(rows), B, _p(loss), _stream()), "b200_mean")
+    return loss, d, correct
+
+
+def colsum(m, cols=None, out=None, accumulate=False):
+    lib = _lib.load()
+    rows, ld = m.shape
+    cols = cols or ld
+    if out is None:
+        out = torch.empty(cols, dtype=F32, device=m.device)
+        accumulate = False
+    _lib.check(lib.b200_colsum_bf16(_p(m), rows, ld, cols, _p(out), 1 if accumulate else 0, _stream()), "b200_colsum_bf16")
+    return out
+
+
+def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=False):
+    lib = _lib.load()
+    rc = lib.b200_sgd_momentum(_p(p), _p(g), _p(buf), p.numel(), lr, momentum, weight_decay, gscale,
+                               1 if first_step else 0, _stream())
+    _lib.check(rc, "b200_sgd_momentum")

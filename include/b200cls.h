@@ -1,0 +1,127 @@
+/* libb200cls.so - C ABI of the B200-native classification training step.
+ *
+ * The reference (KKKSQJ/DeepLearning) has no operator registry on this path: every op is a stock PyTorch call
+ * (nn.Conv2d / nn.BatchNorm2d / nn.Linear / ... -> ATen -> cuDNN / cuBLAS, or oneDNN on CPU), and the only FFI it owns is
+ * the pybind module `swin_window_process` (classification/swin_transformer/kernels/window_process/swin_window_process.cpp:70-131).
+ * Each entry point below names the reference call site whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - plain C, no C++ types, no torch types; all pointers are DEVICE pointers unless stated otherwise.
+ *   - activations are NHWC bf16 (channel count a multiple of 8); parameters/gradients/statistics are fp32.
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library never allocates device memory.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no device synchronisation inside, so every call
+ *     is CUDA-Graph capturable.
+ *   - return 0 on success, negative on failure (B200_EINVAL / B200_EUNSUPPORTED / B200_ECUDA); b200_last_error() returns
+ *     a thread-local message. Launch errors are detected with cudaPeekAtLastError only.
+ */
+#ifndef B200CLS_H_
+#define B200CLS_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_EINVAL (-1)
+#define B200_EUNSUPPORTED (-2)
+#define B200_ECUDA (-3)
+
+#define B200_ACT_NONE 0
+#define B200_ACT_RELU 1
+#define B200_ACT_GELU 2
+
+const char* b200_last_error(void);
+int b200_abi_version(void);
+/* Number of SMs of the current device (used by callers to size workspaces). */
+int b200_sm_count(void);
+
+/* ---- convolution / linear as implicit GEMM on tcgen05 (ksize in {1,3}, stride in {1,2}, pad = ksize/2) --------------
+ * forward:  y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w) (+bias) (act) (+residual)
+ *   w        bf16 [Cout][ksize*ksize*Cin]   (b200_pack_weight mode 0)
+ *   stats    optional fp32 [b200_conv2d_fwd_mtiles()][2][Cout]: per 128-pixel tile sum and sum of squares of y (as stored)
+ *   residual optional bf16, same shape as y, added after bias/act
+ *   out_f32  optional fp32 [B*Ho*Wo][ld_out] - when given the result is written there instead of y (ksize 1 only)
+ * replaces nn.Conv2d.forward / nn.Linear.forward: classification/resnet/models/networks.py:107,111,115,119,218;
+ * classification/vision_transformer/vit_model.py:66,95,109,129,132. A linear layer is the case H=W=1, B=rows. */
+int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
+                    float* stats, const float* bias, int act, const void* residual, float* out_f32, long long ld_out,
+                    void* stream);
+int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride);
+
+/* data gradient: dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout], w) (+residual, same shape as dx; may alias dx)
+ *   wd  bf16 [Cin][ksize*ksize*Cout]  (b200_pack_weight mode 1)
+ *   ksize 1 & stride 2 writes only the even (h,w) pixels of dx; the others keep their previous contents.
+ * replaces the cuDNN backward-data / cuBLAS dgrad autograd runs inside loss.backward() (classification/resnet/utils.py:43). */
+int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, int W, int Cin, int Cout, int ksize,
+                      int stride, const void* residual, void* stream);
+
+/* weight gradient: dw[Cout][Cin][ksize][ksize] (fp32, OIHW) (+)= sum_pixels dy (x) x
+ *   workspace: b200_conv2d_wgrad_workspace_bytes() bytes of scratch for the split-K partial tiles.
+ * replaces the cuDNN backward-filter / cuBLAS wgrad inside loss.backward(). */
+int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
+                      int W, int Cin, int Cout, int ksize, int stride, int accumulate, void* stream);
+size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
+
+/* ---- BatchNorm2d (train: batch statistics, eval: running statistics) ----------------------------------------------------
+ * replaces nn.BatchNorm2d + nn.ReLU (+ residual add) of Bottleneck.forward, classification/resnet/models/networks.py:108-124 */
+int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,
+                     float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
+                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                        const float* running_var, float eps, float* scale, float* shift, void* stream);
+/* y = act(x*scale[c]+shift[c] (+residual)); x,y,residual bf16 [rows][C] */
+int b200_bn_apply(const void* x, const void* residual, void* y, const float* scale, const float* shift, long long rows,
+                  int C, int relu, void* stream);
+/* backward pass 1: partial[b200_bn_bwd_blocks()][2][C] = per-block sums of dz and dz*xhat, dz = g*relu_mask.
+ *   y_out (optional) = saved post-activation output used for the mask; otherwise the mask is recomputed from x.
+ *   dz_out (optional) receives dz as bf16. */
+int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
+                       const float* shift, const float* mean, const float* invstd, int relu, long long rows, int C,
+                       float* partial, void* stream);
+int b200_bn_bwd_blocks(long long rows, int C);
+int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
+                         float* m1, float* m2, void* stream);
+/* backward pass 2: dx = scale*(dz - m1 - xhat*m2); g_is_dz != 0 means `g` already holds dz (mask applied). */
+int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
+                      int relu, long long rows, int C, void* stream);
+
+/* ---- pooling ----------------------------------------------------------------------------------------------------------
+ * stem: y[B,Ho,Wo,C] = maxpool3x3/s2/p1(relu(x*scale+shift)); idx = one byte arg-max tap per element (uint64 per 8 ch)
+ * replaces bn1 -> relu -> maxpool, classification/resnet/models/networks.py:207-209 */
+int b200_bn_relu_maxpool_fwd(const void* x, void* y, void* idx, const float* scale, const float* shift, int B, int H,
+                             int W, int C, void* stream);
+int b200_maxpool_bwd(const void* g_out, const void* idx, void* g_in, int B, int H, int W, int C, void* stream);
+/* global average pool, classification/resnet/models/networks.py:216 */
+int b200_avgpool_fwd(const void* x, void* y, int B, int HW, int C, void* stream);
+int b200_avgpool_bwd(const void* gy, void* gx, int B, int HW, int C, void* stream);
+
+/* ---- loss / misc ------------------------------------------------------------------------------------------------------
+ * CrossEntropyLoss(mean) forward+backward; classification/resnet/train.py:104, utils.py:39-42.
+ *   loss_rows[B] per-sample loss; dlogits (optional) bf16 [B][ld_d] = (softmax - onehot)*gscale; correct (optional) int[B] */
+int b200_softmax_xent(const float* logits, long long ld, const long long* labels, int B, int N, float gscale,
+                      float* loss_rows, void* dlogits, long long ld_d, int* correct, void* stream);
+int b200_mean(const float* v, int n, float* out, void* stream);
+int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, float* out, int accumulate, void* stream);
+
+/* weight packing fp32 OIHW -> bf16 GEMM operand; mode 0: [O][taps*I] (pitch ld_dst), mode 1: [I][taps*O] */
+int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mode, long long ld_dst, void* stream);
+int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
+/* stem im2col from the user's NCHW fp32 batch: a bf16 [B*Ho*Wo][ldk], k=(kh*KW+kw)*Cin+c (networks.py:206 conv1 7x7/2) */
+int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int KH, int KW, int stride, int pad,
+                     int ldk, void* stream);
+
+/* fused SGD(momentum) over a flat fp32 arena; torch.optim.SGD semantics (classification/resnet/train.py:96) */
+int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
+                      float gscale, int first_step, void* stream);
+
+/* bring-up only: override the UMMA shared-memory descriptor strides (which: 0 = forward K-major, 1 = wgrad MN-major) */
+int b200_debug_set_desc(int which, unsigned lbo, unsigned sbo, unsigned kstep);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLS_H_ */

@@ -1,0 +1,221 @@
+"""GPU parity tests of the individual sm_100a kernels against a plain PyTorch fp32 reference of the same op.
+
+Inputs are rounded to bf16 first so that the only differences are accumulation order and the bf16 rounding of outputs.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from deeplearning_b200 import ops
+
+    return ops
+
+
+def _rand(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _ref_conv(x_nhwc, w_oihw, ksize, stride):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = x_nhwc.float().permute(0, 3, 1, 2).contiguous()
+    return F.conv2d(x, w_oihw.float(), stride=stride, padding=ksize // 2)
+
+
+def _close(a, b, rtol, atol, what):
+    a, b = a.float(), b.float()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} bad, max abs err {float(err.max()):.4g} (ref max {float(b.abs().max()):.4g})"
+
+
+CONV_CASES = [
+    # B, H, W, Cin, Cout, k, s
+    (2, 8, 8, 64, 64, 1, 1),
+    (3, 7, 7, 128, 256, 1, 1),
+    (2, 14, 14, 256, 1000, 1, 1),
+    (4, 1, 1, 72, 40, 1, 1),
+    (2, 56, 56, 64, 64, 3, 1),
+    (2, 14, 14, 128, 128, 3, 1),
+    (3, 7, 7, 64, 192, 3, 1),
+    (2, 28, 28, 128, 128, 3, 2),
+    (2, 14, 14, 64, 64, 3, 2),
+    (2, 28, 28, 64, 128, 1, 2),
+    (1, 9, 11, 64, 64, 3, 1),
+    (1, 10, 6, 64, 64, 3, 2),
+]
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", CONV_CASES)
+def test_conv_fwd(B, H, W, Cin, Cout, k, s):
+    ops = _ops()
+    x = _rand(B, H, W, Cin, seed=1)
+    w = _rand(Cout, Cin, k, k, scale=(Cin * k * k) ** -0.5, seed=2)
+    wp = ops.pack_weight(w.float())
+    y, stats = ops.conv2d_fwd(x, wp, k, s, want_stats=True)
+    ref = _ref_conv(x, w, k, s).permute(0, 2, 3, 1)
+    _close(y, ref, 1e-2, 1e-2, "conv fwd")
+    # statistics of the stored (bf16) output
+    yf = y.float().reshape(-1, Cout)
+    _close(stats[:, 0].sum(0), yf.sum(0), 1e-3, 1e-2, "stats sum")
+    _close(stats[:, 1].sum(0), (yf * yf).sum(0), 1e-3, 1e-2, "stats sumsq")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", CONV_CASES)
+def test_conv_dgrad(B, H, W, Cin, Cout, k, s):
+    ops = _ops()
+    w = _rand(Cout, Cin, k, k, scale=(Cout * k * k) ** -0.5, seed=3)
+    Ho, Wo = ops.out_hw(H, k, s), ops.out_hw(W, k, s)
+    dy = _rand(B, Ho, Wo, Cout, seed=4)
+    wd = ops.pack_weight(w.float(), mode=1)
+    x = torch.zeros(B, Cin, H, W, device="cuda", requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    yr = F.conv2d(x, w.float(), stride=s, padding=k // 2)
+    (gx,) = torch.autograd.grad(yr, x, dy.float().permute(0, 3, 1, 2))
+    ref = gx.permute(0, 2, 3, 1)
+    if k == 1 and s == 2:
+        base = _rand(B, H, W, Cin, seed=5)
+        out = base.clone()
+        dx = ops.conv2d_dgrad(dy, wd, (H, W), k, s, residual=out, out=out)
+        ref = ref + base.float()
+    else:
+        res = _rand(B, H, W, Cin, seed=6)
+        dx = ops.conv2d_dgrad(dy, wd, (H, W), k, s, residual=res)
+        ref = ref + res.float()
+    _close(dx, ref, 1e-2, 2e-2, "conv dgrad")
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", CONV_CASES)
+def test_conv_wgrad(B, H, W, Cin, Cout, k, s):
+    ops = _ops()
+    x = _rand(B, H, W, Cin, seed=7)
+    Ho, Wo = ops.out_hw(H, k, s), ops.out_hw(W, k, s)
+    dy = _rand(B, Ho, Wo, Cout, seed=8)
+    w = torch.zeros(Cout, Cin, k, k, device="cuda", requires_grad=True)
+    torch.backends.cudnn.allow_tf32 = False
+    yr = F.conv2d(x.float().permute(0, 3, 1, 2), w, stride=s, padding=k // 2)
+    (gw,) = torch.autograd.grad(yr, w, dy.float().permute(0, 3, 1, 2))
+    dw = ops.conv2d_wgrad(dy, x, k, s)
+    scale = float(gw.abs().max()) + 1e-6
+    _close(dw / scale, gw / scale, 1e-3, 2e-3, "conv wgrad")
+
+
+def test_linear_epilogues():
+    ops = _ops()
+    M, K, N = 300, 200, 136
+    x = _rand(M, 1, 1, K, seed=11)
+    w = _rand(N, K, scale=K ** -0.5, seed=12)
+    b = torch.randn(N, device="cuda")
+    res = _rand(M, 1, 1, N, seed=13)
+    wp = ops.pack_weight(w.float())
+    ref = x.float().reshape(M, K) @ w.float().t() + b
+    y, _ = ops.conv2d_fwd(x, wp, bias=b, act=2, residual=res)
+    _close(y.reshape(M, N), F.gelu(ref) + res.float().reshape(M, N), 1e-2, 1e-2, "bias+gelu+res")
+    y, _ = ops.conv2d_fwd(x, wp, bias=b, act=1)
+    _close(y.reshape(M, N), F.relu(ref), 1e-2, 1e-2, "bias+relu")
+    y, _ = ops.conv2d_fwd(x, wp, bias=b, out_f32=True)
+    _close(y.reshape(M, N), ref, 1e-4, 1e-4, "fp32 out")
+
+
+@pytest.mark.parametrize("rows,C", [(2 * 56 * 56, 64), (1000, 256), (98, 2048)])
+def test_batchnorm_train_fwd_bwd(rows, C):
+    ops = _ops()
+    x = _rand(rows, 1, 1, C, seed=21) * 1.5 + 0.3
+    x = x.to(torch.bfloat16)
+    g = _rand(rows, 1, 1, C, seed=22)
+    res = _rand(rows, 1, 1, C, seed=23)
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.1
+    # identity-weight 1x1 conv just to get the statistics partials through the real epilogue path
+    eye = torch.eye(C, device="cuda").reshape(C, C, 1, 1)
+    y_raw, stats = ops.conv2d_fwd(x, ops.pack_weight(eye), want_stats=True)
+    assert torch.equal(y_raw, x)
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    co = ops.bn_finalize(stats, rows, gamma, beta, 1e-5, 0.1, rm, rv, nbt)
+    xr = x.float().reshape(rows, C).clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    bn = F.batch_norm(xr, rm2, rv2, gr, br, True, 0.1, 1e-5)
+    _close(rm, rm2, 1e-4, 1e-5, "running_mean")
+    _close(rv, rv2, 1e-4, 1e-5, "running_var")
+    assert int(nbt) == 1
+    for use_res in (False, True):
+        out_ref = F.relu(bn + res.float().reshape(rows, C)) if use_res else F.relu(bn)
+        y = ops.bn_apply(x, co, relu=True, residual=res if use_res else None)
+        _close(y.reshape(rows, C), out_ref, 1e-2, 1e-2, "bn apply")
+        gx, ggam, gbet = torch.autograd.grad(out_ref, (xr, gr, br), g.float().reshape(rows, C), retain_graph=True)
+        dx, dgam, dbet, dz = ops.bn_backward(g, x, co, relu=True, y_out=y if use_res else None, want_dz=use_res)
+        # masks can differ where the bf16 output rounds to exactly 0; tolerate through norms
+        sc = float(gx.abs().max())
+        assert float((dx.float().reshape(rows, C) - gx).abs().max()) < 0.05 * sc + 1e-3
+        _close(dgam, ggam, 2e-2, 2e-2 * float(ggam.abs().max()), "dgamma")
+        _close(dbet, gbet, 2e-2, 2e-2 * float(gbet.abs().max()), "dbeta")
+
+
+def test_stem_pool_and_avgpool():
+    ops = _ops()
+    B, H, W, C = 2, 16, 16, 64
+    x = _rand(B, H, W, C, seed=31)
+    co = ops.BnCoeffs(C, "cuda")
+    co.scale.copy_(torch.rand(C, device="cuda") + 0.5)
+    co.shift.copy_(torch.randn(C, device="cuda") * 0.2)
+    y, idx = ops.bn_relu_maxpool_fwd(x, co)
+    a = F.relu(x.float() * co.scale + co.shift).to(torch.bfloat16).float().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(a, 3, 2, 1)
+    assert torch.equal(y.float(), ref.permute(0, 2, 3, 1))
+    g = _rand(B, H // 2, W // 2, C, seed=32)
+    (ga,) = torch.autograd.grad(ref, a, g.float().permute(0, 3, 1, 2))
+    gin = ops.maxpool_bwd(g, idx, (H, W))
+    # ties between equal bf16 activations may route to a different (equal-valued) element: compare window sums
+    _close(gin.float().sum((1, 2)), ga.permute(0, 2, 3, 1).sum((1, 2)), 1e-2, 5e-2, "maxpool bwd mass")
+    nz = (a.permute(0, 2, 3, 1) > 0)
+    match = ((gin.float() - ga.permute(0, 2, 3, 1)).abs() < 1e-2) | ~nz
+    assert match.float().mean() > 0.98
+    z = _rand(3, 7, 7, 128, seed=33)
+    p = ops.avgpool_fwd(z)
+    _close(p, z.float().mean((1, 2)), 1e-2, 1e-2, "avgpool")
+    gz = ops.avgpool_bwd(p, (7, 7))
+    _close(gz, (p.float() / 49)[:, None, None, :].expand(3, 7, 7, 128), 1e-2, 1e-3, "avgpool bwd")
+
+
+def test_softmax_xent_and_sgd():
+    ops = _ops()
+    B, N = 37, 1000
+    logits = torch.randn(B, N, device="cuda") * 3
+    labels = torch.randint(0, N, (B,), device="cuda")
+    lr_ = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lr_, labels)
+    (gl,) = torch.autograd.grad(ref, lr_)
+    loss, d, correct = ops.softmax_xent(logits, labels)
+    assert abs(float(loss) - float(ref)) < 1e-4
+    _close(d[:, :N], gl, 1e-2, 1e-5, "dlogits")
+    assert torch.equal(correct.bool(), logits.argmax(1) == labels)
+    n = 100003
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.SGD([pr], lr=0.1, momentum=0.9, weight_decay=5e-5)
+    buf = torch.zeros(n, device="cuda")
+    for step in range(3):
+        pr.grad = g.clone()
+        opt.step()
+        ops.sgd_momentum_(p, g, buf, 0.1, 0.9, 5e-5, first_step=(step == 0))
+    _close(p, pr.detach(), 1e-5, 1e-6, "sgd")
+
+
+def test_stem_im2col():
+    ops = _ops()
+    x = torch.randn(2, 3, 32, 32, device="cuda")
+    w = torch.randn(64, 3, 7, 7, device="cuda") * 0.1
+    a, Ho, Wo = ops.im2col_nchw(x, 7, 7, 2, 3, 160)
+    wp = ops.pack_weight(w, ld=160)
+    y, _ = ops.conv2d_fwd(a.reshape(-1, 1, 1, 160), wp)
+    ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=3).permute(0, 2, 3, 1)
+    _close(y.reshape(2, Ho, Wo, 64), ref, 1e-2, 1e-2, "stem conv")
