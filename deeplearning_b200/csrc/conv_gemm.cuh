@@ -263,6 +263,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
           continue;
         }
 
+        if (!row_ok) {
+          // rows of a partial pixel box: clipped by the TMA store, and must not pollute the BN statistics
+#pragma unroll
+          for (int j = 0; j < 64; ++j) f[j] = 0.f;
+        }
         // ---- bf16 path: registers -> swizzled staging -> TMA store
         uint8_t* buf = staging + (store_counter & 1) * Cfg::STAGING_BYTES;
         ++store_counter;

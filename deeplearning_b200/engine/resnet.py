@@ -1,0 +1,224 @@
+"""Forward / backward schedule of the ResNet family on the sm_100a kernels.
+
+The whole network is ONE ``torch.autograd.Function``: forward runs conv(+BN statistics in the GEMM epilogue) -> finalize ->
+apply(+ReLU)(+residual) per layer and records the tensors the backward needs on a tape; backward replays the tape with
+BN-backward reduce/apply passes, tcgen05 dgrad and wgrad GEMMs.  Residual additions never get their own pass: the identity
+gradient is added in the epilogue of the first conv's dgrad GEMM.
+
+Mirrors ``ResNet._forward_impl`` / ``Bottleneck.forward`` / ``BasicBlock.forward`` of the reference
+(classification/resnet/models/networks.py:204-220, :104-124, :59-75); activations are NHWC bf16, parameters fp32.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+from .packing import weight_cache
+
+BF16 = torch.bfloat16
+
+
+def _check_conv(conv, name):
+    k = conv.kernel_size[0]
+    if (conv.groups != 1 or conv.dilation != (1, 1) or conv.kernel_size[0] != conv.kernel_size[1] or conv.bias is not None
+            or conv.padding != (k // 2, k // 2) or conv.stride[0] != conv.stride[1] or conv.stride[0] not in (1, 2)):
+        raise NotImplementedError(f"{name}: only dense k x k convolutions with pad=k//2, stride 1/2, no bias run on the "
+                                  f"B200 engine (got {conv})")
+
+
+def _check_bn(bn, name):
+    if not isinstance(bn, nn.BatchNorm2d) or not bn.affine or not bn.track_running_stats or bn.momentum is None:
+        raise NotImplementedError(f"{name}: the B200 engine implements affine nn.BatchNorm2d with running statistics (got {bn})")
+
+
+class _Unit:
+    """Saved state of one conv -> BN (-> ReLU) (-> + residual) application."""
+    __slots__ = ("conv", "bn", "x", "c", "co", "y", "relu", "has_res")
+
+
+def _conv_bn(tape, x, conv, bn, train, relu, residual=None, name=""):
+    _check_conv(conv, name)
+    _check_bn(bn, name)
+    k, s = conv.kernel_size[0], conv.stride[0]
+    wp = weight_cache.get(conv.weight, 0)
+    c, st = ops.conv2d_fwd(x, wp, k, s, want_stats=train)
+    if train:
+        rows = c.numel() // c.shape[-1]
+        co = ops.bn_finalize(st, rows, bn.weight, bn.bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                             bn.num_batches_tracked)
+    else:
+        co = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    y = ops.bn_apply(c, co, relu=relu, residual=residual)
+    if tape is not None:
+        u = _Unit()
+        u.conv, u.bn, u.x, u.c, u.co, u.y, u.relu, u.has_res = conv, bn, x, c, co, y, relu, residual is not None
+        tape.append(u)
+    return y
+
+
+def _block_units(block):
+    """(conv, bn) pairs of the residual branch, in order."""
+    if hasattr(block, "conv3"):
+        return [(block.conv1, block.bn1), (block.conv2, block.bn2), (block.conv3, block.bn3)]
+    return [(block.conv1, block.bn1), (block.conv2, block.bn2)]
+
+
+def forward(model, x, train, want_tape):
+    """x: fp32 NCHW CUDA batch. Returns (logits fp32 [B, num_classes], tape or None)."""
+    if x.dim() != 4 or x.shape[1] != 3:
+        raise ValueError(f"expected an [B,3,H,W] image batch, got {tuple(x.shape)}")
+    x = x.contiguous().float()
+    B = x.shape[0]
+    tape = {"stem": None, "blocks": [], "head": None} if want_tape else None
+    # ---- stem: 7x7/2 conv as patch-matrix GEMM, BN statistics in the epilogue, BN+ReLU+max-pool in one pass
+    conv1, bn1 = model.conv1, model.bn1
+    _check_bn(bn1, "bn1")
+    if conv1.kernel_size != (7, 7) or conv1.stride != (2, 2) or conv1.padding != (3, 3) or conv1.bias is not None:
+        raise NotImplementedError("stem must be the 7x7/2 pad-3 bias-free convolution of the reference")
+    kpad = 160
+    a, Ho, Wo = ops.im2col_nchw(x, 7, 7, 2, 3, kpad)
+    wp = weight_cache.get(conv1.weight, 0, ld=kpad)
+    c1, st = ops.conv2d_fwd(a.view(-1, 1, 1, kpad), wp, want_stats=train)
+    c1 = c1.view(B, Ho, Wo, 64)
+    if train:
+        co1 = ops.bn_finalize(st, B * Ho * Wo, bn1.weight, bn1.bias, bn1.eps, bn1.momentum, bn1.running_mean,
+                              bn1.running_var, bn1.num_batches_tracked)
+    else:
+        co1 = ops.bn_eval_coeffs(bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.eps)
+    h, idx = ops.bn_relu_maxpool_fwd(c1, co1)
+    if want_tape:
+        tape["stem"] = (a, c1, co1, idx, (Ho, Wo))
+    # ---- residual stages
+    for li in range(1, 5):
+        for bi, block in enumerate(getattr(model, f"layer{li}")):
+            units = [] if want_tape else None
+            name = f"layer{li}.{bi}"
+            x_in = h
+            pairs = _block_units(block)
+            for j, (conv, bn) in enumerate(pairs[:-1]):
+                h = _conv_bn(units, h, conv, bn, train, relu=True, name=f"{name}.conv{j + 1}")
+            ds_units = [] if want_tape else None
+            if block.downsample is not None:
+                identity = _conv_bn(ds_units, x_in, block.downsample[0], block.downsample[1], train, relu=False,
+                                    name=f"{name}.downsample")
+            else:
+                identity = x_in
+            conv, bn = pairs[-1]
+            h = _conv_bn(units, h, conv, bn, train, relu=True, residual=identity, name=f"{name}.conv{len(pairs)}")
+            if want_tape:
+                tape["blocks"].append((units, ds_units[0] if ds_units else None, x_in))
+    # ---- head: global average pool + fc (fp32 logits)
+    pooled = ops.avgpool_fwd(h)
+    fc = model.fc
+    if not isinstance(fc, nn.Linear):
+        raise NotImplementedError("model.fc must be an nn.Linear")
+    n_cls = fc.out_features
+    n_pad = (n_cls + 7) // 8 * 8
+    wfc = weight_cache.get(fc.weight, 0, pad_rows=n_pad)
+    bias = None
+    if fc.bias is not None:
+        bias = fc.bias.detach()
+        if n_pad != n_cls:
+            bias = torch.cat([bias, bias.new_zeros(n_pad - n_cls)])
+    logits, _ = ops.conv2d_fwd(pooled.view(B, 1, 1, -1), wfc, bias=bias, out_f32=True)
+    logits = logits.view(B, n_pad)
+    if want_tape:
+        tape["head"] = (pooled, h.shape[1:3], n_cls, n_pad)
+    return (logits[:, :n_cls] if n_pad != n_cls else logits), tape
+
+
+def _unit_backward(u, g, grads, want_dz=False):
+    """Backward of BN(+ReLU) of unit u for upstream gradient g; returns (dc, dz) and records BN param grads."""
+    dc, dgamma, dbeta, dz = ops.bn_backward(g, u.c, u.co, relu=u.relu, y_out=u.y if (u.relu and u.has_res) else None,
+                                            want_dz=want_dz)
+    grads[u.bn.weight.data_ptr()] = dgamma
+    grads[u.bn.bias.data_ptr()] = dbeta
+    return dc, dz
+
+
+def backward(model, tape, dlogits):
+    """dlogits: fp32 [B, num_classes]. Returns {parameter.data_ptr(): fp32 gradient}."""
+    grads = {}
+    pooled, hw, n_cls, n_pad = tape["head"]
+    B = pooled.shape[0]
+    fc = model.fc
+    dl = dlogits.contiguous().float()
+    if n_pad != n_cls:
+        dl = torch.cat([dl, dl.new_zeros(B, n_pad - n_cls)], 1).contiguous()
+    dl16 = ops.cast_bf16(dl).view(B, 1, 1, n_pad)
+    x_fc = pooled.view(B, 1, 1, -1)
+    gw = ops.conv2d_wgrad(dl16, x_fc)
+    grads[fc.weight.data_ptr()] = gw.view(n_pad, -1)[:n_cls]
+    if fc.bias is not None:
+        grads[fc.bias.data_ptr()] = ops.colsum(dl16.view(B, n_pad), cols=n_cls)
+    wfc_d = weight_cache.get(fc.weight, 1, pad_cols=n_pad)
+    dpooled = ops.conv2d_dgrad(dl16, wfc_d, (1, 1))
+    g = ops.avgpool_bwd(dpooled.view(B, -1), hw)
+
+    for units, ds, x_in in reversed(tape["blocks"]):
+        last = units[-1]
+        has_ds = ds is not None
+        # out = relu(bn_last(c) + identity): dz is the gradient of the pre-ReLU sum, shared by both branches
+        dc, dz = _unit_backward(last, g, grads, want_dz=True)
+        for j in range(len(units) - 1, -1, -1):
+            u = units[j]
+            k, s = u.conv.kernel_size[0], u.conv.stride[0]
+            gwj = ops.conv2d_wgrad(dc, u.x, k, s)
+            grads[u.conv.weight.data_ptr()] = gwj
+            wd = weight_cache.get(u.conv.weight, 1)
+            in_hw = tuple(u.x.shape[1:3])
+            if j > 0:
+                g_prev = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
+                dc, _ = _unit_backward(units[j - 1], g_prev, grads)
+            else:
+                if has_ds:
+                    gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
+                else:
+                    gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s, residual=dz)  # + identity-branch gradient
+        if has_ds:
+            dcd, _ = _unit_backward(ds, dz, grads)
+            kd, sd = ds.conv.kernel_size[0], ds.conv.stride[0]
+            grads[ds.conv.weight.data_ptr()] = ops.conv2d_wgrad(dcd, x_in, kd, sd)
+            wdd = weight_cache.get(ds.conv.weight, 1)
+            gx = ops.conv2d_dgrad(dcd, wdd, tuple(x_in.shape[1:3]), kd, sd, residual=gx, out=gx)
+        g = gx
+
+    a, c1, co1, idx, (Ho, Wo) = tape["stem"]
+    g_act = ops.maxpool_bwd(g, idx, (Ho, Wo))
+    dc, dgamma, dbeta, _ = ops.bn_backward(g_act, c1, co1, relu=True)
+    grads[model.bn1.weight.data_ptr()] = dgamma
+    grads[model.bn1.bias.data_ptr()] = dbeta
+    kpad = a.shape[1]
+    gw = ops.conv2d_wgrad(dc.view(-1, 1, 1, 64), a.view(-1, 1, 1, kpad))  # [64, kpad, 1, 1], k = (kh*7+kw)*3 + c
+    grads[model.conv1.weight.data_ptr()] = gw.view(64, kpad)[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+    return grads
+
+
+class _ResNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, model, *params):
+        want_tape = any(ctx.needs_input_grad[2:])
+        logits, tape = forward(model, x, model.training, want_tape)
+        ctx.model, ctx.tape, ctx.params = model, tape, params
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        if ctx.tape is None:
+            raise RuntimeError("backward called on a forward that recorded no tape")
+        grads = backward(ctx.model, ctx.tape, dlogits)
+        ctx.tape = None
+        out = []
+        for p, need in zip(ctx.params, ctx.needs_input_grad[2:]):
+            gp = grads.get(p.data_ptr()) if need else None
+            out.append(gp.reshape(p.shape) if gp is not None else None)
+        return (None, None, *out)
+
+
+def apply(model, x):
+    if not x.is_cuda:
+        raise RuntimeError("deeplearning_b200 ResNet runs on CUDA (sm_100a) tensors only; there is no CPU fallback")
+    params = tuple(model.parameters())
+    if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+        return _ResNetFunction.apply(x, model, *params)
+    logits, _ = forward(model, x, model.training, False)
+    return logits
