@@ -19,29 +19,29 @@ def _bn(state, prefix, x, train, eps=1e-5, momentum=0.1):
     return F.batch_norm(x, rm, rv, state[prefix + ".weight"], state[prefix + ".bias"], train, momentum, eps)
 
 
-def _block(state, p, x, stride, train):
+def _block(state, p, x, stride, train, momentum=0.1):
     bottleneck = (p + ".conv3.weight") in state
     if bottleneck:
-        out = F.relu(_bn(state, p + ".bn1", F.conv2d(x, state[p + ".conv1.weight"]), train))
-        out = F.relu(_bn(state, p + ".bn2", F.conv2d(out, state[p + ".conv2.weight"], stride=stride, padding=1), train))
-        out = _bn(state, p + ".bn3", F.conv2d(out, state[p + ".conv3.weight"]), train)
+        out = F.relu(_bn(state, p + ".bn1", F.conv2d(x, state[p + ".conv1.weight"]), train, momentum=momentum))
+        out = F.relu(_bn(state, p + ".bn2", F.conv2d(out, state[p + ".conv2.weight"], stride=stride, padding=1), train, momentum=momentum))
+        out = _bn(state, p + ".bn3", F.conv2d(out, state[p + ".conv3.weight"]), train, momentum=momentum)
     else:
-        out = F.relu(_bn(state, p + ".bn1", F.conv2d(x, state[p + ".conv1.weight"], stride=stride, padding=1), train))
-        out = _bn(state, p + ".bn2", F.conv2d(out, state[p + ".conv2.weight"], padding=1), train)
+        out = F.relu(_bn(state, p + ".bn1", F.conv2d(x, state[p + ".conv1.weight"], stride=stride, padding=1), train, momentum=momentum))
+        out = _bn(state, p + ".bn2", F.conv2d(out, state[p + ".conv2.weight"], padding=1), train, momentum=momentum)
     if (p + ".downsample.0.weight") in state:
-        x = _bn(state, p + ".downsample.1", F.conv2d(x, state[p + ".downsample.0.weight"], stride=stride), train)
+        x = _bn(state, p + ".downsample.1", F.conv2d(x, state[p + ".downsample.0.weight"], stride=stride), train, momentum=momentum)
     return F.relu(out + x)
 
 
-def resnet_forward(state, x, train=False):
+def resnet_forward(state, x, train=False, momentum=0.1):
     """state: dict with the reference's state_dict keys (tensors may require grad); x: [B,3,H,W] fp32."""
     h = F.conv2d(x, state["conv1.weight"], stride=2, padding=3)
-    h = F.max_pool2d(F.relu(_bn(state, "bn1", h, train)), 3, 2, 1)
+    h = F.max_pool2d(F.relu(_bn(state, "bn1", h, train, momentum=momentum)), 3, 2, 1)
     for li in range(1, 5):
         bi = 0
         while f"layer{li}.{bi}.conv1.weight" in state:
             stride = 2 if (li > 1 and bi == 0) else 1
-            h = _block(state, f"layer{li}.{bi}", h, stride, train)
+            h = _block(state, f"layer{li}.{bi}", h, stride, train, momentum)
             bi += 1
     h = torch.flatten(F.adaptive_avg_pool2d(h, 1), 1)
     return F.linear(h, state["fc.weight"], state["fc.bias"])
