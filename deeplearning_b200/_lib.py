@@ -23,6 +23,7 @@ SIGNATURES = {
     "b200_last_error": (c_char_p, []),
     "b200_abi_version": (_I, []),
     "b200_sm_count": (_I, []),
+    "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_conv2d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     "b200_conv2d_fwd_mtiles": (_I, [_I, _I, _I, _I, _I]),
     "b200_conv2d_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "b200_cast_bf16_to_f32": (_I, [_P, _P, _L, _P]),
     "b200_im2col_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_debug_set_desc": (_I, [_I, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
+    "b200_stem_wgrad_relayout": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200_sgd_momentum": (_I, [_P, _P, _P, _L, _F, _F, _F, _F, _I, _P]),
 }
 

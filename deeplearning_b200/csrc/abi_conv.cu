@@ -100,7 +100,7 @@ int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   q.desc_lbo = g_fwd_lbo;
   q.desc_sbo = g_fwd_sbo;
   conv_gemm_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -127,7 +127,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   q.desc_sbo = g_wg_sbo;
   q.desc_kstep = g_wg_kstep;
   wgrad_gemm_kernel<BLOCK_NG><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -427,7 +427,7 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
   wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 

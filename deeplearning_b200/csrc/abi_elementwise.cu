@@ -37,6 +37,7 @@ extern "C" {
 const char* b200_last_error(void) { return get_error(); }
 int b200_abi_version(void) { return 1; }
 int b200_sm_count(void) { return device_sm_count(); }
+unsigned long long b200_launch_count(void) { return g_launch_count; }
 
 int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
@@ -45,7 +46,7 @@ int b200_bn_finalize(const float* partial, int T, int C, double count, const flo
   bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       partial, T, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, mean, invstd,
       scale, shift);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -53,7 +54,7 @@ int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const floa
                         const float* running_var, float eps, float* scale, float* shift, void* stream) {
   bn_eval_coeffs_kernel<<<(C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(C, gamma, beta, running_mean,
                                                                                        running_var, eps, scale, shift);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -64,7 +65,7 @@ int b200_bn_apply(const void* x, const void* residual, void* y, const float* sca
   bn_apply_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<const uint4*>(residual), static_cast<uint4*>(y), scale, shift, nvec,
       C / 8, relu);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -81,7 +82,7 @@ int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz
   bn_bwd_reduce_kernel<<<pl.blocks, 256, 256 * 17 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out),
       static_cast<uint4*>(dz_out), scale, shift, mean, invstd, relu, rows, C / 8, pl.rows_per_block, partial);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -89,7 +90,7 @@ int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float
                          float* m1, float* m2, void* stream) {
   bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, T, C, count, dgamma,
                                                                                       dbeta, accumulate, m1, m2);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -101,7 +102,7 @@ int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_
   bn_bwd_apply_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out), g_is_dz,
       static_cast<uint4*>(dx), scale, shift, mean, invstd, m1, m2, relu, nvec, C / 8);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -113,7 +114,7 @@ int b200_bn_relu_maxpool_fwd(const void* x, void* y, void* idx, const float* sca
   bn_relu_maxpool_fwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), static_cast<unsigned long long*>(idx), scale, shift, B, H, W,
       C / 8);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -123,7 +124,7 @@ int b200_maxpool_bwd(const void* g_out, const void* idx, void* g_in, int B, int 
   maxpool_bwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g_out), static_cast<const unsigned long long*>(idx), static_cast<uint4*>(g_in), B, H, W,
       C / 8);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -132,7 +133,7 @@ int b200_avgpool_fwd(const void* x, void* y, int B, int HW, int C, void* stream)
   const long long nvec = static_cast<long long>(B) * (C / 8);
   avgpool_fwd_kernel<<<ew_grid(nvec, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), B, HW, C / 8);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 int b200_avgpool_bwd(const void* gy, void* gx, int B, int HW, int C, void* stream) {
@@ -140,7 +141,7 @@ int b200_avgpool_bwd(const void* gy, void* gx, int B, int HW, int C, void* strea
   const long long nvec = static_cast<long long>(B) * HW * (C / 8);
   avgpool_bwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(gy), static_cast<uint4*>(gx), B, HW, C / 8);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -149,20 +150,20 @@ int b200_softmax_xent(const float* logits, long long ld, const long long* labels
   B200_REQUIRE(B > 0 && N > 0, "softmax_xent: empty input");
   softmax_xent_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       logits, ld, labels, N, gscale, loss_rows, static_cast<__nv_bfloat16*>(dlogits), ld_d, correct);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
 int b200_mean(const float* v, int n, float* out, void* stream) {
   mean_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, n, out);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
 int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, float* out, int accumulate, void* stream) {
   colsum_kernel<<<(cols + 63) / 64, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(m), rows, ld, cols, out, accumulate);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -173,20 +174,20 @@ int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mo
   B200_REQUIRE(ld_dst >= need, "pack_weight: ld_dst %lld < %lld", ld_dst, need);
   pack_weight_kernel<<<ew_grid(rows * ld_dst), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       src, static_cast<__nv_bfloat16*>(dst), O, I, taps, mode, ld_dst);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
 int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   cast_f32_bf16_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst),
                                                                                   n);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
   cast_bf16_f32_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(src), dst, n);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -198,7 +199,16 @@ int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int 
   const long long nvec = static_cast<long long>(B) * Ho * Wo * (ldk / 8);
   im2col_nchw_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<uint4*>(a), B, Cin, H, W, KH, KW, stride, pad, Ho, Wo, ldk);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, int taps, int ldk, int accumulate,
+                              void* stream) {
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  stem_wgrad_relayout_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, Cout, Cin, taps,
+                                                                                            ldk, accumulate);
+  B200_LAUNCHED();
   return OK;
 }
 
@@ -206,7 +216,7 @@ int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float l
                       float gscale, int first_step, void* stream) {
   sgd_momentum_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, buf, n, lr, momentum,
                                                                                weight_decay, gscale, first_step);
-  B200_CHECK_CUDA(cudaPeekAtLastError());
+  B200_LAUNCHED();
   return OK;
 }
 

@@ -566,6 +566,20 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restric
   }
 }
 
+// Stem weight gradient: patch-matrix layout [Cout][ldk] with k = tap*Cin + c  ->  OIHW [Cout][Cin][taps].
+__global__ void stem_wgrad_relayout_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout, int Cin,
+                                           int taps, int ldk, int accumulate) {
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int t = static_cast<int>(i % taps);
+    const int c = static_cast<int>((i / taps) % Cin);
+    const int o = static_cast<int>(i / (static_cast<long long>(taps) * Cin));
+    const float v = src[static_cast<long long>(o) * ldk + t * Cin + c];
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Fused SGD with momentum over a flat fp32 arena (torch.optim.SGD semantics, dampening 0, no nesterov):
 //   g' = g*gscale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf

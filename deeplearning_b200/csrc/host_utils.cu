@@ -8,6 +8,7 @@
 namespace b200 {
 
 static thread_local char g_err[1024] = {0};
+unsigned long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;

@@ -38,4 +38,13 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 
 int device_sm_count();
 
+// Number of kernels this library has launched (process-wide); see b200_launch_count().
+extern unsigned long long g_launch_count;
+
+#define B200_LAUNCHED()                                   \
+  do {                                                    \
+    ++::b200::g_launch_count;                             \
+    B200_CHECK_CUDA(cudaPeekAtLastError());               \
+  } while (0)
+
 }  // namespace b200

@@ -14,11 +14,15 @@ from .. import ops
 class _WeightCache:
     def __init__(self):
         self._store = {}
+        self.generation = 0  # bumped by code that updates parameters behind autograd's back (fused optimizer kernels)
+
+    def bump(self):
+        self.generation += 1
 
     def get(self, param, mode, ld=None, pad_rows=None, pad_cols=None):
         key = (id(param), mode, ld, pad_rows, pad_cols)
         hit = self._store.get(key)
-        stamp = (param._version, param.data_ptr())
+        stamp = (param._version, param.data_ptr(), self.generation)
         if hit is not None and hit[0] == stamp and hit[2]() is param:
             return hit[1]
         w = param.detach()

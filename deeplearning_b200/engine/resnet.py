@@ -126,30 +126,56 @@ def forward(model, x, train, want_tape):
     return (logits[:, :n_cls] if n_pad != n_cls else logits), tape
 
 
+class _Grads(dict):
+    """{parameter.data_ptr(): fp32 gradient}. ``sink(param)`` may supply the destination buffer (a view of the flat
+    gradient arena of engine.trainer) so gradients are produced in place instead of in fresh tensors."""
+
+    def __init__(self, sink=None):
+        super().__init__()
+        self.sink = sink
+
+    def dest(self, param):
+        return self.sink(param) if self.sink is not None else None
+
+    def put(self, param, value):
+        self[param.data_ptr()] = value
+
+
 def _unit_backward(u, g, grads, want_dz=False):
     """Backward of BN(+ReLU) of unit u for upstream gradient g; returns (dc, dz) and records BN param grads."""
     dc, dgamma, dbeta, dz = ops.bn_backward(g, u.c, u.co, relu=u.relu, y_out=u.y if (u.relu and u.has_res) else None,
-                                            want_dz=want_dz)
-    grads[u.bn.weight.data_ptr()] = dgamma
-    grads[u.bn.bias.data_ptr()] = dbeta
+                                            want_dz=want_dz, dgamma=grads.dest(u.bn.weight), dbeta=grads.dest(u.bn.bias))
+    grads.put(u.bn.weight, dgamma)
+    grads.put(u.bn.bias, dbeta)
     return dc, dz
 
 
-def backward(model, tape, dlogits):
-    """dlogits: fp32 [B, num_classes]. Returns {parameter.data_ptr(): fp32 gradient}."""
-    grads = {}
+def backward(model, tape, dlogits, sink=None):
+    """dlogits: fp32 [B, num_classes] (or the bf16 [B, n_pad] product of ops.softmax_xent).
+    Returns {parameter.data_ptr(): fp32 gradient}; with ``sink`` the gradients are written into caller-owned buffers."""
+    grads = _Grads(sink)
     pooled, hw, n_cls, n_pad = tape["head"]
     B = pooled.shape[0]
     fc = model.fc
-    dl = dlogits.contiguous().float()
-    if n_pad != n_cls:
-        dl = torch.cat([dl, dl.new_zeros(B, n_pad - n_cls)], 1).contiguous()
-    dl16 = ops.cast_bf16(dl).view(B, 1, 1, n_pad)
+    if dlogits.dtype == BF16 and dlogits.shape[1] == n_pad and dlogits.is_contiguous():
+        dl16 = dlogits.view(B, 1, 1, n_pad)  # already produced by the fused soft-max/cross-entropy kernel
+    else:
+        dl = dlogits.contiguous().float()
+        if n_pad != n_cls:
+            dl = torch.cat([dl, dl.new_zeros(B, n_pad - n_cls)], 1).contiguous()
+        dl16 = ops.cast_bf16(dl).view(B, 1, 1, n_pad)
     x_fc = pooled.view(B, 1, 1, -1)
-    gw = ops.conv2d_wgrad(dl16, x_fc)
-    grads[fc.weight.data_ptr()] = gw.view(n_pad, -1)[:n_cls]
+    dst = grads.dest(fc.weight)
+    if dst is not None and n_pad == n_cls:
+        grads.put(fc.weight, ops.conv2d_wgrad(dl16, x_fc, out=dst.view(n_cls, -1, 1, 1)))
+    else:
+        gw = ops.conv2d_wgrad(dl16, x_fc).view(n_pad, -1)[:n_cls]
+        if dst is not None:
+            dst.copy_(gw)
+            gw = dst
+        grads.put(fc.weight, gw)
     if fc.bias is not None:
-        grads[fc.bias.data_ptr()] = ops.colsum(dl16.view(B, n_pad), cols=n_cls)
+        grads.put(fc.bias, ops.colsum(dl16.view(B, n_pad), cols=n_cls, out=grads.dest(fc.bias)))
     wfc_d = weight_cache.get(fc.weight, 1, pad_cols=n_pad)
     dpooled = ops.conv2d_dgrad(dl16, wfc_d, (1, 1))
     g = ops.avgpool_bwd(dpooled.view(B, -1), hw)
@@ -162,8 +188,7 @@ def backward(model, tape, dlogits):
         for j in range(len(units) - 1, -1, -1):
             u = units[j]
             k, s = u.conv.kernel_size[0], u.conv.stride[0]
-            gwj = ops.conv2d_wgrad(dc, u.x, k, s)
-            grads[u.conv.weight.data_ptr()] = gwj
+            grads.put(u.conv.weight, ops.conv2d_wgrad(dc, u.x, k, s, out=grads.dest(u.conv.weight)))
             wd = weight_cache.get(u.conv.weight, 1)
             in_hw = tuple(u.x.shape[1:3])
             if j > 0:
@@ -177,19 +202,20 @@ def backward(model, tape, dlogits):
         if has_ds:
             dcd, _ = _unit_backward(ds, dz, grads)
             kd, sd = ds.conv.kernel_size[0], ds.conv.stride[0]
-            grads[ds.conv.weight.data_ptr()] = ops.conv2d_wgrad(dcd, x_in, kd, sd)
+            grads.put(ds.conv.weight, ops.conv2d_wgrad(dcd, x_in, kd, sd, out=grads.dest(ds.conv.weight)))
             wdd = weight_cache.get(ds.conv.weight, 1)
             gx = ops.conv2d_dgrad(dcd, wdd, tuple(x_in.shape[1:3]), kd, sd, residual=gx, out=gx)
         g = gx
 
     a, c1, co1, idx, (Ho, Wo) = tape["stem"]
     g_act = ops.maxpool_bwd(g, idx, (Ho, Wo))
-    dc, dgamma, dbeta, _ = ops.bn_backward(g_act, c1, co1, relu=True)
-    grads[model.bn1.weight.data_ptr()] = dgamma
-    grads[model.bn1.bias.data_ptr()] = dbeta
+    dc, dgamma, dbeta, _ = ops.bn_backward(g_act, c1, co1, relu=True, dgamma=grads.dest(model.bn1.weight),
+                                           dbeta=grads.dest(model.bn1.bias))
+    grads.put(model.bn1.weight, dgamma)
+    grads.put(model.bn1.bias, dbeta)
     kpad = a.shape[1]
     gw = ops.conv2d_wgrad(dc.view(-1, 1, 1, 64), a.view(-1, 1, 1, kpad))  # [64, kpad, 1, 1], k = (kh*7+kw)*3 + c
-    grads[model.conv1.weight.data_ptr()] = gw.view(64, kpad)[:, :147].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).contiguous()
+    grads.put(model.conv1.weight, ops.stem_wgrad_relayout(gw.view(64, kpad), 64, 3, 49, out=grads.dest(model.conv1.weight)))
     return grads
 
 

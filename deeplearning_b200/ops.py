@@ -19,6 +19,60 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+# ---------------------------------------------------------------------------------------------------- op-level profiler
+_active_prof = None
+
+
+class Profiler:
+    """Times every C-ABI op with CUDA events on the launching stream and attributes algorithmic flops / bytes to it.
+    Used by bench.py (roofline numbers) and tools/; zero cost when not active."""
+
+    def __init__(self):
+        self.records = []  # (name, flops, bytes, ev0, ev1)
+
+    def __enter__(self):
+        global _active_prof
+        self._prev, _active_prof = _active_prof, self
+        return self
+
+    def __exit__(self, *exc):
+        global _active_prof
+        _active_prof = self._prev
+
+    def summary(self):
+        torch.cuda.synchronize()
+        agg = {}
+        for name, flops, nbytes, e0, e1 in self.records:
+            a = agg.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+            a["calls"] += 1
+            a["ms"] += e0.elapsed_time(e1)
+            a["flops"] += flops
+            a["bytes"] += nbytes
+        return agg
+
+
+class _Span:
+    __slots__ = ("name", "flops", "nbytes", "e0")
+
+    def __init__(self, name, flops, nbytes):
+        self.name, self.flops, self.nbytes = name, flops, nbytes
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e0.record()
+
+    def end(self):
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        _active_prof.records.append((self.name, self.flops, self.nbytes, self.e0, e1))
+
+
+def _span(name, flops=0.0, nbytes=0.0):
+    return _Span(name, flops, nbytes) if _active_prof is not None else None
+
+
+def _nb(*ts):
+    return float(sum(t.numel() * t.element_size() for t in ts if t is not None))
+
+
 def _chk_act(t, name):
     if t.dtype != BF16 or not t.is_cuda or not t.is_contiguous():
         raise ValueError(f"{name}: expected a contiguous CUDA bf16 tensor, got {t.dtype} {t.device} contiguous={t.is_contiguous()}")
@@ -69,7 +123,10 @@ def im2col_nchw(x, KH, KW, stride, pad, ldk):
     Ho = (H + 2 * pad - KH) // stride + 1
     Wo = (W + 2 * pad - KW) // stride + 1
     a = torch.empty(B * Ho * Wo, ldk, dtype=BF16, device=x.device)
+    sp = _span("stem_im2col", 0.0, _nb(x, a))
     _lib.check(lib.b200_im2col_nchw(_p(x), _p(a), B, C, H, W, KH, KW, stride, pad, ldk, _stream()), "b200_im2col_nchw")
+    if sp:
+        sp.end()
     return a, Ho, Wo
 
 
@@ -85,6 +142,7 @@ def conv2d_fwd(x, w_packed, ksize=1, stride=1, want_stats=False, bias=None, act=
     if want_stats:
         T = lib.b200_conv2d_fwd_mtiles(B, H, W, ksize, stride)
         stats = torch.empty(T, 2, Cout, dtype=F32, device=x.device)
+    sp = _span("conv_gemm_fwd", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize)
     if out_f32:
         y = torch.empty(B, Ho, Wo, Cout, dtype=F32, device=x.device)
         rc = lib.b200_conv2d_fwd(_p(x), _p(w_packed), None, B, H, W, Cin, Cout, ksize, stride, _p(stats), _p(bias), act,
@@ -94,6 +152,9 @@ def conv2d_fwd(x, w_packed, ksize=1, stride=1, want_stats=False, bias=None, act=
         rc = lib.b200_conv2d_fwd(_p(x), _p(w_packed), _p(y), B, H, W, Cin, Cout, ksize, stride, _p(stats), _p(bias), act,
                                  _p(residual), None, 0, _stream())
     _lib.check(rc, "b200_conv2d_fwd")
+    if sp:
+        sp.nbytes = _nb(x, w_packed, y, residual)
+        sp.end()
     return y, stats
 
 
@@ -105,8 +166,11 @@ def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=Non
     H, W = in_hw
     Cin = wd_packed.shape[0]
     dx = out if out is not None else torch.empty(B, H, W, Cin, dtype=BF16, device=dy.device)
+    sp = _span("conv_gemm_dgrad", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize, _nb(dy, wd_packed, dx, residual))
     rc = lib.b200_conv2d_dgrad(_p(dy), _p(wd_packed), _p(dx), B, H, W, Cin, Cout, ksize, stride, _p(residual), _stream())
     _lib.check(rc, "b200_conv2d_dgrad")
+    if sp:
+        sp.end()
     return dx
 
 
@@ -134,9 +198,12 @@ def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False):
     if out is None:
         out = torch.empty(Cout, Cin, ksize, ksize, dtype=F32, device=x.device)
         accumulate = False
+    sp = _span("wgrad_gemm", 2.0 * dy.numel() * Cin * ksize * ksize, _nb(dy, x, out))
     rc = lib.b200_conv2d_wgrad(_p(dy), _p(x), _p(out), _p(ws), ws.numel(), B, H, W, Cin, Cout, ksize, stride,
                                1 if accumulate else 0, _stream())
     _lib.check(rc, "b200_conv2d_wgrad")
+    if sp:
+        sp.end()
     return out
 
 
@@ -177,12 +244,15 @@ def bn_apply(x, co, relu=True, residual=None):
     C = x.shape[-1]
     rows = x.numel() // C
     y = torch.empty_like(x)
+    sp = _span("bn_apply", 0.0, _nb(x, y, residual))
     rc = lib.b200_bn_apply(_p(x), _p(residual), _p(y), _p(co.scale), _p(co.shift), rows, C, 1 if relu else 0, _stream())
     _lib.check(rc, "b200_bn_apply")
+    if sp:
+        sp.end()
     return y
 
 
-def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbeta=None):
+def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbeta=None, accumulate=False):
     """Train-mode BN (+ReLU) backward. g: grad wrt the post-activation output; x: raw conv output.
     Returns (dx, dgamma, dbeta, dz) with dz only when want_dz (masked upstream gradient, bf16)."""
     lib = _lib.load()
@@ -193,24 +263,28 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
         raise RuntimeError(f"bn_backward: unsupported channel count {C}")
     partial = torch.empty(nblk, 2, C, dtype=F32, device=x.device)
     dz = torch.empty_like(x) if want_dz else None
+    sp = _span("bn_bwd_reduce", 0.0, _nb(g, x, y_out, dz))
     rc = lib.b200_bn_bwd_reduce(_p(g), _p(x), _p(y_out), _p(dz), _p(co.scale), _p(co.shift), _p(co.mean),
                                 _p(co.invstd), 1 if relu else 0, rows, C, _p(partial), _stream())
     _lib.check(rc, "b200_bn_bwd_reduce")
-    acc = 0
+    if sp:
+        sp.end()
+    acc = 1 if (accumulate and dgamma is not None) else 0
     if dgamma is None:
         dgamma = torch.empty(C, dtype=F32, device=x.device)
         dbeta = torch.empty(C, dtype=F32, device=x.device)
-    else:
-        acc = 1
     m = torch.empty(2, C, dtype=F32, device=x.device)
     rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, float(rows), _p(dgamma), _p(dbeta), acc, _p(m[0]), _p(m[1]),
                                   _stream())
     _lib.check(rc, "b200_bn_bwd_finalize")
     dx = torch.empty_like(x)
     src = dz if want_dz else g
+    sp = _span("bn_bwd_apply", 0.0, _nb(src, x, dx, None if want_dz else y_out))
     rc = lib.b200_bn_bwd_apply(_p(src), _p(x), _p(y_out), 1 if want_dz else 0, _p(dx), _p(co.scale), _p(co.shift),
                                _p(co.mean), _p(co.invstd), _p(m[0]), _p(m[1]), 1 if relu else 0, rows, C, _stream())
     _lib.check(rc, "b200_bn_bwd_apply")
+    if sp:
+        sp.end()
     return dx, dgamma, dbeta, dz
 
 
@@ -221,8 +295,11 @@ def bn_relu_maxpool_fwd(x, co):
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     y = torch.empty(B, Ho, Wo, C, dtype=BF16, device=x.device)
     idx = torch.empty(B, Ho, Wo, C // 8, dtype=torch.int64, device=x.device)
+    sp = _span("bn_relu_maxpool_fwd", 0.0, _nb(x, y, idx))
     rc = lib.b200_bn_relu_maxpool_fwd(_p(x), _p(y), _p(idx), _p(co.scale), _p(co.shift), B, H, W, C, _stream())
     _lib.check(rc, "b200_bn_relu_maxpool_fwd")
+    if sp:
+        sp.end()
     return y, idx
 
 
@@ -231,7 +308,10 @@ def maxpool_bwd(g_out, idx, in_hw):
     B, Ho, Wo, C = g_out.shape
     H, W = in_hw
     g_in = torch.empty(B, H, W, C, dtype=BF16, device=g_out.device)
+    sp = _span("maxpool_bwd", 0.0, _nb(g_out, idx, g_in))
     _lib.check(lib.b200_maxpool_bwd(_p(g_out), _p(idx), _p(g_in), B, H, W, C, _stream()), "b200_maxpool_bwd")
+    if sp:
+        sp.end()
     return g_in
 
 
@@ -285,3 +365,20 @@ def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=
     rc = lib.b200_sgd_momentum(_p(p), _p(g), _p(buf), p.numel(), lr, momentum, weight_decay, gscale,
                                1 if first_step else 0, _stream())
     _lib.check(rc, "b200_sgd_momentum")
+
+
+def stem_wgrad_relayout(src, cout, cin, taps, out=None, accumulate=False):
+    """[Cout][ldk] patch-matrix weight gradient (k = tap*Cin + c) -> OIHW [Cout, Cin, kh, kw] fp32."""
+    lib = _lib.load()
+    ldk = src.shape[1]
+    k = int(round(taps ** 0.5))
+    if out is None:
+        out = torch.empty(cout, cin, k, k, dtype=F32, device=src.device)
+        accumulate = False
+    rc = lib.b200_stem_wgrad_relayout(_p(src), _p(out), cout, cin, taps, ldk, 1 if accumulate else 0, _stream())
+    _lib.check(rc, "b200_stem_wgrad_relayout")
+    return out
+
+
+def launch_count():
+    return int(_lib.load().b200_launch_count())

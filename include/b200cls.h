@@ -36,6 +36,8 @@ const char* b200_last_error(void);
 int b200_abi_version(void);
 /* Number of SMs of the current device (used by callers to size workspaces). */
 int b200_sm_count(void);
+/* Kernels launched by this library so far in this process (bench.py reports the per-step delta as gpu_launches). */
+unsigned long long b200_launch_count(void);
 
 /* ---- convolution / linear as implicit GEMM on tcgen05 (ksize in {1,3}, stride in {1,2}, pad = ksize/2) --------------
  * forward:  y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w) (+bias) (act) (+residual)
@@ -113,6 +115,10 @@ int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream
 /* stem im2col from the user's NCHW fp32 batch: a bf16 [B*Ho*Wo][ldk], k=(kh*KW+kw)*Cin+c (networks.py:206 conv1 7x7/2) */
 int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int KH, int KW, int stride, int pad,
                      int ldk, void* stream);
+
+/* stem weight gradient [Cout][ldk] (k = tap*Cin + c, as produced by b200_conv2d_wgrad on the patch matrix) -> OIHW */
+int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, int taps, int ldk, int accumulate,
+                              void* stream);
 
 /* fused SGD(momentum) over a flat fp32 arena; torch.optim.SGD semantics (classification/resnet/train.py:96) */
 int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay,

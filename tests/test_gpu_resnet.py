@@ -15,21 +15,37 @@ def _models(seed=0, **kw):
     return m.cuda(), state
 
 
-def _autocast_yardstick(state, x, train):
-    """Max-abs logit error of PyTorch's own bf16 autocast on the same weights/input (what bf16 storage costs the reference)."""
+def _torch_ref(state, layers=(3, 4, 6, 3)):
     import torchvision
 
-    ref = torchvision.models.resnet50().cuda()
+    ref = torchvision.models.ResNet(torchvision.models.resnet.Bottleneck, list(layers)).cuda()
     ref.load_state_dict(state)
-    ref.train(train)
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
-    with torch.no_grad():
-        full = ref(x.cuda()).float()
+    return ref
+
+
+def _autocast_yardstick(state, x, train, labels=None, layers=(3, 4, 6, 3)):
+    """What bf16 storage costs the reference itself: PyTorch bf16 autocast vs PyTorch fp32 on the same weights/input.
+    Returns (max-abs logit error, {param: grad rel-L2 error}) (grads only when labels are given)."""
+    ref = _torch_ref(state, layers)
+    ref.train(train)
+    xg = x.cuda()
+    outs, grads = [], []
+    for amp in (False, True):
         ref.load_state_dict(state)
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            half = ref(x.cuda()).float()
-    return float((half - full).abs().max())
+        ref.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp):
+            with torch.set_grad_enabled(labels is not None):
+                o = ref(xg).float()
+        outs.append(o.detach())
+        if labels is not None:
+            F.cross_entropy(o, labels.cuda()).backward()
+            grads.append({n: p.grad.detach().clone() for n, p in ref.named_parameters()})
+    gerr = {}
+    if labels is not None:
+        gerr = {n: float((grads[1][n] - grads[0][n]).norm() / (grads[0][n].norm() + 1e-12)) for n in grads[0]}
+    return float((outs[1] - outs[0]).abs().max()), gerr
 
 
 def test_resnet50_eval_logits_parity():
@@ -48,18 +64,20 @@ def test_resnet50_eval_logits_parity():
         ref = resnet_forward(state, x, train=False)
         got = m(x.cuda()).float().cpu()
     err = float((got - ref).abs().max())
-    yard = _autocast_yardstick(state, x, False)
+    yard, _ = _autocast_yardstick(state, x, False)
     print(f"eval logits max-abs err {err:.4g} (|ref| max {float(ref.abs().max()):.3g}); torch bf16 autocast on the same input: {yard:.4g}")
     assert err <= max(1e-2, 1.5 * yard), (err, yard)  # north_star: 1e-2 for bf16, or no worse than the reference's own bf16
 
 
-def test_resnet50_train_step_parity():
+def _train_step_check(layers, B, hw, grad_slack):
+    from deeplearning_b200.classification.resnet.models.networks import Bottleneck, ResNet
     from oracle.resnet import train_step_grads
 
-    m, state = _models()
-    m.train()
-    B = 64
-    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    torch.manual_seed(0)
+    m = ResNet(Bottleneck, list(layers))
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    x = torch.randn(B, 3, hw, hw, generator=torch.Generator().manual_seed(1))
     labels = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(2))
     state_before = {k: v.clone() for k, v in state.items()}
     ref_logits, ref_loss, ref_grads = train_step_grads(state, x, labels)
@@ -67,24 +85,35 @@ def test_resnet50_train_step_parity():
     loss = F.cross_entropy(out, labels.cuda())
     loss.backward()
     err = float((out.detach().float().cpu() - ref_logits).abs().max())
-    print(f"train logits max-abs err {err:.4g} (|ref| max {float(ref_logits.abs().max()):.3g}); loss {float(loss):.5f} vs {float(ref_loss):.5f}")
-    yard = _autocast_yardstick(state_before, x, True)
-    print(f"torch bf16 autocast train-mode logits error on the same input: {yard:.4g}")
+    yard, gyard = _autocast_yardstick(state_before, x, True, labels, layers)
+    print(f"layers={layers}: train logits max-abs err {err:.4g} (|ref| max {float(ref_logits.abs().max()):.3g}, torch-bf16 "
+          f"yardstick {yard:.4g}); loss {float(loss.detach()):.5f} vs {float(ref_loss):.5f}")
     assert err <= max(1e-2, 1.5 * yard), (err, yard)
-    assert abs(float(loss) - float(ref_loss)) <= 1e-2
-    worst = 0.0
+    assert abs(float(loss.detach()) - float(ref_loss)) <= 1e-2
+    worst = (0.0, "")
     for name, p in m.named_parameters():
         g, r = p.grad.float().cpu(), ref_grads[name]
         rel = float((g - r).norm() / (r.norm() + 1e-12))
-        worst = max(worst, rel)
-        assert rel < 0.15, f"{name}: grad rel-L2 error {rel:.3g}"
-    print(f"worst grad rel-L2 error {worst:.3g}")
+        worst = max(worst, (rel / (gyard[name] + 1e-3), name))
+        assert rel <= grad_slack * gyard[name] + 0.02, f"{name}: grad rel-L2 error {rel:.3g} vs torch-bf16 yardstick {gyard[name]:.3g}"
+    print(f"worst grad error relative to the torch-bf16 yardstick: {worst[0]:.2f}x at {worst[1]}")
     sd = m.state_dict()
     for k in state:
         if "running_" in k:
             assert torch.allclose(sd[k].cpu(), state[k], rtol=2e-2, atol=2e-3), k
         if "num_batches" in k:
             assert int(sd[k]) == int(state[k])
+
+
+def test_resnet14_train_step_parity():
+    """Shallow Bottleneck net: bf16 rounding noise stays small, so gradients must agree with the fp32 oracle closely."""
+    _train_step_check((1, 1, 1, 1), 32, 128, grad_slack=2.0)
+
+
+def test_resnet50_train_step_parity():
+    """Full ResNet-50: at random init train-mode BN amplifies any bf16 rounding ~1.25x per block (the reference's own
+    autocast run shows the same), so the gate is 'no worse than torch bf16 autocast', measured on the same input."""
+    _train_step_check((3, 4, 6, 3), 64, 224, grad_slack=2.0)
 
 
 def test_resnet50_head_surgery_and_small_classes():

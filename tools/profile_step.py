@@ -1,0 +1,22 @@
+"""One ResNet-50 training step inside a cudaProfilerStart/Stop range (for ncu --profile-from-start off).
+python tools/profile_step.py [batch]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from deeplearning_b200.classification.resnet.models.networks import resnet50
+from deeplearning_b200.engine.trainer import TrainStep
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+torch.manual_seed(0)
+m = resnet50().cuda().train()
+tr = TrainStep(m)
+x = torch.randn(B, 3, 224, 224, device="cuda")
+y = torch.randint(0, 1000, (B,), device="cuda")
+for _ in range(2):
+    tr.step(x, y)
+torch.cuda.synchronize()
+torch.cuda.profiler.start()
+loss, _ = tr.step(x, y)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
+print("loss", float(loss))
