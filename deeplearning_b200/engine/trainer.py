@@ -26,62 +26,86 @@ def _engine_for(model):
     raise NotImplementedError(f"no B200 engine schedule for {type(model).__name__}")
 
 
-class TrainStep:
-    def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
-                 broadcast=True):
-        self.model = model
-        self.engine = _engine_for(model)
-        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+class FlatArena:
+    """Parameters, gradients and optimizer state of a model as three contiguous fp32 buffers (device agnostic host logic).
+
+    Every ``p.data`` becomes a view into ``flat_p`` and every ``p.grad`` a view into ``flat_g``; ``all_reduce_grads`` is the
+    single collective of the data-parallel step and ``broadcast`` makes the replicas identical at start-up."""
+
+    def __init__(self, params, process_group=None, world_size=None):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("no trainable parameters")
         self.group = process_group
         if world_size is None:
             world_size = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         self.world = world_size
-        params = [p for p in model.parameters() if p.requires_grad]
-        if not params:
-            raise ValueError("model has no trainable parameters")
-        dev = params[0].device
-        if dev.type != "cuda":
-            raise RuntimeError("TrainStep needs the model on a CUDA (sm_100a) device")
-        offs, total = [], 0
-        for p in params:
-            offs.append(total)
+        dev = self.params[0].device
+        self.offsets, total = [], 0
+        for p in self.params:
+            if p.device != dev or p.dtype != torch.float32:
+                raise ValueError("all parameters must be fp32 tensors on one device")
+            self.offsets.append(total)
             total += (p.numel() + 3) // 4 * 4  # keep every slot 16-byte aligned
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(total, dtype=torch.float32, device=dev)
         self.flat_m = torch.zeros(total, dtype=torch.float32, device=dev)
         self._gviews = {}
         with torch.no_grad():
-            for p, o in zip(params, offs):
+            for p, o in zip(self.params, self.offsets):
                 pv = self.flat_p[o:o + p.numel()].view(p.shape)
                 pv.copy_(p.data)
                 p.data = pv
                 gv = self.flat_g[o:o + p.numel()].view(p.shape)
                 p.grad = gv
                 self._gviews[p.data_ptr()] = gv
-        self.params = params
-        self.steps = 0
-        if self.world > 1 and broadcast:
-            dist.broadcast(self.flat_p, src=0, group=self.group)  # identical replicas (train_with_DDP/train.py:171-176)
-            for b in model.buffers():
-                dist.broadcast(b, src=0, group=self.group)
-        weight_cache.bump()
 
-    def _sink(self, param):
+    def grad_view(self, param):
         return self._gviews.get(param.data_ptr())
+
+    def broadcast(self, buffers=()):
+        if self.world > 1:
+            dist.broadcast(self.flat_p, src=0, group=self.group)  # identical replicas (train_with_DDP/train.py:171-176)
+            for b in buffers:
+                dist.broadcast(b, src=0, group=self.group)
+
+    def all_reduce_grads(self):
+        """SUM over ranks; the 1/world average is folded into the optimizer kernel (``grad_scale``)."""
+        if self.world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
+
+    @property
+    def grad_scale(self):
+        return 1.0 / self.world
+
+
+class TrainStep:
+    def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
+                 broadcast=True):
+        self.model = model
+        self.engine = _engine_for(model)
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.arena = FlatArena(model.parameters(), process_group, world_size)
+        if self.arena.flat_p.device.type != "cuda":
+            raise RuntimeError("TrainStep needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
+        self.world = self.arena.world
+        self.steps = 0
+        if broadcast:
+            self.arena.broadcast(model.buffers())
+        weight_cache.bump()
 
     def step(self, images, labels, lr=None):
         """One training step on this rank's shard. Returns (loss [1] fp32 device tensor, correct int32 [B])."""
-        model = self.model
+        model, arena = self.model, self.arena
         if not model.training:
             model.train()
         logits, tape = self.engine.forward(model, images, True, True)
         n_pad = (logits.shape[1] + 7) // 8 * 8
         loss, dlogits, correct = ops.softmax_xent(logits, labels, want_grad=True, ld_d=n_pad)
-        self.engine.backward(model, tape, dlogits, sink=self._sink)
-        if self.world > 1:
-            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM, group=self.group)
-        ops.sgd_momentum_(self.flat_p, self.flat_g, self.flat_m, self.lr if lr is None else lr, self.momentum,
-                          self.weight_decay, gscale=1.0 / self.world, first_step=(self.steps == 0))
+        self.engine.backward(model, tape, dlogits, sink=arena.grad_view)
+        arena.all_reduce_grads()
+        ops.sgd_momentum_(arena.flat_p, arena.flat_g, arena.flat_m, self.lr if lr is None else lr, self.momentum,
+                          self.weight_decay, gscale=arena.grad_scale, first_step=(self.steps == 0))
         self.steps += 1
         weight_cache.bump()  # parameters changed behind autograd's back -> repack bf16 operands on next use
         return loss, correct

@@ -1,0 +1,112 @@
+"""Pins the oracle against the reference itself and writes the golden fixtures replayed by tests/test_oracle_golden.py.
+
+Run in the build container (needs /root/reference, which does NOT exist on the GPU box):
+    python tests/golden/make_golden.py
+For every model it (1) builds the *reference* module under a fixed seed, (2) checks that the host-side mirror constructor
+of deeplearning_b200 produces a bit-identical state_dict under the same seed, (3) checks that the oracle restatement gives
+bit-identical logits / loss / gradients / buffer updates on the same weights and input, and (4) stores small outputs.
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+def _shim(name, **attrs):
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _grad_norms(named_params):
+    return {n: float(p.grad.double().norm()) for n, p in named_params}
+
+
+def resnet50_fixture():
+    from deeplearning_b200.classification.resnet.models.networks import resnet50 as mine_ctor
+    from oracle.resnet import resnet_forward, train_step_grads
+
+    ref_mod = _load(f"{REF}/classification/resnet/models/networks.py", "ref_resnet_networks")
+    torch.manual_seed(0)
+    ref = ref_mod.resnet50()
+    torch.manual_seed(0)
+    mine = mine_ctor()
+    sr = {k: v.clone() for k, v in ref.state_dict().items()}  # frozen copy of the initial state
+    sm = mine.state_dict()
+    assert list(sr.keys()) == list(sm.keys()) and all(torch.equal(sr[k], sm[k]) for k in sr), "ctor init differs"
+    x_eval = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(1))
+    ref.eval()
+    with torch.no_grad():
+        le = ref(x_eval)
+        lo = resnet_forward({k: v.clone() for k, v in sr.items()}, x_eval, False)
+    assert torch.equal(le, lo), "oracle eval forward differs from the reference"
+    x = torch.randn(4, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    y = torch.randint(0, 1000, (4,), generator=torch.Generator().manual_seed(3))
+    st = {k: v.clone() for k, v in sr.items()}  # snapshot before the reference's train-mode forward updates the buffers
+    ref.train()
+    out = ref(x)
+    loss = F.cross_entropy(out, y)
+    loss.backward()
+    lg, lo_loss, grads = train_step_grads(st, x, y)
+    assert torch.equal(lg, out.detach()) and float(lo_loss) == float(loss.detach())
+    for n, p in ref.named_parameters():
+        assert torch.equal(p.grad, grads[n]), n
+    s2 = ref.state_dict()
+    for k in s2:
+        if "running" in k or "num_batches" in k:
+            assert torch.equal(s2[k], st[k]), k
+    return {"init_abs_sum": {k: float(v.double().abs().sum()) for k, v in sr.items() if v.is_floating_point()},
+            "eval_logits": le.clone(), "train_logits": out.detach().clone(), "train_loss": float(loss.detach()),
+            "grad_norms": _grad_norms(ref.named_parameters()),
+            "running_mean_bn1": s2["bn1.running_mean"].clone(), "running_var_layer4": s2["layer4.2.bn3.running_var"].clone(),
+            "seeds": {"init": 0, "x_eval": 1, "x_train": 2, "labels": 3}, "shapes": {"x_eval": [2, 3, 64, 64], "x_train": [4, 3, 64, 64]}}
+
+
+def mnist_fixture():
+    from deeplearning_b200.classification.mnist.models.network import mnist_cnn, mnist_fcn
+    from oracle.mnist import mnist_cnn_forward, mnist_fcn_forward
+
+    _shim("torchsummary", summary=lambda *a, **k: None)
+    ref_mod = _load(f"{REF}/classification/mnist/models/network.py", "ref_mnist_network")
+    out = {}
+    for name, ctor, ref_ctor, fwd in (("mnist_fcn", mnist_fcn, ref_mod.mnist_fcn, mnist_fcn_forward),
+                                      ("mnist_cnn", mnist_cnn, ref_mod.mnist_cnn, mnist_cnn_forward)):
+        torch.manual_seed(0)
+        ref = ref_ctor(10)
+        torch.manual_seed(0)
+        mine = ctor(10)
+        sr, sm = ref.state_dict(), mine.state_dict()
+        assert list(sr.keys()) == list(sm.keys()) and all(torch.equal(sr[k], sm[k]) for k in sr), name
+        x = torch.randn(64, 3, 28, 28, generator=torch.Generator().manual_seed(1))  # 3x28x28, not 1x28x28
+        y = torch.randint(0, 10, (64,), generator=torch.Generator().manual_seed(2))
+        lg = ref(x)
+        loss = F.cross_entropy(lg, y)
+        loss.backward()
+        assert torch.equal(lg.detach(), fwd(sr, x)), name
+        assert torch.equal(lg.detach(), mine(x).detach()), name
+        out[name] = {"logits": lg.detach().clone(), "loss": float(loss.detach()), "grad_norms": _grad_norms(ref.named_parameters())}
+    return out
+
+
+if __name__ == "__main__":
+    torch.set_num_threads(8)
+    fx = {"resnet50": resnet50_fixture(), "mnist": mnist_fixture(), "torch": torch.__version__}
+    torch.save(fx, os.path.join(HERE, "classification_golden.pt"))
+    print("golden fixtures written:", os.path.join(HERE, "classification_golden.pt"), os.path.getsize(os.path.join(HERE, "classification_golden.pt")), "bytes")

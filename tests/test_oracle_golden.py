@@ -1,0 +1,76 @@
+"""The oracle replayed against the golden fixtures generated from the reference itself (tests/golden/make_golden.py).
+
+The weights are re-created by the host-side mirror constructors under the recorded seed, so these tests pin three things at
+once without /root/reference: constructor init == reference init, oracle forward/backward == reference, fixtures unchanged.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FX = torch.load(os.path.join(HERE, "golden", "classification_golden.pt"), weights_only=False)
+
+
+def _close(a, b, tol=2e-4):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    assert float((a - b).abs().max()) <= tol * (1.0 + float(b.abs().max())), float((a - b).abs().max())
+
+
+def test_resnet50_init_matches_reference():
+    from deeplearning_b200.classification.resnet.models.networks import resnet50
+
+    fx = FX["resnet50"]
+    torch.manual_seed(fx["seeds"]["init"])
+    sd = resnet50().state_dict()
+    for k, v in fx["init_abs_sum"].items():
+        assert abs(float(sd[k].double().abs().sum()) - v) <= 1e-9 * (1 + abs(v)), k
+
+
+def test_resnet50_oracle_matches_reference_outputs():
+    from deeplearning_b200.classification.resnet.models.networks import resnet50
+    from oracle.resnet import resnet_forward, train_step_grads
+
+    fx = FX["resnet50"]
+    torch.manual_seed(fx["seeds"]["init"])
+    state = {k: v.clone() for k, v in resnet50().state_dict().items()}
+    x_eval = torch.randn(*fx["shapes"]["x_eval"], generator=torch.Generator().manual_seed(fx["seeds"]["x_eval"]))
+    with torch.no_grad():
+        _close(resnet_forward({k: v.clone() for k, v in state.items()}, x_eval, False), fx["eval_logits"])
+    x = torch.randn(*fx["shapes"]["x_train"], generator=torch.Generator().manual_seed(fx["seeds"]["x_train"]))
+    y = torch.randint(0, 1000, (x.shape[0],), generator=torch.Generator().manual_seed(fx["seeds"]["labels"]))
+    logits, loss, grads = train_step_grads(state, x, y)
+    _close(logits, fx["train_logits"])
+    assert abs(float(loss) - fx["train_loss"]) < 1e-4
+    for n, g in grads.items():
+        ref = fx["grad_norms"][n]
+        assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
+    _close(state["bn1.running_mean"], fx["running_mean_bn1"])
+    _close(state["layer4.2.bn3.running_var"], fx["running_var_layer4"])
+
+
+@pytest.mark.parametrize("name", ["mnist_fcn", "mnist_cnn"])
+def test_mnist_plumbing_config(name):
+    """BASELINE config 0: mnist net on CPU, synthetic 3x28x28, bs=64 - constructor, oracle and a full step."""
+    from deeplearning_b200.classification.mnist.models import network
+    from oracle import mnist as om
+
+    fx = FX["mnist"][name]
+    torch.manual_seed(0)
+    model = getattr(network, name)(10)
+    x = torch.randn(64, 3, 28, 28, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 10, (64,), generator=torch.Generator().manual_seed(2))
+    fwd = om.mnist_fcn_forward if name == "mnist_fcn" else om.mnist_cnn_forward
+    _close(fwd(model.state_dict(), x), fx["logits"])
+    out = model(x)
+    _close(out.detach(), fx["logits"])
+    loss = F.cross_entropy(out, y)
+    assert abs(float(loss.detach()) - fx["loss"]) < 1e-4
+    loss.backward()
+    for n, p in model.named_parameters():
+        ref = fx["grad_norms"][n]
+        assert abs(float(p.grad.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
+    opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-5)
+    opt.step()
+    assert float(F.cross_entropy(model(x), y)) < float(loss.detach())
