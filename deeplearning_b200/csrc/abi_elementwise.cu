@@ -212,9 +212,9 @@ int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, in
   return OK;
 }
 
-int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
-                      float gscale, int first_step, void* stream) {
-  sgd_momentum_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, buf, n, lr, momentum,
+int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
+                      float weight_decay, float gscale, int first_step, void* stream) {
+  sgd_momentum_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, buf, n, lr, lr_dev, momentum,
                                                                                weight_decay, gscale, first_step);
   B200_LAUNCHED();
   return OK;

@@ -584,7 +584,9 @@ __global__ void stem_wgrad_relayout_kernel(const float* __restrict__ src, float*
 // Fused SGD with momentum over a flat fp32 arena (torch.optim.SGD semantics, dampening 0, no nesterov):
 //   g' = g*gscale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
-                                    long long n, float lr, float momentum, float wd, float gscale, int first_step) {
+                                    long long n, float lr, const float* __restrict__ lr_dev, float momentum, float wd,
+                                    float gscale, int first_step) {
+  if (lr_dev != nullptr) lr = __ldg(lr_dev);  // device-resident learning rate: lets a captured CUDA graph follow a schedule
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float pv = p[i];

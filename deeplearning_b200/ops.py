@@ -360,9 +360,10 @@ def colsum(m, cols=None, out=None, accumulate=False):
     return out
 
 
-def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=False):
+def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=False, lr_dev=None):
+    """lr_dev: optional 1-element fp32 CUDA tensor holding the learning rate (read by the kernel; graph friendly)."""
     lib = _lib.load()
-    rc = lib.b200_sgd_momentum(_p(p), _p(g), _p(buf), p.numel(), lr, momentum, weight_decay, gscale,
+    rc = lib.b200_sgd_momentum(_p(p), _p(g), _p(buf), p.numel(), float(lr), _p(lr_dev), momentum, weight_decay, gscale,
                                1 if first_step else 0, _stream())
     _lib.check(rc, "b200_sgd_momentum")
 

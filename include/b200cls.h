@@ -120,9 +120,10 @@ int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int 
 int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, int taps, int ldk, int accumulate,
                               void* stream);
 
-/* fused SGD(momentum) over a flat fp32 arena; torch.optim.SGD semantics (classification/resnet/train.py:96) */
-int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, float momentum, float weight_decay,
-                      float gscale, int first_step, void* stream);
+/* fused SGD(momentum) over a flat fp32 arena; torch.optim.SGD semantics (classification/resnet/train.py:96).
+ * lr_dev (optional device float*) overrides lr, so a captured CUDA graph can follow the reference's LambdaLR schedule. */
+int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
+                      float weight_decay, float gscale, int first_step, void* stream);
 
 /* bring-up only: override the UMMA shared-memory descriptor strides (which: 0 = forward K-major, 1 = wgrad MN-major) */
 int b200_debug_set_desc(int which, unsigned lbo, unsigned sbo, unsigned kstep);
