@@ -163,12 +163,16 @@ def run_b200(args):
         return float(t)
 
     # ---- device-resident timing ---------------------------------------------------------------------------------
+    launches0 = ops.launch_count()
+    trainer.step_eager(images, labels)          # one eager step: counts this library's kernel launches per step
+    launches_per_step = ops.launch_count() - launches0
+    if not args.eager:
+        trainer.capture(images, labels)         # whole step (fwd+CE+bwd+SGD; all-reduce between two graphs if N>1)
     for _ in range(max(args.warmup, 3)):
         loss, _ = trainer.step(images, labels)
     sync_all()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -176,7 +180,7 @@ def run_b200(args):
     e1.record()
     sync_all()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
-    launches = ops.launch_count() - launches0
+    launches = launches_per_step * args.steps   # graph replays launch the same kernels the eager step does
     clocks = sampler.stop()
     final_loss = float(loss)
     ms_step = ms_total / args.steps
@@ -228,6 +232,7 @@ def run_b200(args):
             "config": {"workload": "classification/resnet ResNet-50 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[1])",
                        "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
                        "optimizer": "SGD(momentum=0.9, weight_decay=5e-5)", "step": "fwd+CE+bwd+allreduce+SGD",
+                       "launch": "eager" if args.eager else "CUDA graph replay",
                        "l2": "working set (~14 GB of activations per step) is far larger than the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
@@ -243,7 +248,7 @@ def run_b200(args):
             "peaks": peaks["_source"]}
         # per-kernel roofline: one extra step with CUDA-event spans around every C-ABI op on the launching stream
         with ops.Profiler() as prof:
-            trainer.step(images, labels)
+            trainer.step_eager(images, labels)
         agg = prof.summary()
         tot = sum(a["ms"] for a in agg.values())
         kernels = []
@@ -285,6 +290,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE config: 256)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="do not capture the step into CUDA graphs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

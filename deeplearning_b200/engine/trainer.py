@@ -94,18 +94,88 @@ class TrainStep:
             self.arena.broadcast(model.buffers())
         weight_cache.bump()
 
-    def step(self, images, labels, lr=None):
-        """One training step on this rank's shard. Returns (loss [1] fp32 device tensor, correct int32 [B])."""
+    # ------------------------------------------------------------------------------------------------ eager step
+    def _fwd_bwd(self, images, labels):
         model, arena = self.model, self.arena
-        if not model.training:
-            model.train()
         logits, tape = self.engine.forward(model, images, True, True)
         n_pad = (logits.shape[1] + 7) // 8 * 8
         loss, dlogits, correct = ops.softmax_xent(logits, labels, want_grad=True, ld_d=n_pad)
         self.engine.backward(model, tape, dlogits, sink=arena.grad_view)
-        arena.all_reduce_grads()
-        ops.sgd_momentum_(arena.flat_p, arena.flat_g, arena.flat_m, self.lr if lr is None else lr, self.momentum,
-                          self.weight_decay, gscale=arena.grad_scale, first_step=(self.steps == 0))
-        self.steps += 1
-        weight_cache.bump()  # parameters changed behind autograd's back -> repack bf16 operands on next use
         return loss, correct
+
+    def _update(self, lr, lr_dev=None):
+        arena = self.arena
+        # momentum buffer starts at zero, so "buf = mu*buf + g" already equals torch's first-step "buf = g"
+        ops.sgd_momentum_(arena.flat_p, arena.flat_g, arena.flat_m, lr, self.momentum, self.weight_decay,
+                          gscale=arena.grad_scale, first_step=False, lr_dev=lr_dev)
+        weight_cache.bump()  # parameters changed behind autograd's back -> repack bf16 operands on next use
+
+    def step_eager(self, images, labels, lr=None):
+        if not self.model.training:
+            self.model.train()
+        loss, correct = self._fwd_bwd(images, labels)
+        self.arena.all_reduce_grads()
+        self._update(self.lr if lr is None else lr)
+        self.steps += 1
+        return loss, correct
+
+    # ------------------------------------------------------------------------------------------------ CUDA-graph step
+    def capture(self, images, labels):
+        """Capture fwd+loss+bwd(+update) into CUDA graphs with static input buffers of the given shapes.
+        world == 1: one graph for the whole step.  world > 1: graph(fwd+bwd) -> NCCL all-reduce -> graph(update)."""
+        if not self.model.training:
+            self.model.train()
+        dev = self.arena.flat_p.device
+        self._g_images = torch.empty_like(images, dtype=torch.float32, device=dev)
+        self._g_labels = torch.empty_like(labels, device=dev)
+        self._g_images.copy_(images)
+        self._g_labels.copy_(labels)
+        self._lr_dev = torch.full((1,), float(self.lr), dtype=torch.float32, device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up: first-launch attribute calls, allocator growth
+            for _ in range(2):
+                self._fwd_bwd(self._g_images, self._g_labels)
+                self.arena.all_reduce_grads()
+                self._update(self.lr, self._lr_dev)
+                self.steps += 1
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self._graph_fb = torch.cuda.CUDAGraph()
+        self._graph_up = None
+        if self.world == 1:
+            with torch.cuda.graph(self._graph_fb):
+                self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels)
+                self._update(self.lr, self._lr_dev)
+        else:
+            with torch.cuda.graph(self._graph_fb):
+                self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels)
+            self._graph_up = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_up, pool=self._graph_fb.pool()):
+                self._update(self.lr, self._lr_dev)
+        self._captured_shape = (tuple(images.shape), tuple(labels.shape))
+        return self
+
+    def step(self, images, labels, lr=None):
+        """One training step on this rank's shard. Returns (loss [1] fp32 device tensor, correct int32 [B]).
+        Replays the captured graphs when ``capture()`` was called with matching shapes, else runs eagerly."""
+        if getattr(self, "_graph_fb", None) is None or (tuple(images.shape), tuple(labels.shape)) != self._captured_shape:
+            return self.step_eager(images, labels, lr)
+        if images.data_ptr() != self._g_images.data_ptr():
+            self._g_images.copy_(images, non_blocking=True)
+        if labels.data_ptr() != self._g_labels.data_ptr():
+            self._g_labels.copy_(labels, non_blocking=True)
+        if lr is not None and lr != self.lr:
+            self.lr = lr
+            self._lr_dev.fill_(float(lr))
+        self._graph_fb.replay()
+        if self._graph_up is not None:
+            self.arena.all_reduce_grads()
+            self._graph_up.replay()
+        self.steps += 1
+        return self._g_loss, self._g_correct
+
+    @property
+    def static_inputs(self):
+        """(images, labels) buffers the captured graph reads; fill them directly to avoid the device-to-device copy."""
+        return self._g_images, self._g_labels
