@@ -29,12 +29,13 @@ SIGNATURES = {
     "b200_conv2d_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200_conv2d_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
-    "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200_reduce_scratch_bytes": (c_size_t, [_I, _I]),
+    "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "b200_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),
     "b200_bn_bwd_reduce": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P, _P]),
     "b200_bn_bwd_blocks": (_I, [_L, _I]),
-    "b200_bn_bwd_finalize": (_I, [_P, _I, _I, _D, _P, _P, _I, _P, _P, _P]),
+    "b200_bn_bwd_finalize": (_I, [_P, _I, _I, _D, _P, _P, _I, _P, _P, _P, c_size_t, _P]),
     "b200_bn_bwd_apply": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P]),
     "b200_bn_relu_maxpool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
@@ -44,6 +45,7 @@ SIGNATURES = {
     "b200_mean": (_I, [_P, _I, _P, _P]),
     "b200_colsum_bf16": (_I, [_P, _L, _L, _I, _P, _I, _P]),
     "b200_pack_weight": (_I, [_P, _P, _I, _I, _I, _I, _L, _P]),
+    "b200_pack_weights_multi": (_I, [_P, _I, _I, _P]),
     "b200_cast_f32_to_bf16": (_I, [_P, _P, _L, _P]),
     "b200_cast_bf16_to_f32": (_I, [_P, _P, _L, _P]),
     "b200_im2col_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -16,6 +16,12 @@ inline int ew_grid(long long work_items, int block = 256) {
   return static_cast<int>(blocks);
 }
 inline bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+inline int reduce_slices(int T) {
+  int s = T / 32;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return s;
+}
 
 struct BnBwdPlan {
   int blocks, rows_per_block;
@@ -23,7 +29,7 @@ struct BnBwdPlan {
 BnBwdPlan plan_bn_bwd(long long rows, int C) {
   const int cvec = C / 8;
   const int rpi = 256 / cvec;
-  long long blocks = static_cast<long long>(device_sm_count()) * 4;
+  long long blocks = static_cast<long long>(device_sm_count()) * 8;
   long long rpb = (rows + blocks - 1) / blocks;
   rpb = ((rpb + rpi - 1) / rpi) * rpi;
   if (rpb < rpi) rpb = rpi;
@@ -39,13 +45,20 @@ int b200_abi_version(void) { return 1; }
 int b200_sm_count(void) { return device_sm_count(); }
 unsigned long long b200_launch_count(void) { return g_launch_count; }
 
+size_t b200_reduce_scratch_bytes(int T, int C) {
+  return 256 + static_cast<size_t>(reduce_slices(T)) * 2 * C * sizeof(double);
+}
+
 int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
-                     float* mean, float* invstd, float* scale, float* shift, void* stream) {
+                     float* mean, float* invstd, float* scale, float* shift, void* scratch, size_t scratch_bytes,
+                     void* stream) {
   B200_REQUIRE(T > 0 && C > 0 && count > 0, "bn_finalize: bad sizes T=%d C=%d", T, C);
-  bn_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B200_REQUIRE(C <= 64 * 32, "bn_finalize: C=%d exceeds 2048", C);
+  B200_REQUIRE(scratch != nullptr && scratch_bytes >= b200_reduce_scratch_bytes(T, C), "bn_finalize: scratch too small");
+  bn_finalize_kernel<<<dim3((C + 31) / 32, reduce_slices(T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       partial, T, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, mean, invstd,
-      scale, shift);
+      scale, shift, scratch);
   B200_LAUNCHED();
   return OK;
 }
@@ -87,9 +100,11 @@ int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz
 }
 
 int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
-                         float* m1, float* m2, void* stream) {
-  bn_bwd_finalize_kernel<<<(C + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(partial, T, C, count, dgamma,
-                                                                                      dbeta, accumulate, m1, m2);
+                         float* m1, float* m2, void* scratch, size_t scratch_bytes, void* stream) {
+  B200_REQUIRE(T > 0 && C > 0 && C <= 64 * 32, "bn_bwd_finalize: bad sizes T=%d C=%d", T, C);
+  B200_REQUIRE(scratch != nullptr && scratch_bytes >= b200_reduce_scratch_bytes(T, C), "bn_bwd_finalize: scratch too small");
+  bn_bwd_finalize_kernel<<<dim3((C + 31) / 32, reduce_slices(T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partial, T, C, count, dgamma, dbeta, accumulate, m1, m2, scratch);
   B200_LAUNCHED();
   return OK;
 }
@@ -97,11 +112,11 @@ int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float
 int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
                       const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
                       int relu, long long rows, int C, void* stream) {
-  B200_REQUIRE(C % 8 == 0, "bn_bwd_apply: C=%d must be a multiple of 8", C);
-  const long long nvec = rows * (C / 8);
-  bn_bwd_apply_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B200_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_bwd_apply: C=%d must be 8*2^k <= 2048", C);
+  const BnBwdPlan pl = plan_bn_bwd(rows, C);
+  bn_bwd_apply_kernel<<<pl.blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out), g_is_dz,
-      static_cast<uint4*>(dx), scale, shift, mean, invstd, m1, m2, relu, nvec, C / 8);
+      static_cast<uint4*>(dx), scale, shift, mean, invstd, m1, m2, relu, rows, C / 8, pl.rows_per_block);
   B200_LAUNCHED();
   return OK;
 }
@@ -178,6 +193,14 @@ int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mo
   return OK;
 }
 
+int b200_pack_weights_multi(const void* table, int n_entries, int total_blocks, void* stream) {
+  B200_REQUIRE(table != nullptr && n_entries > 0 && total_blocks > 0, "pack_weights_multi: empty table");
+  pack_weights_multi_kernel<<<total_blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const long long*>(table), n_entries);
+  B200_LAUNCHED();
+  return OK;
+}
+
 int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   cast_f32_bf16_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, static_cast<__nv_bfloat16*>(dst),
                                                                                   n);
@@ -196,9 +219,10 @@ int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int 
   B200_REQUIRE(ldk % 8 == 0 && ldk >= KH * KW * Cin, "im2col: ldk=%d must be a multiple of 8 and >= %d", ldk,
                KH * KW * Cin);
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  const long long nvec = static_cast<long long>(B) * Ho * Wo * (ldk / 8);
-  im2col_nchw_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, static_cast<uint4*>(a), B, Cin, H, W, KH, KW, stride, pad, Ho, Wo, ldk);
+  const size_t smem = static_cast<size_t>(Cin) * KH * (W + 2 * pad) * sizeof(float);
+  B200_REQUIRE(smem <= 48 * 1024, "im2col: staged rows need %zu bytes of shared memory (> 48 KB)", smem);
+  im2col_nchw_kernel<<<B * Ho, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(a), B, Cin, H, W,
+                                                                               KH, KW, stride, pad, Ho, Wo, ldk);
   B200_LAUNCHED();
   return OK;
 }

@@ -40,20 +40,26 @@ __device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// BatchNorm statistics finalize: partial[T][2][C] (sum, sum of squares per 128-row tile) -> mean/invstd/scale/shift,
-// running-stat update. One block = 32 channels x 8 partial-row groups; accumulation in double.
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int T, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float momentum, float* running_mean, float* running_var, long long* num_batches,
-                                   float* mean_out, float* invstd_out, float* scale_out, float* shift_out) {
+// Column reduction of per-tile partials partial[T][2][C] -> two per-channel sums (double), parallel over T:
+// grid = (ceil(C/32), S); every block reduces its slice of T for 32 channels and publishes it to `scratch`; the last
+// block to finish (ticket counter, reset to zero for the next call) folds the S slices and returns true.
+// scratch layout: [64 x uint32 counters][S][2][C] doubles.
+__device__ __forceinline__ bool reduce_partials_last_block(const float* __restrict__ partial, int T, int C, void* scratch,
+                                                           double& s_out, double& ss_out) {
   __shared__ double sh[2][8][32];
+  __shared__ int is_last;
+  unsigned int* counters = static_cast<unsigned int*>(scratch);
+  double* slices = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
+  const int S = gridDim.y;
+  const int chunk = (T + S - 1) / S;
+  const int t0 = blockIdx.y * chunk, t1 = min(T, t0 + chunk);
   double s = 0.0, ss = 0.0;
   if (c < C) {
-    for (int t = ry; t < T; t += 8) {
-      s += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
-      ss += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
+    for (int t = t0 + ry; t < t1; t += 8) {
+      s += static_cast<double>(__ldg(partial + (static_cast<long long>(t) * 2 + 0) * C + c));
+      ss += static_cast<double>(__ldg(partial + (static_cast<long long>(t) * 2 + 1) * C + c));
     }
   }
   sh[0][ry][cx] = s;
@@ -64,6 +70,53 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int T, int
       s += sh[0][i][cx];
       ss += sh[1][i][cx];
     }
+    slices[(static_cast<long long>(blockIdx.y) * 2 + 0) * C + c] = s;
+    slices[(static_cast<long long>(blockIdx.y) * 2 + 1) * C + c] = ss;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[blockIdx.x], 1u);
+    is_last = (ticket == static_cast<unsigned int>(S - 1));
+    if (is_last) counters[blockIdx.x] = 0;  // ready for the next launch on this stream
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  s = 0.0;
+  ss = 0.0;
+  if (c < C) {
+    for (int k = ry; k < S; k += 8) {
+      s += slices[(static_cast<long long>(k) * 2 + 0) * C + c];
+      ss += slices[(static_cast<long long>(k) * 2 + 1) * C + c];
+    }
+  }
+  __syncthreads();
+  sh[0][ry][cx] = s;
+  sh[1][ry][cx] = ss;
+  __syncthreads();
+  if (ry == 0) {
+    for (int i = 1; i < 8; ++i) {
+      s += sh[0][i][cx];
+      ss += sh[1][i][cx];
+    }
+  }
+  s_out = s;
+  ss_out = ss;
+  return ry == 0 && c < C;
+}
+
+// BatchNorm statistics finalize: partial[T][2][C] (sum, sum of squares per tile) -> mean/invstd/scale/shift,
+// running-stat update (double accumulation).
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int T, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* running_mean, float* running_var, long long* num_batches,
+                                   float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
+                                   void* scratch) {
+  double s, ss;
+  const bool owner = reduce_partials_last_block(partial, T, C, scratch, s, ss);
+  if (owner) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     const double mean = s / count;
     double var = ss / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -71,16 +124,15 @@ __global__ void bn_finalize_kernel(const float* __restrict__ partial, int T, int
     const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
     mean_out[c] = static_cast<float>(mean);
     invstd_out[c] = static_cast<float>(invstd);
-    const float sc = static_cast<float>(g * invstd);
-    scale_out[c] = sc;
+    scale_out[c] = static_cast<float>(g * invstd);
     shift_out[c] = static_cast<float>(b - mean * g * invstd);
     if (running_mean) {
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
       running_mean[c] = static_cast<float>((1.0 - momentum) * running_mean[c] + momentum * mean);
       running_var[c] = static_cast<float>((1.0 - momentum) * running_var[c] + momentum * unbiased);
     }
+    if (num_batches && c == 0) *num_batches += 1;
   }
-  if (num_batches && blockIdx.x == 0 && threadIdx.x == 0) *num_batches += 1;
 }
 
 // Eval-mode BN: scale/shift from running statistics.
@@ -148,27 +200,42 @@ __global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* _
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-  for (long long r = r0 + rsub; r < r1; r += rpi) {
-    const long long i = r * cvec + cg;
-    float gv[8], xv[8];
-    unpack8(__ldg(g + i), gv);
-    unpack8(__ldg(x + i), xv);
-    if (relu) {
-      if (y_out) {
+  const bool mask_from_y = relu && (y_out != nullptr);
+  const bool mask_from_x = relu && (y_out == nullptr);
+  for (long long r = r0 + rsub; r < r1; r += 2 * rpi) {
+    const long long i0 = r * cvec + cg;
+    const long long i1 = (r + rpi) * cvec + cg;
+    const bool has1 = (r + rpi) < r1;
+    uint4 g0 = __ldg(g + i0), x0 = __ldg(x + i0), g1 = g0, x1 = x0, y0 = g0, y1 = g0;
+    if (has1) {
+      g1 = __ldg(g + i1);
+      x1 = __ldg(x + i1);
+    }
+    if (mask_from_y) {
+      y0 = __ldg(y_out + i0);
+      if (has1) y1 = __ldg(y_out + i1);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !has1) break;
+      float gv[8], xv[8];
+      unpack8(h ? g1 : g0, gv);
+      unpack8(h ? x1 : x0, xv);
+      if (mask_from_y) {
         float yv[8];
-        unpack8(__ldg(y_out + i), yv);
+        unpack8(h ? y1 : y0, yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
-      } else {
+      } else if (mask_from_x) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? gv[j] : 0.f;
       }
-    }
-    if (dz_out) dz_out[i] = pack8(gv);
+      if (dz_out) dz_out[h ? i1 : i0] = pack8(gv);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      a1[j] += gv[j];
-      a2[j] = fmaf(gv[j], (xv[j] - mu[j]) * is[j], a2[j]);
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += gv[j];
+        a2[j] = fmaf(gv[j], (xv[j] - mu[j]) * is[j], a2[j]);
+      }
     }
   }
   float* my = red + threadIdx.x * 17;
@@ -202,66 +269,81 @@ __global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* _
 // the apply pass: m1 = dbeta / count, m2 = dgamma / count.
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int T, int C, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                       float* __restrict__ m1, float* __restrict__ m2) {
-  __shared__ double sh[2][8][32];
-  const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  double s = 0.0, ss = 0.0;
-  if (c < C) {
-    for (int t = ry; t < T; t += 8) {
-      s += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 0) * C + c]);
-      ss += static_cast<double>(partial[(static_cast<long long>(t) * 2 + 1) * C + c]);
-    }
-  }
-  sh[0][ry][cx] = s;
-  sh[1][ry][cx] = ss;
-  __syncthreads();
-  if (ry == 0 && c < C) {
-    for (int i = 1; i < 8; ++i) {
-      s += sh[0][i][cx];
-      ss += sh[1][i][cx];
-    }
+                                       float* __restrict__ m1, float* __restrict__ m2, void* scratch) {
+  double s, ss;
+  const bool owner = reduce_partials_last_block(partial, T, C, scratch, s, ss);
+  if (owner) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s) : static_cast<float>(s);
     if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(ss) : static_cast<float>(ss);
-    m1[c] = static_cast<float>(s / count);
-    m2[c] = static_cast<float>(ss / count);
+    if (m1) m1[c] = static_cast<float>(s / count);
+    if (m2) m2[c] = static_cast<float>(ss / count);
   }
 }
 
 // BN backward, pass 2: dx = scale * (dz - m1 - xhat * m2), dz recomputed exactly as in pass 1 (or read from dz_in).
+// Same thread mapping as pass 1 (a thread owns one 8-channel group; per-channel vectors live in registers).
 __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x,
                                     const uint4* __restrict__ y_out, int g_is_dz, uint4* __restrict__ dx,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ m1, const float* __restrict__ m2, int relu,
-                                    long long nvec, int cvec) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % cvec);
-    float sc[8], sh[8], mu[8], is[8], q1[8], q2[8], gv[8], xv[8];
+                                    long long rows, int cvec, int rows_per_block) {
+  const int tpr = cvec, rpi = 256 / tpr;
+  const int cg = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
+  float sc[8], sh[8], a[8], bq[8], cq[8];
+  {
+    float mu[8], is[8], q1[8], q2[8];
     load8f(scale + cg * 8, sc);
     load8f(shift + cg * 8, sh);
     load8f(mean + cg * 8, mu);
     load8f(invstd + cg * 8, is);
     load8f(m1 + cg * 8, q1);
     load8f(m2 + cg * 8, q2);
-    unpack8(__ldg(g + i), gv);
-    unpack8(__ldg(x + i), xv);
-    if (relu && !g_is_dz) {
-      if (y_out) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // dx = sc*(dz - q1 - (x-mu)*is*q2) = a*dz - bq*x + cq
+      a[j] = sc[j];
+      bq[j] = sc[j] * is[j] * q2[j];
+      cq[j] = sc[j] * (mu[j] * is[j] * q2[j] - q1[j]);
+    }
+  }
+  const bool mask_from_x = relu && !g_is_dz && (y_out == nullptr);
+  const bool mask_from_y = relu && !g_is_dz && (y_out != nullptr);
+  const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long r = r0 + rsub; r < r1; r += 2 * rpi) {
+    const long long i0 = r * cvec + cg;
+    const long long i1 = (r + rpi) * cvec + cg;
+    const bool has1 = (r + rpi) < r1;
+    uint4 g0 = __ldg(g + i0), x0 = __ldg(x + i0), g1 = g0, x1 = x0, y0 = g0, y1 = g0;
+    if (has1) {
+      g1 = __ldg(g + i1);
+      x1 = __ldg(x + i1);
+    }
+    if (mask_from_y) {
+      y0 = __ldg(y_out + i0);
+      if (has1) y1 = __ldg(y_out + i1);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !has1) break;
+      float gv[8], xv[8], o[8];
+      unpack8(h ? g1 : g0, gv);
+      unpack8(h ? x1 : x0, xv);
+      if (mask_from_y) {
         float yv[8];
-        unpack8(__ldg(y_out + i), yv);
+        unpack8(h ? y1 : y0, yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
-      } else {
+      } else if (mask_from_x) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = fmaf(xv[j], sc[j], sh[j]) > 0.f ? gv[j] : 0.f;
       }
-    }
-    float o[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = sc[j] * (gv[j] - q1[j] - (xv[j] - mu[j]) * is[j] * q2[j]);
-    dx[i] = pack8(o);
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(a[j], gv[j], fmaf(-bq[j], xv[j], cq[j]));
+      dx[h ? i1 : i0] = pack8(o);
+    }
   }
 }
 
@@ -534,19 +616,29 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
 }
 
 // Stem im2col: x fp32 NCHW [B][Cin][H][W] -> A bf16 [B*Ho*Wo][ldk], k = (kh*KW + kw)*Cin + c, zero padded to ldk.
+// One block per output row (b, oh): the KH input rows of every channel are staged in shared memory with coalesced loads
+// (zero padded left/right), then each thread assembles 16-byte output vectors from shared memory.
 __global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restrict__ a, int B, int Cin, int H, int W,
                                    int KH, int KW, int stride, int pad, int Ho, int Wo, int ldk) {
+  extern __shared__ float srow[];  // [Cin][KH][W + 2*pad]
+  const int Wp = W + 2 * pad;
+  const int b = blockIdx.x / Ho, oh = blockIdx.x % Ho;
+  const int n_in = Cin * KH * Wp;
+  for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
+    const int wp = i % Wp;
+    const int kh = (i / Wp) % KH;
+    const int c = i / (Wp * KH);
+    const int ih = oh * stride - pad + kh, iw = wp - pad;
+    float v = 0.f;
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + ((static_cast<long long>(b) * Cin + c) * H + ih) * W + iw);
+    srow[i] = v;
+  }
+  __syncthreads();
   const int kvec = ldk / 8;
-  const long long nvec = static_cast<long long>(B) * Ho * Wo * kvec;
   const int K = KH * KW * Cin;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int kv = static_cast<int>(i % kvec);
-    long long t = i / kvec;
-    const int ow = static_cast<int>(t % Wo);
-    t /= Wo;
-    const int oh = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
+  uint4* out = a + (static_cast<long long>(b) * Ho + oh) * Wo * kvec;
+  for (int i = threadIdx.x; i < Wo * kvec; i += blockDim.x) {
+    const int kv = i % kvec, ow = i / kvec;
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -556,13 +648,52 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restric
         const int c = k % Cin;
         const int tap = k / Cin;
         const int kw = tap % KW, kh = tap / KW;
-        const int ih = oh * stride - pad + kh, iw = ow * stride - pad + kw;
-        if (ih >= 0 && ih < H && iw >= 0 && iw < W)
-          val = __ldg(x + ((static_cast<long long>(b) * Cin + c) * H + ih) * W + iw);
+        val = srow[(c * KH + kh) * Wp + ow * stride + kw];
       }
       v[j] = val;
     }
-    a[i] = pack8(v);
+    out[i] = pack8(v);
+  }
+}
+
+// Multi-tensor weight packing: one launch packs every conv / linear weight of a model.
+// table[e] = {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out} (int64 each); grid = total blocks.
+__global__ void pack_weights_multi_kernel(const long long* __restrict__ table, int n_entries) {
+  __shared__ int entry;
+  if (threadIdx.x == 0) {
+    int e = 0;
+    while (e + 1 < n_entries && table[(e + 1) * 9 + 7] <= static_cast<long long>(blockIdx.x)) ++e;
+    entry = e;
+  }
+  __syncthreads();
+  const long long* t = table + entry * 9;
+  const float* src = reinterpret_cast<const float*>(t[0]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(t[1]);
+  const int O = static_cast<int>(t[2]), I = static_cast<int>(t[3]), taps = static_cast<int>(t[4]);
+  const int mode = static_cast<int>(t[5]);
+  const long long ld = t[6], first = t[7], rows_out = t[8];
+  const long long next_first = (entry + 1 < n_entries) ? table[(entry + 1) * 9 + 7] : static_cast<long long>(gridDim.x);
+  const long long nblk = next_first - first;
+  const long long total = rows_out * ld;
+  const long long rows_src = mode == 0 ? O : I;
+  for (long long idx = (blockIdx.x - first) * blockDim.x + threadIdx.x; idx < total; idx += nblk * blockDim.x) {
+    const long long r = idx / ld;
+    const long long k = idx % ld;
+    float v = 0.f;
+    if (r < rows_src) {
+      if (mode == 0) {
+        if (k < static_cast<long long>(taps) * I) {
+          const int tap = static_cast<int>(k / I), i = static_cast<int>(k % I);
+          v = src[(r * I + i) * taps + tap];
+        }
+      } else {
+        if (k < static_cast<long long>(taps) * O) {
+          const int tap = static_cast<int>(k / O), o = static_cast<int>(k % O);
+          v = src[(static_cast<long long>(o) * I + r) * taps + tap];
+        }
+      }
+    }
+    dst[idx] = __float2bfloat16_rn(v);
   }
 }
 

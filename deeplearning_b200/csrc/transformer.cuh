@@ -1,0 +1,223 @@
+// HBM-bound passes of the ViT / Swin / ConvNeXt paths: LayerNorm forward/backward (one warp per token row, statistics in
+// fp32 registers), patch extraction from the user's NCHW fp32 batch, class-token row assembly.
+//
+// Reference semantics: nn.LayerNorm over the last dim (biased variance), eps 1e-6 in ViT
+// (classification/vision_transformer/vit_model.py:194), 1e-5 in Swin (classification/swin_transformer/models/swin_transformer.py:509);
+// PatchEmbed = Conv2d(3, D, p, p) -> flatten -> transpose (vit_model.py:56-66); cls/pos (vit_model.py:244-250).
+#pragma once
+#include "common.cuh"
+#include "elementwise.cuh"
+
+namespace b200 {
+
+template <typename T>
+__device__ __forceinline__ void load_row8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void load_row8<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void load_row8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack8(*reinterpret_cast<const uint4*>(p), f);
+}
+template <typename T>
+__device__ __forceinline__ void store_row8(T* p, const float (&f)[8]);
+template <>
+__device__ __forceinline__ void store_row8<float>(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *(reinterpret_cast<float4*>(p) + 1) = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <>
+__device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = pack8(f);
+}
+
+// y = (x - mean) * rstd * gamma + beta.  One warp per row; MAXV = max 8-element vectors per lane (C <= 256*MAXV).
+template <typename TIn, int MAXV>
+__global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int C,
+                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    float v[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        load_row8<TIn>(x + r * C + vi * 8, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+    s = warp_sum(s);
+    const float mean = s / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / C + eps);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float g[8], b[8], o[8];
+        load8f(gamma + vi * 8, g);
+        load8f(beta + vi * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
+        *reinterpret_cast<uint4*>(y + r * C + vi * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat)) (+ add);  partial[block][2][C] = (sum dy, sum dy*xhat)
+template <typename TIn, typename TOut, int MAXV>
+__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, const TOut* __restrict__ add,
+                                     TOut* __restrict__ dx, float* __restrict__ partial, long long rows, int C) {
+  extern __shared__ float red[];  // [warps][2][C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int nvec = C >> 3;
+  float ab[MAXV][8], ag[MAXV][8];
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ab[i][j] = ag[i][j] = 0.f;
+  const long long warp0 = blockIdx.x * static_cast<long long>(nw) + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * nw;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float mu = mean[r], rs = rstd[r];
+    float xh[MAXV][8], dg[MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float xv[8], dv[8], g[8];
+        load_row8<TIn>(x + r * C + vi * 8, xv);
+        unpack8(*reinterpret_cast<const uint4*>(dy + r * C + vi * 8), dv);
+        load8f(gamma + vi * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          dg[i][j] = dv[j] * g[j];
+          s1 += dg[i][j];
+          s2 = fmaf(dg[i][j], xh[i][j], s2);
+          ab[i][j] += dv[j];
+          ag[i][j] = fmaf(dv[j], xh[i][j], ag[i][j]);
+        }
+      }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (dg[i][j] - s1 - xh[i][j] * s2);
+        if (add != nullptr) {
+          float a[8];
+          load_row8<TOut>(add + r * C + vi * 8, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        store_row8<TOut>(dx + r * C + vi * 8, o);
+      }
+    }
+  }
+  // block-level column reduction of the parameter-gradient partials
+  float* mine = red + static_cast<long long>(warp) * 2 * C;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = i * 32 + lane;
+    if (vi < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mine[vi * 8 + j] = ab[i][j];
+        mine[C + vi * 8 + j] = ag[i][j];
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[static_cast<long long>(w) * 2 * C + c];
+    partial[static_cast<long long>(blockIdx.x) * 2 * C + c] = s;
+  }
+}
+
+// Patch extraction: x fp32 NCHW [B][Cin][H][W] -> a bf16 [B*(H/ps)*(W/ps)][Cin*ps*ps], k = c*ps*ps + kh*ps + kw
+// (the flattening order of an OIHW conv weight, so the weight matrix is weight.view(D, -1) unchanged). ps % 8 == 0... or 4.
+__global__ void patchify_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int Cin, int H,
+                                     int W, int ps) {
+  const int ph = H / ps, pw = W / ps;
+  const int K = Cin * ps * ps;
+  const int kv = K / 4;  // 4 consecutive kw per thread (ps is a multiple of 4)
+  const long long total = static_cast<long long>(B) * ph * pw * kv;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k4 = static_cast<int>(i % kv);
+    long long t = i / kv;
+    const int px = static_cast<int>(t % pw);
+    t /= pw;
+    const int py = static_cast<int>(t % ph);
+    const int b = static_cast<int>(t / ph);
+    const int k = k4 * 4;
+    const int kw = k % ps, kh = (k / ps) % ps, c = k / (ps * ps);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(
+        x + ((static_cast<long long>(b) * Cin + c) * H + py * ps + kh) * W + px * ps + kw));
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(a + (static_cast<long long>(b) * ph * pw + py * pw + px) * K + k) = o;
+  }
+}
+
+// ViT class-token row: tokens[b][0][:] = cls[:] + pos[0][:]   (tokens fp32 [B][T][D])
+__global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ tokens,
+                               int B, int T, int D) {
+  const long long total = static_cast<long long>(B) * D;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int d = static_cast<int>(i % D);
+    const long long b = i / D;
+    tokens[b * T * D + d] = cls[d] + pos[d];
+  }
+}
+
+// Sum over the batch of a strided set of rows: out[d] (+)= sum_b g[b*stride_b + d]   (gradient of cls token / pos embed rows)
+__global__ void batch_rowsum_kernel(const float* __restrict__ g, long long stride_b, int B, int D, float* __restrict__ out,
+                                    int accumulate) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += g[b * stride_b + d];
+  out[d] = accumulate ? out[d] + s : s;
+}
+
+}  // namespace b200

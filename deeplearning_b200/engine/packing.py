@@ -1,23 +1,84 @@
 """Derived bf16 GEMM operands of the fp32 master parameters.
 
 The reference keeps OIHW fp32 ``nn.Parameter``s (checkpoints are plain ``state_dict()``s, classification/resnet/train.py:130),
-so the packed [O][taps*I] / [I][taps*O] bf16 copies the tensor cores read are caches, rebuilt whenever the parameter's
-version counter or storage changes (i.e. after every optimizer step or ``load_state_dict``).
+so the packed [O][taps*I] / [I][taps*O] bf16 copies the tensor cores read are caches, rebuilt whenever a parameter's
+version counter or storage changes (optimizer step, ``load_state_dict``) or when ``bump()`` is called by code that updates
+parameters behind autograd's back (the fused optimizer kernel).  A model registers all its weights once (``ModelPack``) so
+that one multi-tensor launch repacks everything; single tensors fall back to ``ops.pack_weight``.
 """
 import weakref
 
 import torch
 
-from .. import ops
+from .. import _lib, ops
+
+
+class ModelPack:
+    """All packed operands of one model, refreshed by ONE kernel launch (b200_pack_weights_multi)."""
+
+    def __init__(self, specs):
+        # specs: list of (param, mode, ld, rows_out)
+        self.specs = specs
+        self.outputs = {}
+        self._ptrs = None
+        self.stamp = None
+        dev = specs[0][0].device
+        rows = []
+        first = 0
+        for (p, mode, ld, rows_out) in specs:
+            O, I = p.shape[0], p.shape[1]
+            taps = p.numel() // (O * I)
+            dst = torch.empty(rows_out, ld, dtype=torch.bfloat16, device=dev)
+            self.outputs[(id(p), mode)] = dst
+            nblk = max(1, min(64, (rows_out * ld + 256 * 16 - 1) // (256 * 16)))
+            rows.append([0, dst.data_ptr(), O, I, taps, mode, ld, first, rows_out])
+            first += nblk
+        self.total_blocks = first
+        self._rows = rows
+        self.table = None
+
+    def _build_table(self):
+        ptrs = tuple(p.data_ptr() for (p, _, _, _) in self.specs)
+        if ptrs != self._ptrs:
+            for r, ptr in zip(self._rows, ptrs):
+                r[0] = ptr
+            dev = self.specs[0][0].device
+            self.table = torch.tensor(self._rows, dtype=torch.int64).to(dev)
+            self._ptrs = ptrs
+
+    def refresh(self, generation):
+        stamp = (generation, tuple((p._version, p.data_ptr()) for (p, _, _, _) in self.specs))
+        if stamp == self.stamp:
+            return
+        self._build_table()
+        lib = _lib.load()
+        rc = lib.b200_pack_weights_multi(self.table.data_ptr(), len(self._rows), self.total_blocks,
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "b200_pack_weights_multi")
+        self.stamp = stamp
+
+    def get(self, param, mode):
+        return self.outputs.get((id(param), mode))
 
 
 class _WeightCache:
     def __init__(self):
         self._store = {}
+        self._packs = weakref.WeakKeyDictionary()  # model -> ModelPack
         self.generation = 0  # bumped by code that updates parameters behind autograd's back (fused optimizer kernels)
 
     def bump(self):
         self.generation += 1
+
+    def model_pack(self, model, spec_fn):
+        """Return the model's ModelPack (built on first use from spec_fn(model)), refreshed for the current parameters."""
+        pack = self._packs.get(model)
+        if pack is None or getattr(pack, "_spec_key", None) != spec_fn.key(model):
+            pack = ModelPack(spec_fn(model))
+            pack._spec_key = spec_fn.key(model)
+            self._packs[model] = pack
+        pack.refresh(self.generation)
+        return pack
 
     def get(self, param, mode, ld=None, pad_rows=None, pad_cols=None):
         key = (id(param), mode, ld, pad_rows, pad_cols)
@@ -41,6 +102,7 @@ class _WeightCache:
 
     def clear(self):
         self._store.clear()
+        self._packs = weakref.WeakKeyDictionary()
 
 
 weight_cache = _WeightCache()

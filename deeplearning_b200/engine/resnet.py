@@ -30,16 +30,44 @@ def _check_bn(bn, name):
         raise NotImplementedError(f"{name}: the B200 engine implements affine nn.BatchNorm2d with running statistics (got {bn})")
 
 
+class _PackSpec:
+    """Which bf16 operands a ResNet needs: forward [O][taps*I] and dgrad [I][taps*O] copies of every conv / fc weight."""
+
+    @staticmethod
+    def key(model):
+        return (model.fc.out_features, id(model.fc))
+
+    def __call__(self, model):
+        specs = []
+        for name, mod in model.named_modules():
+            if isinstance(mod, nn.Conv2d):
+                w = mod.weight
+                O, I, kh, kw = w.shape
+                if name == "conv1":
+                    specs.append((w, 0, 160, O))  # stem patch-matrix layout, K padded 147 -> 160
+                    continue
+                specs.append((w, 0, kh * kw * I, O))
+                specs.append((w, 1, kh * kw * O, I))
+        fc = model.fc
+        n_pad = (fc.out_features + 7) // 8 * 8
+        specs.append((fc.weight, 0, fc.in_features, n_pad))
+        specs.append((fc.weight, 1, n_pad, fc.in_features))
+        return specs
+
+
+_pack_spec = _PackSpec()
+
+
 class _Unit:
     """Saved state of one conv -> BN (-> ReLU) (-> + residual) application."""
     __slots__ = ("conv", "bn", "x", "c", "co", "y", "relu", "has_res")
 
 
-def _conv_bn(tape, x, conv, bn, train, relu, residual=None, name=""):
+def _conv_bn(pack, tape, x, conv, bn, train, relu, residual=None, name=""):
     _check_conv(conv, name)
     _check_bn(bn, name)
     k, s = conv.kernel_size[0], conv.stride[0]
-    wp = weight_cache.get(conv.weight, 0)
+    wp = pack.get(conv.weight, 0)
     c, st = ops.conv2d_fwd(x, wp, k, s, want_stats=train)
     if train:
         rows = c.numel() // c.shape[-1]
@@ -68,7 +96,10 @@ def forward(model, x, train, want_tape):
         raise ValueError(f"expected an [B,3,H,W] image batch, got {tuple(x.shape)}")
     x = x.contiguous().float()
     B = x.shape[0]
-    tape = {"stem": None, "blocks": [], "head": None} if want_tape else None
+    if not isinstance(model.fc, nn.Linear):
+        raise NotImplementedError("model.fc must be an nn.Linear")
+    pack = weight_cache.model_pack(model, _pack_spec)  # one launch repacks every bf16 operand if parameters changed
+    tape = {"stem": None, "blocks": [], "head": None, "pack": pack} if want_tape else None
     # ---- stem: 7x7/2 conv as patch-matrix GEMM, BN statistics in the epilogue, BN+ReLU+max-pool in one pass
     conv1, bn1 = model.conv1, model.bn1
     _check_bn(bn1, "bn1")
@@ -76,7 +107,7 @@ def forward(model, x, train, want_tape):
         raise NotImplementedError("stem must be the 7x7/2 pad-3 bias-free convolution of the reference")
     kpad = 160
     a, Ho, Wo = ops.im2col_nchw(x, 7, 7, 2, 3, kpad)
-    wp = weight_cache.get(conv1.weight, 0, ld=kpad)
+    wp = pack.get(conv1.weight, 0)
     c1, st = ops.conv2d_fwd(a.view(-1, 1, 1, kpad), wp, want_stats=train)
     c1 = c1.view(B, Ho, Wo, 64)
     if train:
@@ -95,25 +126,23 @@ def forward(model, x, train, want_tape):
             x_in = h
             pairs = _block_units(block)
             for j, (conv, bn) in enumerate(pairs[:-1]):
-                h = _conv_bn(units, h, conv, bn, train, relu=True, name=f"{name}.conv{j + 1}")
+                h = _conv_bn(pack, units, h, conv, bn, train, relu=True, name=f"{name}.conv{j + 1}")
             ds_units = [] if want_tape else None
             if block.downsample is not None:
-                identity = _conv_bn(ds_units, x_in, block.downsample[0], block.downsample[1], train, relu=False,
+                identity = _conv_bn(pack, ds_units, x_in, block.downsample[0], block.downsample[1], train, relu=False,
                                     name=f"{name}.downsample")
             else:
                 identity = x_in
             conv, bn = pairs[-1]
-            h = _conv_bn(units, h, conv, bn, train, relu=True, residual=identity, name=f"{name}.conv{len(pairs)}")
+            h = _conv_bn(pack, units, h, conv, bn, train, relu=True, residual=identity, name=f"{name}.conv{len(pairs)}")
             if want_tape:
                 tape["blocks"].append((units, ds_units[0] if ds_units else None, x_in))
     # ---- head: global average pool + fc (fp32 logits)
     pooled = ops.avgpool_fwd(h)
     fc = model.fc
-    if not isinstance(fc, nn.Linear):
-        raise NotImplementedError("model.fc must be an nn.Linear")
     n_cls = fc.out_features
     n_pad = (n_cls + 7) // 8 * 8
-    wfc = weight_cache.get(fc.weight, 0, pad_rows=n_pad)
+    wfc = pack.get(fc.weight, 0)
     bias = None
     if fc.bias is not None:
         bias = fc.bias.detach()
@@ -176,7 +205,8 @@ def backward(model, tape, dlogits, sink=None):
         grads.put(fc.weight, gw)
     if fc.bias is not None:
         grads.put(fc.bias, ops.colsum(dl16.view(B, n_pad), cols=n_cls, out=grads.dest(fc.bias)))
-    wfc_d = weight_cache.get(fc.weight, 1, pad_cols=n_pad)
+    pack = tape["pack"]
+    wfc_d = pack.get(fc.weight, 1)
     dpooled = ops.conv2d_dgrad(dl16, wfc_d, (1, 1))
     g = ops.avgpool_bwd(dpooled.view(B, -1), hw)
 
@@ -189,7 +219,7 @@ def backward(model, tape, dlogits, sink=None):
             u = units[j]
             k, s = u.conv.kernel_size[0], u.conv.stride[0]
             grads.put(u.conv.weight, ops.conv2d_wgrad(dc, u.x, k, s, out=grads.dest(u.conv.weight)))
-            wd = weight_cache.get(u.conv.weight, 1)
+            wd = pack.get(u.conv.weight, 1)
             in_hw = tuple(u.x.shape[1:3])
             if j > 0:
                 g_prev = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
@@ -203,7 +233,7 @@ def backward(model, tape, dlogits, sink=None):
             dcd, _ = _unit_backward(ds, dz, grads)
             kd, sd = ds.conv.kernel_size[0], ds.conv.stride[0]
             grads.put(ds.conv.weight, ops.conv2d_wgrad(dcd, x_in, kd, sd, out=grads.dest(ds.conv.weight)))
-            wdd = weight_cache.get(ds.conv.weight, 1)
+            wdd = pack.get(ds.conv.weight, 1)
             gx = ops.conv2d_dgrad(dcd, wdd, tuple(x_in.shape[1:3]), kd, sd, residual=gx, out=gx)
         g = gx
 

@@ -208,6 +208,19 @@ def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False):
 
 
 # --------------------------------------------------------------------------------------------------------- batch norm
+_scratch_cache = {}
+
+
+def _reduce_scratch(device):
+    """Persistent zero-initialised scratch for the two-level column reductions (ticket counters + slice sums), per stream."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    sc = _scratch_cache.get(key)
+    if sc is None:
+        sc = torch.zeros(256 + 64 * 2 * 2048 * 8, dtype=torch.uint8, device=device)
+        _scratch_cache[key] = sc
+    return sc
+
+
 class BnCoeffs:
     """Per-channel vectors of one BatchNorm application (all fp32 [C])."""
     __slots__ = ("mean", "invstd", "scale", "shift")
@@ -221,9 +234,10 @@ def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_
     lib = _lib.load()
     T, _, C = stats.shape
     co = BnCoeffs(C, stats.device)
+    sc = _reduce_scratch(stats.device)
     rc = lib.b200_bn_finalize(_p(stats), T, C, float(count), _p(gamma), _p(beta), eps, momentum, _p(running_mean),
                               _p(running_var), _p(num_batches_tracked), _p(co.mean), _p(co.invstd), _p(co.scale),
-                              _p(co.shift), _stream())
+                              _p(co.shift), _p(sc), sc.numel(), _stream())
     _lib.check(rc, "b200_bn_finalize")
     return co
 
@@ -274,8 +288,9 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
         dgamma = torch.empty(C, dtype=F32, device=x.device)
         dbeta = torch.empty(C, dtype=F32, device=x.device)
     m = torch.empty(2, C, dtype=F32, device=x.device)
+    sc = _reduce_scratch(x.device)
     rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, float(rows), _p(dgamma), _p(dbeta), acc, _p(m[0]), _p(m[1]),
-                                  _stream())
+                                  _p(sc), sc.numel(), _stream())
     _lib.check(rc, "b200_bn_bwd_finalize")
     dx = torch.empty_like(x)
     src = dz if want_dz else g

@@ -68,9 +68,13 @@ size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout,
 
 /* ---- BatchNorm2d (train: batch statistics, eval: running statistics) ----------------------------------------------------
  * replaces nn.BatchNorm2d + nn.ReLU (+ residual add) of Bottleneck.forward, classification/resnet/models/networks.py:108-124 */
+/* partial[T][2][C] column reductions run on a 2-D grid; `scratch` (b200_reduce_scratch_bytes(T, C) bytes, its first 256
+ * bytes zero on first use - the kernel leaves them zero) carries the slice sums and a ticket counter. One per stream. */
+size_t b200_reduce_scratch_bytes(int T, int C);
 int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,
                      float momentum, float* running_mean, float* running_var, long long* num_batches_tracked,
-                     float* mean, float* invstd, float* scale, float* shift, void* stream);
+                     float* mean, float* invstd, float* scale, float* shift, void* scratch, size_t scratch_bytes,
+                     void* stream);
 int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                         const float* running_var, float eps, float* scale, float* shift, void* stream);
 /* y = act(x*scale[c]+shift[c] (+residual)); x,y,residual bf16 [rows][C] */
@@ -84,7 +88,7 @@ int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz
                        float* partial, void* stream);
 int b200_bn_bwd_blocks(long long rows, int C);
 int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
-                         float* m1, float* m2, void* stream);
+                         float* m1, float* m2, void* scratch, size_t scratch_bytes, void* stream);
 /* backward pass 2: dx = scale*(dz - m1 - xhat*m2); g_is_dz != 0 means `g` already holds dz (mask applied). */
 int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
                       const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
@@ -110,6 +114,8 @@ int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, floa
 
 /* weight packing fp32 OIHW -> bf16 GEMM operand; mode 0: [O][taps*I] (pitch ld_dst), mode 1: [I][taps*O] */
 int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mode, long long ld_dst, void* stream);
+/* all weights of a model in one launch: table[n][9] int64 {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out} */
+int b200_pack_weights_multi(const void* table, int n_entries, int total_blocks, void* stream);
 int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
 /* stem im2col from the user's NCHW fp32 batch: a bf16 [B*Ho*Wo][ldk], k=(kh*KW+kw)*Cin+c (networks.py:206 conv1 7x7/2) */
