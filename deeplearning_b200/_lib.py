@@ -18,6 +18,18 @@ _L = c_longlong
 _F = c_float
 _D = c_double
 
+class View(ctypes.Structure):
+    """b200_view_t"""
+    _fields_ = [("base", c_void_p), ("dim", c_longlong * 3), ("stride", c_longlong * 3)]
+
+
+class GemmArgs(ctypes.Structure):
+    """b200_gemm_args_t"""
+    _fields_ = [("w", c_void_p), ("N", c_int), ("K", c_int), ("bias", c_void_p), ("act", c_int), ("out_f32", c_int),
+                ("residual", ctypes.POINTER(View)), ("residual_f32", c_int), ("aux_out", ctypes.POINTER(View)),
+                ("aux_in", ctypes.POINTER(View)), ("stats", c_void_p)]
+
+
 # name -> (restype, argtypes); must list every symbol of include/b200cls.h (tests/test_abi.py checks this).
 SIGNATURES = {
     "b200_last_error": (c_char_p, []),
@@ -30,6 +42,15 @@ SIGNATURES = {
     "b200_conv2d_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
     "b200_reduce_scratch_bytes": (c_size_t, [_I, _I]),
+    "b200_gemm_ex": (_I, [ctypes.POINTER(View), ctypes.POINTER(View), ctypes.POINTER(GemmArgs), _P]),
+    "b200_layernorm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "b200_layernorm_bwd_blocks": (_I, [_L, _I]),
+    "b200_layernorm_bwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P]),
+    "b200_patchify_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200_cls_row": (_I, [_P, _P, _P, _I, _I, _I, _P]),
+    "b200_batch_rowsum": (_I, [_P, _L, _I, _I, _P, _I, _P]),
+    "b200_attention_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
+    "b200_attention_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "b200_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),

@@ -85,6 +85,74 @@ int encode_view(CUtensorMap* m, const View& v, const Box3& bx) {
   return encode_tmap_bf16(m, v.base, 4, v.dims, v.strides, box);
 }
 
+// The epilogue stores one TMEM lane quadrant (32 consecutive tile rows) per warp: split the 128-pixel box into 4 slabs along
+// its slowest-varying dimensions (all box dims are powers of two, rows are ordered w fastest).
+void quarter_box(const Box3& bx, Box3* qb, int (&o1)[4], int (&o2)[4], int (&o3)[4]) {
+  for (int q = 0; q < 4; ++q) o1[q] = o2[q] = o3[q] = 0;
+  if (bx.b3 >= 4) {
+    *qb = Box3{bx.b1, bx.b2, bx.b3 / 4};
+    for (int q = 0; q < 4; ++q) o3[q] = q * (bx.b3 / 4);
+  } else if (bx.b3 == 2) {
+    *qb = Box3{bx.b1, bx.b2 / 2, 1};  // b1*b2 = 64 -> b2 >= 2 unless b1 = 64
+    if (bx.b2 >= 2) {
+      for (int q = 0; q < 4; ++q) {
+        o2[q] = (q & 1) * (bx.b2 / 2);
+        o3[q] = q >> 1;
+      }
+    } else {
+      *qb = Box3{bx.b1 / 2, 1, 1};
+      for (int q = 0; q < 4; ++q) {
+        o1[q] = (q & 1) * (bx.b1 / 2);
+        o3[q] = q >> 1;
+      }
+    }
+  } else if (bx.b2 >= 4) {
+    *qb = Box3{bx.b1, bx.b2 / 4, 1};
+    for (int q = 0; q < 4; ++q) o2[q] = q * (bx.b2 / 4);
+  } else if (bx.b2 == 2) {
+    *qb = Box3{bx.b1 / 2, 1, 1};
+    for (int q = 0; q < 4; ++q) {
+      o1[q] = (q & 1) * (bx.b1 / 2);
+      o2[q] = q >> 1;
+    }
+  } else {
+    *qb = Box3{bx.b1 / 4, 1, 1};
+    for (int q = 0; q < 4; ++q) o1[q] = q * (bx.b1 / 4);
+  }
+}
+
+// Tile geometry + output tensor map(s) of a GEMM whose output pixels are described by `dv`.
+int setup_output(ConvGemmParams& p, const View& dv, int N, int out_f32, const View* auxv) {
+  const long long d1 = dv.dims[1], d2 = dv.dims[2], d3 = dv.dims[3];
+  const Box3 bx = choose_box(d1, d2, d3, 128);
+  p.box1 = bx.b1, p.box2 = bx.b2, p.box3 = bx.b3;
+  p.dim1 = static_cast<int>(d1), p.dim2 = static_cast<int>(d2), p.dim3 = static_cast<int>(d3);
+  p.tiles1 = static_cast<int>((d1 + bx.b1 - 1) / bx.b1);
+  p.tiles2 = static_cast<int>((d2 + bx.b2 - 1) / bx.b2);
+  p.tiles3 = static_cast<int>((d3 + bx.b3 - 1) / bx.b3);
+  p.N = N;
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  p.n_tiles = (N + BN - 1) / BN;
+  Box3 qb;
+  quarter_box(bx, &qb, p.qoff1, p.qoff2, p.qoff3);
+  p.out_f32 = out_f32;
+  if (dv.base != nullptr) {
+    uint32_t box[4] = {out_f32 ? 32u : 64u, (uint32_t)qb.b1, (uint32_t)qb.b2, (uint32_t)qb.b3};
+    int rc = out_f32 ? encode_tmap_f32(&p.d_map, dv.base, 4, dv.dims, dv.strides, box)
+                     : encode_tmap_bf16(&p.d_map, dv.base, 4, dv.dims, dv.strides, box);
+    if (rc) return rc;
+  }
+  p.has_aux_out = 0;
+  if (auxv != nullptr) {
+    uint32_t box[4] = {64u, (uint32_t)qb.b1, (uint32_t)qb.b2, (uint32_t)qb.b3};
+    int rc = encode_tmap_bf16(&p.aux_map, auxv->base, 4, auxv->dims, auxv->strides, box);
+    if (rc) return rc;
+    p.has_aux_out = 1;
+  }
+  return OK;
+}
+Box3 box_of(const ConvGemmParams& p) { return Box3{p.box1, p.box2, p.box3}; }
+
 template <int BLOCK_N>
 int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   using Cfg = ConvGemmCfg<BLOCK_N>;
@@ -99,7 +167,7 @@ int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   ConvGemmParams q = p;
   q.desc_lbo = g_fwd_lbo;
   q.desc_sbo = g_fwd_sbo;
-  conv_gemm_kernel<BLOCK_N><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
+  conv_gemm_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
   B200_LAUNCHED();
   return OK;
 }
@@ -186,7 +254,8 @@ int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride) {
   const long long d2 = flat ? 1 : Ho;
   const long long d3 = flat ? 1 : B;
   const Box3 bx = choose_box(d1, d2, d3, 128);
-  return static_cast<int>(((d1 + bx.b1 - 1) / bx.b1) * ((d2 + bx.b2 - 1) / bx.b2) * ((d3 + bx.b3 - 1) / bx.b3));
+  // one statistics row per 32-pixel slab (4 per 128-pixel tile)
+  return 4 * static_cast<int>(((d1 + bx.b1 - 1) / bx.b1) * ((d2 + bx.b2 - 1) / bx.b2) * ((d3 + bx.b3 - 1) / bx.b3));
 }
 
 int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
@@ -206,19 +275,17 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
   const long long d1 = flat ? static_cast<long long>(B) * H * W : Wo;
   const long long d2 = flat ? 1 : Ho;
   const long long d3 = flat ? 1 : B;
-  const Box3 bx = choose_box(d1, d2, d3, 128);
-  p.box1 = bx.b1, p.box2 = bx.b2, p.box3 = bx.b3;
-  p.dim1 = static_cast<int>(d1), p.dim2 = static_cast<int>(d2), p.dim3 = static_cast<int>(d3);
-  p.tiles1 = static_cast<int>((d1 + bx.b1 - 1) / bx.b1);
-  p.tiles2 = static_cast<int>((d2 + bx.b2 - 1) / bx.b2);
-  p.tiles3 = static_cast<int>((d3 + bx.b3 - 1) / bx.b3);
-  p.N = Cout;
+  int rc;
+  {
+    View dv = flat ? make_flat_view(y, d1, Cout) : make_view(y, B, Ho, Wo, Cout, 1, 0, 0);
+    if (out_f32 != nullptr) dv.base = nullptr;  // direct fp32 stores, no TMA map
+    if ((rc = setup_output(p, dv, Cout, 0, nullptr))) return rc;
+  }
+  const Box3 bx = box_of(p);
   const int BN = block_n_for(Cout);
-  p.n_tiles = (Cout + BN - 1) / BN;
   p.k_per_tap = Cin;
   p.k_blocks_per_tap = (Cin + 63) / 64;
   p.num_taps = ksize * ksize;
-  int rc;
   if (flat) {
     if ((rc = encode_view(&p.a_maps[0], make_flat_view(x, d1, Cin), bx))) return rc;
     for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
@@ -258,18 +325,14 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
     uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
     if ((rc = encode_tmap_bf16(&p.b_map, w, 2, dims, strides, box))) return rc;
   }
-  {
-    View dv = flat ? make_flat_view(y, d1, Cout) : make_view(y, B, Ho, Wo, Cout, 1, 0, 0);
-    if ((rc = encode_view(&p.d_map, dv, bx))) return rc;
-  }
   p.stats = stats;
   p.bias = bias;
   p.act = act;
-  p.residual = static_cast<const __nv_bfloat16*>(residual);
+  p.residual = residual;
   p.rs1 = Cout;
   p.rs2 = static_cast<long long>(d1) * Cout;
   p.rs3 = static_cast<long long>(d1) * d2 * Cout;
-  p.out_f32 = out_f32;
+  p.out_direct = out_f32;
   p.ld_out = ld_out;
   return dispatch_conv_gemm(p, Cout, st);
 }
@@ -302,18 +365,10 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
       // output (dx) view for this launch
       View dv = flat ? make_flat_view(dx, static_cast<long long>(B) * H * W, Cin)
                      : make_view(dx, B, H, W, Cin, stride, ph, pw);
-      const long long d1 = dv.dims[1], d2 = dv.dims[2], d3 = dv.dims[3];
-      const Box3 bx = choose_box(d1, d2, d3, 128);
-      p.box1 = bx.b1, p.box2 = bx.b2, p.box3 = bx.b3;
-      p.dim1 = static_cast<int>(d1), p.dim2 = static_cast<int>(d2), p.dim3 = static_cast<int>(d3);
-      p.tiles1 = static_cast<int>((d1 + bx.b1 - 1) / bx.b1);
-      p.tiles2 = static_cast<int>((d2 + bx.b2 - 1) / bx.b2);
-      p.tiles3 = static_cast<int>((d3 + bx.b3 - 1) / bx.b3);
-      p.N = Cin;
-      p.n_tiles = (Cin + BN - 1) / BN;
+      if ((rc = setup_output(p, dv, Cin, 0, nullptr))) return rc;
+      const Box3 bx = box_of(p);
       p.k_per_tap = Cout;
       p.k_blocks_per_tap = (Cout + 63) / 64;
-      if ((rc = encode_view(&p.d_map, dv, bx))) return rc;
       View av = flat ? make_flat_view(dy, static_cast<long long>(B) * H * W, Cout)
                      : make_view(dy, B, Ho, Wo, Cout, 1, 0, 0);
       if ((rc = encode_view(&p.a_maps[0], av, bx))) return rc;
@@ -348,8 +403,7 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
       }
       p.num_taps = nt;
       if (residual != nullptr) {
-        p.residual = reinterpret_cast<const __nv_bfloat16*>(static_cast<const char*>(residual) +
-                                                            (static_cast<const char*>(dv.base) - static_cast<const char*>(dx)));
+        p.residual = static_cast<const char*>(residual) + (static_cast<const char*>(dv.base) - static_cast<const char*>(dx));
         p.rs1 = static_cast<long long>(dv.strides[1]);
         p.rs2 = static_cast<long long>(dv.strides[2]);
         p.rs3 = static_cast<long long>(dv.strides[3]);
@@ -358,6 +412,61 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
     }
   }
   return OK;
+}
+
+int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_args_t* g, void* stream) {
+  B200_REQUIRE(a != nullptr && out != nullptr && g != nullptr && g->w != nullptr, "gemm_ex: null argument");
+  B200_REQUIRE(g->N % 8 == 0 && g->K % 8 == 0, "gemm_ex: N=%d / K=%d must be multiples of 8", g->N, g->K);
+  for (int i = 0; i < 3; ++i)
+    B200_REQUIRE(a->dim[i] == out->dim[i] && a->dim[i] > 0, "gemm_ex: a/out pixel extents differ in dim %d", i);
+  B200_REQUIRE(!(g->aux_out != nullptr && g->out_f32), "gemm_ex: aux_out needs a bf16 primary output");
+  B200_REQUIRE(!(g->stats != nullptr && g->out_f32), "gemm_ex: stats need a bf16 output");
+  auto to_view = [](const b200_view_t* v, int C) {
+    View r;
+    r.base = v->base;
+    r.dims[0] = C;
+    r.strides[0] = 1;
+    for (int i = 0; i < 3; ++i) {
+      r.dims[i + 1] = static_cast<uint64_t>(v->dim[i]);
+      r.strides[i + 1] = static_cast<uint64_t>(v->stride[i]);
+    }
+    return r;
+  };
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  View dv = to_view(out, g->N);
+  View auxv;
+  if (g->aux_out) auxv = to_view(g->aux_out, g->N);
+  if ((rc = setup_output(p, dv, g->N, g->out_f32, g->aux_out ? &auxv : nullptr))) return rc;
+  const Box3 bx = box_of(p);
+  // TMA needs non-zero strides that are multiples of 16 bytes for the activation operand
+  if ((rc = encode_view(&p.a_maps[0], to_view(a, g->K), bx))) return rc;
+  for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+  p.num_taps = 1;
+  p.k_per_tap = g->K;
+  p.k_blocks_per_tap = (g->K + 63) / 64;
+  const int BN = block_n_for(g->N);
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(g->K), static_cast<uint64_t>(g->N)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(g->K)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    if ((rc = encode_tmap_bf16(&p.b_map, g->w, 2, dims, strides, box))) return rc;
+  }
+  p.stats = g->stats;
+  p.bias = g->bias;
+  p.act = g->act;
+  if (g->residual) {
+    p.residual = g->residual->base;
+    p.res_f32 = g->residual_f32;
+    p.rs1 = g->residual->stride[0], p.rs2 = g->residual->stride[1], p.rs3 = g->residual->stride[2];
+  }
+  if (g->act == B200_ACT_GELU_GRAD) {
+    B200_REQUIRE(g->aux_in != nullptr, "gemm_ex: B200_ACT_GELU_GRAD needs aux_in");
+    p.aux_in = static_cast<const __nv_bfloat16*>(g->aux_in->base);
+    p.as1 = g->aux_in->stride[0], p.as2 = g->aux_in->stride[1], p.as3 = g->aux_in->stride[2];
+  }
+  return dispatch_conv_gemm(p, g->N, static_cast<cudaStream_t>(stream));
 }
 
 size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {

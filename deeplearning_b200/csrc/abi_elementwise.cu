@@ -219,9 +219,11 @@ int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int 
   B200_REQUIRE(ldk % 8 == 0 && ldk >= KH * KW * Cin, "im2col: ldk=%d must be a multiple of 8 and >= %d", ldk,
                KH * KW * Cin);
   const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  const size_t smem = static_cast<size_t>(Cin) * KH * (W + 2 * pad) * sizeof(float);
+  const size_t smem = static_cast<size_t>(Cin) * KH * (W + 2 * pad) * sizeof(float) + static_cast<size_t>(ldk) * sizeof(int);
   B200_REQUIRE(smem <= 48 * 1024, "im2col: staged rows need %zu bytes of shared memory (> 48 KB)", smem);
-  im2col_nchw_kernel<<<B * Ho, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(a), B, Cin, H, W,
+  const int threads = (ldk / 8) * (256 / (ldk / 8) > 0 ? 256 / (ldk / 8) : 1);  // a multiple of the k-octet count
+  B200_REQUIRE(ldk / 8 <= 256, "im2col: ldk=%d too large", ldk);
+  im2col_nchw_kernel<<<B * Ho, threads, smem, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(a), B, Cin, H, W,
                                                                                KH, KW, stride, pad, Ho, Wo, ldk);
   B200_LAUNCHED();
   return OK;

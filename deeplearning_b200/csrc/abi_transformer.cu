@@ -1,0 +1,175 @@
+// C-ABI entry points of the transformer-side kernels: LayerNorm, patch extraction, attention (tcgen05) forward/backward.
+#include <string.h>
+
+#include "../../include/b200cls.h"
+#include "attention.cuh"
+#include "host_utils.h"
+#include "transformer.cuh"
+
+using namespace b200;
+
+namespace {
+inline int grid_for(long long items, int per_block, int cap_mult = 16) {
+  long long blocks = (items + per_block - 1) / per_block;
+  const long long cap = static_cast<long long>(device_sm_count()) * cap_mult;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+int ln_bwd_blocks(long long rows) {
+  long long b = static_cast<long long>(device_sm_count()) * 2;
+  if (b > (rows + 7) / 8) b = (rows + 7) / 8;
+  return static_cast<int>(b < 1 ? 1 : b);
+}
+int encode3(CUtensorMap* m, const void* base, long long cols, long long T, long long B, int box_rows) {
+  uint64_t dims[3] = {static_cast<uint64_t>(cols), static_cast<uint64_t>(T), static_cast<uint64_t>(B)};
+  uint64_t strides[3] = {1, static_cast<uint64_t>(cols), static_cast<uint64_t>(cols) * T};
+  uint32_t box[3] = {64, static_cast<uint32_t>(box_rows), 1};
+  return encode_tmap_bf16(m, base, 3, dims, strides, box);
+}
+}  // namespace
+
+extern "C" {
+
+int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* y, float* mean,
+                       float* rstd, long long rows, int C, float eps, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && C <= 3072, "layernorm_fwd: C=%d must be a multiple of 8 and <= 3072", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(rows, 8);
+  __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y);
+  if (C <= 1024) {
+    if (x_f32)
+      layernorm_fwd_kernel<float, 4><<<grid, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
+    else
+      layernorm_fwd_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
+  } else {
+    if (x_f32)
+      layernorm_fwd_kernel<float, 12><<<grid, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
+    else
+      layernorm_fwd_kernel<__nv_bfloat16, 12><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
+  }
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_layernorm_bwd_blocks(long long rows, int C) {
+  if (C % 8 != 0 || C > 1024) return -1;
+  return ln_bwd_blocks(rows);
+}
+
+int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* mean, const float* rstd, const float* gamma,
+                       const void* add, void* dx, int dx_f32, float* partial, long long rows, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 8 and <= 1024", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = ln_bwd_blocks(rows);
+  const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
+  const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
+#define LN_BWD(TI, TO)                                                                                              \
+  do {                                                                                                              \
+    static bool cfg = false;                                                                                        \
+    if (!cfg) {                                                                                                     \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TI, TO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           8 * 2 * 1024 * (int)sizeof(float)));                                     \
+      cfg = true;                                                                                                   \
+    }                                                                                                               \
+    layernorm_bwd_kernel<TI, TO, 4><<<grid, 256, smem, st>>>(dyp, static_cast<const TI*>(x), mean, rstd, gamma,      \
+                                                             static_cast<const TO*>(add), static_cast<TO*>(dx),    \
+                                                             partial, rows, C);                                     \
+  } while (0)
+  if (x_f32 && dx_f32)
+    LN_BWD(float, float);
+  else if (x_f32 && !dx_f32)
+    LN_BWD(float, __nv_bfloat16);
+  else if (!x_f32 && dx_f32)
+    LN_BWD(__nv_bfloat16, float);
+  else
+    LN_BWD(__nv_bfloat16, __nv_bfloat16);
+#undef LN_BWD
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_patchify_nchw(const float* x, void* a, int B, int Cin, int H, int W, int ps, void* stream) {
+  B200_REQUIRE(ps % 4 == 0 && H % ps == 0 && W % ps == 0 && W % 4 == 0, "patchify: patch %d must divide %dx%d (multiples of 4)", ps, H, W);
+  const long long total = static_cast<long long>(B) * (H / ps) * (W / ps) * (Cin * ps * ps / 4);
+  patchify_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(a), B, Cin, H, W, ps);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_cls_row(const float* cls, const float* pos, float* tokens, int B, int T, int D, void* stream) {
+  cls_row_kernel<<<grid_for(static_cast<long long>(B) * D, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cls, pos, tokens, B, T, D);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_batch_rowsum(const float* g, long long stride_b, int B, int D, float* out, int accumulate, void* stream) {
+  batch_rowsum_kernel<<<(D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, stride_b, B, D, out, accumulate);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float scale, void* stream) {
+  B200_REQUIRE(T >= 1 && T <= 256, "attention_fwd: T=%d unsupported (1..256 tokens)", T);
+  B200_REQUIRE(B > 0 && H > 0, "attention_fwd: empty problem");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AttnFwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B, p.H = H, p.T = T;
+  p.Tpad = (T + 15) / 16 * 16;
+  p.mblocks = (T + 127) / 128;
+  p.scale = scale;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.lse = lse;
+  const long long HD = static_cast<long long>(H) * 64;
+  int rc;
+  if ((rc = encode3(&p.q_map, qkv, 3 * HD, T, B, 128))) return rc;
+  if ((rc = encode3(&p.kv_map, qkv, 3 * HD, T, B, p.Tpad))) return rc;
+  if ((rc = encode3(&p.o_map, out, HD, T, B, 128))) return rc;
+  static bool cfg = false;
+  if (!cfg) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    cfg = true;
+  }
+  attn_fwd_kernel<<<B * H * p.mblocks, 160, kAttnSmemBytes, st>>>(p);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                       int B, int T, int H, float scale, void* stream) {
+  B200_REQUIRE(T >= 1 && T <= 256, "attention_bwd: T=%d unsupported (1..256 tokens)", T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  {
+    const long long rows = static_cast<long long>(B) * T * H;
+    attn_delta_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out), delta, B, T, H);
+    B200_LAUNCHED();
+  }
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B, p.H = H, p.T = T;
+  p.Tpad = (T + 15) / 16 * 16;
+  p.mblocks = (T + 127) / 128;
+  p.scale = scale;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.lse = lse;
+  p.delta = delta;
+  const long long HD = static_cast<long long>(H) * 64;
+  int rc;
+  if ((rc = encode3(&p.q_map, qkv, 3 * HD, T, B, 128))) return rc;
+  if ((rc = encode3(&p.kv_map, qkv, 3 * HD, T, B, p.Tpad))) return rc;
+  if ((rc = encode3(&p.do_map, dout, HD, T, B, 128))) return rc;
+  if ((rc = encode3(&p.dqkv_map, dqkv, 3 * HD, T, B, 128))) return rc;
+  static bool cfg = false;
+  if (!cfg) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmemBytes));
+    cfg = true;
+  }
+  attn_bwd_kernel<<<B * H, 160, kAttnBwdSmemBytes, st>>>(p);
+  B200_LAUNCHED();
+  return OK;
+}
+
+}  // extern "C"

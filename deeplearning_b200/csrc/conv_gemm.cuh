@@ -24,26 +24,33 @@ constexpr int kMaxTaps = 16;
 struct alignas(64) ConvGemmParams {
   CUtensorMap a_maps[4];
   CUtensorMap b_map;
-  CUtensorMap d_map;
+  CUtensorMap d_map;    // output, box = one warp's slab: (64 bf16 | 32 fp32 channels) x 32 pixels (a quarter of the tile box)
+  CUtensorMap aux_map;  // optional second output (pre-activation), same geometry as d_map (bf16)
   int num_taps;
   int k_per_tap;         // Cin (elements of K per tap)
   int k_blocks_per_tap;  // ceil(Cin / 64)
   int tiles1, tiles2, tiles3;
   int box1, box2, box3;
-  int dim1, dim2, dim3;  // output pixel extents (for row->address mapping of residual / fp32 output)
+  int dim1, dim2, dim3;  // output pixel extents (row -> pixel mapping of the residual / aux / fp32 paths)
+  int qoff1[4], qoff2[4], qoff3[4];  // pixel offset of TMEM quadrant q's 32-row slab inside the tile box
   int n_tiles;
   int N;
   int8_t tap_map[kMaxTaps];  // which activation view (phase) the tap reads
   int8_t tap_o1[kMaxTaps];   // pixel offset along dim1 (w)
   int8_t tap_o2[kMaxTaps];   // pixel offset along dim2 (h)
   int8_t tap_w[kMaxTaps];    // which k_per_tap-wide slice of the weight matrix the tap multiplies
-  float* stats;             // [m_tiles][2][N] partial sums, or null
+  float* stats;             // [4*m_tiles][2][N] partial sums (one row per 32-pixel slab), or null
   const float* bias;        // [N] or null
-  int act;                  // 0 none, 1 relu, 2 gelu(erf)
-  const __nv_bfloat16* residual;  // bf16 tensor added in the epilogue (pixel strides rs1..rs3, in elements) or null
+  int act;                  // 0 none, 1 relu, 2 gelu(erf), 3 multiply by gelu'(aux_in) (backward of 2)
+  int out_f32;              // 1: d_map is fp32 (32-channel slabs)
+  int res_f32;              // 1: residual tensor is fp32
+  int has_aux_out;          // 1: also store the pre-activation through aux_map
+  const void* residual;     // tensor added in the epilogue (pixel strides rs1..rs3, in elements) or null
   long long rs1, rs2, rs3;
+  const __nv_bfloat16* aux_in;  // act == 3: pre-activation tensor (pixel strides as1..as3)
+  long long as1, as2, as3;
   uint32_t desc_lbo, desc_sbo;  // K-major smem descriptor strides (bytes): 16 / 1024
-  float* out_f32;           // direct fp32 output ([pixels][ld_out]) or null -> bf16 TMA store
+  float* out_direct;        // direct fp32 output ([pixels][ld_out]) for tiny N (logits) or null
   long long ld_out;
 };
 
@@ -53,27 +60,32 @@ struct ConvGemmCfg {
   static constexpr int BLOCK_K = 64;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 5 : 6);
+  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 6);
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_BYTES = 128 * 128;  // one 128x64 bf16 chunk
-  static constexpr int STATS_BYTES = 4 * 2 * 64 * 4;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int SLAB_BYTES = 32 * 128;                       // one warp's 32 rows x 128 B
+  static constexpr int STAGING_BYTES = EPI_WARPS * 2 * SLAB_BYTES;  // double-buffered per warp
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGING_BYTES + STATS_BYTES + BAR_BYTES + 1024;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
+  return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
   uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES;
-  float* stats_smem = reinterpret_cast<float*>(staging + 2 * Cfg::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(stats_smem) + Cfg::STATS_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + Cfg::STAGING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tmem_full = bars + 2 * STAGES;
@@ -85,6 +97,11 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
   const int m_tiles = p.tiles1 * p.tiles2 * p.tiles3;
   const int num_tiles = m_tiles * p.n_tiles;
   const int num_kb = p.num_taps * p.k_blocks_per_tap;
+  // Epilogue work units: 64 bf16 (or 32 fp32) channels x one warp's 32 rows. Two warps share a TMEM lane quadrant and
+  // take alternate units; with a single unit per tile the second warp of each pair has nothing to do.
+  const int unit_cols = p.out_f32 ? 32 : 64;
+  const int units = BLOCK_N / unit_cols;
+  const int active_epi_warps = units >= 2 ? 8 : 4;
 
   if (warp_idx == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
@@ -96,7 +113,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], active_epi_warps);  // one arrive per active epilogue warp
     }
     fence_mbar_init();
   }
@@ -173,14 +190,17 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
         }
       }
     }
-  } else {
-    // ===================== Epilogue (4 warps, 128 threads) =====================
-    const int q = warp_idx & 3;          // TMEM lane quadrant this warp may access
-    const int row = q * 32 + lane;       // row of the 128-row tile owned by this thread
-    const int epi_tid = threadIdx.x - 64;
+  } else if (warp_idx - 2 < active_epi_warps) {
+    // ===================== Epilogue: 8 independent warps, no CTA-level barriers =====================
+    const int ew = warp_idx - 2;
+    const int q = warp_idx & 3;   // TMEM lane quadrant this warp may access
+    const int pair = ew >> 2;     // which of the two warps sharing the quadrant
+    const int row = q * 32 + lane;
+    uint8_t* my_stage = staging + ew * 2 * Cfg::SLAB_BYTES;
+    uint32_t store_counter = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t store_counter = 0;  // counts issued TMA stores (selects the staging buffer)
+    const int nsub = p.out_f32 ? 1 : 2;  // 32-column TMEM loads per unit
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -188,147 +208,185 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const __grid_constant
       const int t2 = (m_tile / p.tiles1) % p.tiles2;
       const int t3 = m_tile / (p.tiles1 * p.tiles2);
       const int c1 = t1 * p.box1, c2 = t2 * p.box2, c3 = t3 * p.box3;
-      // Row -> pixel mapping (used by residual / fp32 output paths).
       const int i1 = row % p.box1;
       const int i2 = (row / p.box1) % p.box2;
       const int i3 = row / (p.box1 * p.box2);
       const int p1 = c1 + i1, p2 = c2 + i2, p3 = c3 + i3;
       const bool row_ok = (p1 < p.dim1) && (p2 < p.dim2) && (p3 < p.dim3);
-      const long long pix = (static_cast<long long>(p3) * p.dim2 + p2) * p.dim1 + p1;
+      const int s1 = c1 + p.qoff1[q], s2 = c2 + p.qoff2[q], s3 = c3 + p.qoff3[q];
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 
+      int last_unit = pair;
+      while (last_unit + 2 < units) last_unit += 2;
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
-        const int n0 = n_tile * BLOCK_N + ch * 64;
-        uint32_t v[2][32];
-        tmem_ld_32x32(tmem_acc + ch * 64, v[0]);
-        tmem_ld_32x32(tmem_acc + ch * 64 + 32, v[1]);
-        tmem_ld_wait();
-        if (ch == BLOCK_N / 64 - 1) {
-          // all TMEM reads of this accumulator are done -> hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        if (n0 >= p.N) continue;  // fully out-of-range column chunk (N not a multiple of BLOCK_N)
-
-        float f[64];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          f[j] = __uint_as_float(v[0][j]);
-          f[32 + j] = __uint_as_float(v[1][j]);
-        }
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 64; ++j) {
-            const int n = n0 + j;
-            f[j] += (n < p.N) ? __ldg(p.bias + n) : 0.0f;
+      for (int u = pair; u < units; u += 2) {
+        const int n0 = n_tile * BLOCK_N + u * unit_cols;
+        const bool chunk_live = n0 < p.N;  // warp-uniform
+        uint8_t* buf = my_stage + (store_counter & 1) * Cfg::SLAB_BYTES;
+        uint8_t* buf_aux = my_stage + ((store_counter + 1) & 1) * Cfg::SLAB_BYTES;
+        if (chunk_live && p.out_direct == nullptr) {
+          // the TMA store that last used `buf` (two stores ago) must have finished reading it
+          if (lane == 0) {
+            if (p.has_aux_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
+          __syncwarp();
         }
-        if (p.act == 1) {
+#pragma unroll 1
+        for (int h = 0; h < nsub; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_acc + u * unit_cols + h * 32, v);
+          tmem_ld_wait();
+          if (u == last_unit && h == nsub - 1) {
+            // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          if (!chunk_live) continue;
+          const int nc = n0 + h * 32;  // first channel of this 32-column group
+          float f[32];
 #pragma unroll
-          for (int j = 0; j < 64; ++j) f[j] = fmaxf(f[j], 0.0f);
-        } else if (p.act == 2) {
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) f[j] = gelu_erf(f[j]);
-        }
-        if (p.residual != nullptr && row_ok) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + n0);
+            for (int j = 0; j < 32; ++j) f[j] += (nc + j < p.N) ? __ldg(p.bias + nc + j) : 0.0f;
+          }
+          if (p.has_aux_out) {
+            // pre-activation copy (bf16) for the backward pass
+            uint8_t* rowp = buf_aux + lane * 128;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            if (n0 + j * 8 < p.N) {
-              const uint4 r = __ldg(rp + j);
-              f[j * 8 + 0] += bf16_lo(r.x);
-              f[j * 8 + 1] += bf16_hi(r.x);
-              f[j * 8 + 2] += bf16_lo(r.y);
-              f[j * 8 + 3] += bf16_hi(r.y);
-              f[j * 8 + 4] += bf16_lo(r.z);
-              f[j * 8 + 5] += bf16_hi(r.z);
-              f[j * 8 + 6] += bf16_lo(r.w);
-              f[j * 8 + 7] += bf16_hi(r.w);
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              const float z = row_ok ? 1.f : 0.f;
+              w.x = pack_bf16x2(f[j * 8 + 0] * z, f[j * 8 + 1] * z);
+              w.y = pack_bf16x2(f[j * 8 + 2] * z, f[j * 8 + 3] * z);
+              w.z = pack_bf16x2(f[j * 8 + 4] * z, f[j * 8 + 5] * z);
+              w.w = pack_bf16x2(f[j * 8 + 6] * z, f[j * 8 + 7] * z);
+              *reinterpret_cast<uint4*>(rowp + (((h * 4 + j) ^ (lane & 7)) << 4)) = w;
+            }
+          }
+          if (p.act == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          } else if (p.act == 3 && row_ok) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + p3 * p.as3 + p2 * p.as2 + p1 * p.as1 + nc);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (nc + j * 8 < p.N) {
+                float a[8];
+                unpack8(__ldg(ap + j), a);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[j * 8 + i] *= gelu_erf_grad(a[i]);
+              }
+            }
+          }
+          if (p.residual != nullptr && row_ok) {
+            const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc;
+            if (p.res_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (nc + j * 4 < p.N) {
+                  const float4 r = __ldg(rp + j);
+                  f[j * 4 + 0] += r.x;
+                  f[j * 4 + 1] += r.y;
+                  f[j * 4 + 2] += r.z;
+                  f[j * 4 + 3] += r.w;
+                }
+              }
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                if (nc + j * 8 < p.N) {
+                  float r[8];
+                  unpack8(__ldg(rp + j), r);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[j * 8 + i] += r[i];
+                }
+              }
+            }
+          }
+          if (p.out_direct != nullptr) {
+            if (row_ok) {
+              const long long pix = (static_cast<long long>(p3) * p.dim2 + p2) * p.dim1 + p1;
+              float* op = p.out_direct + pix * p.ld_out + nc;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) op[j] = f[j];
+            }
+            continue;
+          }
+          if (!row_ok) {
+            // rows of a partial pixel box: clipped by the TMA store, and must not pollute the BN statistics
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = 0.f;
+          }
+          uint8_t* rowp = buf + lane * 128;
+          if (p.out_f32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(f[j * 4 + 0], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 w;
+              w.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
+              w.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
+              w.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
+              w.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
+              *reinterpret_cast<uint4*>(rowp + (((h * 4 + j) ^ (lane & 7)) << 4)) = w;
             }
           }
         }
-
-        if (p.out_f32 != nullptr) {
-          if (row_ok) {
-            float* op = p.out_f32 + pix * p.ld_out + n0;
-#pragma unroll
-            for (int j = 0; j < 64; ++j)
-              if (n0 + j < p.N) op[j] = f[j];
-          }
-          continue;
-        }
-
-        if (!row_ok) {
-          // rows of a partial pixel box: clipped by the TMA store, and must not pollute the BN statistics
-#pragma unroll
-          for (int j = 0; j < 64; ++j) f[j] = 0.f;
-        }
-        // ---- bf16 path: registers -> swizzled staging -> TMA store
-        uint8_t* buf = staging + (store_counter & 1) * Cfg::STAGING_BYTES;
-        ++store_counter;
-        if (epi_tid == 0) tma_store_wait_read<1>();  // the store that used this buffer two chunks ago has drained
-        named_bar_sync(1, 128);
-        {
-          uint8_t* rowp = buf + row * 128;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint4 w;
-            w.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-            w.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-            w.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-            w.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-            *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = w;
-          }
-        }
+        if (!chunk_live || p.out_direct != nullptr) continue;
+        __syncwarp();
         if (p.stats != nullptr) {
-          // Column sums over this warp's 32 rows, read back from the (bf16-rounded) staging tile:
-          // lane l owns columns 2l, 2l+1; bank-conflict-free thanks to the 128B swizzle.
-          __syncwarp();
-          float s0 = 0.f, s1 = 0.f, ss0 = 0.f, ss1 = 0.f;
+          // Column sums over this warp's 32 rows, read back from the (bf16-rounded) slab: lane l owns columns 2l, 2l+1;
+          // bank-conflict-free thanks to the 128B swizzle. One partial row per (tile, quadrant): no cross-warp traffic.
+          float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            const int rr = q * 32 + r;
             const uint32_t w =
-                *reinterpret_cast<const uint32_t*>(buf + rr * 128 + ((((lane >> 2) ^ (rr & 7)) << 4) | ((lane & 3) << 2)));
+                *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
             const float a = bf16_lo(w), b = bf16_hi(w);
-            s0 += a;
-            s1 += b;
-            ss0 = fmaf(a, a, ss0);
-            ss1 = fmaf(b, b, ss1);
+            a0 += a;
+            a1 += b;
+            q0 = fmaf(a, a, q0);
+            q1 = fmaf(b, b, q1);
           }
-          float* sp = stats_smem + q * 128;  // [q][2][64]
-          sp[2 * lane] = s0;
-          sp[2 * lane + 1] = s1;
-          sp[64 + 2 * lane] = ss0;
-          sp[64 + 2 * lane + 1] = ss1;
+          const int col = n0 + 2 * lane;
+          if (col < p.N) {
+            float* sp = p.stats + (static_cast<long long>(m_tile) * 4 + q) * 2 * p.N + col;
+            *reinterpret_cast<float2*>(sp) = make_float2(a0, a1);
+            *reinterpret_cast<float2*>(sp + p.N) = make_float2(q0, q1);
+          }
         }
         fence_proxy_async_smem();
-        named_bar_sync(2, 128);
-        if (epi_tid == 0) {
-          tma_store_4d(&p.d_map, buf, n0, c1, c2, c3);
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_4d(&p.d_map, buf, n0, s1, s2, s3);
           tma_store_commit();
-        }
-        if (p.stats != nullptr) {
-          const int which = epi_tid >> 6;  // 0 = sum, 1 = sum of squares
-          const int col = epi_tid & 63;
-          if (n0 + col < p.N) {
-            const float t = stats_smem[0 * 128 + which * 64 + col] + stats_smem[1 * 128 + which * 64 + col] +
-                            stats_smem[2 * 128 + which * 64 + col] + stats_smem[3 * 128 + which * 64 + col];
-            p.stats[(static_cast<long long>(m_tile) * 2 + which) * p.N + n0 + col] = t;
+          if (p.has_aux_out) {
+            tma_store_4d(&p.aux_map, buf_aux, n0, s1, s2, s3);
+            tma_store_commit();
           }
         }
+        store_counter += p.has_aux_out ? 2 : 1;
       }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
-    if (epi_tid == 0) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   tc_fence_before();

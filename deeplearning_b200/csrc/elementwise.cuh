@@ -11,34 +11,6 @@
 
 namespace b200 {
 
-struct bf16x8 {
-  uint4 u;
-};
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  f[0] = bf16_lo(u.x);
-  f[1] = bf16_hi(u.x);
-  f[2] = bf16_lo(u.y);
-  f[3] = bf16_hi(u.y);
-  f[4] = bf16_lo(u.z);
-  f[5] = bf16_hi(u.z);
-  f[6] = bf16_lo(u.w);
-  f[7] = bf16_hi(u.w);
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-  uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]);
-  u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]);
-  u.w = pack_bf16x2(f[6], f[7]);
-  return u;
-}
-__device__ __forceinline__ void load8f(const float* __restrict__ p, float (&f)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
-  f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-
 // ------------------------------------------------------------------------------------------------------------------
 // Column reduction of per-tile partials partial[T][2][C] -> two per-channel sums (double), parallel over T:
 // grid = (ceil(C/32), S); every block reduces its slice of T for 32 channels and publishes it to `scratch`; the last
@@ -620,10 +592,20 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ src, floa
 // (zero padded left/right), then each thread assembles 16-byte output vectors from shared memory.
 __global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restrict__ a, int B, int Cin, int H, int W,
                                    int KH, int KW, int stride, int pad, int Ho, int Wo, int ldk) {
-  extern __shared__ float srow[];  // [Cin][KH][W + 2*pad]
+  extern __shared__ float srow[];  // [Cin][KH][W + 2*pad] floats, then int lut[ldk]
   const int Wp = W + 2 * pad;
   const int b = blockIdx.x / Ho, oh = blockIdx.x % Ho;
   const int n_in = Cin * KH * Wp;
+  int* lut = reinterpret_cast<int*>(srow + n_in);  // k -> offset of tap (kh,kw), channel c inside srow (or -1)
+  const int K = KH * KW * Cin;
+  for (int k = threadIdx.x; k < ldk; k += blockDim.x) {
+    int off = -1;
+    if (k < K) {
+      const int c = k % Cin, tap = k / Cin;
+      off = (c * KH + tap / KW) * Wp + tap % KW;
+    }
+    lut[k] = off;
+  }
   for (int i = threadIdx.x; i < n_in; i += blockDim.x) {
     const int wp = i % Wp;
     const int kh = (i / Wp) % KH;
@@ -635,24 +617,20 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restric
   }
   __syncthreads();
   const int kvec = ldk / 8;
-  const int K = KH * KW * Cin;
   uint4* out = a + (static_cast<long long>(b) * Ho + oh) * Wo * kvec;
-  for (int i = threadIdx.x; i < Wo * kvec; i += blockDim.x) {
-    const int kv = i % kvec, ow = i / kvec;
-    float v[8];
+  // thread -> fixed k-octet (its 8 lut entries stay in registers), strides over output pixels
+  const int kv = threadIdx.x % kvec;
+  const int ow0 = threadIdx.x / kvec, ow_step = blockDim.x / kvec;
+  if (ow0 < ow_step) {
+    int off[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kv * 8 + j;
-      float val = 0.f;
-      if (k < K) {
-        const int c = k % Cin;
-        const int tap = k / Cin;
-        const int kw = tap % KW, kh = tap / KW;
-        val = srow[(c * KH + kh) * Wp + ow * stride + kw];
-      }
-      v[j] = val;
+    for (int j = 0; j < 8; ++j) off[j] = lut[kv * 8 + j];
+    for (int ow = ow0; ow < Wo; ow += ow_step) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = off[j] >= 0 ? srow[off[j] + ow * stride] : 0.f;
+      out[ow * kvec + kv] = pack8(v);
     }
-    out[i] = pack8(v);
   }
 }
 

@@ -36,8 +36,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+static int encode_tmap_any(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_elems, const uint32_t* box, int elem_bytes, CUtensorMapDataType dt);
+
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                      const uint32_t* box) {
+  return encode_tmap_any(out, base, rank, dims, strides_elems, box, 2, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box) {
+  return encode_tmap_any(out, base, rank, dims, strides_elems, box, 4, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+}
+
+static int encode_tmap_any(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                           const uint64_t* strides_elems, const uint32_t* box, int elem_bytes, CUtensorMapDataType dt) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -51,7 +63,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
     gdim[i] = dims[i];
     bx[i] = box[i];
     es[i] = 1;
-    if (i > 0) gstr[i - 1] = strides_elems[i] * 2;  // bytes
+    if (i > 0) gstr[i - 1] = strides_elems[i] * elem_bytes;  // bytes
   }
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) {
     set_error("tensor map base %p not 16-byte aligned", base);
@@ -63,7 +75,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
       return EINVAL_;
     }
   }
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

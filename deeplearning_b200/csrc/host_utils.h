@@ -35,6 +35,9 @@ enum : int { OK = 0, EINVAL_ = -1, EUNSUPPORTED_ = -2, ECUDA_ = -3 };
 // (innermost first, stride[0] == 1 implied); box in elements. Returns 0 on success.
 int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
                      const uint32_t* box);
+// Same for fp32 tensors (4-byte elements; a 128B-swizzled box holds at most 32 of them in the innermost dimension).
+int encode_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                    const uint32_t* box);
 
 int device_sm_count();
 

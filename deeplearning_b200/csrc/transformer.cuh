@@ -6,7 +6,7 @@
 // PatchEmbed = Conv2d(3, D, p, p) -> flatten -> transpose (vit_model.py:56-66); cls/pos (vit_model.py:244-250).
 #pragma once
 #include "common.cuh"
-#include "elementwise.cuh"
+
 
 namespace b200 {
 

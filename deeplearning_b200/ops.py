@@ -398,3 +398,155 @@ def stem_wgrad_relayout(src, cout, cin, taps, out=None, accumulate=False):
 
 def launch_count():
     return int(_lib.load().b200_launch_count())
+
+
+# --------------------------------------------------------------------------------------------------------- general GEMM
+def _view(t, channels, pix_dims=None, pix_strides=None):
+    """b200_view_t of a tensor whose last dim is the channel dim (stride 1). Default: all leading dims flattened."""
+    v = _lib.View()
+    v.base = t.data_ptr()
+    if pix_dims is None:
+        rows = t.numel() // channels
+        pix_dims, pix_strides = (rows, 1, 1), (channels, rows * channels, rows * channels)
+    for i in range(3):
+        v.dim[i] = int(pix_dims[i])
+        v.stride[i] = int(pix_strides[i])
+    return v
+
+
+def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, aux_out=False, aux_in=None,
+         a_view=None, out_view=None, residual_view=None, want_stats=False):
+    """out[rows, N] = epilogue(a[rows, K] @ w_packed[N, K]^T). `*_view` = (pix_dims, pix_strides) for strided layouts.
+    Returns (out, aux) where aux is the bf16 pre-activation copy when aux_out=True."""
+    import ctypes
+
+    lib = _lib.load()
+    N, K = w_packed.shape
+    rows = a.numel() // K
+    if out is None:
+        out = torch.empty(*a.shape[:-1], N, dtype=F32 if out_f32 else BF16, device=a.device)
+    out_f32 = out.dtype == F32
+    av = _view(a, K, *(a_view or (None, None)))
+    ov = _view(out, N, *(out_view or (None, None))) if out_view is None else _view(out, N, *out_view)
+    args = _lib.GemmArgs()
+    args.w, args.N, args.K = w_packed.data_ptr(), N, K
+    args.bias = _p(bias)
+    args.act = act
+    args.out_f32 = 1 if out_f32 else 0
+    keep = []
+    if residual is not None:
+        rv = _view(residual, N, *(residual_view or (None, None)))
+        keep.append(rv)
+        args.residual = ctypes.pointer(rv)
+        args.residual_f32 = 1 if residual.dtype == F32 else 0
+    aux = None
+    if aux_out:
+        aux = torch.empty(*a.shape[:-1], N, dtype=BF16, device=a.device)
+        xv = _view(aux, N)
+        keep.append(xv)
+        args.aux_out = ctypes.pointer(xv)
+    if aux_in is not None:
+        iv = _view(aux_in, N)
+        keep.append(iv)
+        args.aux_in = ctypes.pointer(iv)
+    sp = _span("conv_gemm_fwd", 2.0 * rows * N * K, _nb(a, w_packed, out, residual, aux, aux_in))
+    rc = lib.b200_gemm_ex(ctypes.byref(av), ctypes.byref(ov), ctypes.byref(args), _stream())
+    _lib.check(rc, "b200_gemm_ex")
+    if sp:
+        sp.end()
+    return out, aux
+
+
+# --------------------------------------------------------------------------------------------------------- layer norm
+def layernorm_fwd(x, gamma, beta, eps):
+    """x [..., C] fp32 or bf16 -> (y bf16, mean, rstd)."""
+    lib = _lib.load()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    stat = torch.empty(2, rows, dtype=F32, device=x.device)
+    sp = _span("layernorm_fwd", 0.0, _nb(x, y))
+    rc = lib.b200_layernorm_fwd(_p(x), 1 if x.dtype == F32 else 0, _p(gamma), _p(beta), _p(y), _p(stat[0]), _p(stat[1]),
+                                rows, C, eps, _stream())
+    _lib.check(rc, "b200_layernorm_fwd")
+    if sp:
+        sp.end()
+    return y, stat[0], stat[1]
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, add=None, dx_dtype=BF16, dgamma=None, dbeta=None):
+    """Returns (dx [+ add], dgamma, dbeta)."""
+    lib = _lib.load()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    nblk = lib.b200_layernorm_bwd_blocks(rows, C)
+    if nblk <= 0:
+        raise RuntimeError(f"layernorm_bwd: unsupported width {C}")
+    partial = torch.empty(nblk, 2, C, dtype=F32, device=x.device)
+    dx = torch.empty(x.shape, dtype=dx_dtype, device=x.device)
+    sp = _span("layernorm_bwd", 0.0, _nb(dy, x, dx, add))
+    rc = lib.b200_layernorm_bwd(_p(dy), _p(x), 1 if x.dtype == F32 else 0, _p(mean), _p(rstd), _p(gamma), _p(add), _p(dx),
+                                1 if dx_dtype == F32 else 0, _p(partial), rows, C, _stream())
+    _lib.check(rc, "b200_layernorm_bwd")
+    if sp:
+        sp.end()
+    if dgamma is None:
+        dgamma = torch.empty(C, dtype=F32, device=x.device)
+        dbeta = torch.empty(C, dtype=F32, device=x.device)
+    sc = _reduce_scratch(x.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, 1.0, _p(dgamma), _p(dbeta), 0, None, None, _p(sc), sc.numel(), _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    return dx, dgamma, dbeta
+
+
+# --------------------------------------------------------------------------------------------------------- ViT pieces
+def patchify_nchw(x, ps):
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    a = torch.empty(B, (H // ps) * (W // ps), C * ps * ps, dtype=BF16, device=x.device)
+    sp = _span("patchify", 0.0, _nb(x, a))
+    _lib.check(lib.b200_patchify_nchw(_p(x), _p(a), B, C, H, W, ps, _stream()), "b200_patchify_nchw")
+    if sp:
+        sp.end()
+    return a
+
+
+def cls_row_(tokens, cls, pos):
+    lib = _lib.load()
+    B, T, D = tokens.shape
+    _lib.check(lib.b200_cls_row(_p(cls), _p(pos), _p(tokens), B, T, D, _stream()), "b200_cls_row")
+
+
+def batch_rowsum(g, stride_b, B, D, out=None, accumulate=False):
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(D, dtype=F32, device=g.device)
+        accumulate = False
+    _lib.check(lib.b200_batch_rowsum(_p(g), stride_b, B, D, _p(out), 1 if accumulate else 0, _stream()), "b200_batch_rowsum")
+    return out
+
+
+def attention_fwd(qkv, H, scale):
+    """qkv bf16 [B, T, 3*H*64] -> (out bf16 [B, T, H*64], lse fp32 [B, H, T])."""
+    lib = _lib.load()
+    B, T, _ = qkv.shape
+    out = torch.empty(B, T, H * 64, dtype=BF16, device=qkv.device)
+    lse = torch.empty(B, H, T, dtype=F32, device=qkv.device)
+    sp = _span("attention_fwd", 4.0 * B * H * T * T * 64, _nb(qkv, out))
+    _lib.check(lib.b200_attention_fwd(_p(qkv), _p(out), _p(lse), B, T, H, scale, _stream()), "b200_attention_fwd")
+    if sp:
+        sp.end()
+    return out, lse
+
+
+def attention_bwd(qkv, out, dout, lse, H, scale):
+    lib = _lib.load()
+    B, T, _ = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B, H, T, dtype=F32, device=qkv.device)
+    sp = _span("attention_bwd", 10.0 * B * H * T * T * 64, _nb(qkv, out, dout, dqkv))
+    rc = lib.b200_attention_bwd(_p(qkv), _p(out), _p(dout), _p(lse), _p(delta), _p(dqkv), B, T, H, scale, _stream())
+    _lib.check(rc, "b200_attention_bwd")
+    if sp:
+        sp.end()
+    return dqkv

@@ -31,6 +31,7 @@ extern "C" {
 #define B200_ACT_NONE 0
 #define B200_ACT_RELU 1
 #define B200_ACT_GELU 2
+#define B200_ACT_GELU_GRAD 3 /* multiply the accumulator by gelu'(aux_in) - backward of B200_ACT_GELU */
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
@@ -65,6 +66,56 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
 int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
                       int W, int Cin, int Cout, int ksize, int stride, int accumulate, void* stream);
 size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
+
+/* ---- general GEMM with strided pixel views (transformer layers, patch embedding) ----------------------------------------
+ * out[pixel, n] = epilogue( sum_k a[pixel, k] * w[n, k] ), pixels = dim[0] x dim[1] x dim[2] (w fastest), channel stride 1.
+ * `a` and `out` must have identical pixel extents; strides are in elements and let `out`/`residual` be token-offset or
+ * batch-broadcast views (e.g. ViT: rows 1.. of [B,197,D], residual = pos_embed with batch stride 0).
+ * replaces nn.Linear / PatchEmbed conv + the surrounding bias / GELU / residual-add elementwise ops of
+ * classification/vision_transformer/vit_model.py:66,95,109,127-133,159-160. */
+typedef struct {
+  const void* base;     /* first element of the view (bf16 unless stated otherwise) */
+  long long dim[3];     /* pixel extents (w, h, n); use 1 for unused dims */
+  long long stride[3];  /* element strides of the pixel dims */
+} b200_view_t;
+
+typedef struct {
+  const void* w;               /* bf16 [N][K] (b200_pack_weight mode 0) */
+  int N, K;
+  const float* bias;           /* [N] or NULL */
+  int act;                     /* B200_ACT_* */
+  int out_f32;                 /* 1: `out` is an fp32 tensor (residual stream) */
+  const b200_view_t* residual; /* added after bias/act, or NULL */
+  int residual_f32;
+  const b200_view_t* aux_out;  /* bf16 copy of the pre-activation (act == GELU), or NULL */
+  const b200_view_t* aux_in;   /* act == B200_ACT_GELU_GRAD: pre-activation tensor */
+  float* stats;                /* optional per-32-row-slab column sum / sum of squares, or NULL */
+} b200_gemm_args_t;
+
+int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_args_t* args, void* stream);
+
+/* ---- LayerNorm over the last dim, one warp per row (vit_model.py:194 eps 1e-6; swin_transformer.py:509 eps 1e-5) ------------
+ * x is fp32 (x_f32) or bf16, y bf16; mean/rstd [rows] are kept for the backward pass.
+ * backward: dx = rstd*(dy*gamma - mean(dy*gamma) - xhat*mean(dy*gamma*xhat)) (+ add), dx/add fp32 or bf16;
+ * partial[b200_layernorm_bwd_blocks()][2][C] = per-block (sum dy, sum dy*xhat), folded by b200_bn_bwd_finalize. */
+int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* y, float* mean,
+                       float* rstd, long long rows, int C, float eps, void* stream);
+int b200_layernorm_bwd_blocks(long long rows, int C);
+int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* mean, const float* rstd, const float* gamma,
+                       const void* add, void* dx, int dx_f32, float* partial, long long rows, int C, void* stream);
+
+/* ---- ViT patch embedding helpers (vit_model.py:56-66,244-250) ---------------------------------------------------------------
+ * patchify: NCHW fp32 -> bf16 [B*(H/ps)*(W/ps)][Cin*ps*ps] with k = c*ps*ps + kh*ps + kw (= conv weight.view(D,-1) order) */
+int b200_patchify_nchw(const float* x, void* a, int B, int Cin, int H, int W, int ps, void* stream);
+int b200_cls_row(const float* cls, const float* pos, float* tokens, int B, int T, int D, void* stream);
+int b200_batch_rowsum(const float* g, long long stride_b, int B, int D, float* out, int accumulate, void* stream);
+
+/* ---- multi-head self-attention, head_dim 64, T <= 256 tokens, on tcgen05 (vit_model.py:95-108) ---------------------------------
+ * qkv bf16 [B][T][3][H][64] (the qkv Linear output as is), out bf16 [B][T][H*64], lse fp32 [B][H][T].
+ * backward: dqkv bf16 [B][T][3][H][64]; delta fp32 [B][H][T] is scratch. Scores / probabilities never touch HBM. */
+int b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float scale, void* stream);
+int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
+                       int B, int T, int H, float scale, void* stream);
 
 /* ---- BatchNorm2d (train: batch statistics, eval: running statistics) ----------------------------------------------------
  * replaces nn.BatchNorm2d + nn.ReLU (+ residual add) of Bottleneck.forward, classification/resnet/models/networks.py:108-124 */
