@@ -48,7 +48,10 @@ SIGNATURES = {
     "b200_layernorm_bwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P]),
     "b200_patchify_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200_cls_row": (_I, [_P, _P, _P, _I, _I, _I, _P]),
-    "b200_batch_rowsum": (_I, [_P, _L, _I, _I, _P, _I, _P]),
+    "b200_batch_rowsum": (_I, [_P, _I, _L, _I, _I, _P, _I, _P]),
+    "b200_copy_rows": (_I, [_P, _L, _P, _L, _L, _L, _P]),
+    "b200_colsum_partial_slices": (_I, [_L]),
+    "b200_colsum_partial": (_I, [_P, _L, _L, _I, _P, _P]),
     "b200_attention_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "b200_attention_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),

@@ -46,7 +46,7 @@ int b200_sm_count(void) { return device_sm_count(); }
 unsigned long long b200_launch_count(void) { return g_launch_count; }
 
 size_t b200_reduce_scratch_bytes(int T, int C) {
-  return 256 + static_cast<size_t>(reduce_slices(T)) * 2 * C * sizeof(double);
+  return 1024 + static_cast<size_t>(reduce_slices(T)) * 2 * C * sizeof(double);
 }
 
 int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,
@@ -54,7 +54,7 @@ int b200_bn_finalize(const float* partial, int T, int C, double count, const flo
                      float* mean, float* invstd, float* scale, float* shift, void* scratch, size_t scratch_bytes,
                      void* stream) {
   B200_REQUIRE(T > 0 && C > 0 && count > 0, "bn_finalize: bad sizes T=%d C=%d", T, C);
-  B200_REQUIRE(C <= 64 * 32, "bn_finalize: C=%d exceeds 2048", C);
+  B200_REQUIRE(C <= 256 * 32, "bn_finalize: C=%d exceeds 8192", C);
   B200_REQUIRE(scratch != nullptr && scratch_bytes >= b200_reduce_scratch_bytes(T, C), "bn_finalize: scratch too small");
   bn_finalize_kernel<<<dim3((C + 31) / 32, reduce_slices(T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       partial, T, C, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, mean, invstd,
@@ -101,7 +101,7 @@ int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz
 
 int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
                          float* m1, float* m2, void* scratch, size_t scratch_bytes, void* stream) {
-  B200_REQUIRE(T > 0 && C > 0 && C <= 64 * 32, "bn_bwd_finalize: bad sizes T=%d C=%d", T, C);
+  B200_REQUIRE(T > 0 && C > 0 && C <= 256 * 32, "bn_bwd_finalize: bad sizes T=%d C=%d", T, C);
   B200_REQUIRE(scratch != nullptr && scratch_bytes >= b200_reduce_scratch_bytes(T, C), "bn_bwd_finalize: scratch too small");
   bn_bwd_finalize_kernel<<<dim3((C + 31) / 32, reduce_slices(T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       partial, T, C, count, dgamma, dbeta, accumulate, m1, m2, scratch);

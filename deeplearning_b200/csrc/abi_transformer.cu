@@ -104,8 +104,38 @@ int b200_cls_row(const float* cls, const float* pos, float* tokens, int B, int T
   return OK;
 }
 
-int b200_batch_rowsum(const float* g, long long stride_b, int B, int D, float* out, int accumulate, void* stream) {
-  batch_rowsum_kernel<<<(D + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, stride_b, B, D, out, accumulate);
+int b200_batch_rowsum(const void* g, int g_f32, long long stride_b, int B, int D, float* out, int accumulate,
+                      void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g_f32)
+    batch_rowsum_kernel<float><<<(D + 255) / 256, 256, 0, st>>>(static_cast<const float*>(g), stride_b, B, D, out, accumulate);
+  else
+    batch_rowsum_kernel<__nv_bfloat16><<<(D + 255) / 256, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(g), stride_b, B, D, out, accumulate);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_copy_rows(const void* src, long long src_pitch_bytes, void* dst, long long dst_pitch_bytes, long long rows,
+                   long long row_bytes, void* stream) {
+  B200_REQUIRE(row_bytes % 16 == 0 && src_pitch_bytes % 16 == 0 && dst_pitch_bytes % 16 == 0,
+               "copy_rows: sizes must be multiples of 16 bytes");
+  copy_rows_kernel<<<grid_for(rows * (row_bytes / 16), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint8_t*>(src), src_pitch_bytes, static_cast<uint8_t*>(dst), dst_pitch_bytes, rows, row_bytes);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_colsum_partial_slices(long long rows) {
+  long long s = rows / 64;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return static_cast<int>(s);
+}
+
+int b200_colsum_partial(const void* m, long long rows, long long ld, int cols, float* partial, void* stream) {
+  const int S = b200_colsum_partial_slices(rows);
+  colsum_partial_kernel<<<dim3((cols + 63) / 64, S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(m), rows, ld, cols, partial);
   B200_LAUNCHED();
   return OK;
 }

@@ -15,13 +15,13 @@ namespace b200 {
 // Column reduction of per-tile partials partial[T][2][C] -> two per-channel sums (double), parallel over T:
 // grid = (ceil(C/32), S); every block reduces its slice of T for 32 channels and publishes it to `scratch`; the last
 // block to finish (ticket counter, reset to zero for the next call) folds the S slices and returns true.
-// scratch layout: [64 x uint32 counters][S][2][C] doubles.
+// scratch layout: [256 x uint32 counters][S][2][C] doubles.
 __device__ __forceinline__ bool reduce_partials_last_block(const float* __restrict__ partial, int T, int C, void* scratch,
                                                            double& s_out, double& ss_out) {
   __shared__ double sh[2][8][32];
   __shared__ int is_last;
   unsigned int* counters = static_cast<unsigned int*>(scratch);
-  double* slices = reinterpret_cast<double*>(static_cast<char*>(scratch) + 256);
+  double* slices = reinterpret_cast<double*>(static_cast<char*>(scratch) + 1024);
   const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cx;
   const int S = gridDim.y;

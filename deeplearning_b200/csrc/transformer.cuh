@@ -210,13 +210,47 @@ __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __res
   }
 }
 
+// Strided 2-D copy of 16-byte vectors: dst[r][0:cols] = src[r][0:cols] with independent row pitches (in bytes).
+__global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long long src_pitch, uint8_t* __restrict__ dst,
+                                 long long dst_pitch, long long rows, long long row_bytes) {
+  const long long vecs = row_bytes >> 4;
+  const long long total = rows * vecs;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / vecs, v = i % vecs;
+    *reinterpret_cast<uint4*>(dst + r * dst_pitch + (v << 4)) = __ldg(reinterpret_cast<const uint4*>(src + r * src_pitch + (v << 4)));
+  }
+}
+
+// Column-sum partials of a bf16 matrix [rows][ld]: partial[slice][2][cols] (second plane zero), folded by the BN finalize
+// machinery.  Block = 64 columns x 4 row lanes.
+__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ m, long long rows, long long ld, int cols,
+                                      float* __restrict__ partial) {
+  __shared__ float sh[4][64];
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cx;
+  const int S = gridDim.y;
+  const long long chunk = (rows + S - 1) / S;
+  const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + ry; r < r1; r += 4) s += __bfloat162float(m[r * ld + c]);
+  sh[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    partial[(static_cast<long long>(blockIdx.y) * 2 + 0) * cols + c] = sh[0][cx] + sh[1][cx] + sh[2][cx] + sh[3][cx];
+    partial[(static_cast<long long>(blockIdx.y) * 2 + 1) * cols + c] = 0.f;
+  }
+}
+
 // Sum over the batch of a strided set of rows: out[d] (+)= sum_b g[b*stride_b + d]   (gradient of cls token / pos embed rows)
-__global__ void batch_rowsum_kernel(const float* __restrict__ g, long long stride_b, int B, int D, float* __restrict__ out,
+template <typename T>
+__global__ void batch_rowsum_kernel(const T* __restrict__ g, long long stride_b, int B, int D, float* __restrict__ out,
                                     int accumulate) {
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   float s = 0.f;
-  for (int b = 0; b < B; ++b) s += g[b * stride_b + d];
+  for (int b = 0; b < B; ++b) s += static_cast<float>(g[b * stride_b + d]);
   out[d] = accumulate ? out[d] + s : s;
 }
 

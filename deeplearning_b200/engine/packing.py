@@ -17,7 +17,7 @@ class ModelPack:
     """All packed operands of one model, refreshed by ONE kernel launch (b200_pack_weights_multi)."""
 
     def __init__(self, specs):
-        # specs: list of (param, mode, ld, rows_out)
+        # specs: list of (param, mode, ld, rows_out[, (O, I, taps) override for weights consumed as a flat [O][K] matrix])
         self.specs = specs
         self.outputs = {}
         self._ptrs = None
@@ -25,9 +25,13 @@ class ModelPack:
         dev = specs[0][0].device
         rows = []
         first = 0
-        for (p, mode, ld, rows_out) in specs:
-            O, I = p.shape[0], p.shape[1]
-            taps = p.numel() // (O * I)
+        for spec in specs:
+            p, mode, ld, rows_out = spec[:4]
+            if len(spec) > 4 and spec[4] is not None:
+                O, I, taps = spec[4]
+            else:
+                O, I = p.shape[0], p.shape[1]
+                taps = p.numel() // (O * I)
             dst = torch.empty(rows_out, ld, dtype=torch.bfloat16, device=dev)
             self.outputs[(id(p), mode)] = dst
             nblk = max(1, min(64, (rows_out * ld + 256 * 16 - 1) // (256 * 16)))
@@ -38,7 +42,7 @@ class ModelPack:
         self.table = None
 
     def _build_table(self):
-        ptrs = tuple(p.data_ptr() for (p, _, _, _) in self.specs)
+        ptrs = tuple(spec[0].data_ptr() for spec in self.specs)
         if ptrs != self._ptrs:
             for r, ptr in zip(self._rows, ptrs):
                 r[0] = ptr
@@ -47,7 +51,7 @@ class ModelPack:
             self._ptrs = ptrs
 
     def refresh(self, generation):
-        stamp = (generation, tuple((p._version, p.data_ptr()) for (p, _, _, _) in self.specs))
+        stamp = (generation, tuple((spec[0]._version, spec[0].data_ptr()) for spec in self.specs))
         if stamp == self.stamp:
             return
         self._build_table()

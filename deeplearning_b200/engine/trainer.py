@@ -23,6 +23,12 @@ def _engine_for(model):
         from . import resnet
 
         return resnet
+    from ..classification.vision_transformer.vit_model import VisionTransformer
+
+    if isinstance(model, VisionTransformer):
+        from . import vit
+
+        return vit
     raise NotImplementedError(f"no B200 engine schedule for {type(model).__name__}")
 
 

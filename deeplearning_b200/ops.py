@@ -216,7 +216,7 @@ def _reduce_scratch(device):
     key = (device, torch.cuda.current_stream().cuda_stream)
     sc = _scratch_cache.get(key)
     if sc is None:
-        sc = torch.zeros(256 + 64 * 2 * 2048 * 8, dtype=torch.uint8, device=device)
+        sc = torch.zeros(1024 + 64 * 2 * 8192 * 8, dtype=torch.uint8, device=device)
         _scratch_cache[key] = sc
     return sc
 
@@ -401,10 +401,11 @@ def launch_count():
 
 
 # --------------------------------------------------------------------------------------------------------- general GEMM
-def _view(t, channels, pix_dims=None, pix_strides=None):
-    """b200_view_t of a tensor whose last dim is the channel dim (stride 1). Default: all leading dims flattened."""
+def _view(t, channels, pix_dims=None, pix_strides=None, offset=0):
+    """b200_view_t of a tensor whose last dim is the channel dim (stride 1). Default: all leading dims flattened.
+    `offset` (elements) moves the base, e.g. to skip the class-token row of a [B, T, D] tensor."""
     v = _lib.View()
-    v.base = t.data_ptr()
+    v.base = t.data_ptr() + offset * t.element_size()
     if pix_dims is None:
         rows = t.numel() // channels
         pix_dims, pix_strides = (rows, 1, 1), (channels, rows * channels, rows * channels)
@@ -415,7 +416,7 @@ def _view(t, channels, pix_dims=None, pix_strides=None):
 
 
 def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, aux_out=False, aux_in=None,
-         a_view=None, out_view=None, residual_view=None, want_stats=False):
+         a_view=None, out_view=None, residual_view=None, out_offset=0, want_stats=False):
     """out[rows, N] = epilogue(a[rows, K] @ w_packed[N, K]^T). `*_view` = (pix_dims, pix_strides) for strided layouts.
     Returns (out, aux) where aux is the bf16 pre-activation copy when aux_out=True."""
     import ctypes
@@ -427,7 +428,7 @@ def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, 
         out = torch.empty(*a.shape[:-1], N, dtype=F32 if out_f32 else BF16, device=a.device)
     out_f32 = out.dtype == F32
     av = _view(a, K, *(a_view or (None, None)))
-    ov = _view(out, N, *(out_view or (None, None))) if out_view is None else _view(out, N, *out_view)
+    ov = _view(out, N, *(out_view or (None, None)), offset=out_offset)
     args = _lib.GemmArgs()
     args.w, args.N, args.K = w_packed.data_ptr(), N, K
     args.bias = _p(bias)
@@ -517,12 +518,40 @@ def cls_row_(tokens, cls, pos):
     _lib.check(lib.b200_cls_row(_p(cls), _p(pos), _p(tokens), B, T, D, _stream()), "b200_cls_row")
 
 
-def batch_rowsum(g, stride_b, B, D, out=None, accumulate=False):
+def batch_rowsum(g, stride_b, B, D, out=None, accumulate=False, offset=0):
+    """out[d] (+)= sum_b g.flat[offset + b*stride_b + d]  (g fp32 or bf16)."""
     lib = _lib.load()
     if out is None:
         out = torch.empty(D, dtype=F32, device=g.device)
         accumulate = False
-    _lib.check(lib.b200_batch_rowsum(_p(g), stride_b, B, D, _p(out), 1 if accumulate else 0, _stream()), "b200_batch_rowsum")
+    ptr = g.data_ptr() + offset * g.element_size()
+    rc = lib.b200_batch_rowsum(ptr, 1 if g.dtype == F32 else 0, stride_b, B, D, _p(out), 1 if accumulate else 0, _stream())
+    _lib.check(rc, "b200_batch_rowsum")
+    return out
+
+
+def copy_rows(src, src_offset, src_pitch, dst, dst_offset, dst_pitch, rows, cols):
+    """dst.flat[dst_offset + r*dst_pitch + c] = src.flat[src_offset + r*src_pitch + c] (same dtype; 16-byte granularity)."""
+    lib = _lib.load()
+    es = src.element_size()
+    rc = lib.b200_copy_rows(src.data_ptr() + src_offset * es, src_pitch * es, dst.data_ptr() + dst_offset * es,
+                            dst_pitch * es, rows, cols * es, _stream())
+    _lib.check(rc, "b200_copy_rows")
+
+
+def colsum_tall(m, cols=None, out=None):
+    """Column sums of a tall bf16 matrix [rows, ld] (bias gradients) using the two-level reduction."""
+    lib = _lib.load()
+    rows, ld = m.shape
+    cols = cols or ld
+    S = lib.b200_colsum_partial_slices(rows)
+    partial = torch.empty(S, 2, cols, dtype=F32, device=m.device)
+    _lib.check(lib.b200_colsum_partial(_p(m), rows, ld, cols, _p(partial), _stream()), "b200_colsum_partial")
+    if out is None:
+        out = torch.empty(cols, dtype=F32, device=m.device)
+    sc = _reduce_scratch(m.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), S, cols, 1.0, None, _p(out), 0, None, None, _p(sc), sc.numel(), _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
     return out
 
 

@@ -108,7 +108,14 @@ int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* me
  * patchify: NCHW fp32 -> bf16 [B*(H/ps)*(W/ps)][Cin*ps*ps] with k = c*ps*ps + kh*ps + kw (= conv weight.view(D,-1) order) */
 int b200_patchify_nchw(const float* x, void* a, int B, int Cin, int H, int W, int ps, void* stream);
 int b200_cls_row(const float* cls, const float* pos, float* tokens, int B, int T, int D, void* stream);
-int b200_batch_rowsum(const float* g, long long stride_b, int B, int D, float* out, int accumulate, void* stream);
+int b200_batch_rowsum(const void* g, int g_f32, long long stride_b, int B, int D, float* out, int accumulate,
+                      void* stream);
+/* strided 2-D copy (16-byte granularity), e.g. gathering the class-token rows of a [B,T,D] tensor */
+int b200_copy_rows(const void* src, long long src_pitch_bytes, void* dst, long long dst_pitch_bytes, long long rows,
+                   long long row_bytes, void* stream);
+/* bias gradients of tall matrices: partial[b200_colsum_partial_slices(rows)][2][cols], folded by b200_bn_bwd_finalize */
+int b200_colsum_partial_slices(long long rows);
+int b200_colsum_partial(const void* m, long long rows, long long ld, int cols, float* partial, void* stream);
 
 /* ---- multi-head self-attention, head_dim 64, T <= 256 tokens, on tcgen05 (vit_model.py:95-108) ---------------------------------
  * qkv bf16 [B][T][3][H][64] (the qkv Linear output as is), out bf16 [B][T][H*64], lse fp32 [B][H][T].
@@ -119,7 +126,7 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
 
 /* ---- BatchNorm2d (train: batch statistics, eval: running statistics) ----------------------------------------------------
  * replaces nn.BatchNorm2d + nn.ReLU (+ residual add) of Bottleneck.forward, classification/resnet/models/networks.py:108-124 */
-/* partial[T][2][C] column reductions run on a 2-D grid; `scratch` (b200_reduce_scratch_bytes(T, C) bytes, its first 256
+/* partial[T][2][C] column reductions run on a 2-D grid; `scratch` (b200_reduce_scratch_bytes(T, C) bytes, its first 1024
  * bytes zero on first use - the kernel leaves them zero) carries the slice sums and a ticket counter. One per stream. */
 size_t b200_reduce_scratch_bytes(int T, int C);
 int b200_bn_finalize(const float* partial, int T, int C, double count, const float* gamma, const float* beta, float eps,

@@ -1,0 +1,41 @@
+"""Oracle: the reference ViT forward restated functionally in fp32 PyTorch
+(classification/vision_transformer/vit_model.py): PatchEmbed conv -> flatten -> transpose (:59-68); cls concat + pos add
+(:244-250); Block = x + attn(LN(x)); x + mlp(LN(x)) (:158-161) with Attention (:88-111: qkv Linear, (q@k^T)*scale, softmax,
+@v, proj) and Mlp (:127-133: fc1, exact-erf GELU, fc2); final LN eps 1e-6 (:194,252), cls row, optional pre_logits
+Linear+Tanh (:218-221), head (:268).  All dropouts are p=0 in the BASELINE configuration."""
+import torch
+import torch.nn.functional as F
+
+
+def vit_forward(s, x, num_heads=12, patch=16, eps=1e-6, train=False):
+    B = x.shape[0]
+    h = F.conv2d(x, s["patch_embed.proj.weight"], s["patch_embed.proj.bias"], stride=patch).flatten(2).transpose(1, 2)
+    h = torch.cat([s["cls_token"].expand(B, -1, -1), h], 1) + s["pos_embed"]
+    D = h.shape[-1]
+    hd = D // num_heads
+    i = 0
+    while f"blocks.{i}.norm1.weight" in s:
+        p = f"blocks.{i}."
+        y = F.layer_norm(h, (D,), s[p + "norm1.weight"], s[p + "norm1.bias"], eps)
+        qkv = F.linear(y, s[p + "attn.qkv.weight"], s.get(p + "attn.qkv.bias"))
+        T = qkv.shape[1]
+        q, k, v = qkv.reshape(B, T, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+        att = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(-1)
+        y = (att @ v).transpose(1, 2).reshape(B, T, D)
+        h = h + F.linear(y, s[p + "attn.proj.weight"], s[p + "attn.proj.bias"])
+        y = F.layer_norm(h, (D,), s[p + "norm2.weight"], s[p + "norm2.bias"], eps)
+        y = F.linear(F.gelu(F.linear(y, s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"])), s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"])
+        h = h + y
+        i += 1
+    h = F.layer_norm(h, (D,), s["norm.weight"], s["norm.bias"], eps)[:, 0]
+    if "pre_logits.fc.weight" in s:
+        h = torch.tanh(F.linear(h, s["pre_logits.fc.weight"], s["pre_logits.fc.bias"]))
+    return F.linear(h, s["head.weight"], s["head.bias"])
+
+
+def train_step_grads(state, x, labels, **kw):
+    params = {k: v.detach().clone().requires_grad_(True) for k, v in state.items() if v.is_floating_point()}
+    logits = vit_forward(params, x, train=True, **kw)
+    loss = F.cross_entropy(logits, labels)
+    grads = torch.autograd.grad(loss, list(params.values()), allow_unused=True)
+    return logits.detach(), loss.detach(), {k: (g if g is not None else torch.zeros_like(params[k])) for k, g in zip(params, grads)}

@@ -91,7 +91,7 @@ def test_patch_embed_into_token_rows():
     tokens = torch.empty(B, T, D, dtype=torch.float32, device="cuda")
     ops.gemm(a, wp, bias=bias, out=tokens,
              a_view=((P, B, 1), (3 * ps * ps, P * 3 * ps * ps, 0)),
-             out_view=((P, B, 1), (D, T * D, 0)), residual=pos[0, 1:], residual_view=((P, B, 1), (D, 0, 0)))
+             out_view=((P, B, 1), (D, T * D, 0)), out_offset=D, residual=pos[0, 1:], residual_view=((P, B, 1), (D, 0, 0)))
     ops.cls_row_(tokens, cls.reshape(-1), pos.reshape(-1))
     ref = F.conv2d(x.to(torch.bfloat16).float(), wconv.to(torch.bfloat16).float(), bias, stride=ps).flatten(2).transpose(1, 2)
     ref = torch.cat([cls.expand(B, -1, -1), ref], 1) + pos
