@@ -21,8 +21,13 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GFLOP_PER_IMG = 24.53      # fwd+bwd = 3 x forward, GEMM-like ops only
-MB_PER_IMG = 3 * 43.8      # algorithmic HBM bytes, ideal per-layer fusion, bf16, fwd+bwd
+# per-image algorithmic work, fwd+bwd = 3 x forward: GFLOP (GEMM-like ops) and MB of HBM traffic
+MODELS = {
+    "resnet50": {"gflop": 24.53, "mb": 3 * 43.8, "batch": 256,
+                 "workload": "classification/resnet ResNet-50 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[1])"},
+    "vit_b16": {"gflop": 105.38, "mb": 3 * 73.9, "batch": 256,
+                "workload": "classification/vision_transformer ViT-B/16 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[2])"},
+}
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -128,7 +133,6 @@ def run_b200(args):
     import torch.distributed as dist
 
     from deeplearning_b200 import ops
-    from deeplearning_b200.classification.resnet.models.networks import resnet50
     from deeplearning_b200.engine.trainer import TrainStep
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -141,9 +145,17 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    spec = MODELS[args.model]
+    B = args.batch or spec["batch"]
     torch.manual_seed(0)  # identical init on every rank (and broadcast from rank 0 inside TrainStep)
-    model = resnet50().to(dev).train()
+    if args.model == "resnet50":
+        from deeplearning_b200.classification.resnet.models.networks import resnet50
+
+        model = resnet50().to(dev).train()
+    else:
+        from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
+
+        model = vit_base_patch16_224_in21k(num_classes=1000, has_logits=False).to(dev).train()
     trainer = TrainStep(model, lr=0.01, momentum=0.9, weight_decay=5e-5)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images = torch.randn(B, 3, 224, 224, device=dev, generator=g)
@@ -226,10 +238,10 @@ def run_b200(args):
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
     h2d = B * 3 * 224 * 224 * 4 + B * 8
 
-    line = {"metric": "images/sec (ResNet-50 training step)", "value": value, "unit": "images/sec", "n_gpus": world,
+    line = {"metric": f"images/sec ({args.model} training step)", "value": value, "unit": "images/sec", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "classification/resnet ResNet-50 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[1])",
+            "config": {"workload": spec["workload"],
                        "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
                        "optimizer": "SGD(momentum=0.9, weight_decay=5e-5)", "step": "fwd+CE+bwd+allreduce+SGD",
                        "launch": "eager" if args.eager else "CUDA graph replay",
@@ -243,8 +255,8 @@ def run_b200(args):
         # whole-step roofline: the step is HBM-bound on this design; both fractions are reported
         per_gpu = value / world
         line["step_roofline"] = {
-            "hbm_frac": per_gpu * MB_PER_IMG * 1e6 / (peaks["hbm_gbs"] * 1e9),
-            "tensor_frac": per_gpu * GFLOP_PER_IMG * 1e9 / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * 1e12),
+            "hbm_frac": per_gpu * spec["mb"] * 1e6 / (peaks["hbm_gbs"] * 1e9),
+            "tensor_frac": per_gpu * spec["gflop"] * 1e9 / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * 1e12),
             "peaks": peaks["_source"]}
         # per-kernel roofline: one extra step with CUDA-event spans around every C-ABI op on the launching stream
         with ops.Profiler() as prof:
@@ -273,7 +285,7 @@ def run_b200(args):
                             "how": "CUDA-event spans on the launching stream over one extra step after the timed region; "
                                    "algorithmic bytes = tensors read+written once per launch"}
         line["kernels"] = kernels
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and args.model == "resnet50":
             cb = cpu_reference_run(3, 1, batch=16, budget_s=30.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -287,7 +299,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE config: 256)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the BASELINE config's, 256)")
+    ap.add_argument("--model", default="resnet50", choices=sorted(MODELS), help="resnet50 = BASELINE configs[1] (headline)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into CUDA graphs")
