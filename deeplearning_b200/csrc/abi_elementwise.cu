@@ -88,23 +88,23 @@ int b200_bn_bwd_blocks(long long rows, int C) {
 }
 
 int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
-                       const float* shift, const float* mean, const float* invstd, int relu, long long rows, int C,
-                       float* partial, void* stream) {
+                       const float* shift, int relu, long long rows, int C, float* partial, void* stream) {
   B200_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_bwd_reduce: C=%d must be 8*2^k <= 2048", C);
   const BnBwdPlan pl = plan_bn_bwd(rows, C);
   bn_bwd_reduce_kernel<<<pl.blocks, 256, 256 * 17 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out),
-      static_cast<uint4*>(dz_out), scale, shift, mean, invstd, relu, rows, C / 8, pl.rows_per_block, partial);
+      static_cast<uint4*>(dz_out), scale, shift, relu, rows, C / 8, pl.rows_per_block, partial);
   B200_LAUNCHED();
   return OK;
 }
 
 int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
-                         float* m1, float* m2, void* scratch, size_t scratch_bytes, void* stream) {
+                         float* m1, float* m2, const float* mean, const float* invstd, void* scratch,
+                         size_t scratch_bytes, void* stream) {
   B200_REQUIRE(T > 0 && C > 0 && C <= 256 * 32, "bn_bwd_finalize: bad sizes T=%d C=%d", T, C);
   B200_REQUIRE(scratch != nullptr && scratch_bytes >= b200_reduce_scratch_bytes(T, C), "bn_bwd_finalize: scratch too small");
   bn_bwd_finalize_kernel<<<dim3((C + 31) / 32, reduce_slices(T)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      partial, T, C, count, dgamma, dbeta, accumulate, m1, m2, scratch);
+      partial, T, C, count, dgamma, dbeta, accumulate, m1, m2, mean, invstd, scratch);
   B200_LAUNCHED();
   return OK;
 }

@@ -152,28 +152,28 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ x, const uint4* __rest
 //   mask source: y_out (saved post-activation output, used when a residual was added) if given, else recomputed from
 //   x*scale+shift > 0; relu == 0 -> no mask.  Optionally stores dz (bf16) for reuse (identity-branch gradient).
 // Block = 256 threads; each thread owns one 8-channel group and strides over rows. partial[blocks][2][C].
-__global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x,
-                                     const uint4* __restrict__ y_out, uint4* __restrict__ dz_out,
-                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
-                                     long long rows, int cvec, int rows_per_block, float* __restrict__ partial) {
+__global__ void __launch_bounds__(256, 3)
+bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const uint4* __restrict__ y_out,
+                     uint4* __restrict__ dz_out, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
+                     long long rows, int cvec, int rows_per_block, float* __restrict__ partial) {
   extern __shared__ float red[];  // [256][17]
   const int tpr = cvec;                  // threads per row (power of two, <= 256)
   const int rpi = 256 / tpr;             // rows per iteration
   const int cg = threadIdx.x % tpr;
   const int rsub = threadIdx.x / tpr;
-  float sc[8], sh[8], mu[8], is[8];
-  load8f(scale + cg * 8, sc);
-  load8f(shift + cg * 8, sh);
-  load8f(mean + cg * 8, mu);
-  load8f(invstd + cg * 8, is);
+  const bool mask_from_y = relu && (y_out != nullptr);
+  const bool mask_from_x = relu && (y_out == nullptr);
+  float sc[8], sh[8];
+  if (mask_from_x) {
+    load8f(scale + cg * 8, sc);
+    load8f(shift + cg * 8, sh);
+  }
+  // accumulates sum(dz) and sum(dz * x) with the RAW x; the finalize kernel turns the latter into sum(dz * xhat)
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
   const long long r0 = static_cast<long long>(blockIdx.x) * rows_per_block;
   const long long r1 = min(rows, r0 + rows_per_block);
-  const bool mask_from_y = relu && (y_out != nullptr);
-  const bool mask_from_x = relu && (y_out == nullptr);
   for (long long r = r0 + rsub; r < r1; r += 2 * rpi) {
     const long long i0 = r * cvec + cg;
     const long long i1 = (r + rpi) * cvec + cg;
@@ -206,7 +206,7 @@ __global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* _
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += gv[j];
-        a2[j] = fmaf(gv[j], (xv[j] - mu[j]) * is[j], a2[j]);
+        a2[j] = fmaf(gv[j], xv[j], a2[j]);
       }
     }
   }
@@ -241,11 +241,14 @@ __global__ void bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* _
 // the apply pass: m1 = dbeta / count, m2 = dgamma / count.
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int T, int C, double count,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate,
-                                       float* __restrict__ m1, float* __restrict__ m2, void* scratch) {
+                                       float* __restrict__ m1, float* __restrict__ m2, const float* __restrict__ mean,
+                                       const float* __restrict__ invstd, void* scratch) {
   double s, ss;
   const bool owner = reduce_partials_last_block(partial, T, C, scratch, s, ss);
   if (owner) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    // the reduce pass accumulated sum(dz * x) with the raw x: sum(dz * xhat) = invstd * (sum(dz*x) - mean * sum(dz))
+    if (mean != nullptr) ss = static_cast<double>(invstd[c]) * (ss - static_cast<double>(mean[c]) * s);
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + static_cast<float>(s) : static_cast<float>(s);
     if (dgamma) dgamma[c] = accumulate ? dgamma[c] + static_cast<float>(ss) : static_cast<float>(ss);
     if (m1) m1[c] = static_cast<float>(s / count);

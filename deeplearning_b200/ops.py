@@ -278,8 +278,8 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     partial = torch.empty(nblk, 2, C, dtype=F32, device=x.device)
     dz = torch.empty_like(x) if want_dz else None
     sp = _span("bn_bwd_reduce", 0.0, _nb(g, x, y_out, dz))
-    rc = lib.b200_bn_bwd_reduce(_p(g), _p(x), _p(y_out), _p(dz), _p(co.scale), _p(co.shift), _p(co.mean),
-                                _p(co.invstd), 1 if relu else 0, rows, C, _p(partial), _stream())
+    rc = lib.b200_bn_bwd_reduce(_p(g), _p(x), _p(y_out), _p(dz), _p(co.scale), _p(co.shift), 1 if relu else 0, rows, C,
+                                _p(partial), _stream())
     _lib.check(rc, "b200_bn_bwd_reduce")
     if sp:
         sp.end()
@@ -290,7 +290,7 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     m = torch.empty(2, C, dtype=F32, device=x.device)
     sc = _reduce_scratch(x.device)
     rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, float(rows), _p(dgamma), _p(dbeta), acc, _p(m[0]), _p(m[1]),
-                                  _p(sc), sc.numel(), _stream())
+                                  _p(co.mean), _p(co.invstd), _p(sc), sc.numel(), _stream())
     _lib.check(rc, "b200_bn_bwd_finalize")
     dx = torch.empty_like(x)
     src = dz if want_dz else g
@@ -495,7 +495,8 @@ def layernorm_bwd(dy, x, mean, rstd, gamma, add=None, dx_dtype=BF16, dgamma=None
         dgamma = torch.empty(C, dtype=F32, device=x.device)
         dbeta = torch.empty(C, dtype=F32, device=x.device)
     sc = _reduce_scratch(x.device)
-    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, 1.0, _p(dgamma), _p(dbeta), 0, None, None, _p(sc), sc.numel(), _stream())
+    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, 1.0, _p(dgamma), _p(dbeta), 0, None, None, None, None, _p(sc),
+                                  sc.numel(), _stream())
     _lib.check(rc, "b200_bn_bwd_finalize")
     return dx, dgamma, dbeta
 
@@ -550,7 +551,8 @@ def colsum_tall(m, cols=None, out=None):
     if out is None:
         out = torch.empty(cols, dtype=F32, device=m.device)
     sc = _reduce_scratch(m.device)
-    rc = lib.b200_bn_bwd_finalize(_p(partial), S, cols, 1.0, None, _p(out), 0, None, None, _p(sc), sc.numel(), _stream())
+    rc = lib.b200_bn_bwd_finalize(_p(partial), S, cols, 1.0, None, _p(out), 0, None, None, None, None, _p(sc), sc.numel(),
+                                  _stream())
     _lib.check(rc, "b200_bn_bwd_finalize")
     return out
 

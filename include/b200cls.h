@@ -138,15 +138,16 @@ int b200_bn_eval_coeffs(int C, const float* gamma, const float* beta, const floa
 /* y = act(x*scale[c]+shift[c] (+residual)); x,y,residual bf16 [rows][C] */
 int b200_bn_apply(const void* x, const void* residual, void* y, const float* scale, const float* shift, long long rows,
                   int C, int relu, void* stream);
-/* backward pass 1: partial[b200_bn_bwd_blocks()][2][C] = per-block sums of dz and dz*xhat, dz = g*relu_mask.
+/* backward pass 1: partial[b200_bn_bwd_blocks()][2][C] = per-block sums of dz and dz*x (raw x), dz = g*relu_mask;
+ * b200_bn_bwd_finalize(mean, invstd) turns the second into sum(dz*xhat).
  *   y_out (optional) = saved post-activation output used for the mask; otherwise the mask is recomputed from x.
  *   dz_out (optional) receives dz as bf16. */
 int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
-                       const float* shift, const float* mean, const float* invstd, int relu, long long rows, int C,
-                       float* partial, void* stream);
+                       const float* shift, int relu, long long rows, int C, float* partial, void* stream);
 int b200_bn_bwd_blocks(long long rows, int C);
 int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
-                         float* m1, float* m2, void* scratch, size_t scratch_bytes, void* stream);
+                         float* m1, float* m2, const float* mean, const float* invstd, void* scratch,
+                         size_t scratch_bytes, void* stream);
 /* backward pass 2: dx = scale*(dz - m1 - xhat*m2); g_is_dz != 0 means `g` already holds dz (mask applied). */
 int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
                       const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,

@@ -105,8 +105,42 @@ def mnist_fixture():
     return out
 
 
+def vit_fixture():
+    from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k as mine_ctor
+    from oracle.vit import train_step_grads, vit_forward
+
+    ref_mod = _load(f"{REF}/classification/vision_transformer/vit_model.py", "ref_vit_model")
+    out = {}
+    for has_logits in (False, True):
+        torch.manual_seed(0)
+        ref = ref_mod.vit_base_patch16_224_in21k(num_classes=1000, has_logits=has_logits)
+        torch.manual_seed(0)
+        mine = mine_ctor(num_classes=1000, has_logits=has_logits)
+        sr = {k: v.clone() for k, v in ref.state_dict().items()}
+        sm = mine.state_dict()
+        assert list(sr) == list(sm) and all(torch.equal(sr[k], sm[k]) for k in sr), "ViT ctor init differs"
+        x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+        y = torch.randint(0, 1000, (2,), generator=torch.Generator().manual_seed(2))
+        ref.eval()
+        with torch.no_grad():
+            le = ref(x)
+            assert torch.equal(le, vit_forward(sr, x)), "oracle ViT forward differs from the reference"
+        ref.train()
+        lt = ref(x)
+        loss = F.cross_entropy(lt, y)
+        loss.backward()
+        lg, lo, grads = train_step_grads(sr, x, y)
+        assert torch.equal(lg, lt.detach()) and float(lo) == float(loss.detach())
+        for n, p in ref.named_parameters():
+            assert torch.equal(p.grad, grads[n]), n
+        out[f"has_logits={has_logits}"] = {"init_abs_sum": {k: float(v.double().abs().sum()) for k, v in sr.items()},
+                                           "eval_logits": le.clone(), "train_loss": float(loss.detach()),
+                                           "grad_norms": _grad_norms(ref.named_parameters())}
+    return out
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    fx = {"resnet50": resnet50_fixture(), "mnist": mnist_fixture(), "torch": torch.__version__}
+    fx = {"resnet50": resnet50_fixture(), "mnist": mnist_fixture(), "vit_b16": vit_fixture(), "torch": torch.__version__}
     torch.save(fx, os.path.join(HERE, "classification_golden.pt"))
     print("golden fixtures written:", os.path.join(HERE, "classification_golden.pt"), os.path.getsize(os.path.join(HERE, "classification_golden.pt")), "bytes")

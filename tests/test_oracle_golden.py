@@ -74,3 +74,24 @@ def test_mnist_plumbing_config(name):
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-5)
     opt.step()
     assert float(F.cross_entropy(model(x), y)) < float(loss.detach())
+
+
+@pytest.mark.parametrize("has_logits", [False, True])
+def test_vit_b16_init_and_oracle_match_reference(has_logits):
+    from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
+    from oracle.vit import train_step_grads, vit_forward
+
+    fx = FX["vit_b16"][f"has_logits={has_logits}"]
+    torch.manual_seed(0)
+    state = {k: v.clone() for k, v in vit_base_patch16_224_in21k(num_classes=1000, has_logits=has_logits).state_dict().items()}
+    for k, v in fx["init_abs_sum"].items():
+        assert abs(float(state[k].double().abs().sum()) - v) <= 1e-9 * (1 + abs(v)), k
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 1000, (2,), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        _close(vit_forward(state, x), fx["eval_logits"])
+    _, loss, grads = train_step_grads(state, x, y)
+    assert abs(float(loss) - fx["train_loss"]) < 1e-4
+    for n, g in grads.items():
+        ref = fx["grad_norms"][n]
+        assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n

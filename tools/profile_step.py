@@ -3,12 +3,17 @@ python tools/profile_step.py [batch]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from deeplearning_b200.classification.resnet.models.networks import resnet50
 from deeplearning_b200.engine.trainer import TrainStep
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+which = sys.argv[2] if len(sys.argv) > 2 else "resnet50"
 torch.manual_seed(0)
-m = resnet50().cuda().train()
+if which == "resnet50":
+    from deeplearning_b200.classification.resnet.models.networks import resnet50
+    m = resnet50().cuda().train()
+else:
+    from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
+    m = vit_base_patch16_224_in21k(num_classes=1000, has_logits=False).cuda().train()
 tr = TrainStep(m)
 x = torch.randn(B, 3, 224, 224, device="cuda")
 y = torch.randint(0, 1000, (B,), device="cuda")
