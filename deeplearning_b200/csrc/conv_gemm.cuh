@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         for (int kb = 0; kb < num_kb; ++kb) {
           const int tap = kb / p.k_blocks_per_tap;
           const int cb = kb - tap * p.k_blocks_per_tap;
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -163,11 +163,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_backoff(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
           const uint32_t b_addr = a_addr + Cfg::A_BYTES;
@@ -196,11 +196,31 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const int q = warp_idx & 3;   // TMEM lane quadrant this warp may access
     const int pair = ew >> 2;     // which of the two warps sharing the quadrant
     const int row = q * 32 + lane;
-    uint8_t* my_stage = staging + ew * 2 * Cfg::SLAB_BYTES;
+    const uint32_t stage_s = smem_u32(staging + ew * 2 * Cfg::SLAB_BYTES);
+    const uint32_t row_s = lane * 128;          // this thread's row inside a slab
+    const uint32_t sw = (lane & 7) << 4;        // 128B-swizzle XOR term of that row
+    // statistics read-back: lane owns columns 2*lane, 2*lane+1 -> 4-byte word `lane` of every row
+    uint32_t stat_off[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) stat_off[m] = m * 128 + ((((lane >> 2) ^ m) << 4) | ((lane & 3) << 2));
+    // kernel parameters used in the inner loops, hoisted into registers
+    const int N = p.N;
+    const float* const bias = p.bias;
+    const int act = p.act;
+    const bool has_res = p.residual != nullptr;
+    const bool has_aux = p.has_aux_out != 0;
+    const bool out_f32 = p.out_f32 != 0;
+    float* const out_direct = p.out_direct;
+    float* const stats = p.stats;
+    const bool need_rowmap = has_res || act == 3 || out_direct != nullptr || p.dim1 % p.box1 != 0 ||
+                             p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0;
+    const bool full_cols = (N % BLOCK_N) == 0;  // no partially valid 32-column group anywhere
     uint32_t store_counter = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const int nsub = p.out_f32 ? 1 : 2;  // 32-column TMEM loads per unit
+    const int nsub = out_f32 ? 1 : 2;  // 32-column TMEM loads per unit
+    int last_unit = pair;
+    while (last_unit + 2 < units) last_unit += 2;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
@@ -208,29 +228,31 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       const int t2 = (m_tile / p.tiles1) % p.tiles2;
       const int t3 = m_tile / (p.tiles1 * p.tiles2);
       const int c1 = t1 * p.box1, c2 = t2 * p.box2, c3 = t3 * p.box3;
-      const int i1 = row % p.box1;
-      const int i2 = (row / p.box1) % p.box2;
-      const int i3 = row / (p.box1 * p.box2);
-      const int p1 = c1 + i1, p2 = c2 + i2, p3 = c3 + i3;
-      const bool row_ok = (p1 < p.dim1) && (p2 < p.dim2) && (p3 < p.dim3);
+      int p1 = 0, p2 = 0, p3 = 0;
+      bool row_ok = true;
+      if (need_rowmap) {
+        const int i1 = row % p.box1;
+        const int i2 = (row / p.box1) % p.box2;
+        const int i3 = row / (p.box1 * p.box2);
+        p1 = c1 + i1, p2 = c2 + i2, p3 = c3 + i3;
+        row_ok = (p1 < p.dim1) && (p2 < p.dim2) && (p3 < p.dim3);
+      }
       const int s1 = c1 + p.qoff1[q], s2 = c2 + p.qoff2[q], s3 = c3 + p.qoff3[q];
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 
-      int last_unit = pair;
-      while (last_unit + 2 < units) last_unit += 2;
 #pragma unroll 1
       for (int u = pair; u < units; u += 2) {
         const int n0 = n_tile * BLOCK_N + u * unit_cols;
-        const bool chunk_live = n0 < p.N;  // warp-uniform
-        uint8_t* buf = my_stage + (store_counter & 1) * Cfg::SLAB_BYTES;
-        uint8_t* buf_aux = my_stage + ((store_counter + 1) & 1) * Cfg::SLAB_BYTES;
-        if (chunk_live && p.out_direct == nullptr) {
-          // the TMA store that last used `buf` (two stores ago) must have finished reading it
+        const bool chunk_live = n0 < N;  // warp-uniform
+        const uint32_t buf_s = stage_s + (store_counter & 1) * Cfg::SLAB_BYTES;
+        const uint32_t aux_s = stage_s + ((store_counter + 1) & 1) * Cfg::SLAB_BYTES;
+        if (chunk_live && out_direct == nullptr) {
+          // the TMA store that last used this slab (two stores ago) must have finished reading it
           if (lane == 0) {
-            if (p.has_aux_out) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+            if (has_aux) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
           }
           __syncwarp();
         }
@@ -250,35 +272,41 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias != nullptr) {
+          if (bias != nullptr) {
+            if (full_cols) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] += (nc + j < p.N) ? __ldg(p.bias + nc + j) : 0.0f;
-          }
-          if (p.has_aux_out) {
-            // pre-activation copy (bf16) for the backward pass
-            uint8_t* rowp = buf_aux + lane * 128;
+              for (int j = 0; j < 8; ++j) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nc) + j);
+                f[j * 4 + 0] += b4.x;
+                f[j * 4 + 1] += b4.y;
+                f[j * 4 + 2] += b4.z;
+                f[j * 4 + 3] += b4.w;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 w;
-              const float z = row_ok ? 1.f : 0.f;
-              w.x = pack_bf16x2(f[j * 8 + 0] * z, f[j * 8 + 1] * z);
-              w.y = pack_bf16x2(f[j * 8 + 2] * z, f[j * 8 + 3] * z);
-              w.z = pack_bf16x2(f[j * 8 + 4] * z, f[j * 8 + 5] * z);
-              w.w = pack_bf16x2(f[j * 8 + 6] * z, f[j * 8 + 7] * z);
-              *reinterpret_cast<uint4*>(rowp + (((h * 4 + j) ^ (lane & 7)) << 4)) = w;
+              for (int j = 0; j < 32; ++j) f[j] += (nc + j < N) ? __ldg(bias + nc + j) : 0.0f;
             }
           }
-          if (p.act == 1) {
+          if (has_aux) {
+            // pre-activation copy (bf16) for the backward pass
+            const float z = row_ok ? 1.f : 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts128(aux_s + row_s + ((((h * 4 + j) << 4)) ^ sw), pack_bf16x2(f[j * 8 + 0] * z, f[j * 8 + 1] * z),
+                     pack_bf16x2(f[j * 8 + 2] * z, f[j * 8 + 3] * z), pack_bf16x2(f[j * 8 + 4] * z, f[j * 8 + 5] * z),
+                     pack_bf16x2(f[j * 8 + 6] * z, f[j * 8 + 7] * z));
+          }
+          if (act == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-          } else if (p.act == 2) {
+          } else if (act == 2) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          } else if (p.act == 3 && row_ok) {
+          } else if (act == 3 && row_ok) {
             const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + p3 * p.as3 + p2 * p.as2 + p1 * p.as1 + nc);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              if (nc + j * 8 < p.N) {
+              if (full_cols || nc + j * 8 < N) {
                 float a[8];
                 unpack8(__ldg(ap + j), a);
 #pragma unroll
@@ -286,13 +314,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               }
             }
           }
-          if (p.residual != nullptr && row_ok) {
+          if (has_res && row_ok) {
             const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc;
             if (p.res_f32) {
               const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                if (nc + j * 4 < p.N) {
+                if (full_cols || nc + j * 4 < N) {
                   const float4 r = __ldg(rp + j);
                   f[j * 4 + 0] += r.x;
                   f[j * 4 + 1] += r.y;
@@ -304,7 +332,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                if (nc + j * 8 < p.N) {
+                if (full_cols || nc + j * 8 < N) {
                   float r[8];
                   unpack8(__ldg(rp + j), r);
 #pragma unroll
@@ -313,13 +341,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               }
             }
           }
-          if (p.out_direct != nullptr) {
+          if (out_direct != nullptr) {
             if (row_ok) {
               const long long pix = (static_cast<long long>(p3) * p.dim2 + p2) * p.dim1 + p1;
-              float* op = p.out_direct + pix * p.ld_out + nc;
+              float* op = out_direct + pix * p.ld_out + nc;
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (nc + j < p.N) op[j] = f[j];
+                if (nc + j < N) op[j] = f[j];
             }
             continue;
           }
@@ -328,58 +356,60 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = 0.f;
           }
-          uint8_t* rowp = buf + lane * 128;
-          if (p.out_f32) {
+          if (out_f32) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(rowp + ((j ^ (lane & 7)) << 4)) =
-                  make_float4(f[j * 4 + 0], f[j * 4 + 1], f[j * 4 + 2], f[j * 4 + 3]);
+              sts128(buf_s + row_s + ((j << 4) ^ sw), __float_as_uint(f[j * 4 + 0]), __float_as_uint(f[j * 4 + 1]),
+                     __float_as_uint(f[j * 4 + 2]), __float_as_uint(f[j * 4 + 3]));
           } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 w;
-              w.x = pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]);
-              w.y = pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]);
-              w.z = pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]);
-              w.w = pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]);
-              *reinterpret_cast<uint4*>(rowp + (((h * 4 + j) ^ (lane & 7)) << 4)) = w;
-            }
+            for (int j = 0; j < 4; ++j)
+              sts128(buf_s + row_s + (((h * 4 + j) << 4) ^ sw), pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]),
+                     pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]), pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]),
+                     pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]));
           }
         }
-        if (!chunk_live || p.out_direct != nullptr) continue;
+        if (!chunk_live || out_direct != nullptr) continue;
         __syncwarp();
-        if (p.stats != nullptr) {
+        if (stats != nullptr) {
           // Column sums over this warp's 32 rows, read back from the (bf16-rounded) slab: lane l owns columns 2l, 2l+1;
-          // bank-conflict-free thanks to the 128B swizzle. One partial row per (tile, quadrant): no cross-warp traffic.
-          float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
-#pragma unroll 8
+          // bank-conflict-free thanks to the 128B swizzle; packed fp32x2 adds / fmas. One partial row per (tile, quadrant).
+          uint64_t a_s = 0, a_q = 0;
+#pragma unroll
           for (int r = 0; r < 32; ++r) {
-            const uint32_t w =
-                *reinterpret_cast<const uint32_t*>(buf + r * 128 + ((((lane >> 2) ^ (r & 7)) << 4) | ((lane & 3) << 2)));
-            const float a = bf16_lo(w), b = bf16_hi(w);
-            a0 += a;
-            a1 += b;
-            q0 = fmaf(a, a, q0);
-            q1 = fmaf(b, b, q1);
+            const uint32_t w = lds32(buf_s + (r >> 3) * 1024 + stat_off[r & 7]);
+            const uint64_t x2 = f2_pack(bf16_lo(w), bf16_hi(w));
+            a_s = f2_add(a_s, x2);
+            a_q = f2_fma(x2, x2, a_q);
           }
           const int col = n0 + 2 * lane;
-          if (col < p.N) {
-            float* sp = p.stats + (static_cast<long long>(m_tile) * 4 + q) * 2 * p.N + col;
-            *reinterpret_cast<float2*>(sp) = make_float2(a0, a1);
-            *reinterpret_cast<float2*>(sp + p.N) = make_float2(q0, q1);
+          if (col < N) {
+            float s_lo, s_hi, q_lo, q_hi;
+            f2_unpack(a_s, s_lo, s_hi);
+            f2_unpack(a_q, q_lo, q_hi);
+            float* sp = stats + (static_cast<long long>(m_tile) * 4 + q) * 2 * N + col;
+            *reinterpret_cast<float2*>(sp) = make_float2(s_lo, s_hi);
+            *reinterpret_cast<float2*>(sp + N) = make_float2(q_lo, q_hi);
           }
         }
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          tma_store_4d(&p.d_map, buf, n0, s1, s2, s3);
+          // (cp.async.bulk takes a shared-window address: reuse the 32-bit slab address)
+          asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                           reinterpret_cast<uint64_t>(&p.d_map)),
+                       "r"(buf_s), "r"(n0), "r"(s1), "r"(s2), "r"(s3)
+                       : "memory");
           tma_store_commit();
-          if (p.has_aux_out) {
-            tma_store_4d(&p.aux_map, buf_aux, n0, s1, s2, s3);
+          if (has_aux) {
+            asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                             reinterpret_cast<uint64_t>(&p.aux_map)),
+                         "r"(aux_s), "r"(n0), "r"(s1), "r"(s2), "r"(s3)
+                         : "memory");
             tma_store_commit();
           }
         }
-        store_counter += p.has_aux_out ? 2 : 1;
+        store_counter += has_aux ? 2 : 1;
       }
       if (++acc == 2) {
         acc = 0;
