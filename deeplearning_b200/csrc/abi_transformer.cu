@@ -17,7 +17,7 @@ inline int grid_for(long long items, int per_block, int cap_mult = 16) {
   return static_cast<int>(blocks);
 }
 int ln_bwd_blocks(long long rows) {
-  long long b = static_cast<long long>(device_sm_count()) * 2;
+  long long b = static_cast<long long>(device_sm_count()) * 3;
   if (b > (rows + 7) / 8) b = (rows + 7) / 8;
   return static_cast<int>(b < 1 ? 1 : b);
 }
@@ -64,17 +64,28 @@ int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* me
   const int grid = ln_bwd_blocks(rows);
   const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
   const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
-#define LN_BWD(TI, TO)                                                                                              \
+#define LN_BWD_V(TI, TO, MV)                                                                                       \
   do {                                                                                                              \
     static bool cfg = false;                                                                                        \
     if (!cfg) {                                                                                                     \
-      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TI, TO, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TI, TO, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            8 * 2 * 1024 * (int)sizeof(float)));                                     \
       cfg = true;                                                                                                   \
     }                                                                                                               \
-    layernorm_bwd_kernel<TI, TO, 4><<<grid, 256, smem, st>>>(dyp, static_cast<const TI*>(x), mean, rstd, gamma,      \
-                                                             static_cast<const TO*>(add), static_cast<TO*>(dx),    \
-                                                             partial, rows, C);                                     \
+    layernorm_bwd_kernel<TI, TO, MV><<<grid, 256, smem, st>>>(dyp, static_cast<const TI*>(x), mean, rstd, gamma,     \
+                                                              static_cast<const TO*>(add), static_cast<TO*>(dx),   \
+                                                              partial, rows, C);                                    \
+  } while (0)
+#define LN_BWD(TI, TO)                  \
+  do {                                  \
+    if (C <= 256)                       \
+      LN_BWD_V(TI, TO, 1);              \
+    else if (C <= 512)                  \
+      LN_BWD_V(TI, TO, 2);              \
+    else if (C <= 768)                  \
+      LN_BWD_V(TI, TO, 3);              \
+    else                                \
+      LN_BWD_V(TI, TO, 4);              \
   } while (0)
   if (x_f32 && dx_f32)
     LN_BWD(float, float);
@@ -85,6 +96,7 @@ int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* me
   else
     LN_BWD(__nv_bfloat16, __nv_bfloat16);
 #undef LN_BWD
+#undef LN_BWD_V
   B200_LAUNCHED();
   return OK;
 }

@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   // take alternate units; with a single unit per tile the second warp of each pair has nothing to do.
   const int unit_cols = p.out_f32 ? 32 : 64;
   const int units = BLOCK_N / unit_cols;
-  const int active_epi_warps = units >= 2 ? 8 : 4;
+  // (with one unit per tile the two warps of a pair alternate TILES instead: pair p drains accumulator buffer p)
+  const int arrivals_per_acc = units >= 2 ? 8 : 4;
 
   if (warp_idx == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_maps[i]);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], active_epi_warps);  // one arrive per active epilogue warp
+      mbar_init(&tmem_empty[i], arrivals_per_acc);  // one arrive per epilogue warp that drains this buffer
     }
     fence_mbar_init();
   }
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         }
       }
     }
-  } else if (warp_idx - 2 < active_epi_warps) {
+  } else {
     // ===================== Epilogue: 8 independent warps, no CTA-level barriers =====================
     const int ew = warp_idx - 2;
     const int q = warp_idx & 3;   // TMEM lane quadrant this warp may access
@@ -216,12 +217,16 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                              p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0;
     const bool full_cols = (N % BLOCK_N) == 0;  // no partially valid 32-column group anywhere
     uint32_t store_counter = 0;
-    int acc = 0;
-    uint32_t acc_phase = 0;
     const int nsub = out_f32 ? 1 : 2;  // 32-column TMEM loads per unit
-    int last_unit = pair;
+    const bool split_tiles = units < 2;  // single unit: the pair alternates tiles
+    const int u_first = split_tiles ? 0 : pair;
+    int last_unit = u_first;
     while (last_unit + 2 < units) last_unit += 2;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      if (split_tiles && (it & 1) != pair) continue;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int t1 = m_tile % p.tiles1;
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       const uint32_t tmem_acc = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 
 #pragma unroll 1
-      for (int u = pair; u < units; u += 2) {
+      for (int u = u_first; u < units; u += 2) {
         const int n0 = n_tile * BLOCK_N + u * unit_cols;
         const bool chunk_live = n0 < N;  // warp-uniform
         const uint32_t buf_s = stage_s + (store_counter & 1) * Cfg::SLAB_BYTES;
@@ -410,10 +415,6 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           }
         }
         store_counter += has_aux ? 2 : 1;
-      }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
       }
     }
     if (lane == 0) tma_store_wait_all<0>();

@@ -93,19 +93,19 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __r
 }
 
 // dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat)) (+ add);  partial[block][2][C] = (sum dy, sum dy*xhat)
+// The per-column parameter-gradient accumulators live in shared memory (one private [2][C] slice per warp, updated with
+// conflict-free float4 read-modify-writes) so that the register budget only has to hold one row.
 template <typename TIn, typename TOut, int MAXV>
-__global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x,
-                                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ gamma, const TOut* __restrict__ add,
-                                     TOut* __restrict__ dx, float* __restrict__ partial, long long rows, int C) {
+__global__ void __launch_bounds__(256, 3)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
+                     const float* __restrict__ rstd, const float* __restrict__ gamma, const TOut* __restrict__ add,
+                     TOut* __restrict__ dx, float* __restrict__ partial, long long rows, int C) {
   extern __shared__ float red[];  // [warps][2][C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int nvec = C >> 3;
-  float ab[MAXV][8], ag[MAXV][8];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ab[i][j] = ag[i][j] = 0.f;
+  float* mine = red + static_cast<long long>(warp) * 2 * C;
+  for (int i = lane; i < 2 * C; i += 32) mine[i] = 0.f;
+  __syncwarp();
   const long long warp0 = blockIdx.x * static_cast<long long>(nw) + warp;
   const long long nwarps = static_cast<long long>(gridDim.x) * nw;
   for (long long r = warp0; r < rows; r += nwarps) {
@@ -120,15 +120,23 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
         load_row8<TIn>(x + r * C + vi * 8, xv);
         unpack8(*reinterpret_cast<const uint4*>(dy + r * C + vi * 8), dv);
         load8f(gamma + vi * 8, g);
+        float4* ab = reinterpret_cast<float4*>(mine + vi * 8);
+        float4* ag = reinterpret_cast<float4*>(mine + C + vi * 8);
+        float4 b0 = ab[0], b1 = ab[1], g0 = ag[0], g1 = ag[1];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[i][j] = (xv[j] - mu) * rs;
           dg[i][j] = dv[j] * g[j];
           s1 += dg[i][j];
           s2 = fmaf(dg[i][j], xh[i][j], s2);
-          ab[i][j] += dv[j];
-          ag[i][j] = fmaf(dv[j], xh[i][j], ag[i][j]);
         }
+        b0.x += dv[0]; b0.y += dv[1]; b0.z += dv[2]; b0.w += dv[3];
+        b1.x += dv[4]; b1.y += dv[5]; b1.z += dv[6]; b1.w += dv[7];
+        g0.x = fmaf(dv[0], xh[i][0], g0.x); g0.y = fmaf(dv[1], xh[i][1], g0.y);
+        g0.z = fmaf(dv[2], xh[i][2], g0.z); g0.w = fmaf(dv[3], xh[i][3], g0.w);
+        g1.x = fmaf(dv[4], xh[i][4], g1.x); g1.y = fmaf(dv[5], xh[i][5], g1.y);
+        g1.z = fmaf(dv[6], xh[i][6], g1.z); g1.w = fmaf(dv[7], xh[i][7], g1.w);
+        ab[0] = b0; ab[1] = b1; ag[0] = g0; ag[1] = g1;
       }
     }
     s1 = warp_sum(s1) / C;
@@ -147,19 +155,6 @@ __global__ void layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const
           for (int j = 0; j < 8; ++j) o[j] += a[j];
         }
         store_row8<TOut>(dx + r * C + vi * 8, o);
-      }
-    }
-  }
-  // block-level column reduction of the parameter-gradient partials
-  float* mine = red + static_cast<long long>(warp) * 2 * C;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = i * 32 + lane;
-    if (vi < nvec) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        mine[vi * 8 + j] = ab[i][j];
-        mine[C + vi * 8 + j] = ag[i][j];
       }
     }
   }
