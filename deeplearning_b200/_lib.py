@@ -25,7 +25,8 @@ class View(ctypes.Structure):
 
 class GemmArgs(ctypes.Structure):
     """b200_gemm_args_t"""
-    _fields_ = [("w", c_void_p), ("N", c_int), ("K", c_int), ("bias", c_void_p), ("act", c_int), ("out_f32", c_int),
+    _fields_ = [("w", c_void_p), ("N", c_int), ("K", c_int), ("bias", c_void_p), ("colscale", c_void_p), ("act", c_int),
+                ("out_f32", c_int),
                 ("residual", ctypes.POINTER(View)), ("residual_f32", c_int), ("aux_out", ctypes.POINTER(View)),
                 ("aux_in", ctypes.POINTER(View)), ("stats", c_void_p)]
 
@@ -43,7 +44,7 @@ SIGNATURES = {
     "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
     "b200_reduce_scratch_bytes": (c_size_t, [_I, _I]),
     "b200_gemm_ex": (_I, [ctypes.POINTER(View), ctypes.POINTER(View), ctypes.POINTER(GemmArgs), _P]),
-    "b200_layernorm_fwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _L, _I, _F, _P]),
+    "b200_layernorm_fwd": (_I, [_P, _I, _P, _P, _P, _I, _P, _P, _L, _I, _F, _P]),
     "b200_layernorm_bwd_blocks": (_I, [_L, _I]),
     "b200_layernorm_bwd": (_I, [_P, _P, _I, _P, _P, _P, _P, _P, _I, _P, _L, _I, _P]),
     "b200_patchify_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
@@ -54,6 +55,16 @@ SIGNATURES = {
     "b200_colsum_partial": (_I, [_P, _L, _L, _I, _P, _P]),
     "b200_attention_fwd": (_I, [_P, _P, _P, _I, _I, _I, _F, _P]),
     "b200_attention_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
+    "b200_conv2d_wgrad_set_rowscale": (_I, [_P]),
+    "b200_dwconv7_pack": (_I, [_P, _P, _I, _P]),
+    "b200_dwconv7": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "b200_dwconv7_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I]),
+    "b200_dwconv7_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _P]),
+    "b200_avgpool_any": (_I, [_P, _I, _P, _I, _I, _I, _P]),
+    "b200_colsum_prod_partial": (_I, [_P, _P, _L, _L, _I, _P, _P]),
+    "b200_layerscale_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
+    "b200_conv2d_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "b200_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
     "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),
     "b200_bn_apply": (_I, [_P, _P, _P, _P, _P, _L, _I, _I, _P]),

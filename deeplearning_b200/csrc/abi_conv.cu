@@ -13,6 +13,8 @@ namespace {
 // Descriptor strides; overridable through b200_debug_set_desc() for bring-up experiments only.
 uint32_t g_fwd_lbo = 16, g_fwd_sbo = 1024;
 uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024, g_wg_kstep = 2048;
+// one-shot per-output-channel multiplier for the next b200_conv2d_wgrad call (see b200_conv2d_wgrad_set_rowscale)
+thread_local const float* g_wgrad_rowscale = nullptr;
 
 struct Box3 {
   int b1, b2, b3;
@@ -39,7 +41,8 @@ Box3 choose_box(long long d1, long long d2, long long d3, int P) {
   return best;
 }
 
-inline int out_dim(int in, int ksize, int stride) { return (in + 2 * (ksize / 2) - ksize) / stride + 1; }
+inline int pad_of(int ksize) { return ksize == 2 ? 0 : ksize / 2; }  // 2x2/s2 patch-merging convs are unpadded
+inline int out_dim(int in, int ksize, int stride) { return (in + 2 * pad_of(ksize) - ksize) / stride + 1; }
 
 // 4-D activation view descriptor (channels innermost).
 struct View {
@@ -258,13 +261,22 @@ int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride) {
   return 4 * static_cast<int>(((d1 + bx.b1 - 1) / bx.b1) * ((d2 + bx.b2 - 1) / bx.b2) * ((d3 + bx.b3 - 1) / bx.b3));
 }
 
+static thread_local int g_conv_out_f32_tma = 0;
+
+int b200_conv2d_fwd_f32(const void* x, const void* w, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                        int stride, const float* bias, void* stream) {
+  g_conv_out_f32_tma = 1;
+  const int rc = b200_conv2d_fwd(x, w, y, B, H, W, Cin, Cout, ksize, stride, nullptr, bias, 0, nullptr, nullptr, 0, stream);
+  g_conv_out_f32_tma = 0;
+  return rc;
+}
+
 int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
                     float* stats, const float* bias, int act, const void* residual, float* out_f32, long long ld_out,
                     void* stream) {
-  B200_REQUIRE(ksize == 1 || ksize == 3, "conv2d_fwd: ksize %d unsupported (1 or 3)", ksize);
+  B200_REQUIRE(ksize == 1 || ksize == 3 || (ksize == 2 && stride == 2), "conv2d_fwd: ksize %d / stride %d unsupported", ksize, stride);
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_fwd: stride %d unsupported (1 or 2)", stride);
   B200_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_fwd: Cin=%d / Cout=%d must be multiples of 8", Cin, Cout);
-  B200_REQUIRE(ksize == 1 || Cin % 64 == 0, "conv2d_fwd: 3x3 needs Cin %% 64 == 0 (got %d)", Cin);
   B200_REQUIRE(B > 0 && H > 0 && W > 0, "conv2d_fwd: empty input");
   B200_REQUIRE(out_f32 == nullptr || (ksize == 1 && stride == 1), "conv2d_fwd: fp32 output only for 1x1/s1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -279,7 +291,7 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
   {
     View dv = flat ? make_flat_view(y, d1, Cout) : make_view(y, B, Ho, Wo, Cout, 1, 0, 0);
     if (out_f32 != nullptr) dv.base = nullptr;  // direct fp32 stores, no TMA map
-    if ((rc = setup_output(p, dv, Cout, 0, nullptr))) return rc;
+    if ((rc = setup_output(p, dv, Cout, g_conv_out_f32_tma, nullptr))) return rc;
   }
   const Box3 bx = box_of(p);
   const int BN = block_n_for(Cout);
@@ -307,7 +319,7 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
         if ((rc = encode_view(&p.a_maps[ph * 2 + pw], make_view(x, B, H, W, Cin, 2, ph, pw), bx))) return rc;
-    const int pad = ksize / 2;
+    const int pad = pad_of(ksize);
     for (int kh = 0; kh < ksize; ++kh)
       for (int kw = 0; kw < ksize; ++kw) {
         const int t = kh * ksize + kw;
@@ -339,10 +351,9 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
 
 int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, int W, int Cin, int Cout, int ksize,
                       int stride, const void* residual, void* stream) {
-  B200_REQUIRE(ksize == 1 || ksize == 3, "conv2d_dgrad: ksize %d unsupported", ksize);
+  B200_REQUIRE(ksize == 1 || ksize == 3 || (ksize == 2 && stride == 2), "conv2d_dgrad: ksize %d / stride %d unsupported", ksize, stride);
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_dgrad: stride %d unsupported", stride);
   B200_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_dgrad: Cin=%d / Cout=%d must be multiples of 8", Cin, Cout);
-  B200_REQUIRE(ksize == 1 || Cout % 64 == 0, "conv2d_dgrad: 3x3 needs Cout %% 64 == 0 (got %d)", Cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int Ho = out_dim(H, ksize, stride), Wo = out_dim(W, ksize, stride);
   const int taps = ksize * ksize;
@@ -355,7 +366,7 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
     uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
     if ((rc = encode_tmap_bf16(&b_map, wd, 2, dims, strides, box))) return rc;
   }
-  const int nphase = (stride == 2 && ksize == 3) ? 2 : 1;  // phases per spatial dim that need their own launch
+  const int nphase = (stride == 2 && ksize >= 2) ? 2 : 1;  // phases per spatial dim that need their own launch
   for (int ph = 0; ph < nphase; ++ph) {
     for (int pw = 0; pw < nphase; ++pw) {
       ConvGemmParams p;
@@ -387,6 +398,11 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
             p.tap_w[nt] = static_cast<int8_t>(kh * 3 + kw);
             ++nt;
           }
+      } else if (ksize == 2) {
+        // 2x2 / stride 2, unpadded: input pixel (2j+ph, 2i+pw) is touched by exactly one tap, (kh,kw) = (ph,pw), from (j,i)
+        p.tap_map[0] = 0, p.tap_o1[0] = 0, p.tap_o2[0] = 0;
+        p.tap_w[0] = static_cast<int8_t>(ph * 2 + pw);
+        nt = 1;
       } else {
         // stride 2, 3x3, pad 1: input row ih = 2j+ph receives taps kh with (ih + 1 - kh) even, from oh = (ih+1-kh)/2
         for (int kh = 0; kh < 3; ++kh) {
@@ -455,6 +471,7 @@ int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_a
   }
   p.stats = g->stats;
   p.bias = g->bias;
+  p.colscale = g->colscale;
   p.act = g->act;
   if (g->residual) {
     p.residual = g->residual->base;
@@ -469,6 +486,11 @@ int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_a
   return dispatch_conv_gemm(p, g->N, static_cast<cudaStream_t>(stream));
 }
 
+int b200_conv2d_wgrad_set_rowscale(const float* rowscale) {
+  g_wgrad_rowscale = rowscale;
+  return OK;
+}
+
 size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
   const WgradPlan pl = plan_wgrad(B, H, W, Cin, Cout, ksize, stride);
   return static_cast<size_t>(pl.splits) * Cout * pl.taps * Cin * sizeof(float);
@@ -476,7 +498,7 @@ size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout,
 
 int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
                       int W, int Cin, int Cout, int ksize, int stride, int accumulate, void* stream) {
-  B200_REQUIRE(ksize == 1 || ksize == 3, "conv2d_wgrad: ksize %d unsupported", ksize);
+  B200_REQUIRE(ksize == 1 || ksize == 3 || (ksize == 2 && stride == 2), "conv2d_wgrad: ksize %d / stride %d unsupported", ksize, stride);
   B200_REQUIRE(stride == 1 || stride == 2, "conv2d_wgrad: stride %d unsupported", stride);
   B200_REQUIRE(Cin % 8 == 0 && Cout % 8 == 0, "conv2d_wgrad: Cin=%d / Cout=%d must be multiples of 8", Cin, Cout);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -516,7 +538,7 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw)
         if ((rc = encode_view(&p.x_maps[ph * 2 + pw], make_view(x, B, H, W, Cin, 2, ph, pw), pl.box))) return rc;
-    const int pad = ksize / 2;
+    const int pad = pad_of(ksize);
     for (int kh = 0; kh < ksize; ++kh)
       for (int kw = 0; kw < ksize; ++kw) {
         const int t = kh * ksize + kw;
@@ -535,7 +557,8 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   const long long total = static_cast<long long>(Cout) * Cin * pl.taps;
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate);
+  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale);
+  g_wgrad_rowscale = nullptr;
   B200_LAUNCHED();
   return OK;
 }

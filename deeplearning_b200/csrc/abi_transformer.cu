@@ -4,6 +4,7 @@
 #include "../../include/b200cls.h"
 #include "attention.cuh"
 #include "host_utils.h"
+#include "convnext.cuh"
 #include "transformer.cuh"
 
 using namespace b200;
@@ -31,23 +32,30 @@ int encode3(CUtensorMap* m, const void* base, long long cols, long long T, long 
 
 extern "C" {
 
-int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* y, float* mean,
+int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int y_f32, float* mean,
                        float* rstd, long long rows, int C, float eps, void* stream) {
   B200_REQUIRE(C % 8 == 0 && C <= 3072, "layernorm_fwd: C=%d must be a multiple of 8 and <= 3072", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(rows, 8);
-  __nv_bfloat16* yo = static_cast<__nv_bfloat16*>(y);
-  if (C <= 1024) {
-    if (x_f32)
-      layernorm_fwd_kernel<float, 4><<<grid, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
-    else
-      layernorm_fwd_kernel<__nv_bfloat16, 4><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
-  } else {
-    if (x_f32)
-      layernorm_fwd_kernel<float, 12><<<grid, 256, 0, st>>>(static_cast<const float*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
-    else
-      layernorm_fwd_kernel<__nv_bfloat16, 12><<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(x), gamma, beta, yo, mean, rstd, rows, C, eps);
-  }
+#define LN_FWD(TI, TY, MV) \
+  layernorm_fwd_kernel<TI, TY, MV><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps)
+#define LN_FWD_T(MV)                                   \
+  do {                                                 \
+    if (x_f32 && y_f32)                                \
+      LN_FWD(float, float, MV);                        \
+    else if (x_f32)                                    \
+      LN_FWD(float, __nv_bfloat16, MV);                \
+    else if (y_f32)                                    \
+      LN_FWD(__nv_bfloat16, float, MV);                \
+    else                                               \
+      LN_FWD(__nv_bfloat16, __nv_bfloat16, MV);        \
+  } while (0)
+  if (C <= 1024)
+    LN_FWD_T(4);
+  else
+    LN_FWD_T(12);
+#undef LN_FWD_T
+#undef LN_FWD
   B200_LAUNCHED();
   return OK;
 }
@@ -148,6 +156,102 @@ int b200_colsum_partial(const void* m, long long rows, long long ld, int cols, f
   const int S = b200_colsum_partial_slices(rows);
   colsum_partial_kernel<<<dim3((cols + 63) / 64, S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(m), rows, ld, cols, partial);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_dwconv7_pack(const float* w, float* wt, int C, void* stream) {
+  dwconv7_pack_kernel<<<(49 * C + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(w, wt, C);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_dwconv7(const void* in, int in_f32, const float* wt, const float* bias, const void* add, void* out, int out_f32,
+                 int flip, int B, int H, int W, int C, void* stream) {
+  B200_REQUIRE(C % 4 == 0, "dwconv7: C=%d must be a multiple of 4", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long total = static_cast<long long>(B) * H * ((W + 3) / 4) * (C / 4);
+  const int grid = grid_for(total, 128, 32);
+#define DW(TI, TO, F) \
+  dwconv7_kernel<TI, TO, F><<<grid, 128, 0, st>>>(static_cast<const TI*>(in), wt, bias, static_cast<const TO*>(add), static_cast<TO*>(out), B, H, W, C)
+  if (in_f32 && !out_f32 && !flip)
+    DW(float, __nv_bfloat16, false);
+  else if (!in_f32 && !out_f32 && flip)
+    DW(__nv_bfloat16, __nv_bfloat16, true);
+  else if (!in_f32 && out_f32 && flip)
+    DW(__nv_bfloat16, float, true);
+  else if (in_f32 && out_f32 && !flip)
+    DW(float, float, false);
+  else {
+    set_error("dwconv7: unsupported type combination in_f32=%d out_f32=%d flip=%d", in_f32, out_f32, flip);
+    return EUNSUPPORTED_;
+  }
+#undef DW
+  B200_LAUNCHED();
+  return OK;
+}
+
+static int dw_wgrad_blocks_y(int B, int H) {
+  long long rows = static_cast<long long>(B) * H;
+  long long by = device_sm_count() * 2;
+  if (by > rows) by = rows;
+  return static_cast<int>(by < 1 ? 1 : by);
+}
+
+size_t b200_dwconv7_wgrad_workspace_bytes(int B, int H, int W, int C) {
+  (void)W;
+  return static_cast<size_t>(dw_wgrad_blocks_y(B, H)) * 49 * C * sizeof(float);
+}
+
+int b200_dwconv7_wgrad(const void* du, const float* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
+                       int W, int C, int accumulate, void* stream) {
+  B200_REQUIRE(C % 4 == 0, "dwconv7_wgrad: C=%d must be a multiple of 4", C);
+  const int by = dw_wgrad_blocks_y(B, H);
+  B200_REQUIRE(workspace != nullptr && workspace_bytes >= static_cast<size_t>(by) * 49 * C * sizeof(float),
+               "dwconv7_wgrad: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long rows = static_cast<long long>(B) * H;
+  const int rpb = static_cast<int>((rows + by - 1) / by);
+  dwconv7_wgrad_kernel<<<dim3((C / 4 + 31) / 32, by), 224, 0, st>>>(static_cast<const __nv_bfloat16*>(du), x,
+                                                                    static_cast<float*>(workspace), B, H, W, C, rpb);
+  B200_LAUNCHED();
+  dwconv7_wgrad_finalize_kernel<<<(49 * C + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), by, C, dw, accumulate);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_avgpool_any(const void* x, int x_f32, float* y, int B, int HW, int C, void* stream) {
+  B200_REQUIRE(C % 4 == 0, "avgpool_any: C=%d must be a multiple of 4", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(static_cast<long long>(B) * (C / 4), 128);
+  if (x_f32)
+    avgpool_any_fwd_kernel<float><<<grid, 128, 0, st>>>(static_cast<const float*>(x), y, B, HW, C);
+  else
+    avgpool_any_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(x), y, B, HW, C);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_colsum_prod_partial(const void* a, const void* b, long long rows, long long ld, int cols, float* partial,
+                             void* stream) {
+  const int S = b200_colsum_partial_slices(rows);
+  colsum_prod_partial_kernel<<<dim3((cols + 63) / 64, S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), rows, ld, cols, partial);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_layerscale_grads(const float* G, const float* W2, const float* b2, const float* gsum, const float* gamma,
+                          float* dW2, float* db2, float* dgamma, int C, int K, void* stream) {
+  layerscale_grads_kernel<<<C, 256, 0, static_cast<cudaStream_t>(stream)>>>(G, W2, b2, gsum, gamma, dW2, db2, dgamma, C, K);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, long long n, const float* hyper,
+               float beta1, float beta2, float eps, float gscale, void* stream) {
+  adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, wd, n, hyper, beta1, beta2,
+                                                                               eps, gscale);
   B200_LAUNCHED();
   return OK;
 }

@@ -41,6 +41,7 @@ struct alignas(64) ConvGemmParams {
   int8_t tap_w[kMaxTaps];    // which k_per_tap-wide slice of the weight matrix the tap multiplies
   float* stats;             // [4*m_tiles][2][N] partial sums (one row per 32-pixel slab), or null
   const float* bias;        // [N] or null
+  const float* colscale;    // [N] per-channel multiplier applied after bias/activation (layer scale), or null
   int act;                  // 0 none, 1 relu, 2 gelu(erf), 3 multiply by gelu'(aux_in) (backward of 2)
   int out_f32;              // 1: d_map is fp32 (32-channel slabs)
   int res_f32;              // 1: residual tensor is fp32
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     // kernel parameters used in the inner loops, hoisted into registers
     const int N = p.N;
     const float* const bias = p.bias;
+    const float* const colscale = p.colscale;
     const int act = p.act;
     const bool has_res = p.residual != nullptr;
     const bool has_aux = p.has_aux_out != 0;
@@ -318,6 +320,10 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                 for (int i = 0; i < 8; ++i) f[j * 8 + i] *= gelu_erf_grad(a[i]);
               }
             }
+          }
+          if (colscale != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= (full_cols || nc + j < N) ? __ldg(colscale + nc + j) : 0.0f;
           }
           if (has_res && row_ok) {
             const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc;

@@ -1,0 +1,264 @@
+// ConvNeXt-specific passes: 7x7 depthwise convolution forward / backward (CUDA cores, register-tiled strips of 4 output
+// pixels x 4 channels, NHWC), global average pool of the fp32 stream, column sums of an elementwise product (layer-scale
+// gradient) and the fused AdamW update.
+//
+// Reference: Block.forward of classification/convNext/models/networks.py:92-105 (dwconv 7x7 pad 3 groups=dim WITH bias ->
+// LN -> Linear -> GELU -> Linear -> gamma * x -> shortcut add), ConvNeXt.forward_features :160-165 (x.mean([-2,-1]) -> LN),
+// AdamW with decay / no-decay groups: classification/convNext/train.py:96,102 and utils.py:144-166.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y));
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, const float4& v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, const float4& v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, const float4& v) {
+  uint2 u;
+  u.x = pack_bf16x2(v.x, v.y);
+  u.y = pack_bf16x2(v.z, v.w);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// out[b,h,w,c] = bias[c] + sum_{kh,kw} wt[tap][c] * in[b, h+dh, w+dw, c]   (dh = kh-3, or 3-kh when FLIP) (+ add)
+// wt is the tap-major copy [49][C] of the [C,1,7,7] parameter. One thread: 4 consecutive output pixels x 4 channels.
+template <typename TIn, typename TOut, bool FLIP>
+__global__ void __launch_bounds__(128) dwconv7_kernel(const TIn* __restrict__ in, const float* __restrict__ wt,
+                                                       const float* __restrict__ bias, const TOut* __restrict__ add,
+                                                       TOut* __restrict__ out, int B, int H, int W, int C) {
+  const int c4n = C >> 2;
+  const int wstrips = (W + 3) >> 2;
+  const long long total = static_cast<long long>(B) * H * wstrips * c4n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    long long t = i / c4n;
+    const int w0 = static_cast<int>(t % wstrips) * 4;
+    t /= wstrips;
+    const int h = static_cast<int>(t % H);
+    const int b = static_cast<int>(t / H);
+    float4 acc[4];
+    const float4 bz = bias ? __ldg(reinterpret_cast<const float4*>(bias + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = bz;
+#pragma unroll 1
+    for (int kh = 0; kh < 7; ++kh) {
+      const int hh = h + kh - 3;
+      if (hh < 0 || hh >= H) continue;
+      const int krow = FLIP ? (6 - kh) : kh;
+      float4 wv[7];
+#pragma unroll
+      for (int kw = 0; kw < 7; ++kw)
+        wv[kw] = __ldg(reinterpret_cast<const float4*>(wt + static_cast<long long>(krow * 7 + (FLIP ? 6 - kw : kw)) * C + c));
+      const TIn* rowp = in + ((static_cast<long long>(b) * H + hh) * W) * C + c;
+#pragma unroll
+      for (int iw = 0; iw < 10; ++iw) {
+        const int ww = w0 + iw - 3;
+        if (ww < 0 || ww >= W) continue;
+        const float4 xv = ld4<TIn>(rowp + static_cast<long long>(ww) * C);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int kw = iw - j;
+          if (kw >= 0 && kw < 7) {
+            acc[j].x = fmaf(xv.x, wv[kw].x, acc[j].x);
+            acc[j].y = fmaf(xv.y, wv[kw].y, acc[j].y);
+            acc[j].z = fmaf(xv.z, wv[kw].z, acc[j].z);
+            acc[j].w = fmaf(xv.w, wv[kw].w, acc[j].w);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (w0 + j < W) {
+        const long long o = ((static_cast<long long>(b) * H + h) * W + w0 + j) * C + c;
+        float4 v = acc[j];
+        if (add != nullptr) {
+          const float4 a = ld4<TOut>(add + o);
+          v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+        }
+        st4<TOut>(out + o, v);
+      }
+    }
+  }
+}
+
+// Weight gradient partials: part[blockIdx.y][tap][c] = sum over this block's (b,h) rows of du[b,h,w,c] * x[b,h+kh-3,w+kw-3,c].
+// Block = 32 channel-quads x 7 kernel rows (224 threads); a thread keeps its 7 (kw) x 4 (channel) accumulators in registers.
+__global__ void __launch_bounds__(224) dwconv7_wgrad_kernel(const __nv_bfloat16* __restrict__ du, const float* __restrict__ x,
+                                                            float* __restrict__ part, int B, int H, int W, int C,
+                                                            int rows_per_block) {
+  const int cq = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int kh = threadIdx.x >> 5;  // 0..6
+  const int c = cq * 4;
+  const bool active = c < C;
+  float4 acc[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const long long nrows = static_cast<long long>(B) * H;
+  const long long r0 = static_cast<long long>(blockIdx.y) * rows_per_block;
+  const long long r1 = min(nrows, r0 + rows_per_block);
+  if (active) {
+    for (long long r = r0; r < r1; ++r) {
+      const int h = static_cast<int>(r % H);
+      const long long b = r / H;
+      const int hh = h + kh - 3;
+      if (hh < 0 || hh >= H) continue;
+      const __nv_bfloat16* dup = du + (r * W) * C + c;
+      const float* xp = x + ((b * H + hh) * W) * C + c;
+      for (int w0 = 0; w0 < W; w0 += 4) {
+        float4 d[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          d[j] = (w0 + j < W) ? ld4<__nv_bfloat16>(dup + static_cast<long long>(w0 + j) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int iw = 0; iw < 10; ++iw) {
+          const int ww = w0 + iw - 3;
+          if (ww < 0 || ww >= W) continue;
+          const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + static_cast<long long>(ww) * C));
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int kw = iw - j;
+            if (kw >= 0 && kw < 7) {
+              acc[kw].x = fmaf(d[j].x, xv.x, acc[kw].x);
+              acc[kw].y = fmaf(d[j].y, xv.y, acc[kw].y);
+              acc[kw].z = fmaf(d[j].z, xv.z, acc[kw].z);
+              acc[kw].w = fmaf(d[j].w, xv.w, acc[kw].w);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int kw = 0; kw < 7; ++kw)
+      *reinterpret_cast<float4*>(part + (static_cast<long long>(blockIdx.y) * 49 + kh * 7 + kw) * C + c) = acc[kw];
+  }
+}
+
+// dW[c][tap] (+)= sum_t part[t][tap][c]   ([C,1,7,7] parameter layout)
+__global__ void dwconv7_wgrad_finalize_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ dw,
+                                              int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over tap*C + c (coalesced reads)
+  if (i >= 49 * C) return;
+  const int c = i % C, tap = i / C;
+  float s = 0.f;
+  for (int t = 0; t < T; ++t) s += part[static_cast<long long>(t) * 49 * C + i];
+  float* o = dw + static_cast<long long>(c) * 49 + tap;
+  *o = accumulate ? *o + s : s;
+}
+
+// [C,1,7,7] fp32 parameter -> tap-major [49][C] copy
+__global__ void dwconv7_pack_kernel(const float* __restrict__ w, float* __restrict__ wt, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 49 * C) return;
+  const int c = i % C, tap = i / C;
+  wt[i] = w[static_cast<long long>(c) * 49 + tap];
+}
+
+// Global average pool of a [B][HW][C] tensor (fp32 or bf16) -> fp32 [B][C]; backward broadcasts g/HW (bf16 out).
+template <typename TIn>
+__global__ void avgpool_any_fwd_kernel(const TIn* __restrict__ x, float* __restrict__ y, int B, int HW, int C) {
+  const int c4n = C >> 2;
+  const long long total = static_cast<long long>(B) * c4n;
+  const float inv = 1.0f / HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(i % c4n) * 4;
+    const long long b = i / c4n;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = 0; p < HW; ++p) {
+      const float4 v = ld4<TIn>(x + (b * HW + p) * C + c);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    *reinterpret_cast<float4*>(y + b * C + c) = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+  }
+}
+
+// partial[slice][2][cols]: plane 0 = column sums of a[r][c] * b[r][c] (b optional), plane 1 = 0
+__global__ void colsum_prod_partial_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ bmat,
+                                           long long rows, long long ld, int cols, float* __restrict__ partial) {
+  __shared__ float sh[4][64];
+  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cx;
+  const int S = gridDim.y;
+  const long long chunk = (rows + S - 1) / S;
+  const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
+  float s = 0.f;
+  if (c < cols)
+    for (long long r = r0 + ry; r < r1; r += 4) {
+      const float av = __bfloat162float(a[r * ld + c]);
+      s += bmat ? av * __bfloat162float(bmat[r * ld + c]) : av;
+    }
+  sh[ry][cx] = s;
+  __syncthreads();
+  if (ry == 0 && c < cols) {
+    partial[(static_cast<long long>(blockIdx.y) * 2 + 0) * cols + c] = sh[0][cx] + sh[1][cx] + sh[2][cx] + sh[3][cx];
+    partial[(static_cast<long long>(blockIdx.y) * 2 + 1) * cols + c] = 0.f;
+  }
+}
+
+// Layer-scale bookkeeping of a ConvNeXt block, from the UNSCALED weight gradient G = g^T post of pwconv2 (out = gamma*(W2 post + b2)):
+//   dgamma[c] = sum_k W2[c,k] G[c,k] + b2[c] * gsum[c] ;  dW2[c,:] = gamma[c] * G[c,:] ;  db2[c] = gamma[c] * gsum[c]
+// (gsum = column sums of the upstream gradient g). One block per output channel c.
+__global__ void layerscale_grads_kernel(const float* __restrict__ G, const float* __restrict__ W2,
+                                        const float* __restrict__ b2, const float* __restrict__ gsum,
+                                        const float* __restrict__ gamma, float* __restrict__ dW2, float* __restrict__ db2,
+                                        float* __restrict__ dgamma, int C, int K) {
+  __shared__ float sh[8];
+  const int c = blockIdx.x;
+  const float ga = gamma ? gamma[c] : 1.0f;
+  float dot = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float gv = G[static_cast<long long>(c) * K + k];
+    dot = fmaf(W2[static_cast<long long>(c) * K + k], gv, dot);
+    dW2[static_cast<long long>(c) * K + k] = ga * gv;
+  }
+  dot = warp_sum(dot);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += sh[i];
+    const float gs = gsum[c];
+    if (dgamma) dgamma[c] = t + (b2 ? b2[c] : 0.f) * gs;
+    if (db2) db2[c] = ga * gs;
+  }
+}
+
+// Fused AdamW over flat fp32 arenas (torch.optim.AdamW semantics, amsgrad off):
+//   p *= 1 - lr*wd[i];  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+// hyper (device) = {lr, 1 - b1^t, 1 - b2^t}: kept on the device so a captured CUDA graph follows the schedule.
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, const float* __restrict__ wd, long long n,
+                             const float* __restrict__ hyper, float beta1, float beta2, float eps, float gscale) {
+  const float lr = __ldg(hyper), bc1 = __ldg(hyper + 1), bc2 = __ldg(hyper + 2);
+  const float step = lr / bc1, rsq = rsqrtf(bc2);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * gscale;
+    float pi = p[i] * (1.0f - lr * wd[i]);
+    const float mi = fmaf(beta1, m[i], (1.0f - beta1) * gi);
+    const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    pi -= step * mi / (sqrtf(vi) * rsq + eps);
+    p[i] = pi;
+  }
+}
+
+}  // namespace b200

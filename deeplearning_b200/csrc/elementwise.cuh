@@ -638,22 +638,24 @@ __global__ void im2col_nchw_kernel(const float* __restrict__ x, uint4* __restric
 }
 
 // Multi-tensor weight packing: one launch packs every conv / linear weight of a model.
-// table[e] = {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out} (int64 each); grid = total blocks.
+// table[e] = {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out, oscale} (int64 each); grid = total blocks.
+// oscale (optional fp32 [O]) multiplies every weight of output channel o (layer scale folded into the dgrad operand).
 __global__ void pack_weights_multi_kernel(const long long* __restrict__ table, int n_entries) {
   __shared__ int entry;
   if (threadIdx.x == 0) {
     int e = 0;
-    while (e + 1 < n_entries && table[(e + 1) * 9 + 7] <= static_cast<long long>(blockIdx.x)) ++e;
+    while (e + 1 < n_entries && table[(e + 1) * 10 + 7] <= static_cast<long long>(blockIdx.x)) ++e;
     entry = e;
   }
   __syncthreads();
-  const long long* t = table + entry * 9;
+  const long long* t = table + entry * 10;
   const float* src = reinterpret_cast<const float*>(t[0]);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(t[1]);
   const int O = static_cast<int>(t[2]), I = static_cast<int>(t[3]), taps = static_cast<int>(t[4]);
   const int mode = static_cast<int>(t[5]);
   const long long ld = t[6], first = t[7], rows_out = t[8];
-  const long long next_first = (entry + 1 < n_entries) ? table[(entry + 1) * 9 + 7] : static_cast<long long>(gridDim.x);
+  const float* oscale = reinterpret_cast<const float*>(t[9]);
+  const long long next_first = (entry + 1 < n_entries) ? table[(entry + 1) * 10 + 7] : static_cast<long long>(gridDim.x);
   const long long nblk = next_first - first;
   const long long total = rows_out * ld;
   const long long rows_src = mode == 0 ? O : I;
@@ -666,11 +668,13 @@ __global__ void pack_weights_multi_kernel(const long long* __restrict__ table, i
         if (k < static_cast<long long>(taps) * I) {
           const int tap = static_cast<int>(k / I), i = static_cast<int>(k % I);
           v = src[(r * I + i) * taps + tap];
+          if (oscale) v *= oscale[r];
         }
       } else {
         if (k < static_cast<long long>(taps) * O) {
           const int tap = static_cast<int>(k / O), o = static_cast<int>(k % O);
           v = src[(static_cast<long long>(o) * I + r) * taps + tap];
+          if (oscale) v *= oscale[o];
         }
       }
     }

@@ -36,9 +36,9 @@ __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloat16* p, cons
 }
 
 // y = (x - mean) * rstd * gamma + beta.  One warp per row; MAXV = max 8-element vectors per lane (C <= 256*MAXV).
-template <typename TIn, int MAXV>
+template <typename TIn, typename TY, int MAXV>
 __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                     const float* __restrict__ beta, TY* __restrict__ y,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int C,
                                      float eps) {
   const int lane = threadIdx.x & 31;
@@ -86,7 +86,7 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __r
         load8f(beta + vi * 8, b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], b[j]);
-        *reinterpret_cast<uint4*>(y + r * C + vi * 8) = pack8(o);
+        store_row8<TY>(y + r * C + vi * 8, o);
       }
     }
   }

@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
 
 // grad[cout][cin][tap] (OIHW, fp32) (+)= sum_s partial[s][cout][tap*Cin + cin]
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
-                                    int Cin, int taps, int accumulate) {
+                                    int Cin, int taps, int accumulate, const float* __restrict__ rowscale) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   const long long slice = total;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -223,6 +223,7 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     const int cout = static_cast<int>(t / taps);
     float s = 0.f;
     for (int k = 0; k < splits; ++k) s += partial[k * slice + i];
+    if (rowscale != nullptr) s *= __ldg(rowscale + cout);
     const long long o = (static_cast<long long>(cout) * Cin + cin) * taps + tap;
     grad[o] = accumulate ? grad[o] + s : s;
   }

@@ -17,7 +17,8 @@ class ModelPack:
     """All packed operands of one model, refreshed by ONE kernel launch (b200_pack_weights_multi)."""
 
     def __init__(self, specs):
-        # specs: list of (param, mode, ld, rows_out[, (O, I, taps) override for weights consumed as a flat [O][K] matrix])
+        # specs: list of (param, mode, ld, rows_out[, (O, I, taps) override for weights consumed as a flat [O][K] matrix
+        #                 [, oscale parameter: fp32 [O] multiplier folded into the packed copy]])
         self.specs = specs
         self.outputs = {}
         self._ptrs = None
@@ -35,23 +36,25 @@ class ModelPack:
             dst = torch.empty(rows_out, ld, dtype=torch.bfloat16, device=dev)
             self.outputs[(id(p), mode)] = dst
             nblk = max(1, min(64, (rows_out * ld + 256 * 16 - 1) // (256 * 16)))
-            rows.append([0, dst.data_ptr(), O, I, taps, mode, ld, first, rows_out])
+            rows.append([0, dst.data_ptr(), O, I, taps, mode, ld, first, rows_out, 0])
             first += nblk
         self.total_blocks = first
         self._rows = rows
         self.table = None
 
     def _build_table(self):
-        ptrs = tuple(spec[0].data_ptr() for spec in self.specs)
+        ptrs = tuple((spec[0].data_ptr(), spec[5].data_ptr() if len(spec) > 5 and spec[5] is not None else 0) for spec in self.specs)
         if ptrs != self._ptrs:
-            for r, ptr in zip(self._rows, ptrs):
+            for r, (ptr, _), spec in zip(self._rows, ptrs, self.specs):
                 r[0] = ptr
+                r[9] = spec[5].data_ptr() if len(spec) > 5 and spec[5] is not None else 0
             dev = self.specs[0][0].device
             self.table = torch.tensor(self._rows, dtype=torch.int64).to(dev)
             self._ptrs = ptrs
 
     def refresh(self, generation):
-        stamp = (generation, tuple((spec[0]._version, spec[0].data_ptr()) for spec in self.specs))
+        stamp = (generation, tuple((spec[0]._version, spec[0].data_ptr(), spec[5]._version if len(spec) > 5 and spec[5] is not None else 0)
+                                   for spec in self.specs))
         if stamp == self.stamp:
             return
         self._build_table()

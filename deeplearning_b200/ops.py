@@ -79,7 +79,8 @@ def _chk_act(t, name):
 
 
 def out_hw(h, ksize, stride):
-    return (h + 2 * (ksize // 2) - ksize) // stride + 1
+    pad = 0 if ksize == 2 else ksize // 2
+    return (h + 2 * pad - ksize) // stride + 1
 
 
 # --------------------------------------------------------------------------------------------------------- packing
@@ -186,8 +187,8 @@ def _workspace(nbytes, device):
     return ws
 
 
-def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False):
-    """dw fp32 OIHW [Cout, Cin, k, k] = sum over pixels of dy (x) x."""
+def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False, rowscale=None):
+    """dw fp32 OIHW [Cout, Cin, k, k] = sum over pixels of dy (x) x  (row `cout` optionally scaled by rowscale[cout])."""
     lib = _lib.load()
     _chk_act(dy, "dy")
     _chk_act(x, "x")
@@ -199,6 +200,8 @@ def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False):
         out = torch.empty(Cout, Cin, ksize, ksize, dtype=F32, device=x.device)
         accumulate = False
     sp = _span("wgrad_gemm", 2.0 * dy.numel() * Cin * ksize * ksize, _nb(dy, x, out))
+    if rowscale is not None:
+        lib.b200_conv2d_wgrad_set_rowscale(_p(rowscale))
     rc = lib.b200_conv2d_wgrad(_p(dy), _p(x), _p(out), _p(ws), ws.numel(), B, H, W, Cin, Cout, ksize, stride,
                                1 if accumulate else 0, _stream())
     _lib.check(rc, "b200_conv2d_wgrad")
@@ -416,7 +419,7 @@ def _view(t, channels, pix_dims=None, pix_strides=None, offset=0):
 
 
 def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, aux_out=False, aux_in=None,
-         a_view=None, out_view=None, residual_view=None, out_offset=0, want_stats=False):
+         a_view=None, out_view=None, residual_view=None, out_offset=0, want_stats=False, colscale=None):
     """out[rows, N] = epilogue(a[rows, K] @ w_packed[N, K]^T). `*_view` = (pix_dims, pix_strides) for strided layouts.
     Returns (out, aux) where aux is the bf16 pre-activation copy when aux_out=True."""
     import ctypes
@@ -432,6 +435,7 @@ def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, 
     args = _lib.GemmArgs()
     args.w, args.N, args.K = w_packed.data_ptr(), N, K
     args.bias = _p(bias)
+    args.colscale = _p(colscale)
     args.act = act
     args.out_f32 = 1 if out_f32 else 0
     keep = []
@@ -459,16 +463,16 @@ def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, 
 
 
 # --------------------------------------------------------------------------------------------------------- layer norm
-def layernorm_fwd(x, gamma, beta, eps):
-    """x [..., C] fp32 or bf16 -> (y bf16, mean, rstd)."""
+def layernorm_fwd(x, gamma, beta, eps, out_dtype=BF16):
+    """x [..., C] fp32 or bf16 -> (y bf16 (or fp32), mean, rstd)."""
     lib = _lib.load()
     C = x.shape[-1]
     rows = x.numel() // C
-    y = torch.empty(x.shape, dtype=BF16, device=x.device)
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     stat = torch.empty(2, rows, dtype=F32, device=x.device)
     sp = _span("layernorm_fwd", 0.0, _nb(x, y))
-    rc = lib.b200_layernorm_fwd(_p(x), 1 if x.dtype == F32 else 0, _p(gamma), _p(beta), _p(y), _p(stat[0]), _p(stat[1]),
-                                rows, C, eps, _stream())
+    rc = lib.b200_layernorm_fwd(_p(x), 1 if x.dtype == F32 else 0, _p(gamma), _p(beta), _p(y), 1 if out_dtype == F32 else 0,
+                                _p(stat[0]), _p(stat[1]), rows, C, eps, _stream())
     _lib.check(rc, "b200_layernorm_fwd")
     if sp:
         sp.end()
@@ -581,3 +585,103 @@ def attention_bwd(qkv, out, dout, lse, H, scale):
     if sp:
         sp.end()
     return dqkv
+
+
+# --------------------------------------------------------------------------------------------------------- ConvNeXt pieces
+def dwconv7_pack(w):
+    """[C,1,7,7] fp32 parameter -> tap-major [49, C] fp32 copy."""
+    lib = _lib.load()
+    C = w.shape[0]
+    wt = torch.empty(49, C, dtype=F32, device=w.device)
+    _lib.check(lib.b200_dwconv7_pack(_p(w.detach()), _p(wt), C, _stream()), "b200_dwconv7_pack")
+    return wt
+
+
+def dwconv7(x, wt, bias=None, add=None, out_dtype=BF16, flip=False):
+    """7x7 depthwise conv (pad 3) on NHWC x; flip=True is the data-gradient (correlation with the flipped kernel)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    out = torch.empty(B, H, W, C, dtype=out_dtype, device=x.device)
+    sp = _span("dwconv7", 2.0 * 49 * x.numel(), _nb(x, out, add))
+    rc = lib.b200_dwconv7(_p(x), 1 if x.dtype == F32 else 0, _p(wt), _p(bias), _p(add), _p(out), 1 if out_dtype == F32 else 0,
+                          1 if flip else 0, B, H, W, C, _stream())
+    _lib.check(rc, "b200_dwconv7")
+    if sp:
+        sp.end()
+    return out
+
+
+def dwconv7_wgrad(du, x, out=None, accumulate=False):
+    """dw [C,1,7,7] = sum_pixels du * x_shifted (du bf16, x fp32, both NHWC)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    nbytes = lib.b200_dwconv7_wgrad_workspace_bytes(B, H, W, C)
+    ws = _workspace(nbytes, x.device)
+    if out is None:
+        out = torch.empty(C, 1, 7, 7, dtype=F32, device=x.device)
+        accumulate = False
+    sp = _span("dwconv7_wgrad", 2.0 * 49 * x.numel(), _nb(du, x))
+    rc = lib.b200_dwconv7_wgrad(_p(du), _p(x), _p(out), _p(ws), ws.numel(), B, H, W, C, 1 if accumulate else 0, _stream())
+    _lib.check(rc, "b200_dwconv7_wgrad")
+    if sp:
+        sp.end()
+    return out
+
+
+def avgpool_any(x):
+    """[B, H, W, C] (fp32 or bf16) -> fp32 [B, C] mean over H*W."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    y = torch.empty(B, C, dtype=F32, device=x.device)
+    _lib.check(lib.b200_avgpool_any(_p(x), 1 if x.dtype == F32 else 0, _p(y), B, H * W, C, _stream()), "b200_avgpool_any")
+    return y
+
+
+def colsum_prod(a, b=None, out=None):
+    """Column sums of a*b (bf16 [rows, C] each; b optional)."""
+    lib = _lib.load()
+    rows, C = a.shape
+    S = lib.b200_colsum_partial_slices(rows)
+    partial = torch.empty(S, 2, C, dtype=F32, device=a.device)
+    _lib.check(lib.b200_colsum_prod_partial(_p(a), _p(b), rows, C, C, _p(partial), _stream()), "b200_colsum_prod_partial")
+    if out is None:
+        out = torch.empty(C, dtype=F32, device=a.device)
+    sc = _reduce_scratch(a.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), S, C, 1.0, None, _p(out), 0, None, None, None, None, _p(sc), sc.numel(),
+                                  _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    return out
+
+
+def adamw_(p, g, m, v, wd, hyper, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0):
+    """hyper: fp32 CUDA tensor {lr, 1-beta1^t, 1-beta2^t}."""
+    lib = _lib.load()
+    rc = lib.b200_adamw(_p(p), _p(g), _p(m), _p(v), _p(wd), p.numel(), _p(hyper), beta1, beta2, eps, gscale, _stream())
+    _lib.check(rc, "b200_adamw")
+
+
+def layerscale_grads(G, W2, b2, gsum, gamma, dW2=None, db2=None, dgamma=None):
+    lib = _lib.load()
+    C, K = W2.shape
+    dW2 = torch.empty(C, K, dtype=F32, device=G.device) if dW2 is None else dW2
+    db2 = torch.empty(C, dtype=F32, device=G.device) if db2 is None else db2
+    dgamma = torch.empty(C, dtype=F32, device=G.device) if dgamma is None else dgamma
+    rc = lib.b200_layerscale_grads(_p(G), _p(W2), _p(b2), _p(gsum), _p(gamma), _p(dW2), _p(db2), _p(dgamma), C, K, _stream())
+    _lib.check(rc, "b200_layerscale_grads")
+    return dW2, db2, dgamma
+
+
+def conv2d_fwd_f32(x, w_packed, ksize, stride, bias=None):
+    """Convolution with fp32 NHWC output (+bias): feeds the fp32 residual stream (ConvNeXt 2x2/s2 downsample)."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    Ho, Wo = out_hw(H, ksize, stride), out_hw(W, ksize, stride)
+    y = torch.empty(B, Ho, Wo, Cout, dtype=F32, device=x.device)
+    sp = _span("conv_gemm_fwd", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize, _nb(x, w_packed, y))
+    rc = lib.b200_conv2d_fwd_f32(_p(x), _p(w_packed), _p(y), B, H, W, Cin, Cout, ksize, stride, _p(bias), _stream())
+    _lib.check(rc, "b200_conv2d_fwd_f32")
+    if sp:
+        sp.end()
+    return y

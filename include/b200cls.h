@@ -40,7 +40,7 @@ int b200_sm_count(void);
 /* Kernels launched by this library so far in this process (bench.py reports the per-step delta as gpu_launches). */
 unsigned long long b200_launch_count(void);
 
-/* ---- convolution / linear as implicit GEMM on tcgen05 (ksize in {1,3}, stride in {1,2}, pad = ksize/2) --------------
+/* ---- convolution / linear as implicit GEMM on tcgen05 (ksize in {1,3} pad ksize/2, stride in {1,2}; or 2x2/s2 unpadded) ----
  * forward:  y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w) (+bias) (act) (+residual)
  *   w        bf16 [Cout][ksize*ksize*Cin]   (b200_pack_weight mode 0)
  *   stats    optional fp32 [b200_conv2d_fwd_mtiles()][2][Cout]: per 128-pixel tile sum and sum of squares of y (as stored)
@@ -52,6 +52,9 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
                     float* stats, const float* bias, int act, const void* residual, float* out_f32, long long ld_out,
                     void* stream);
 int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride);
+/* same convolution writing an fp32 NHWC output (+bias) through TMA - ConvNeXt downsample conv feeding the fp32 stream */
+int b200_conv2d_fwd_f32(const void* x, const void* w, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
+                        int stride, const float* bias, void* stream);
 
 /* data gradient: dx[B,H,W,Cin] = conv_transpose(dy[B,Ho,Wo,Cout], w) (+residual, same shape as dx; may alias dx)
  *   wd  bf16 [Cin][ksize*ksize*Cout]  (b200_pack_weight mode 1)
@@ -66,6 +69,8 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
 int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
                       int W, int Cin, int Cout, int ksize, int stride, int accumulate, void* stream);
 size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
+/* one-shot (this thread, next b200_conv2d_wgrad call): multiply gradient row `cout` by rowscale[cout] (layer scale) */
+int b200_conv2d_wgrad_set_rowscale(const float* rowscale);
 
 /* ---- general GEMM with strided pixel views (transformer layers, patch embedding) ----------------------------------------
  * out[pixel, n] = epilogue( sum_k a[pixel, k] * w[n, k] ), pixels = dim[0] x dim[1] x dim[2] (w fastest), channel stride 1.
@@ -83,6 +88,7 @@ typedef struct {
   const void* w;               /* bf16 [N][K] (b200_pack_weight mode 0) */
   int N, K;
   const float* bias;           /* [N] or NULL */
+  const float* colscale;       /* [N] multiplier applied after bias/act, before the residual (ConvNeXt layer scale), or NULL */
   int act;                     /* B200_ACT_* */
   int out_f32;                 /* 1: `out` is an fp32 tensor (residual stream) */
   const b200_view_t* residual; /* added after bias/act, or NULL */
@@ -98,7 +104,7 @@ int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_a
  * x is fp32 (x_f32) or bf16, y bf16; mean/rstd [rows] are kept for the backward pass.
  * backward: dx = rstd*(dy*gamma - mean(dy*gamma) - xhat*mean(dy*gamma*xhat)) (+ add), dx/add fp32 or bf16;
  * partial[b200_layernorm_bwd_blocks()][2][C] = per-block (sum dy, sum dy*xhat), folded by b200_bn_bwd_finalize. */
-int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* y, float* mean,
+int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float* beta, void* y, int y_f32, float* mean,
                        float* rstd, long long rows, int C, float eps, void* stream);
 int b200_layernorm_bwd_blocks(long long rows, int C);
 int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* mean, const float* rstd, const float* gamma,
@@ -123,6 +129,29 @@ int b200_colsum_partial(const void* m, long long rows, long long ld, int cols, f
 int b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, float scale, void* stream);
 int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                        int B, int T, int H, float scale, void* stream);
+
+/* ---- ConvNeXt (classification/convNext/models/networks.py:92-105,160-165) ---------------------------------------------------
+ * 7x7 depthwise conv, pad 3, NHWC: out = bias + sum_taps wt[tap][c]*in[...]; wt = tap-major [49][C] copy (b200_dwconv7_pack).
+ * flip != 0 correlates with the flipped kernel (data gradient); `add` (same type as out) is summed into the result. */
+int b200_dwconv7_pack(const float* w, float* wt, int C, void* stream);
+int b200_dwconv7(const void* in, int in_f32, const float* wt, const float* bias, const void* add, void* out, int out_f32,
+                 int flip, int B, int H, int W, int C, void* stream);
+/* weight gradient dw [C][49] (+)= sum du * x_shifted; workspace = b200_dwconv7_wgrad_workspace_bytes() */
+size_t b200_dwconv7_wgrad_workspace_bytes(int B, int H, int W, int C);
+int b200_dwconv7_wgrad(const void* du, const float* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
+                       int W, int C, int accumulate, void* stream);
+/* global average pool of [B][HW][C] (fp32 or bf16) -> fp32 [B][C] */
+int b200_avgpool_any(const void* x, int x_f32, float* y, int B, int HW, int C, void* stream);
+/* partial[b200_colsum_partial_slices(rows)][2][cols] of column sums of a*b (b optional): layer-scale / bias gradients */
+int b200_colsum_prod_partial(const void* a, const void* b, long long rows, long long ld, int cols, float* partial,
+                             void* stream);
+/* layer-scale gradients from the unscaled pwconv2 weight gradient G [C][K]: dgamma, dW2 = gamma*G, db2 = gamma*gsum */
+int b200_layerscale_grads(const float* G, const float* W2, const float* b2, const float* gsum, const float* gamma,
+                          float* dW2, float* db2, float* dgamma, int C, int K, void* stream);
+/* fused AdamW over flat fp32 arenas; wd = per-element weight decay (0 for the no-decay group, convNext/utils.py:144-166);
+ * hyper = device {lr, 1-beta1^t, 1-beta2^t} */
+int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, long long n, const float* hyper,
+               float beta1, float beta2, float eps, float gscale, void* stream);
 
 /* ---- BatchNorm2d (train: batch statistics, eval: running statistics) ----------------------------------------------------
  * replaces nn.BatchNorm2d + nn.ReLU (+ residual add) of Bottleneck.forward, classification/resnet/models/networks.py:108-124 */
@@ -173,7 +202,8 @@ int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, floa
 
 /* weight packing fp32 OIHW -> bf16 GEMM operand; mode 0: [O][taps*I] (pitch ld_dst), mode 1: [I][taps*O] */
 int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mode, long long ld_dst, void* stream);
-/* all weights of a model in one launch: table[n][9] int64 {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out} */
+/* all weights of a model in one launch: table[n][10] int64 {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out,
+ * oscale (optional fp32 [O] multiplier per output channel, 0 = none)} */
 int b200_pack_weights_multi(const void* table, int n_entries, int total_blocks, void* stream);
 int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
