@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200_colsum_prod_partial": (_I, [_P, _P, _L, _L, _I, _P, _P]),
     "b200_layerscale_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "b200_conv2d_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "b200_adamw_tick": (_I, [_P, _F, _F, _P]),
     "b200_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
     "b200_bn_finalize": (_I, [_P, _I, _I, _D, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_bn_eval_coeffs": (_I, [_I, _P, _P, _P, _P, _F, _P, _P, _P]),

@@ -248,6 +248,12 @@ int b200_layerscale_grads(const float* G, const float* W2, const float* b2, cons
   return OK;
 }
 
+int b200_adamw_tick(float* hyper, float beta1, float beta2, void* stream) {
+  adamw_tick_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(hyper, beta1, beta2);
+  B200_LAUNCHED();
+  return OK;
+}
+
 int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, long long n, const float* hyper,
                float beta1, float beta2, float eps, float gscale, void* stream) {
   adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, wd, n, hyper, beta1, beta2,

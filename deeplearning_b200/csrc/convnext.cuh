@@ -243,6 +243,18 @@ __global__ void layerscale_grads_kernel(const float* __restrict__ G, const float
 // Fused AdamW over flat fp32 arenas (torch.optim.AdamW semantics, amsgrad off):
 //   p *= 1 - lr*wd[i];  m = b1*m + (1-b1)*g;  v = b2*v + (1-b2)*g*g;  p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
 // hyper (device) = {lr, 1 - b1^t, 1 - b2^t}: kept on the device so a captured CUDA graph follows the schedule.
+// hyper = {lr, 1-beta1^t, 1-beta2^t, beta1^t, beta2^t}: advances t by one (single thread), entirely on the device so the
+// optimizer step can be replayed inside a CUDA graph.
+__global__ void adamw_tick_kernel(float* __restrict__ hyper, float beta1, float beta2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const float p1 = hyper[3] * beta1, p2 = hyper[4] * beta2;
+    hyper[3] = p1;
+    hyper[4] = p2;
+    hyper[1] = 1.0f - p1;
+    hyper[2] = 1.0f - p2;
+  }
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, const float* __restrict__ wd, long long n,
                              const float* __restrict__ hyper, float beta1, float beta2, float eps, float gscale) {

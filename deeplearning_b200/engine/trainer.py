@@ -29,6 +29,12 @@ def _engine_for(model):
         from . import vit
 
         return vit
+    from ..classification.convNext.models.networks import ConvNeXt
+
+    if isinstance(model, ConvNeXt):
+        from . import convnext
+
+        return convnext
     raise NotImplementedError(f"no B200 engine schedule for {type(model).__name__}")
 
 
@@ -85,17 +91,39 @@ class FlatArena:
         return 1.0 / self.world
 
 
+def no_decay_rule(name, param):
+    """Weight-decay grouping of the reference AdamW recipes: 1-D parameters and biases are not decayed
+    (classification/convNext/utils.py:144-166 ``get_params_groups``)."""
+    return param.dim() == 1 or name.endswith(".bias")
+
+
 class TrainStep:
     def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
-                 broadcast=True):
+                 broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None):
+        """optimizer="sgd": torch.optim.SGD(momentum, weight_decay on every parameter) - resnet/vit train.py:96,94.
+        optimizer="adamw": torch.optim.AdamW(betas, eps, weight_decay) with the reference's decay / no-decay groups
+        (``no_decay(name, param) -> bool``, default ``no_decay_rule``) - convNext/train.py:96,102."""
         self.model = model
         self.engine = _engine_for(model)
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.optimizer, self.betas, self.eps = optimizer, betas, eps
+        if optimizer not in ("sgd", "adamw"):
+            raise ValueError(f"unknown optimizer {optimizer!r}")
         self.arena = FlatArena(model.parameters(), process_group, world_size)
         if self.arena.flat_p.device.type != "cuda":
             raise RuntimeError("TrainStep needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
         self.world = self.arena.world
         self.steps = 0
+        if optimizer == "adamw":
+            arena = self.arena
+            rule = no_decay or no_decay_rule
+            names = {p.data_ptr(): n for n, p in model.named_parameters()}
+            arena.flat_v = torch.zeros_like(arena.flat_p)
+            arena.flat_wd = torch.zeros_like(arena.flat_p)
+            for p, o in zip(arena.params, arena.offsets):
+                if not rule(names.get(p.data_ptr(), ""), p):
+                    arena.flat_wd[o:o + p.numel()] = weight_decay
+            self._hyper = torch.tensor([lr, 0.0, 0.0, 1.0, 1.0], dtype=torch.float32, device=arena.flat_p.device)
         if broadcast:
             self.arena.broadcast(model.buffers())
         weight_cache.bump()
@@ -111,10 +139,21 @@ class TrainStep:
 
     def _update(self, lr, lr_dev=None):
         arena = self.arena
+        if self.optimizer == "adamw":
+            if lr != self._hyper_lr():
+                self._hyper[0:1].fill_(float(lr))
+                self._hyper_lr_value = float(lr)
+            ops.adamw_(arena.flat_p, arena.flat_g, arena.flat_m, arena.flat_v, arena.flat_wd, self._hyper, self.betas[0],
+                       self.betas[1], self.eps, gscale=arena.grad_scale)
+            weight_cache.bump()
+            return
         # momentum buffer starts at zero, so "buf = mu*buf + g" already equals torch's first-step "buf = g"
         ops.sgd_momentum_(arena.flat_p, arena.flat_g, arena.flat_m, lr, self.momentum, self.weight_decay,
                           gscale=arena.grad_scale, first_step=False, lr_dev=lr_dev)
         weight_cache.bump()  # parameters changed behind autograd's back -> repack bf16 operands on next use
+
+    def _hyper_lr(self):
+        return getattr(self, "_hyper_lr_value", self.lr)
 
     def step_eager(self, images, labels, lr=None):
         if not self.model.training:
@@ -174,6 +213,9 @@ class TrainStep:
         if lr is not None and lr != self.lr:
             self.lr = lr
             self._lr_dev.fill_(float(lr))
+            if self.optimizer == "adamw":
+                self._hyper[0:1].fill_(float(lr))
+                self._hyper_lr_value = float(lr)
         self._graph_fb.replay()
         if self._graph_up is not None:
             self.arena.all_reduce_grads()

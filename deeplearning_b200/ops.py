@@ -653,9 +653,11 @@ def colsum_prod(a, b=None, out=None):
     return out
 
 
-def adamw_(p, g, m, v, wd, hyper, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0):
-    """hyper: fp32 CUDA tensor {lr, 1-beta1^t, 1-beta2^t}."""
+def adamw_(p, g, m, v, wd, hyper, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0, tick=True):
+    """hyper: fp32 CUDA tensor {lr, 1-beta1^t, 1-beta2^t, beta1^t, beta2^t} (init {lr, 0, 0, 1, 1}); tick advances t first."""
     lib = _lib.load()
+    if tick:
+        _lib.check(lib.b200_adamw_tick(_p(hyper), beta1, beta2, _stream()), "b200_adamw_tick")
     rc = lib.b200_adamw(_p(p), _p(g), _p(m), _p(v), _p(wd), p.numel(), _p(hyper), beta1, beta2, eps, gscale, _stream())
     _lib.check(rc, "b200_adamw")
 

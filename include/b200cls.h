@@ -149,7 +149,9 @@ int b200_colsum_prod_partial(const void* a, const void* b, long long rows, long 
 int b200_layerscale_grads(const float* G, const float* W2, const float* b2, const float* gsum, const float* gamma,
                           float* dW2, float* db2, float* dgamma, int C, int K, void* stream);
 /* fused AdamW over flat fp32 arenas; wd = per-element weight decay (0 for the no-decay group, convNext/utils.py:144-166);
- * hyper = device {lr, 1-beta1^t, 1-beta2^t} */
+ * hyper = device {lr, 1-beta1^t, 1-beta2^t, beta1^t, beta2^t}; b200_adamw_tick advances t by one on the device
+ * (initialise hyper to {lr, 0, 0, 1, 1}), so the whole update is CUDA-graph replayable. */
+int b200_adamw_tick(float* hyper, float beta1, float beta2, void* stream);
 int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, long long n, const float* hyper,
                float beta1, float beta2, float eps, float gscale, void* stream);
 

@@ -139,8 +139,41 @@ def vit_fixture():
     return out
 
 
+def convnext_fixture():
+    from deeplearning_b200.classification.convNext.models.networks import convnext_tiny as mine_ctor
+    from oracle.convnext import convnext_forward, train_step_grads
+
+    ref_mod = _load(f"{REF}/classification/convNext/models/networks.py", "ref_convnext_networks")
+    torch.manual_seed(0)
+    ref = ref_mod.convnext_tiny(1000)
+    torch.manual_seed(0)
+    mine = mine_ctor(1000)
+    sr = {k: v.clone() for k, v in ref.state_dict().items()}
+    sm = mine.state_dict()
+    assert list(sr) == list(sm) and all(torch.equal(sr[k], sm[k]) for k in sr), "ConvNeXt ctor init differs"
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 1000, (2,), generator=torch.Generator().manual_seed(2))
+    ref.eval()
+    with torch.no_grad():
+        le = ref(x)
+        assert torch.equal(le, convnext_forward(sr, x)), "oracle ConvNeXt forward differs from the reference"
+    for mod in ref.modules():  # parity protocol: stochastic depth off
+        if hasattr(mod, "drop_path"):
+            mod.drop_path = torch.nn.Identity()
+    ref.train()
+    lt = ref(x)
+    loss = F.cross_entropy(lt, y)
+    loss.backward()
+    lg, lo, grads = train_step_grads(sr, x, y)
+    assert torch.equal(lg, lt.detach()) and float(lo) == float(loss.detach())
+    for n, p in ref.named_parameters():
+        assert torch.equal(p.grad, grads[n]), n
+    return {"init_abs_sum": {k: float(v.double().abs().sum()) for k, v in sr.items()}, "eval_logits": le.clone(),
+            "train_loss": float(loss.detach()), "grad_norms": _grad_norms(ref.named_parameters())}
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    fx = {"resnet50": resnet50_fixture(), "mnist": mnist_fixture(), "vit_b16": vit_fixture(), "torch": torch.__version__}
+    fx = {"resnet50": resnet50_fixture(), "mnist": mnist_fixture(), "vit_b16": vit_fixture(), "convnext_tiny": convnext_fixture(), "torch": torch.__version__}
     torch.save(fx, os.path.join(HERE, "classification_golden.pt"))
     print("golden fixtures written:", os.path.join(HERE, "classification_golden.pt"), os.path.getsize(os.path.join(HERE, "classification_golden.pt")), "bytes")

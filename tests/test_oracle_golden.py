@@ -95,3 +95,23 @@ def test_vit_b16_init_and_oracle_match_reference(has_logits):
     for n, g in grads.items():
         ref = fx["grad_norms"][n]
         assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
+
+
+def test_convnext_tiny_init_and_oracle_match_reference():
+    from deeplearning_b200.classification.convNext.models.networks import convnext_tiny
+    from oracle.convnext import convnext_forward, train_step_grads
+
+    fx = FX["convnext_tiny"]
+    torch.manual_seed(0)
+    state = {k: v.clone() for k, v in convnext_tiny(1000).state_dict().items()}
+    for k, v in fx["init_abs_sum"].items():
+        assert abs(float(state[k].double().abs().sum()) - v) <= 1e-9 * (1 + abs(v)), k
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 1000, (2,), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        _close(convnext_forward(state, x), fx["eval_logits"])
+    _, loss, grads = train_step_grads(state, x, y)
+    assert abs(float(loss) - fx["train_loss"]) < 1e-3
+    for n, g in grads.items():
+        ref = fx["grad_norms"][n]
+        assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
