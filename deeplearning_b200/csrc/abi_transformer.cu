@@ -6,6 +6,7 @@
 #include "host_utils.h"
 #include "convnext.cuh"
 #include "transformer.cuh"
+#include "window_attention.cuh"
 
 using namespace b200;
 
@@ -258,6 +259,125 @@ int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, lo
                float beta1, float beta2, float eps, float gscale, void* stream) {
   adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, wd, n, hyper, beta1, beta2,
                                                                                eps, gscale);
+  B200_LAUNCHED();
+  return OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- Swin
+static int wattn_grid(int nH) {
+  int per_head = (device_sm_count() * 3 + nH - 1) / nH;
+  if (per_head < 1) per_head = 1;
+  return per_head * nH;
+}
+static int wattn_check(int B, int H, int W, int nH, int shift) {
+  B200_REQUIRE(B > 0 && nH > 0 && H % 7 == 0 && W % 7 == 0, "window attention: H=%d W=%d must be multiples of the 7x7 window", H, W);
+  B200_REQUIRE(shift >= 0 && shift < 7, "window attention: shift %d out of range", shift);
+  return OK;
+}
+
+int b200_window_attention_fwd(const void* qkv, void* out, const float* bias, const float* mask, float* lse, int B, int H,
+                              int W, int nH, int shift, float scale, void* stream) {
+  int rc = wattn_check(B, H, W, nH, shift);
+  if (rc) return rc;
+  WAttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.bias = bias, p.mask = mask, p.lse = lse;
+  p.B = B, p.H = H, p.W = W, p.nH = nH, p.shift = shift, p.scale = scale;
+  static bool cfg = false;
+  if (!cfg) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWAttnFwdSmem));
+    cfg = true;
+  }
+  int grid = wattn_grid(nH);
+  const int total = B * (H / 7) * (W / 7);
+  if (grid > total * nH) grid = total * nH;
+  wattn_fwd_kernel<<<grid, 160, kWAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* bias, const float* mask,
+                              const float* lse, void* dqkv, float* dbias, int B, int H, int W, int nH, int shift,
+                              float scale, void* stream) {
+  int rc = wattn_check(B, H, W, nH, shift);
+  if (rc) return rc;
+  WAttnParams p;
+  memset(&p, 0, sizeof(p));
+  p.qkv = static_cast<const __nv_bfloat16*>(qkv);
+  p.o = static_cast<const __nv_bfloat16*>(out);
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.bias = bias, p.mask = mask, p.lse = const_cast<float*>(lse), p.dbias = dbias;
+  p.B = B, p.H = H, p.W = W, p.nH = nH, p.shift = shift, p.scale = scale;
+  static bool cfg = false;
+  if (!cfg) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWAttnBwdSmem));
+    cfg = true;
+  }
+  int grid = wattn_grid(nH);
+  const int total = B * (H / 7) * (W / 7);
+  if (grid > total * nH) grid = total * nH;
+  wattn_bwd_kernel<<<grid, 160, kWAttnBwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_window_bias_gather(const float* table, const long long* index, float* bias, int nH, void* stream) {
+  wattn_bias_gather_kernel<<<(nH * 49 * 49 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, index, bias, nH);
+  B200_LAUNCHED();
+  return OK;
+}
+int b200_window_bias_scatter(const float* dbias, const long long* index, float* dtable, int nH, void* stream) {
+  wattn_bias_scatter_kernel<<<(nH * 49 * 49 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(dbias, index, dtable, nH);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_window_partition(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_bytes,
+                          void* stream) {
+  B200_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_partition: %dx%d not divisible by window %d", H, W, ws);
+  B200_REQUIRE((static_cast<long long>(C) * elem_bytes) % 16 == 0, "window_partition: C*elem_bytes must be a multiple of 16");
+  const int cvec = C * elem_bytes / 16;
+  window_partition_kernel<<<grid_for(static_cast<long long>(B) * H * W * cvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, cvec, shift, ws);
+  B200_LAUNCHED();
+  return OK;
+}
+int b200_window_merge(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_bytes,
+                      void* stream) {
+  B200_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_merge: %dx%d not divisible by window %d", H, W, ws);
+  B200_REQUIRE((static_cast<long long>(C) * elem_bytes) % 16 == 0, "window_merge: C*elem_bytes must be a multiple of 16");
+  const int cvec = C * elem_bytes / 16;
+  window_merge_kernel<<<grid_for(static_cast<long long>(B) * H * W * cvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, cvec, shift, ws);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_patch_merge_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                            int B, int H, int W, int C, float eps, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && 4 * C <= 2048 && H % 2 == 0 && W % 2 == 0, "patch_merge_ln: C=%d H=%d W=%d unsupported", C, H, W);
+  const long long rows = static_cast<long long>(B) * (H / 2) * (W / 2);
+  patch_merge_ln_fwd_kernel<8><<<grid_for(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, gamma, beta, static_cast<__nv_bfloat16*>(y), mean, rstd, B, H, W, C, eps);
+  B200_LAUNCHED();
+  return OK;
+}
+int b200_patch_merge_ln_bwd_blocks(long long rows) { return ln_bwd_blocks(rows); }
+int b200_patch_merge_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                            void* dx, float* partial, int B, int H, int W, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && 4 * C <= 2048 && H % 2 == 0 && W % 2 == 0, "patch_merge_ln_bwd: C=%d H=%d W=%d unsupported", C, H, W);
+  const long long rows = static_cast<long long>(B) * (H / 2) * (W / 2);
+  const size_t smem = static_cast<size_t>(8) * 2 * 4 * C * sizeof(float);
+  static bool cfg = false;
+  if (!cfg) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(patch_merge_ln_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * 2048 * 4));
+    cfg = true;
+  }
+  patch_merge_ln_bwd_kernel<8><<<ln_bwd_blocks(rows), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), x, mean, rstd, gamma, static_cast<__nv_bfloat16*>(dx), partial, B, H, W, C);
   B200_LAUNCHED();
   return OK;
 }

@@ -166,6 +166,146 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict
   }
 }
 
+// Swin PatchMerging front half (classification/swin_transformer/models/swin_transformer.py:333-343): gather the 2x2 neighbourhood
+// [x(0,0), x(1,0), x(0,1), x(1,1)] (row offset first, as the reference concatenates x0,x1,x2,x3) of the fp32 stream
+// [B][H][W][C] into one 4C vector and LayerNorm it -> y bf16 [B*(H/2)*(W/2)][4C].  One warp per output row.
+template <int MAXV>
+__global__ void patch_merge_ln_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                          const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
+                                          float* __restrict__ mean_out, float* __restrict__ rstd_out, int B, int H, int W,
+                                          int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int C4 = 4 * C, nvec = C4 >> 3, cvec = C >> 3;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long rows = static_cast<long long>(B) * Ho * Wo;
+  const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const int ow = static_cast<int>(r % Wo);
+    const int oh = static_cast<int>((r / Wo) % Ho);
+    const long long b = r / (static_cast<long long>(Wo) * Ho);
+    float v[MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        const int seg = vi / cvec, cv = vi - seg * cvec;  // seg 0..3 -> (dh, dw) = (seg & 1, seg >> 1)
+        const float* src = x + ((b * H + 2 * oh + (seg & 1)) * W + 2 * ow + (seg >> 1)) * C + cv * 8;
+        load_row8<float>(src, v[i]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i][j];
+      }
+    }
+    s = warp_sum(s);
+    const float mean = s / C4;
+    float ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = v[i][j] - mean;
+          ss = fmaf(d, d, ss);
+        }
+      }
+    }
+    ss = warp_sum(ss);
+    const float rstd = rsqrtf(ss / C4 + eps);
+    if (lane == 0) {
+      mean_out[r] = mean;
+      rstd_out[r] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        float g[8], bb[8], o[8];
+        load8f(gamma + vi * 8, g);
+        load8f(beta + vi * 8, bb);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, g[j], bb[j]);
+        *reinterpret_cast<uint4*>(y + r * C4 + vi * 8) = pack8(o);
+      }
+    }
+  }
+}
+
+// Backward of the above: dx (bf16 [B][H][W][C], every pixel written exactly once) from dy bf16 [rows][4C];
+// partial[block][2][4C] = (sum dy, sum dy*xhat) for the LayerNorm parameter gradients.
+template <int MAXV>
+__global__ void __launch_bounds__(256, 2)
+patch_merge_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
+                          float* __restrict__ partial, int B, int H, int W, int C) {
+  extern __shared__ float red[];  // [warps][2][4C]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int C4 = 4 * C, nvec = C4 >> 3, cvec = C >> 3;
+  const int Ho = H / 2, Wo = W / 2;
+  const long long rows = static_cast<long long>(B) * Ho * Wo;
+  float* mine = red + static_cast<long long>(warp) * 2 * C4;
+  for (int i = lane; i < 2 * C4; i += 32) mine[i] = 0.f;
+  __syncwarp();
+  const long long warp0 = blockIdx.x * static_cast<long long>(nw) + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * nw;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const int ow = static_cast<int>(r % Wo);
+    const int oh = static_cast<int>((r / Wo) % Ho);
+    const long long b = r / (static_cast<long long>(Wo) * Ho);
+    const float mu = mean[r], rs = rstd[r];
+    float xh[MAXV][8], dg[MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        const int seg = vi / cvec, cv = vi - seg * cvec;
+        float xv[8], dv[8], g[8];
+        load_row8<float>(x + ((b * H + 2 * oh + (seg & 1)) * W + 2 * ow + (seg >> 1)) * C + cv * 8, xv);
+        unpack8(*reinterpret_cast<const uint4*>(dy + r * C4 + vi * 8), dv);
+        load8f(gamma + vi * 8, g);
+        float4* ab = reinterpret_cast<float4*>(mine + vi * 8);
+        float4* ag = reinterpret_cast<float4*>(mine + C4 + vi * 8);
+        float4 b0 = ab[0], b1 = ab[1], g0 = ag[0], g1 = ag[1];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = (xv[j] - mu) * rs;
+          dg[i][j] = dv[j] * g[j];
+          s1 += dg[i][j];
+          s2 = fmaf(dg[i][j], xh[i][j], s2);
+        }
+        b0.x += dv[0]; b0.y += dv[1]; b0.z += dv[2]; b0.w += dv[3];
+        b1.x += dv[4]; b1.y += dv[5]; b1.z += dv[6]; b1.w += dv[7];
+        g0.x = fmaf(dv[0], xh[i][0], g0.x); g0.y = fmaf(dv[1], xh[i][1], g0.y);
+        g0.z = fmaf(dv[2], xh[i][2], g0.z); g0.w = fmaf(dv[3], xh[i][3], g0.w);
+        g1.x = fmaf(dv[4], xh[i][4], g1.x); g1.y = fmaf(dv[5], xh[i][5], g1.y);
+        g1.z = fmaf(dv[6], xh[i][6], g1.z); g1.w = fmaf(dv[7], xh[i][7], g1.w);
+        ab[0] = b0; ab[1] = b1; ag[0] = g0; ag[1] = g1;
+      }
+    }
+    s1 = warp_sum(s1) / C4;
+    s2 = warp_sum(s2) / C4;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * 32 + lane;
+      if (vi < nvec) {
+        const int seg = vi / cvec, cv = vi - seg * cvec;
+        float o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (dg[i][j] - s1 - xh[i][j] * s2);
+        *reinterpret_cast<uint4*>(dx + ((b * H + 2 * oh + (seg & 1)) * W + 2 * ow + (seg >> 1)) * C + cv * 8) = pack8(o);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C4; c += blockDim.x) {
+    float s = 0.f;
+    for (int w = 0; w < nw; ++w) s += red[static_cast<long long>(w) * 2 * C4 + c];
+    partial[static_cast<long long>(blockIdx.x) * 2 * C4 + c] = s;
+  }
+}
+
 // Patch extraction: x fp32 NCHW [B][Cin][H][W] -> a bf16 [B*(H/ps)*(W/ps)][Cin*ps*ps], k = c*ps*ps + kh*ps + kw
 // (the flattening order of an OIHW conv weight, so the weight matrix is weight.view(D, -1) unchanged). ps % 8 == 0... or 4.
 __global__ void patchify_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int Cin, int H,

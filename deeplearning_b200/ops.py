@@ -687,3 +687,109 @@ def conv2d_fwd_f32(x, w_packed, ksize, stride, bias=None):
     if sp:
         sp.end()
     return y
+
+
+# --------------------------------------------------------------------------------------------------------- Swin pieces
+def window_bias_gather(table, index, nH):
+    """relative_position_bias_table [(2*7-1)^2, nH] + relative_position_index [49,49] int64 -> dense fp32 [nH,49,49]."""
+    lib = _lib.load()
+    bias = torch.empty(nH, 49, 49, dtype=F32, device=table.device)
+    _lib.check(lib.b200_window_bias_gather(_p(table), _p(index), _p(bias), nH, _stream()), "b200_window_bias_gather")
+    return bias
+
+
+def window_bias_scatter(dbias, index, dtable):
+    lib = _lib.load()
+    nH = dbias.shape[0]
+    _lib.check(lib.b200_window_bias_scatter(_p(dbias), _p(index), _p(dtable), nH, _stream()), "b200_window_bias_scatter")
+    return dtable
+
+
+def window_attention_fwd(qkv, nH, bias, mask, shift, scale):
+    """qkv bf16 [B,H,W,3*nH*32] (natural pixel order) -> (out bf16 [B,H,W,nH*32], lse fp32 [B,nW,nH,49])."""
+    lib = _lib.load()
+    B, H, W, _ = qkv.shape
+    C = nH * 32
+    nW = (H // 7) * (W // 7)
+    out = torch.empty(B, H, W, C, dtype=BF16, device=qkv.device)
+    lse = torch.empty(B, nW, nH, 49, dtype=F32, device=qkv.device)
+    sp = _span("window_attention_fwd", 4.0 * B * nW * nH * 49 * 49 * 32, _nb(qkv, out))
+    rc = lib.b200_window_attention_fwd(_p(qkv), _p(out), _p(bias), _p(mask), _p(lse), B, H, W, nH, shift, scale, _stream())
+    _lib.check(rc, "b200_window_attention_fwd")
+    if sp:
+        sp.end()
+    return out, lse
+
+
+def window_attention_bwd(qkv, out, dout, bias, mask, lse, nH, shift, scale):
+    """Returns (dqkv bf16 like qkv, dbias fp32 [nH,49,49])."""
+    lib = _lib.load()
+    B, H, W, _ = qkv.shape
+    nW = (H // 7) * (W // 7)
+    dqkv = torch.empty_like(qkv)
+    dbias = torch.zeros(nH, 49, 49, dtype=F32, device=qkv.device)
+    sp = _span("window_attention_bwd", 10.0 * B * nW * nH * 49 * 49 * 32, _nb(qkv, out, dout, dqkv))
+    rc = lib.b200_window_attention_bwd(_p(qkv), _p(out), _p(dout), _p(bias), _p(mask), _p(lse), _p(dqkv), _p(dbias), B, H, W,
+                                       nH, shift, scale, _stream())
+    _lib.check(rc, "b200_window_attention_bwd")
+    if sp:
+        sp.end()
+    return dqkv, dbias
+
+
+def window_partition(x, shift, ws):
+    """window_partition(torch.roll(x, (shift, shift), (1, 2))): [B,H,W,C] -> [B*nW, ws, ws, C] (any 2/4-byte dtype)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    out = torch.empty(B * (H // ws) * (W // ws), ws, ws, C, dtype=x.dtype, device=x.device)
+    rc = lib.b200_window_partition(_p(x), _p(out), B, H, W, C, shift, ws, x.element_size(), _stream())
+    _lib.check(rc, "b200_window_partition")
+    return out
+
+
+def window_merge(xw, B, H, W, shift, ws):
+    """torch.roll(window_reverse(xw), (shift, shift), (1, 2)): [B*nW, ws, ws, C] -> [B,H,W,C]."""
+    lib = _lib.load()
+    C = xw.shape[-1]
+    out = torch.empty(B, H, W, C, dtype=xw.dtype, device=xw.device)
+    rc = lib.b200_window_merge(_p(xw), _p(out), B, H, W, C, shift, ws, xw.element_size(), _stream())
+    _lib.check(rc, "b200_window_merge")
+    return out
+
+
+def patch_merge_ln_fwd(x, gamma, beta, eps):
+    """x fp32 [B,H,W,C] -> (y bf16 [B*H/2*W/2, 4C] = LN(concat 2x2), mean, rstd)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    rows = B * (H // 2) * (W // 2)
+    y = torch.empty(rows, 4 * C, dtype=BF16, device=x.device)
+    stat = torch.empty(2, rows, dtype=F32, device=x.device)
+    sp = _span("patch_merge_ln_fwd", 0.0, _nb(x, y))
+    rc = lib.b200_patch_merge_ln_fwd(_p(x), _p(gamma), _p(beta), _p(y), _p(stat[0]), _p(stat[1]), B, H, W, C, eps, _stream())
+    _lib.check(rc, "b200_patch_merge_ln_fwd")
+    if sp:
+        sp.end()
+    return y, stat[0], stat[1]
+
+
+def patch_merge_ln_bwd(dy, x, mean, rstd, gamma, dgamma=None, dbeta=None):
+    """Returns (dx bf16 [B,H,W,C], dgamma, dbeta)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    rows = B * (H // 2) * (W // 2)
+    nblk = lib.b200_patch_merge_ln_bwd_blocks(rows)
+    partial = torch.empty(nblk, 2, 4 * C, dtype=F32, device=x.device)
+    dx = torch.empty(B, H, W, C, dtype=BF16, device=x.device)
+    sp = _span("patch_merge_ln_bwd", 0.0, _nb(dy, x, dx))
+    rc = lib.b200_patch_merge_ln_bwd(_p(dy), _p(x), _p(mean), _p(rstd), _p(gamma), _p(dx), _p(partial), B, H, W, C, _stream())
+    _lib.check(rc, "b200_patch_merge_ln_bwd")
+    if sp:
+        sp.end()
+    if dgamma is None:
+        dgamma = torch.empty(4 * C, dtype=F32, device=x.device)
+        dbeta = torch.empty(4 * C, dtype=F32, device=x.device)
+    sc = _reduce_scratch(x.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, 4 * C, 1.0, _p(dgamma), _p(dbeta), 0, None, None, None, None, _p(sc),
+                                  sc.numel(), _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    return dx, dgamma, dbeta

@@ -130,6 +130,35 @@ int b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int
 int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const float* lse, float* delta, void* dqkv,
                        int B, int T, int H, float scale, void* stream);
 
+/* ---- Swin (classification/swin_transformer/models/swin_transformer.py) -----------------------------------------------------
+ * Shifted-window attention, 7x7 windows, head_dim 32, on tcgen05. qkv bf16 [B][H][W][3*nH*32] in natural (un-rolled) pixel
+ * order; torch.roll / window_partition / window_reverse (:251-280) are folded into the gather / scatter addressing.
+ * bias = dense [nH][49][49] (b200_window_bias_gather of relative_position_bias_table[relative_position_index], :131-134);
+ * mask = attn_mask buffer [nW][49][49] (0 / -100, :215-238) for shifted blocks or NULL; lse fp32 [B][nW][nH][49].
+ * backward: dqkv same layout as qkv; dbias dense [nH][49][49] must be zeroed by the caller (atomics), then
+ * b200_window_bias_scatter adds it into the table gradient. */
+int b200_window_attention_fwd(const void* qkv, void* out, const float* bias, const float* mask, float* lse, int B, int H,
+                              int W, int nH, int shift, float scale, void* stream);
+int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* bias, const float* mask,
+                              const float* lse, void* dqkv, float* dbias, int B, int H, int W, int nH, int shift,
+                              float scale, void* stream);
+int b200_window_bias_gather(const float* table, const long long* index, float* bias, int nH, void* stream);
+int b200_window_bias_scatter(const float* dbias, const long long* index, float* dtable, int nH, void* stream);
+/* The reference's own operator FFI (kernels/window_process/swin_window_process.cpp:70-131), any 2/4-byte element type:
+ *   partition: out[B*nW][ws][ws][C] = window_partition(roll(in[B][H][W][C], shifts=(shift, shift)))   (forward)
+ *   merge:     out[B][H][W][C] = roll(window_reverse(in[B*nW][ws][ws][C]), shifts=(shift, shift))
+ * roll_and_window_partition_backward(g, s) == merge(g, -s), window_merge_and_roll_backward(g, s) == partition(g, -s). */
+int b200_window_partition(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_bytes,
+                          void* stream);
+int b200_window_merge(const void* in, void* out, int B, int H, int W, int C, int shift, int ws, int elem_bytes,
+                      void* stream);
+/* PatchMerging front half (:333-343): 2x2 gather-concat of the fp32 stream + LayerNorm(4C) -> bf16 [B*H/2*W/2][4C] */
+int b200_patch_merge_ln_fwd(const float* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd,
+                            int B, int H, int W, int C, float eps, void* stream);
+int b200_patch_merge_ln_bwd_blocks(long long rows);
+int b200_patch_merge_ln_bwd(const void* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                            void* dx, float* partial, int B, int H, int W, int C, void* stream);
+
 /* ---- ConvNeXt (classification/convNext/models/networks.py:92-105,160-165) ---------------------------------------------------
  * 7x7 depthwise conv, pad 3, NHWC: out = bias + sum_taps wt[tap][c]*in[...]; wt = tap-major [49][C] copy (b200_dwconv7_pack).
  * flip != 0 correlates with the flipped kernel (data gradient); `add` (same type as out) is summed into the result. */
