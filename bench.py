@@ -29,7 +29,10 @@ MODELS = {
                 "workload": "classification/vision_transformer ViT-B/16 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[2])"},
     "convnext_tiny": {"gflop": 26.73, "mb": 3 * 54.2, "batch": 256,
                       "workload": "classification/convNext ConvNeXt-T bf16, synthetic 3x224x224, bs=256/GPU, drop_path 0 (BASELINE.json configs[4])"},
+    "swin_tiny": {"gflop": 26.94, "mb": 3 * 60.1, "batch": 128,
+                  "workload": "classification/swin_transformer Swin-T bf16, synthetic 3x224x224, bs=128/GPU, drop_path 0 (BASELINE.json configs[3])"},
 }
+ADAMW_MODELS = ("convnext_tiny", "swin_tiny")   # AdamW(lr 5e-4, wd 5e-2): convNext/train.py:96,102; swin config.py:133-162
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
@@ -158,12 +161,16 @@ def run_b200(args):
         from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
 
         model = vit_base_patch16_224_in21k(num_classes=1000, has_logits=False).to(dev).train()
+    elif args.model == "swin_tiny":
+        from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer
+
+        model = SwinTransformer(drop_path_rate=0.0).to(dev).train()   # Swin-T defaults, stochastic depth off
     else:
         from deeplearning_b200.classification.convNext.models.networks import ConvNeXt
 
         # convnext_tiny(1000) with stochastic depth off
         model = ConvNeXt(depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], num_classes=1000, drop_path_rate=0.0).to(dev).train()
-    if args.model == "convnext_tiny":   # AdamW(lr 5e-4, wd 5e-2) with the reference's decay groups (convNext/train.py:96,102)
+    if args.model in ADAMW_MODELS:      # AdamW(lr 5e-4, wd 5e-2) with the reference's decay groups
         trainer = TrainStep(model, lr=5e-4, weight_decay=5e-2, optimizer="adamw")
     else:                               # SGD(momentum 0.9, wd 5e-5) (resnet/train.py:96, vision_transformer/train.py:94)
         trainer = TrainStep(model, lr=0.01, momentum=0.9, weight_decay=5e-5)
@@ -253,7 +260,7 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": spec["workload"],
                        "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "optimizer": "AdamW(lr=5e-4, wd=5e-2, decay groups)" if args.model == "convnext_tiny" else "SGD(momentum=0.9, weight_decay=5e-5)",
+                       "optimizer": "AdamW(lr=5e-4, wd=5e-2, decay groups)" if args.model in ADAMW_MODELS else "SGD(momentum=0.9, weight_decay=5e-5)",
                        "step": "fwd+CE+bwd+allreduce+optimizer",
                        "launch": "eager" if args.eager else "CUDA graph replay",
                        "l2": "working set (~14 GB of activations per step) is far larger than the 126 MB L2; no flush needed"},

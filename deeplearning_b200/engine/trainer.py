@@ -35,6 +35,12 @@ def _engine_for(model):
         from . import convnext
 
         return convnext
+    from ..classification.swin_transformer.models.swin_transformer import SwinTransformer
+
+    if isinstance(model, SwinTransformer):
+        from . import swin
+
+        return swin
     raise NotImplementedError(f"no B200 engine schedule for {type(model).__name__}")
 
 
@@ -97,6 +103,19 @@ def no_decay_rule(name, param):
     return param.dim() == 1 or name.endswith(".bias")
 
 
+def model_no_decay_rule(model):
+    """Decay grouping of the reference Swin recipe (classification/swin_transformer/utils/optimizer.py:41-63
+    ``set_weight_decay``): 1-D parameters, biases, names in ``model.no_weight_decay()`` and names containing a keyword of
+    ``model.no_weight_decay_keywords()`` are not decayed."""
+    skip = set(model.no_weight_decay()) if hasattr(model, "no_weight_decay") else set()
+    keywords = tuple(model.no_weight_decay_keywords()) if hasattr(model, "no_weight_decay_keywords") else ()
+
+    def rule(name, param):
+        return no_decay_rule(name, param) or name in skip or any(k in name for k in keywords)
+
+    return rule
+
+
 class TrainStep:
     def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
                  broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None):
@@ -116,7 +135,7 @@ class TrainStep:
         self.steps = 0
         if optimizer == "adamw":
             arena = self.arena
-            rule = no_decay or no_decay_rule
+            rule = no_decay or model_no_decay_rule(model)
             names = {p.data_ptr(): n for n, p in model.named_parameters()}
             arena.flat_v = torch.zeros_like(arena.flat_p)
             arena.flat_wd = torch.zeros_like(arena.flat_p)

@@ -172,8 +172,59 @@ def convnext_fixture():
             "train_loss": float(loss.detach()), "grad_norms": _grad_norms(ref.named_parameters())}
 
 
+def swin_fixture():
+    from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer as mine_ctor
+    from oracle.swin import swin_forward, train_step_grads
+
+    class _DropPath(torch.nn.Module):  # timm is not installed: the three names the reference file imports from it
+        def __init__(self, p=None):
+            super().__init__()
+            self.drop_prob = p
+
+        def forward(self, x):
+            return x
+
+    _shim("timm")
+    _shim("timm.models")
+    _shim("timm.models.layers", DropPath=_DropPath, trunc_normal_=torch.nn.init.trunc_normal_,
+          to_2tuple=lambda x: tuple(x) if isinstance(x, (tuple, list)) else (x, x))
+    ref_mod = _load(f"{REF}/classification/swin_transformer/models/swin_transformer.py", "ref_swin_transformer")
+    torch.manual_seed(0)
+    ref = ref_mod.SwinTransformer(drop_path_rate=0.0)   # Swin-T defaults; parity protocol: stochastic depth off
+    torch.manual_seed(0)
+    mine = mine_ctor(drop_path_rate=0.0)
+    sr = {k: v.clone() for k, v in ref.state_dict().items()}
+    sm = mine.state_dict()
+    assert list(sr) == list(sm) and all(torch.equal(sr[k], sm[k]) for k in sr), "Swin ctor init differs"
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 1000, (2,), generator=torch.Generator().manual_seed(2))
+    ref.eval()
+    with torch.no_grad():
+        le = ref(x)
+        assert torch.equal(le, swin_forward(sr, x)), "oracle Swin forward differs from the reference"
+    ref.train()
+    lt = ref(x)
+    loss = F.cross_entropy(lt, y)
+    loss.backward()
+    lg, lo, grads = train_step_grads(sr, x, y)
+    assert torch.equal(lg, lt.detach()) and float(lo) == float(loss.detach())
+    for n, p in ref.named_parameters():
+        assert torch.equal(p.grad, grads[n]), n
+    return {"init_abs_sum": {k: float(v.double().abs().sum()) for k, v in sr.items()}, "eval_logits": le.clone(),
+            "train_loss": float(loss.detach()), "grad_norms": _grad_norms(ref.named_parameters())}
+
+
+FIXTURES = {"resnet50": resnet50_fixture, "mnist": mnist_fixture, "vit_b16": vit_fixture, "convnext_tiny": convnext_fixture,
+            "swin_tiny": swin_fixture}
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
-    fx = {"resnet50": resnet50_fixture(), "mnist": mnist_fixture(), "vit_b16": vit_fixture(), "convnext_tiny": convnext_fixture(), "torch": torch.__version__}
-    torch.save(fx, os.path.join(HERE, "classification_golden.pt"))
+    path = os.path.join(HERE, "classification_golden.pt")
+    only = sys.argv[1:]   # e.g. `make_golden.py swin_tiny` refreshes one entry and keeps the others
+    fx = torch.load(path, weights_only=False) if only else {}
+    for name, fn in FIXTURES.items():
+        if not only or name in only:
+            fx[name] = fn()
+    fx["torch"] = torch.__version__
+    torch.save(fx, path)
     print("golden fixtures written:", os.path.join(HERE, "classification_golden.pt"), os.path.getsize(os.path.join(HERE, "classification_golden.pt")), "bytes")

@@ -47,3 +47,39 @@ def test_pretrained_needs_network():
 
     with pytest.raises(RuntimeError):
         resnet50(pretrained=True)
+
+
+def test_swin_state_dict_layout_and_decay_groups():
+    from deeplearning_b200.classification.swin_transformer.models.build import build_model
+    from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer
+    from deeplearning_b200.engine.trainer import model_no_decay_rule
+    from types import SimpleNamespace as NS
+
+    m = SwinTransformer(drop_path_rate=0.0)
+    sd = m.state_dict()
+    assert sum(p.numel() for p in m.parameters()) == 28288354
+    assert sd["patch_embed.proj.weight"].shape == (96, 3, 4, 4) and sd["patch_embed.norm.weight"].shape == (96,)
+    assert sd["layers.0.blocks.0.attn.relative_position_bias_table"].shape == (169, 3)
+    assert sd["layers.0.blocks.0.attn.relative_position_index"].shape == (49, 49)
+    assert sd["layers.0.blocks.1.attn_mask"].shape == (64, 49, 49) and "layers.0.blocks.0.attn_mask" not in sd
+    assert "layers.3.blocks.1.attn_mask" not in sd          # 7x7 stage: window == resolution, shift forced to 0 (:187-190)
+    assert sd["layers.2.downsample.reduction.weight"].shape == (768, 1536) and sd["layers.2.downsample.norm.weight"].shape == (1536,)
+    assert sd["head.weight"].shape == (1000, 768)
+    mask = sd["layers.1.blocks.1.attn_mask"]
+    assert set(mask.unique().tolist()) == {0.0, -100.0}
+    rule = model_no_decay_rule(m)
+    named = dict(m.named_parameters())
+    nd = {n for n, p in named.items() if rule(n, p)}
+    assert "layers.0.blocks.0.attn.relative_position_bias_table" in nd and "norm.weight" in nd and "head.bias" in nd
+    assert "head.weight" not in nd and "layers.0.blocks.0.attn.qkv.weight" not in nd
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.randn(1, 3, 224, 224))
+    cfg = NS(MODEL=NS(TYPE="swin", NUM_CLASSES=10, DROP_RATE=0.0, DROP_PATH_RATE=0.0,
+                      SWIN=NS(PATCH_SIZE=4, IN_CHANS=3, EMBED_DIM=96, DEPTHS=[2, 2], NUM_HEADS=[3, 6], WINDOW_SIZE=7, MLP_RATIO=4.,
+                              QKV_BIAS=True, QK_SCALE=None, APE=False, PATCH_NORM=True)),
+             DATA=NS(IMG_SIZE=224), TRAIN=NS(USE_CHECKPOINT=False), FUSED_WINDOW_PROCESS=True)
+    small = build_model(cfg)
+    assert small.head.weight.shape == (10, 192) and len(small.layers) == 2
+    cfg.MODEL.TYPE = "swinv2"
+    with pytest.raises(NotImplementedError):
+        build_model(cfg)

@@ -115,3 +115,23 @@ def test_convnext_tiny_init_and_oracle_match_reference():
     for n, g in grads.items():
         ref = fx["grad_norms"][n]
         assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
+
+
+def test_swin_tiny_init_and_oracle_match_reference():
+    from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer
+    from oracle.swin import swin_forward, train_step_grads
+
+    fx = FX["swin_tiny"]
+    torch.manual_seed(0)
+    state = {k: v.clone() for k, v in SwinTransformer(drop_path_rate=0.0).state_dict().items()}
+    for k, v in fx["init_abs_sum"].items():
+        assert abs(float(state[k].double().abs().sum()) - v) <= 1e-9 * (1 + abs(v)), k
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(1))
+    y = torch.randint(0, 1000, (2,), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        _close(swin_forward(state, x), fx["eval_logits"])
+    _, loss, grads = train_step_grads(state, x, y)
+    assert abs(float(loss) - fx["train_loss"]) < 1e-4
+    for n, g in grads.items():
+        ref = fx["grad_norms"][n]
+        assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
