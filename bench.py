@@ -268,6 +268,14 @@ def run_b200(args):
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss}
 
+    # per-kernel roofline: one extra step with CUDA-event spans around every C-ABI op on the launching stream.  Every rank
+    # runs the step (it contains the gradient all-reduce); only rank 0 records spans.
+    if rank == 0:
+        with ops.Profiler() as prof:
+            trainer.step_eager(images, labels)
+    else:
+        trainer.step_eager(images, labels)
+    sync_all()
     if rank == 0:
         peaks = load_peaks()
         # whole-step roofline: the step is HBM-bound on this design; both fractions are reported
@@ -276,9 +284,6 @@ def run_b200(args):
             "hbm_frac": per_gpu * spec["mb"] * 1e6 / (peaks["hbm_gbs"] * 1e9),
             "tensor_frac": per_gpu * spec["gflop"] * 1e9 / (peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]) * 1e12),
             "peaks": peaks["_source"]}
-        # per-kernel roofline: one extra step with CUDA-event spans around every C-ABI op on the launching stream
-        with ops.Profiler() as prof:
-            trainer.step_eager(images, labels)
         agg = prof.summary()
         tot = sum(a["ms"] for a in agg.values())
         kernels = []
