@@ -38,7 +38,7 @@ SIGNATURES = {
     "b200_sm_count": (_I, []),
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_conv2d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
-    "b200_conv2d_fwd_mtiles": (_I, [_I, _I, _I, _I, _I]),
+    "b200_conv2d_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
     "b200_conv2d_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200_conv2d_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),
@@ -82,6 +82,8 @@ SIGNATURES = {
     "b200_bn_bwd_blocks": (_I, [_L, _I]),
     "b200_bn_bwd_finalize": (_I, [_P, _I, _I, _D, _P, _P, _I, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_bn_bwd_apply": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P]),
+    "b200_bn_bwd_reduce_pooled": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
+    "b200_bn_bwd_apply_pooled": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_bn_relu_maxpool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -156,6 +156,14 @@ int setup_output(ConvGemmParams& p, const View& dv, int N, int out_f32, const Vi
 }
 Box3 box_of(const ConvGemmParams& p) { return Box3{p.box1, p.box2, p.box3}; }
 
+// Persistent grid. With BN statistics every CTA must keep seeing the same channel block (tile % n_tiles), so the grid is
+// rounded down to a multiple of n_tiles.
+int conv_grid(int tiles, int n_tiles, bool stats) {
+  int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  if (stats) grid = grid / n_tiles * n_tiles;
+  return grid;
+}
+
 template <int BLOCK_N>
 int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   using Cfg = ConvGemmCfg<BLOCK_N>;
@@ -166,7 +174,8 @@ int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
     configured = true;
   }
   const int tiles = p.tiles1 * p.tiles2 * p.tiles3 * p.n_tiles;
-  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  const int grid = conv_grid(tiles, p.n_tiles, p.stats != nullptr);
+  B200_REQUIRE(grid > 0, "conv_gemm: %d channel blocks exceed the SM count (BN statistics need grid %% n_tiles == 0)", p.n_tiles);
   ConvGemmParams q = p;
   q.desc_lbo = g_fwd_lbo;
   q.desc_sbo = g_fwd_sbo;
@@ -250,15 +259,21 @@ int b200_debug_set_desc(int which, unsigned lbo, unsigned sbo, unsigned kstep) {
   return OK;
 }
 
-int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride) {
+int b200_conv2d_fwd_stats_rows(int B, int H, int W, int Cout, int ksize, int stride) {
   const int Ho = out_dim(H, ksize, stride), Wo = out_dim(W, ksize, stride);
   const bool flat = (ksize == 1 && stride == 1);
   const long long d1 = flat ? static_cast<long long>(B) * H * W : Wo;
   const long long d2 = flat ? 1 : Ho;
   const long long d3 = flat ? 1 : B;
   const Box3 bx = choose_box(d1, d2, d3, 128);
-  // one statistics row per 32-pixel slab (4 per 128-pixel tile)
-  return 4 * static_cast<int>(((d1 + bx.b1 - 1) / bx.b1) * ((d2 + bx.b2 - 1) / bx.b2) * ((d3 + bx.b3 - 1) / bx.b3));
+  const long long m_tiles = ((d1 + bx.b1 - 1) / bx.b1) * ((d2 + bx.b2 - 1) / bx.b2) * ((d3 + bx.b3 - 1) / bx.b3);
+  const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  const int n_tiles = (Cout + BN - 1) / BN;
+  const long long tiles = m_tiles * n_tiles;
+  const int grid = conv_grid(tiles > (1 << 30) ? (1 << 30) : static_cast<int>(tiles), n_tiles, true);
+  // one partial row per (CTA group, TMEM quadrant); the two warps of a quadrant write separate rows when they alternate
+  // tiles (64-channel tiles) and disjoint column units of one row otherwise
+  return grid / n_tiles * (BN == 64 ? 8 : 4);
 }
 
 static thread_local int g_conv_out_f32_tma = 0;

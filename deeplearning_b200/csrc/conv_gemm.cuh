@@ -39,7 +39,7 @@ struct alignas(64) ConvGemmParams {
   int8_t tap_o1[kMaxTaps];   // pixel offset along dim1 (w)
   int8_t tap_o2[kMaxTaps];   // pixel offset along dim2 (h)
   int8_t tap_w[kMaxTaps];    // which k_per_tap-wide slice of the weight matrix the tap multiplies
-  float* stats;             // [4*m_tiles][2][N] partial sums (one row per 32-pixel slab), or null
+  float* stats;             // [stats_rows][2][N] per-CTA partial sums (see conv_stats_rows), or null; needs grid % n_tiles == 0
   const float* bias;        // [N] or null
   const float* colscale;    // [N] per-channel multiplier applied after bias/activation (layer scale), or null
   int act;                  // 0 none, 1 relu, 2 gelu(erf), 3 multiply by gelu'(aux_in) (backward of 2)
@@ -224,6 +224,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const int u_first = split_tiles ? 0 : pair;
     int last_unit = u_first;
     while (last_unit + 2 < units) last_unit += 2;
+    // Train-mode BN statistics: every epilogue warp keeps running column sums of the slabs it stored (its 32 TMEM lanes x
+    // its 64-column units; the launch guarantees grid % n_tiles == 0, so a CTA always sees the same channel block) and
+    // writes ONE partial row at the end of the kernel - ~150 x 4 rows per conv instead of one per 32 pixels.
+    constexpr int UN = BLOCK_N >= 128 ? BLOCK_N / 128 : 1;
+    uint64_t run_s[UN], run_q[UN];
+#pragma unroll
+    for (int k = 0; k < UN; ++k) run_s[k] = 0, run_q[k] = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if (split_tiles && (it & 1) != pair) continue;
@@ -384,7 +391,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         __syncwarp();
         if (stats != nullptr) {
           // Column sums over this warp's 32 rows, read back from the (bf16-rounded) slab: lane l owns columns 2l, 2l+1;
-          // bank-conflict-free thanks to the 128B swizzle; packed fp32x2 adds / fmas. One partial row per (tile, quadrant).
+          // bank-conflict-free thanks to the 128B swizzle; packed fp32x2 adds / fmas, folded into the running sums.
           uint64_t a_s = 0, a_q = 0;
 #pragma unroll
           for (int r = 0; r < 32; ++r) {
@@ -393,14 +400,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             a_s = f2_add(a_s, x2);
             a_q = f2_fma(x2, x2, a_q);
           }
-          const int col = n0 + 2 * lane;
-          if (col < N) {
-            float s_lo, s_hi, q_lo, q_hi;
-            f2_unpack(a_s, s_lo, s_hi);
-            f2_unpack(a_q, q_lo, q_hi);
-            float* sp = stats + (static_cast<long long>(m_tile) * 4 + q) * 2 * N + col;
-            *reinterpret_cast<float2*>(sp) = make_float2(s_lo, s_hi);
-            *reinterpret_cast<float2*>(sp + N) = make_float2(q_lo, q_hi);
+          const int ui = u >> 1;
+#pragma unroll
+          for (int k = 0; k < UN; ++k) {
+            if (k == ui) {
+              run_s[k] = f2_add(run_s[k], a_s);
+              run_q[k] = f2_add(run_q[k], a_q);
+            }
           }
         }
         fence_proxy_async_smem();
@@ -421,6 +427,23 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           }
         }
         store_counter += has_aux ? 2 : 1;
+      }
+    }
+    if (stats != nullptr) {
+      const int n_tile = blockIdx.x % p.n_tiles, grp = blockIdx.x / p.n_tiles;
+      const int srow = split_tiles ? (grp * 4 + q) * 2 + pair : grp * 4 + q;
+#pragma unroll
+      for (int k = 0; k < UN; ++k) {
+        const int u = u_first + 2 * k;
+        const int col = n_tile * BLOCK_N + u * unit_cols + 2 * lane;
+        if (u < units && col < N) {
+          float s_lo, s_hi, q_lo, q_hi;
+          f2_unpack(run_s[k], s_lo, s_hi);
+          f2_unpack(run_q[k], q_lo, q_hi);
+          float* sp = stats + static_cast<long long>(srow) * 2 * N + col;
+          *reinterpret_cast<float2*>(sp) = make_float2(s_lo, s_hi);
+          *reinterpret_cast<float2*>(sp + N) = make_float2(q_lo, q_hi);
+        }
       }
     }
     if (lane == 0) tma_store_wait_all<0>();

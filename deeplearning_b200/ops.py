@@ -27,12 +27,17 @@ class Profiler:
     """Times every C-ABI op with CUDA events on the launching stream and attributes algorithmic flops / bytes to it.
     Used by bench.py (roofline numbers) and tools/; zero cost when not active."""
 
-    def __init__(self):
+    def __init__(self, run_ahead_ms=0.0):
+        """run_ahead_ms > 0: park the stream on a spin kernel for about that long first, so the host enqueues the profiled
+        region ahead of the device and the event spans measure kernel time, not host launch gaps."""
         self.records = []  # (name, flops, bytes, ev0, ev1)
+        self.run_ahead_ms = run_ahead_ms
 
     def __enter__(self):
         global _active_prof
         self._prev, _active_prof = _active_prof, self
+        if self.run_ahead_ms > 0:
+            torch.cuda._sleep(int(self.run_ahead_ms * 1.9e6))  # cycles at ~1.9 GHz
         return self
 
     def __exit__(self, *exc):
@@ -141,7 +146,7 @@ def conv2d_fwd(x, w_packed, ksize=1, stride=1, want_stats=False, bias=None, act=
     Ho, Wo = out_hw(H, ksize, stride), out_hw(W, ksize, stride)
     stats = None
     if want_stats:
-        T = lib.b200_conv2d_fwd_mtiles(B, H, W, ksize, stride)
+        T = lib.b200_conv2d_fwd_stats_rows(B, H, W, Cout, ksize, stride)
         stats = torch.empty(T, 2, Cout, dtype=F32, device=x.device)
     sp = _span("conv_gemm_fwd", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize)
     if out_f32:
@@ -304,6 +309,40 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     if sp:
         sp.end()
     return dx, dgamma, dbeta, dz
+
+
+def bn_backward_pooled(g_pool, idx, x, co, dgamma=None, dbeta=None):
+    """Backward of bn -> relu -> maxpool(3x3/2) given the gradient of the POOLED output: the max-pool backward is gathered
+    on the fly inside both BN-backward passes. x: raw conv output [B,H,W,C]. Returns (dx, dgamma, dbeta)."""
+    lib = _lib.load()
+    B, H, W, C = x.shape
+    rows = B * H * W
+    nblk = lib.b200_bn_bwd_blocks(rows, C)
+    if nblk <= 0:
+        raise RuntimeError(f"bn_backward_pooled: unsupported channel count {C}")
+    partial = torch.empty(nblk, 2, C, dtype=F32, device=x.device)
+    sp = _span("bn_bwd_reduce", 0.0, _nb(g_pool, idx, x))
+    rc = lib.b200_bn_bwd_reduce_pooled(_p(g_pool), _p(idx), _p(x), _p(co.scale), _p(co.shift), B, H, W, C, _p(partial),
+                                       _stream())
+    _lib.check(rc, "b200_bn_bwd_reduce_pooled")
+    if sp:
+        sp.end()
+    if dgamma is None:
+        dgamma = torch.empty(C, dtype=F32, device=x.device)
+        dbeta = torch.empty(C, dtype=F32, device=x.device)
+    m = torch.empty(2, C, dtype=F32, device=x.device)
+    sc = _reduce_scratch(x.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, float(rows), _p(dgamma), _p(dbeta), 0, _p(m[0]), _p(m[1]),
+                                  _p(co.mean), _p(co.invstd), _p(sc), sc.numel(), _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    dx = torch.empty_like(x)
+    sp = _span("bn_bwd_apply", 0.0, _nb(g_pool, idx, x, dx))
+    rc = lib.b200_bn_bwd_apply_pooled(_p(g_pool), _p(idx), _p(x), _p(dx), _p(co.scale), _p(co.shift), _p(co.mean),
+                                      _p(co.invstd), _p(m[0]), _p(m[1]), B, H, W, C, _stream())
+    _lib.check(rc, "b200_bn_bwd_apply_pooled")
+    if sp:
+        sp.end()
+    return dx, dgamma, dbeta
 
 
 # --------------------------------------------------------------------------------------------------------- pooling

@@ -43,7 +43,8 @@ unsigned long long b200_launch_count(void);
 /* ---- convolution / linear as implicit GEMM on tcgen05 (ksize in {1,3} pad ksize/2, stride in {1,2}; or 2x2/s2 unpadded) ----
  * forward:  y[B,Ho,Wo,Cout] = conv(x[B,H,W,Cin], w) (+bias) (act) (+residual)
  *   w        bf16 [Cout][ksize*ksize*Cin]   (b200_pack_weight mode 0)
- *   stats    optional fp32 [b200_conv2d_fwd_mtiles()][2][Cout]: per 128-pixel tile sum and sum of squares of y (as stored)
+ *   stats    optional fp32 [b200_conv2d_fwd_stats_rows()][2][Cout]: partial sum / sum of squares of y (as stored), one row
+ *            per (persistent CTA group, 32-lane TMEM quadrant) - a few hundred rows; feed them to b200_bn_finalize
  *   residual optional bf16, same shape as y, added after bias/act
  *   out_f32  optional fp32 [B*Ho*Wo][ld_out] - when given the result is written there instead of y (ksize 1 only)
  * replaces nn.Conv2d.forward / nn.Linear.forward: classification/resnet/models/networks.py:107,111,115,119,218;
@@ -51,7 +52,7 @@ unsigned long long b200_launch_count(void);
 int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, int Cin, int Cout, int ksize, int stride,
                     float* stats, const float* bias, int act, const void* residual, float* out_f32, long long ld_out,
                     void* stream);
-int b200_conv2d_fwd_mtiles(int B, int H, int W, int ksize, int stride);
+int b200_conv2d_fwd_stats_rows(int B, int H, int W, int Cout, int ksize, int stride);
 /* same convolution writing an fp32 NHWC output (+bias) through TMA - ConvNeXt downsample conv feeding the fp32 stream */
 int b200_conv2d_fwd_f32(const void* x, const void* w, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                         int stride, const float* bias, void* stream);
@@ -212,6 +213,14 @@ int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float
 int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
                       const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
                       int relu, long long rows, int C, void* stream);
+/* Stem fusion (bn1 -> relu -> maxpool 3x3/2, classification/resnet/models/networks.py:207-209): the same two passes with
+ * the upstream gradient gathered on the fly from the POOLED gradient g_pool [B,Ho,Wo,C] and the arg-max bytes written by
+ * b200_bn_relu_maxpool_fwd, so the dense max-pool backward tensor is never materialised. x, dx: [B,H,W,C]. */
+int b200_bn_bwd_reduce_pooled(const void* g_pool, const void* idx, const void* x, const float* scale, const float* shift,
+                              int B, int H, int W, int C, float* partial, void* stream);
+int b200_bn_bwd_apply_pooled(const void* g_pool, const void* idx, const void* x, void* dx, const float* scale,
+                             const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
+                             int B, int H, int W, int C, void* stream);
 
 /* ---- pooling ----------------------------------------------------------------------------------------------------------
  * stem: y[B,Ho,Wo,C] = maxpool3x3/s2/p1(relu(x*scale+shift)); idx = one byte arg-max tap per element (uint64 per 8 ch)

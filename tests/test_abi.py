@@ -30,9 +30,11 @@ def test_no_compute_calls_without_gpu_but_metadata_works():
     lib = _lib.load()
     assert lib.b200_abi_version() >= 1
     # pure host-side planners are usable without a device
-    # one BN-statistics partial row per 32-pixel slab of the output
-    assert lib.b200_conv2d_fwd_mtiles(256, 56, 56, 3, 1) == 256 * 56 * 56 // 32
-    assert lib.b200_conv2d_fwd_mtiles(256, 56, 56, 1, 1) == 256 * 56 * 56 // 32
+    # BN statistics rows: (persistent CTAs / channel blocks) x 4 TMEM quadrants (x2 when the warp pair alternates tiles)
+    assert lib.b200_conv2d_fwd_stats_rows(256, 56, 56, 64, 3, 1) == 148 * 8
+    assert lib.b200_conv2d_fwd_stats_rows(256, 56, 56, 256, 1, 1) == 148 * 4
+    assert lib.b200_conv2d_fwd_stats_rows(256, 7, 7, 2048, 1, 1) == 144 // 8 * 4
+    assert lib.b200_conv2d_fwd_stats_rows(1, 8, 8, 64, 1, 1) == 8
     assert lib.b200_conv2d_wgrad_workspace_bytes(256, 56, 56, 64, 64, 3, 1) > 0
     assert lib.b200_bn_bwd_blocks(256 * 56 * 56, 64) > 0
     assert lib.b200_bn_bwd_blocks(100, 96) == -1  # unsupported channel count is reported, not guessed
