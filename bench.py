@@ -270,6 +270,8 @@ def run_b200(args):
 
     # per-kernel roofline: one extra step with CUDA-event spans around every C-ABI op on the launching stream.  Every rank
     # runs the step (it contains the gradient all-reduce); only rank 0 records spans.
+    trainer.step_eager(images, labels)   # torch.cuda.graph() emptied the allocator cache: re-warm it outside the spans
+    sync_all()
     if rank == 0:
         with ops.Profiler(run_ahead_ms=120.0) as prof:
             trainer.step_eager(images, labels)

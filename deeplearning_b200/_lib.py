@@ -82,8 +82,6 @@ SIGNATURES = {
     "b200_bn_bwd_blocks": (_I, [_L, _I]),
     "b200_bn_bwd_finalize": (_I, [_P, _I, _I, _D, _P, _P, _I, _P, _P, _P, _P, _P, c_size_t, _P]),
     "b200_bn_bwd_apply": (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P, _I, _L, _I, _P]),
-    "b200_bn_bwd_reduce_pooled": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P]),
-    "b200_bn_bwd_apply_pooled": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_bn_relu_maxpool_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_maxpool_bwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "b200_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _P]),

@@ -87,26 +87,15 @@ int b200_bn_bwd_blocks(long long rows, int C) {
   return plan_bn_bwd(rows, C).blocks;
 }
 
-static int bn_bwd_reduce_impl(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
-                              const float* shift, int relu, long long rows, int C, float* partial, PoolSrc ps, void* stream) {
+int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
+                       const float* shift, int relu, long long rows, int C, float* partial, void* stream) {
   B200_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_bwd_reduce: C=%d must be 8*2^k <= 2048", C);
   const BnBwdPlan pl = plan_bn_bwd(rows, C);
   bn_bwd_reduce_kernel<<<pl.blocks, 256, 256 * 17 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out),
-      static_cast<uint4*>(dz_out), scale, shift, relu, rows, C / 8, pl.rows_per_block, partial, ps);
+      static_cast<uint4*>(dz_out), scale, shift, relu, rows, C / 8, pl.rows_per_block, partial);
   B200_LAUNCHED();
   return OK;
-}
-int b200_bn_bwd_reduce(const void* g, const void* x, const void* y_out, void* dz_out, const float* scale,
-                       const float* shift, int relu, long long rows, int C, float* partial, void* stream) {
-  return bn_bwd_reduce_impl(g, x, y_out, dz_out, scale, shift, relu, rows, C, partial, PoolSrc{nullptr, 0, 0, 0, 0}, stream);
-}
-int b200_bn_bwd_reduce_pooled(const void* g_pool, const void* idx, const void* x, const float* scale, const float* shift,
-                              int B, int H, int W, int C, float* partial, void* stream) {
-  B200_REQUIRE(idx != nullptr, "bn_bwd_reduce_pooled: idx is null");
-  const PoolSrc ps{static_cast<const unsigned long long*>(idx), H, W, (H - 1) / 2 + 1, (W - 1) / 2 + 1};
-  return bn_bwd_reduce_impl(g_pool, x, nullptr, nullptr, scale, shift, 1, static_cast<long long>(B) * H * W, C, partial, ps,
-                            stream);
 }
 
 int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float* dgamma, float* dbeta, int accumulate,
@@ -120,30 +109,16 @@ int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float
   return OK;
 }
 
-static int bn_bwd_apply_impl(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
-                             const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
-                             int relu, long long rows, int C, PoolSrc ps, void* stream) {
+int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
+                      const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
+                      int relu, long long rows, int C, void* stream) {
   B200_REQUIRE(C % 8 == 0 && pow2(C / 8) && C / 8 <= 256, "bn_bwd_apply: C=%d must be 8*2^k <= 2048", C);
   const BnBwdPlan pl = plan_bn_bwd(rows, C);
   bn_bwd_apply_kernel<<<pl.blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g), static_cast<const uint4*>(x), static_cast<const uint4*>(y_out), g_is_dz,
-      static_cast<uint4*>(dx), scale, shift, mean, invstd, m1, m2, relu, rows, C / 8, pl.rows_per_block, ps);
+      static_cast<uint4*>(dx), scale, shift, mean, invstd, m1, m2, relu, rows, C / 8, pl.rows_per_block);
   B200_LAUNCHED();
   return OK;
-}
-int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
-                      const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
-                      int relu, long long rows, int C, void* stream) {
-  return bn_bwd_apply_impl(g, x, y_out, g_is_dz, dx, scale, shift, mean, invstd, m1, m2, relu, rows, C,
-                           PoolSrc{nullptr, 0, 0, 0, 0}, stream);
-}
-int b200_bn_bwd_apply_pooled(const void* g_pool, const void* idx, const void* x, void* dx, const float* scale,
-                             const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
-                             int B, int H, int W, int C, void* stream) {
-  B200_REQUIRE(idx != nullptr, "bn_bwd_apply_pooled: idx is null");
-  const PoolSrc ps{static_cast<const unsigned long long*>(idx), H, W, (H - 1) / 2 + 1, (W - 1) / 2 + 1};
-  return bn_bwd_apply_impl(g_pool, x, nullptr, 0, dx, scale, shift, mean, invstd, m1, m2, 1,
-                           static_cast<long long>(B) * H * W, C, ps, stream);
 }
 
 int b200_bn_relu_maxpool_fwd(const void* x, void* y, void* idx, const float* scale, const float* shift, int B, int H,

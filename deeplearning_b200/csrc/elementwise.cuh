@@ -148,44 +148,6 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ x, const uint4* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Stem fusion: the upstream gradient of bn1+relu is the 3x3/2 max-pool backward of the pooled gradient. Instead of
-// materialising that (mostly zero) [B,H,W,C] tensor, the BN-backward kernels gather it on the fly: pixel (h, w) receives
-// the pooled gradient of every window whose recorded arg-max tap points at it (<= 4 windows).
-struct PoolSrc {
-  const unsigned long long* idx;  // [B,Ho,Wo,C/8] one arg-max byte per channel, or null: g is a dense [rows][C] tensor
-  int H, W, Ho, Wo;
-};
-__device__ __forceinline__ uint4 pooled_grad8(const uint4* __restrict__ g_out, const PoolSrc& ps, long long row, int cvec,
-                                              int cg) {
-  const int w = static_cast<int>(row % ps.W);
-  const long long t = row / ps.W;
-  const int h = static_cast<int>(t % ps.H);
-  const long long b = t / ps.H;
-  float acc[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-#pragma unroll
-  for (int kh = 0; kh < 3; ++kh) {
-    const int th = h + 1 - kh;
-    if (th < 0 || (th & 1) || (th >> 1) >= ps.Ho) continue;
-#pragma unroll
-    for (int kw = 0; kw < 3; ++kw) {
-      const int tw = w + 1 - kw;
-      if (tw < 0 || (tw & 1) || (tw >> 1) >= ps.Wo) continue;
-      const long long o = ((b * ps.Ho + (th >> 1)) * ps.Wo + (tw >> 1)) * cvec + cg;
-      const unsigned long long pk = __ldg(ps.idx + o);
-      float gv[8];
-      unpack8(__ldg(g_out + o), gv);
-      const unsigned int tap = kh * 3 + kw;
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (static_cast<unsigned int>((pk >> (8 * j)) & 0xFF) == tap) acc[j] += gv[j];
-    }
-  }
-  return pack8(acc);
-}
-
-// ------------------------------------------------------------------------------------------------------------------
 // BatchNorm backward, pass 1: dz = g * relu_mask; per-channel partial sums of dz and dz * xhat.
 //   mask source: y_out (saved post-activation output, used when a residual was added) if given, else recomputed from
 //   x*scale+shift > 0; relu == 0 -> no mask.  Optionally stores dz (bf16) for reuse (identity-branch gradient).
@@ -193,7 +155,7 @@ __device__ __forceinline__ uint4 pooled_grad8(const uint4* __restrict__ g_out, c
 __global__ void __launch_bounds__(256, 3)
 bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, const uint4* __restrict__ y_out,
                      uint4* __restrict__ dz_out, const float* __restrict__ scale, const float* __restrict__ shift, int relu,
-                     long long rows, int cvec, int rows_per_block, float* __restrict__ partial, PoolSrc ps) {
+                     long long rows, int cvec, int rows_per_block, float* __restrict__ partial) {
   extern __shared__ float red[];  // [256][17]
   const int tpr = cvec;                  // threads per row (power of two, <= 256)
   const int rpi = 256 / tpr;             // rows per iteration
@@ -216,11 +178,9 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ g, const uint4* __restrict__ x, c
     const long long i0 = r * cvec + cg;
     const long long i1 = (r + rpi) * cvec + cg;
     const bool has1 = (r + rpi) < r1;
-    const bool pooled = ps.idx != nullptr;
-    uint4 g0 = pooled ? pooled_grad8(g, ps, r, cvec, cg) : __ldg(g + i0), x0 = __ldg(x + i0), g1 = g0, x1 = x0, y0 = g0,
-          y1 = g0;
+    uint4 g0 = __ldg(g + i0), x0 = __ldg(x + i0), g1 = g0, x1 = x0, y0 = g0, y1 = g0;
     if (has1) {
-      g1 = pooled ? pooled_grad8(g, ps, r + rpi, cvec, cg) : __ldg(g + i1);
+      g1 = __ldg(g + i1);
       x1 = __ldg(x + i1);
     }
     if (mask_from_y) {
@@ -303,7 +263,7 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
                                     const float* __restrict__ scale, const float* __restrict__ shift,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ m1, const float* __restrict__ m2, int relu,
-                                    long long rows, int cvec, int rows_per_block, PoolSrc ps) {
+                                    long long rows, int cvec, int rows_per_block) {
   const int tpr = cvec, rpi = 256 / tpr;
   const int cg = threadIdx.x % tpr, rsub = threadIdx.x / tpr;
   float sc[8], sh[8], a[8], bq[8], cq[8];
@@ -331,11 +291,9 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
     const long long i0 = r * cvec + cg;
     const long long i1 = (r + rpi) * cvec + cg;
     const bool has1 = (r + rpi) < r1;
-    const bool pooled = ps.idx != nullptr;
-    uint4 g0 = pooled ? pooled_grad8(g, ps, r, cvec, cg) : __ldg(g + i0), x0 = __ldg(x + i0), g1 = g0, x1 = x0, y0 = g0,
-          y1 = g0;
+    uint4 g0 = __ldg(g + i0), x0 = __ldg(x + i0), g1 = g0, x1 = x0, y0 = g0, y1 = g0;
     if (has1) {
-      g1 = pooled ? pooled_grad8(g, ps, r + rpi, cvec, cg) : __ldg(g + i1);
+      g1 = __ldg(g + i1);
       x1 = __ldg(x + i1);
     }
     if (mask_from_y) {

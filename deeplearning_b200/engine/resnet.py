@@ -238,9 +238,9 @@ def backward(model, tape, dlogits, sink=None):
         g = gx
 
     a, c1, co1, idx, (Ho, Wo) = tape["stem"]
-    # maxpool backward is gathered inside the two BN-backward passes (the dense [B,112,112,64] gradient never exists)
-    dc, dgamma, dbeta = ops.bn_backward_pooled(g, idx, c1, co1, dgamma=grads.dest(model.bn1.weight),
-                                               dbeta=grads.dest(model.bn1.bias))
+    g_act = ops.maxpool_bwd(g, idx, (Ho, Wo))
+    dc, dgamma, dbeta, _ = ops.bn_backward(g_act, c1, co1, relu=True, dgamma=grads.dest(model.bn1.weight),
+                                           dbeta=grads.dest(model.bn1.bias))
     grads.put(model.bn1.weight, dgamma)
     grads.put(model.bn1.bias, dbeta)
     kpad = a.shape[1]

@@ -311,40 +311,6 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     return dx, dgamma, dbeta, dz
 
 
-def bn_backward_pooled(g_pool, idx, x, co, dgamma=None, dbeta=None):
-    """Backward of bn -> relu -> maxpool(3x3/2) given the gradient of the POOLED output: the max-pool backward is gathered
-    on the fly inside both BN-backward passes. x: raw conv output [B,H,W,C]. Returns (dx, dgamma, dbeta)."""
-    lib = _lib.load()
-    B, H, W, C = x.shape
-    rows = B * H * W
-    nblk = lib.b200_bn_bwd_blocks(rows, C)
-    if nblk <= 0:
-        raise RuntimeError(f"bn_backward_pooled: unsupported channel count {C}")
-    partial = torch.empty(nblk, 2, C, dtype=F32, device=x.device)
-    sp = _span("bn_bwd_reduce", 0.0, _nb(g_pool, idx, x))
-    rc = lib.b200_bn_bwd_reduce_pooled(_p(g_pool), _p(idx), _p(x), _p(co.scale), _p(co.shift), B, H, W, C, _p(partial),
-                                       _stream())
-    _lib.check(rc, "b200_bn_bwd_reduce_pooled")
-    if sp:
-        sp.end()
-    if dgamma is None:
-        dgamma = torch.empty(C, dtype=F32, device=x.device)
-        dbeta = torch.empty(C, dtype=F32, device=x.device)
-    m = torch.empty(2, C, dtype=F32, device=x.device)
-    sc = _reduce_scratch(x.device)
-    rc = lib.b200_bn_bwd_finalize(_p(partial), nblk, C, float(rows), _p(dgamma), _p(dbeta), 0, _p(m[0]), _p(m[1]),
-                                  _p(co.mean), _p(co.invstd), _p(sc), sc.numel(), _stream())
-    _lib.check(rc, "b200_bn_bwd_finalize")
-    dx = torch.empty_like(x)
-    sp = _span("bn_bwd_apply", 0.0, _nb(g_pool, idx, x, dx))
-    rc = lib.b200_bn_bwd_apply_pooled(_p(g_pool), _p(idx), _p(x), _p(dx), _p(co.scale), _p(co.shift), _p(co.mean),
-                                      _p(co.invstd), _p(m[0]), _p(m[1]), B, H, W, C, _stream())
-    _lib.check(rc, "b200_bn_bwd_apply_pooled")
-    if sp:
-        sp.end()
-    return dx, dgamma, dbeta
-
-
 # --------------------------------------------------------------------------------------------------------- pooling
 def bn_relu_maxpool_fwd(x, co):
     lib = _lib.load()

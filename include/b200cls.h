@@ -213,15 +213,6 @@ int b200_bn_bwd_finalize(const float* partial, int T, int C, double count, float
 int b200_bn_bwd_apply(const void* g, const void* x, const void* y_out, int g_is_dz, void* dx, const float* scale,
                       const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
                       int relu, long long rows, int C, void* stream);
-/* Stem fusion (bn1 -> relu -> maxpool 3x3/2, classification/resnet/models/networks.py:207-209): the same two passes with
- * the upstream gradient gathered on the fly from the POOLED gradient g_pool [B,Ho,Wo,C] and the arg-max bytes written by
- * b200_bn_relu_maxpool_fwd, so the dense max-pool backward tensor is never materialised. x, dx: [B,H,W,C]. */
-int b200_bn_bwd_reduce_pooled(const void* g_pool, const void* idx, const void* x, const float* scale, const float* shift,
-                              int B, int H, int W, int C, float* partial, void* stream);
-int b200_bn_bwd_apply_pooled(const void* g_pool, const void* idx, const void* x, void* dx, const float* scale,
-                             const float* shift, const float* mean, const float* invstd, const float* m1, const float* m2,
-                             int B, int H, int W, int C, void* stream);
-
 /* ---- pooling ----------------------------------------------------------------------------------------------------------
  * stem: y[B,Ho,Wo,C] = maxpool3x3/s2/p1(relu(x*scale+shift)); idx = one byte arg-max tap per element (uint64 per 8 ch)
  * replaces bn1 -> relu -> maxpool, classification/resnet/models/networks.py:207-209 */
