@@ -37,24 +37,28 @@ int b200_layernorm_fwd(const void* x, int x_f32, const float* gamma, const float
                        float* rstd, long long rows, int C, float eps, void* stream) {
   B200_REQUIRE(C % 8 == 0 && C <= 3072, "layernorm_fwd: C=%d must be a multiple of 8 and <= 3072", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int grid = grid_for(rows, 8);
-#define LN_FWD(TI, TY, MV) \
-  layernorm_fwd_kernel<TI, TY, MV><<<grid, 256, 0, st>>>(static_cast<const TI*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps)
-#define LN_FWD_T(MV)                                   \
+#define LN_FWD(TI, TY, MV, LPR)                                                                                      \
+  layernorm_fwd_kernel<TI, TY, MV, LPR><<<grid_for((rows + 32 / LPR - 1) / (32 / LPR), 8), 256, 0, st>>>(            \
+      static_cast<const TI*>(x), gamma, beta, static_cast<TY*>(y), mean, rstd, rows, C, eps)
+#define LN_FWD_T(MV, LPR)                              \
   do {                                                 \
     if (x_f32 && y_f32)                                \
-      LN_FWD(float, float, MV);                        \
+      LN_FWD(float, float, MV, LPR);                   \
     else if (x_f32)                                    \
-      LN_FWD(float, __nv_bfloat16, MV);                \
+      LN_FWD(float, __nv_bfloat16, MV, LPR);           \
     else if (y_f32)                                    \
-      LN_FWD(__nv_bfloat16, float, MV);                \
+      LN_FWD(__nv_bfloat16, float, MV, LPR);           \
     else                                               \
-      LN_FWD(__nv_bfloat16, __nv_bfloat16, MV);        \
+      LN_FWD(__nv_bfloat16, __nv_bfloat16, MV, LPR);   \
   } while (0)
-  if (C <= 1024)
-    LN_FWD_T(4);
+  if (C <= 128)
+    LN_FWD_T(2, 8);     // 4 rows per warp (ConvNeXt / Swin stage 1: C = 96)
+  else if (C <= 256)
+    LN_FWD_T(2, 16);    // 2 rows per warp (C = 192)
+  else if (C <= 1024)
+    LN_FWD_T(4, 32);
   else
-    LN_FWD_T(12);
+    LN_FWD_T(12, 32);
 #undef LN_FWD_T
 #undef LN_FWD
   B200_LAUNCHED();
@@ -71,30 +75,33 @@ int b200_layernorm_bwd(const void* dy, const void* x, int x_f32, const float* me
   B200_REQUIRE(C % 8 == 0 && C <= 1024, "layernorm_bwd: C=%d must be a multiple of 8 and <= 1024", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = ln_bwd_blocks(rows);
-  const size_t smem = static_cast<size_t>(8) * 2 * C * sizeof(float);
   const __nv_bfloat16* dyp = static_cast<const __nv_bfloat16*>(dy);
-#define LN_BWD_V(TI, TO, MV)                                                                                       \
+#define LN_BWD_V(TI, TO, MV, LPR)                                                                                   \
   do {                                                                                                              \
     static bool cfg = false;                                                                                        \
     if (!cfg) {                                                                                                     \
-      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TI, TO, MV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(layernorm_bwd_kernel<TI, TO, MV, LPR>,                                   \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,                             \
                                            8 * 2 * 1024 * (int)sizeof(float)));                                     \
       cfg = true;                                                                                                   \
     }                                                                                                               \
-    layernorm_bwd_kernel<TI, TO, MV><<<grid, 256, smem, st>>>(dyp, static_cast<const TI*>(x), mean, rstd, gamma,     \
-                                                              static_cast<const TO*>(add), static_cast<TO*>(dx),   \
-                                                              partial, rows, C);                                    \
+    const size_t smem = static_cast<size_t>(8) * (32 / LPR) * 2 * C * sizeof(float);                                \
+    layernorm_bwd_kernel<TI, TO, MV, LPR><<<grid, 256, smem, st>>>(dyp, static_cast<const TI*>(x), mean, rstd,      \
+                                                                   gamma, static_cast<const TO*>(add),             \
+                                                                   static_cast<TO*>(dx), partial, rows, C);         \
   } while (0)
 #define LN_BWD(TI, TO)                  \
   do {                                  \
-    if (C <= 256)                       \
-      LN_BWD_V(TI, TO, 1);              \
+    if (C <= 128)                       \
+      LN_BWD_V(TI, TO, 2, 8);           \
+    else if (C <= 256)                  \
+      LN_BWD_V(TI, TO, 2, 16);          \
     else if (C <= 512)                  \
-      LN_BWD_V(TI, TO, 2);              \
+      LN_BWD_V(TI, TO, 2, 32);          \
     else if (C <= 768)                  \
-      LN_BWD_V(TI, TO, 3);              \
+      LN_BWD_V(TI, TO, 3, 32);          \
     else                                \
-      LN_BWD_V(TI, TO, 4);              \
+      LN_BWD_V(TI, TO, 4, 32);          \
   } while (0)
   if (x_f32 && dx_f32)
     LN_BWD(float, float);
@@ -167,14 +174,30 @@ int b200_dwconv7_pack(const float* w, float* wt, int C, void* stream) {
   return OK;
 }
 
+static bool dw_tiled(int H, int W, int C) { return H % kDwTile == 0 && W % kDwTile == 0 && C % kDwCh == 0; }
+
 int b200_dwconv7(const void* in, int in_f32, const float* wt, const float* bias, const void* add, void* out, int out_f32,
                  int flip, int B, int H, int W, int C, void* stream) {
   B200_REQUIRE(C % 4 == 0, "dwconv7: C=%d must be a multiple of 4", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long total = static_cast<long long>(B) * H * ((W + 3) / 4) * (C / 4);
   const int grid = grid_for(total, 128, 32);
-#define DW(TI, TO, F) \
-  dwconv7_kernel<TI, TO, F><<<grid, 128, 0, st>>>(static_cast<const TI*>(in), wt, bias, static_cast<const TO*>(add), static_cast<TO*>(out), B, H, W, C)
+  const bool tiled = dw_tiled(H, W, C);
+  const long long tgrid = tiled ? static_cast<long long>(B) * (H / kDwTile) * (W / kDwTile) * (C / kDwCh) : 0;
+  B200_REQUIRE(tgrid < (1ll << 31), "dwconv7: tensor too large");
+  constexpr int kTileSmem = kDwHalo * kDwHalo * kDwCh * sizeof(float);
+#define DW(TI, TO, F)                                                                                                     \
+  if (tiled) {                                                                                                            \
+    static bool cfg = false;                                                                                              \
+    if (!cfg) {                                                                                                           \
+      B200_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_tile_kernel<TI, TO, F>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                           kTileSmem));                                                                   \
+      cfg = true;                                                                                                         \
+    }                                                                                                                     \
+    dwconv7_tile_kernel<TI, TO, F><<<static_cast<unsigned>(tgrid), 128, kTileSmem, st>>>(                                 \
+        static_cast<const TI*>(in), wt, bias, static_cast<const TO*>(add), static_cast<TO*>(out), B, H, W, C);            \
+  } else                                                                                                                  \
+    dwconv7_kernel<TI, TO, F><<<grid, 128, 0, st>>>(static_cast<const TI*>(in), wt, bias, static_cast<const TO*>(add), static_cast<TO*>(out), B, H, W, C)
   if (in_f32 && !out_f32 && !flip)
     DW(float, __nv_bfloat16, false);
   else if (!in_f32 && !out_f32 && flip)
@@ -199,14 +222,45 @@ static int dw_wgrad_blocks_y(int B, int H) {
   return static_cast<int>(by < 1 ? 1 : by);
 }
 
+struct DwWgradPlan {
+  int blocks_y, tiles_per_cta;
+};
+static DwWgradPlan dw_wgrad_tile_plan(int B, int H, int W, int C) {
+  const long long tiles = static_cast<long long>(B) * (H / kDwTile) * (W / kDwTile);
+  long long by = (6ll * device_sm_count() + C / kDwCh - 1) / (C / kDwCh);  // two waves of 3 CTAs per SM over all channel groups
+  if (by > tiles) by = tiles;
+  if (by < 1) by = 1;
+  const int tpc = static_cast<int>((tiles + by - 1) / by);
+  return DwWgradPlan{static_cast<int>((tiles + tpc - 1) / tpc), tpc};
+}
+
 size_t b200_dwconv7_wgrad_workspace_bytes(int B, int H, int W, int C) {
-  (void)W;
-  return static_cast<size_t>(dw_wgrad_blocks_y(B, H)) * 49 * C * sizeof(float);
+  const int by = dw_tiled(H, W, C) ? dw_wgrad_tile_plan(B, H, W, C).blocks_y : dw_wgrad_blocks_y(B, H);
+  return static_cast<size_t>(by) * 49 * C * sizeof(float);
 }
 
 int b200_dwconv7_wgrad(const void* du, const float* x, float* dw, void* workspace, size_t workspace_bytes, int B, int H,
                        int W, int C, int accumulate, void* stream) {
   B200_REQUIRE(C % 4 == 0, "dwconv7_wgrad: C=%d must be a multiple of 4", C);
+  if (dw_tiled(H, W, C)) {
+    const DwWgradPlan pl = dw_wgrad_tile_plan(B, H, W, C);
+    B200_REQUIRE(workspace != nullptr && workspace_bytes >= static_cast<size_t>(pl.blocks_y) * 49 * C * sizeof(float),
+                 "dwconv7_wgrad: workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    constexpr int kSmem = (kDwHalo * kDwHalo * 4 + kDwTile * kDwTile * 2) * kDwCh;  // fp32 x halo + bf16 du tile
+    static bool cfg = false;
+    if (!cfg) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(dwconv7_wgrad_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+      cfg = true;
+    }
+    dwconv7_wgrad_tile_kernel<<<dim3(C / kDwCh, pl.blocks_y), 128, kSmem, st>>>(
+        static_cast<const __nv_bfloat16*>(du), x, static_cast<float*>(workspace), B, H, W, C, pl.tiles_per_cta);
+    B200_LAUNCHED();
+    dwconv7_wgrad_finalize_kernel<<<(49 * C + 255) / 256, 256, 0, st>>>(static_cast<const float*>(workspace), pl.blocks_y, C,
+                                                                        dw, accumulate);
+    B200_LAUNCHED();
+    return OK;
+  }
   const int by = dw_wgrad_blocks_y(B, H);
   B200_REQUIRE(workspace != nullptr && workspace_bytes >= static_cast<size_t>(by) * 49 * C * sizeof(float),
                "dwconv7_wgrad: workspace too small");
@@ -439,7 +493,7 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmemBytes));
     cfg = true;
   }
-  attn_bwd_kernel<<<B * H, 160, kAttnBwdSmemBytes, st>>>(p);
+  attn_bwd_kernel<<<B * H, 288, kAttnBwdSmemBytes, st>>>(p);
   B200_LAUNCHED();
   return OK;
 }

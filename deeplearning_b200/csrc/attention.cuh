@@ -231,7 +231,7 @@ struct alignas(64) AttnBwdParams {
 
 constexpr int kAttnBwdSmemBytes = 32768 * 2 + 16384 * 2 + 65536 * 2 + 256 + 1024;
 
-__global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+__global__ void __launch_bounds__(288, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;
@@ -265,11 +265,11 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       mbar_init(bar_kv, 1);
       mbar_init(bar_q, 1);
       mbar_init(bar_s, 1);
-      mbar_init(bar_p, 4);
+      mbar_init(bar_p, 8);
       mbar_init(bar_dp, 1);
-      mbar_init(bar_ds, 4);
+      mbar_init(bar_ds, 8);
       mbar_init(bar_dq, 1);
-      mbar_init(bar_free, 4);
+      mbar_init(bar_free, 8);
       fence_mbar_init();
     }
     __syncwarp();
@@ -343,10 +343,16 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       }
     }
   } else {
-    const int row = warp_idx * 32 + lane;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
+    // 8 soft-max warps: two per TMEM lane quadrant (warp_idx % 4); the pair splits the key columns of every row in half
+    const int quad = warp_idx & 3;
+    const int pair = warp_idx > 4 ? 1 : 0;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     const int nfull = p.Tpad / 32;
     const bool tail16 = (p.Tpad & 31) != 0;
+    const int nchunks = nfull + (tail16 ? 1 : 0);
+    const int c_begin = pair == 0 ? 0 : (nchunks + 1) / 2;
+    const int c_end = pair == 0 ? (nchunks + 1) / 2 : nchunks;
     const long long bh = static_cast<long long>(b) * p.H + h;
     for (int mb = 0; mb < p.mblocks; ++mb) {
       const uint32_t ph = mb & 1;
@@ -370,19 +376,20 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
           *reinterpret_cast<uint4*>(sP + (col >> 6) * 16384 + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)) = pack8(e);
         }
       };
-      for (int c = 0; c < nfull; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-        tmem_ld_wait();
-        emit_p(v, c * 32, 32);
+      for (int c = c_begin; c < c_end; ++c) {
+        if (c < nfull) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + kColS + c * 32, v);
+          tmem_ld_wait();
+          emit_p(v, c * 32, 32);
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x16(lane_addr + kColS + nfull * 32, v);
+          tmem_ld_wait();
+          emit_p(v, nfull * 32, 16);
+        }
       }
-      if (tail16) {
-        uint32_t v[16];
-        tmem_ld_32x16(lane_addr + kColS + nfull * 32, v);
-        tmem_ld_wait();
-        emit_p(v, nfull * 32, 16);
-      }
-      if (p.Tpad < 256) {
+      if (pair == 1 && p.Tpad < 256) {
         // zero the key columns [Tpad, next multiple of 64) that the P^T / dS^T MMAs (M = 128 keys) still read
         const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int cend = ((p.Tpad + 127) / 128) * 128;
@@ -410,17 +417,18 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
           *reinterpret_cast<uint4*>(sdS + off) = pack8(e);
         }
       };
-      for (int c = 0; c < nfull; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-        tmem_ld_wait();
-        emit_ds(v, c * 32, 32);
-      }
-      if (tail16) {
-        uint32_t v[16];
-        tmem_ld_32x16(lane_addr + kColS + nfull * 32, v);
-        tmem_ld_wait();
-        emit_ds(v, nfull * 32, 16);
+      for (int c = c_begin; c < c_end; ++c) {
+        if (c < nfull) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + kColS + c * 32, v);
+          tmem_ld_wait();
+          emit_ds(v, c * 32, 32);
+        } else {
+          uint32_t v[16];
+          tmem_ld_32x16(lane_addr + kColS + nfull * 32, v);
+          tmem_ld_wait();
+          emit_ds(v, nfull * 32, 16);
+        }
       }
       tc_fence_before();
       fence_proxy_async_smem();
@@ -430,8 +438,8 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       mbar_wait(bar_dq, ph);
       tc_fence_after();
       uint8_t* stg = sdO;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = pair;  // each warp of the pair drains one 32-column half of dQ
         uint32_t v[32];
         tmem_ld_32x32(lane_addr + kColS + c * 32, v);
         tmem_ld_wait();
@@ -445,13 +453,13 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (threadIdx.x == 0) {
         tma_store_3d(&p.dqkv_map, stg, h * 64, mb * 128, b);
         tma_store_commit();
         tma_store_wait_read<0>();
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free);
     }
@@ -462,8 +470,8 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
         if (j * 128 >= p.Tpad) break;
         uint8_t* stg = sP + (which * 2 + j) * 16384;
         const uint32_t col0 = (which == 0 ? kColDK : kColDV) + j * 64;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
+        {
+          const int c = pair;
           uint32_t v[32];
           tmem_ld_32x32(lane_addr + col0 + c * 32, v);
           tmem_ld_wait();
@@ -479,7 +487,7 @@ __global__ void __launch_bounds__(160, 1) attn_bwd_kernel(const __grid_constant_
     }
     tc_fence_before();
     fence_proxy_async_smem();
-    named_bar_sync(1, 128);
+    named_bar_sync(1, 256);
     if (threadIdx.x == 0) {
       for (int which = 0; which < 2; ++which)
         for (int j = 0; j < 2; ++j) {

@@ -150,6 +150,173 @@ __global__ void __launch_bounds__(224) dwconv7_wgrad_kernel(const __nv_bfloat16*
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Tiled 7x7 depthwise kernels (H, W multiples of 14 and C a multiple of 32 - every ConvNeXt stage but the 7x7 one).
+// A CTA stages the fp32 halo (20 x 20 pixels x 32 channels, zero padded) of a 14 x 14 output tile in shared memory; each of
+// its 4 warps owns a 7 x 7 output block and each lane ONE channel, so every shared load is a conflict-free 128-byte row
+// and the 49 filter taps of the lane's channel live in registers. Per input row a thread issues 13 shared loads for up
+// to 343 FMAs (the naive strip kernel above: ~1 load per 11 FMAs from L1): the loop is FP32-FMA bound.
+constexpr int kDwTile = 14, kDwHalo = 20, kDwCh = 32;
+
+// 16 / 8-byte asynchronous global -> shared copies; src_bytes == 0 zero-fills the destination (the conv's zero padding)
+__device__ __forceinline__ void dw_cp_async16(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void dw_cp_async8(uint32_t dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void dw_cp_async_wait() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// Stage ROWS x COLS pixels x 32 channels starting at (h0, w0) (zero outside the image) for a 128-thread CTA.
+// fp32 sources are copied asynchronously as they are; bf16 sources are widened to fp32 on the way (RAW = keep bf16).
+template <typename TIn, int ROWS, int COLS, bool RAW = false>
+__device__ __forceinline__ void dw_fill_tile(void* s, const TIn* __restrict__ src, long long b, int h0, int w0, int H, int W,
+                                             int C, int c0) {
+  constexpr int N = ROWS * COLS * (kDwCh / 4);
+  const int part = threadIdx.x & 7;
+  const TIn* base = src + (b * H * W) * C + c0 + part * 4;
+  const uint32_t s_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(s));
+#pragma unroll 5
+  for (int k = threadIdx.x; k < N; k += 128) {
+    const int pix = k >> 3;
+    const int py = pix / COLS, px = pix - py * COLS;
+    const int hh = h0 + py, ww = w0 + px;
+    const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
+    const TIn* g = ok ? base + (static_cast<long long>(hh) * W + ww) * C : base;
+    if constexpr (sizeof(TIn) == 4) {
+      dw_cp_async16(s_u32 + (pix * kDwCh + part * 4) * 4, g, ok ? 16 : 0);
+    } else if constexpr (RAW) {
+      dw_cp_async8(s_u32 + (pix * kDwCh + part * 4) * 2, g, ok ? 8 : 0);
+    } else {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok) v = ld4<TIn>(g);
+      *reinterpret_cast<float4*>(static_cast<float*>(s) + pix * kDwCh + part * 4) = v;
+    }
+  }
+}
+
+template <typename TIn, typename TOut, bool FLIP>
+__global__ void __launch_bounds__(128, 4) dwconv7_tile_kernel(const TIn* __restrict__ in, const float* __restrict__ wt,
+                                                              const float* __restrict__ bias, const TOut* __restrict__ add,
+                                                              TOut* __restrict__ out, int B, int H, int W, int C) {
+  extern __shared__ float dw_smem[];  // [20][20][32]
+  const int cgroups = C / kDwCh, tiles_w = W / kDwTile, tiles_h = H / kDwTile;
+  int t = blockIdx.x;
+  const int cg = t % cgroups;
+  t /= cgroups;
+  const int tw = t % tiles_w;
+  t /= tiles_w;
+  const int th = t % tiles_h;
+  const long long b = t / tiles_h;
+  const int c0 = cg * kDwCh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  dw_fill_tile<TIn, kDwHalo, kDwHalo>(dw_smem, in, b, th * kDwTile - 3, tw * kDwTile - 3, H, W, C, c0);
+  float w[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) w[k] = __ldg(wt + static_cast<long long>(FLIP ? 48 - k : k) * C + c0 + lane);
+  const float bz = bias ? __ldg(bias + c0 + lane) : 0.f;
+  dw_cp_async_wait();
+  __syncthreads();
+  const int by = warp >> 1, bx = warp & 1;
+  const float* sp = dw_smem + ((by * 7) * kDwHalo + bx * 7) * kDwCh + lane;
+  float acc[7][7];
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int q = 0; q < 7; ++q) acc[r][q] = bz;
+#pragma unroll
+  for (int i = 0; i < 13; ++i) {
+    float xin[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) xin[j] = sp[(i * kDwHalo + j) * kDwCh];
+#pragma unroll
+    for (int kh = 0; kh < 7; ++kh) {
+      const int r = i - kh;
+      if (r < 0 || r >= 7) continue;
+#pragma unroll
+      for (int q = 0; q < 7; ++q)
+#pragma unroll
+        for (int kw = 0; kw < 7; ++kw) acc[r][q] = fmaf(w[kh * 7 + kw], xin[q + kw], acc[r][q]);
+    }
+  }
+  const int oh = th * kDwTile + by * 7, ow = tw * kDwTile + bx * 7;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const long long o = ((b * H + oh + r) * W + ow + q) * C + c0 + lane;
+      float v = acc[r][q];
+      if (add != nullptr) v += static_cast<float>(add[o]);
+      out[o] = static_cast<TOut>(v);
+    }
+  }
+}
+
+// Weight gradient on the same tiling: acc[kh][kw] += du[r][q] * x[r+kh][q+kw] over the lane's channel; a CTA walks
+// `tiles_per_cta` tiles of one 32-channel group and writes one partial row part[blockIdx.y][tap][c].
+__global__ void __launch_bounds__(128, 3) dwconv7_wgrad_tile_kernel(const __nv_bfloat16* __restrict__ du,
+                                                                    const float* __restrict__ x, float* __restrict__ part,
+                                                                    int B, int H, int W, int C, int tiles_per_cta) {
+  extern __shared__ float dw_smem[];  // x halo fp32 [20][20][32] | du tile bf16 [14][14][32]
+  float* s_x = dw_smem;
+  const __nv_bfloat16* s_d = reinterpret_cast<const __nv_bfloat16*>(dw_smem + kDwHalo * kDwHalo * kDwCh);
+  const int tiles_w = W / kDwTile, tiles_h = H / kDwTile;
+  const long long ntiles = static_cast<long long>(B) * tiles_h * tiles_w;
+  const int c0 = blockIdx.x * kDwCh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int by = warp >> 1, bx = warp & 1;
+  float acc[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) acc[k] = 0.f;
+  const long long t0 = static_cast<long long>(blockIdx.y) * tiles_per_cta;
+  const long long t1 = min(ntiles, t0 + tiles_per_cta);
+  for (long long t = t0; t < t1; ++t) {
+    const int tw = static_cast<int>(t % tiles_w);
+    const int th = static_cast<int>((t / tiles_w) % tiles_h);
+    const long long b = t / (static_cast<long long>(tiles_w) * tiles_h);
+    __syncthreads();  // previous tile fully consumed
+    dw_fill_tile<float, kDwHalo, kDwHalo>(s_x, x, b, th * kDwTile - 3, tw * kDwTile - 3, H, W, C, c0);
+    dw_fill_tile<__nv_bfloat16, kDwTile, kDwTile, true>(dw_smem + kDwHalo * kDwHalo * kDwCh, du, b, th * kDwTile,
+                                                        tw * kDwTile, H, W, C, c0);
+    dw_cp_async_wait();
+    __syncthreads();
+    float d[7][7];
+#pragma unroll
+    for (int r = 0; r < 7; ++r)
+#pragma unroll
+      for (int q = 0; q < 7; ++q) d[r][q] = __bfloat162float(s_d[((by * 7 + r) * kDwTile + bx * 7 + q) * kDwCh + lane]);
+    const float* sp = s_x + ((by * 7) * kDwHalo + bx * 7) * kDwCh + lane;
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      float xin[13];
+#pragma unroll
+      for (int j = 0; j < 13; ++j) xin[j] = sp[(i * kDwHalo + j) * kDwCh];
+#pragma unroll
+      for (int kh = 0; kh < 7; ++kh) {
+        const int r = i - kh;
+        if (r < 0 || r >= 7) continue;
+#pragma unroll
+        for (int q = 0; q < 7; ++q)
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw) acc[kh * 7 + kw] = fmaf(d[r][q], xin[q + kw], acc[kh * 7 + kw]);
+      }
+    }
+  }
+  // fold the four warps (fixed order: deterministic), then one partial row per CTA
+  __syncthreads();
+  float* red = dw_smem;  // [4][49][32]
+#pragma unroll
+  for (int k = 0; k < 49; ++k) red[(warp * 49 + k) * 32 + lane] = acc[k];
+  __syncthreads();
+  for (int k = warp; k < 49; k += 4) {
+    const float v = red[(0 * 49 + k) * 32 + lane] + red[(1 * 49 + k) * 32 + lane] + red[(2 * 49 + k) * 32 + lane] +
+                    red[(3 * 49 + k) * 32 + lane];
+    part[(static_cast<long long>(blockIdx.y) * 49 + k) * C + c0 + lane] = v;
+  }
+}
+
 // dW[c][tap] (+)= sum_t part[t][tap][c]   ([C,1,7,7] parameter layout)
 __global__ void dwconv7_wgrad_finalize_kernel(const float* __restrict__ part, int T, int C, float* __restrict__ dw,
                                               int accumulate) {

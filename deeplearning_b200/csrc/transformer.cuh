@@ -35,35 +35,47 @@ __device__ __forceinline__ void store_row8<__nv_bfloat16>(__nv_bfloat16* p, cons
   *reinterpret_cast<uint4*>(p) = pack8(f);
 }
 
-// y = (x - mean) * rstd * gamma + beta.  One warp per row; MAXV = max 8-element vectors per lane (C <= 256*MAXV).
-template <typename TIn, typename TY, int MAXV>
+// Sum over the LPR lanes (a power of two) that share a row.
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int off = LPR / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+// y = (x - mean) * rstd * gamma + beta.  LPR lanes per row (32 / LPR rows per warp: narrow rows such as C = 96 keep every
+// lane busy); MAXV = max 8-element vectors per lane (C <= 8 * LPR * MAXV).
+template <typename TIn, typename TY, int MAXV, int LPR = 32>
 __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, TY* __restrict__ y,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int C,
                                      float eps) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int nvec = C >> 3;
   const long long warp0 = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  for (long long r = warp0; r < rows; r += nwarps) {
+  for (long long rb = warp0 * RPW; rb < rows; rb += nwarps * RPW) {
+    const long long r = rb + grp;
+    const bool live = r < rows;
     float v[MAXV][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
         load_row8<TIn>(x + r * C + vi * 8, v[i]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) s += v[i][j];
       }
     }
-    s = warp_sum(s);
+    s = group_sum<LPR>(s);
     const float mean = s / C;
     float ss = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float d = v[i][j] - mean;
@@ -71,16 +83,16 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __r
         }
       }
     }
-    ss = warp_sum(ss);
+    ss = group_sum<LPR>(ss);
     const float rstd = rsqrtf(ss / C + eps);
-    if (lane == 0) {
+    if (live && sub == 0) {
       if (mean_out) mean_out[r] = mean;
       if (rstd_out) rstd_out[r] = rstd;
     }
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
         float g[8], b[8], o[8];
         load8f(gamma + vi * 8, g);
         load8f(beta + vi * 8, b);
@@ -95,27 +107,31 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __r
 // dx = rstd * (dy*gamma - mean_c(dy*gamma) - xhat * mean_c(dy*gamma*xhat)) (+ add);  partial[block][2][C] = (sum dy, sum dy*xhat)
 // The per-column parameter-gradient accumulators live in shared memory (one private [2][C] slice per warp, updated with
 // conflict-free float4 read-modify-writes) so that the register budget only has to hold one row.
-template <typename TIn, typename TOut, int MAXV>
+template <typename TIn, typename TOut, int MAXV, int LPR = 32>
 __global__ void __launch_bounds__(256, 3)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const TOut* __restrict__ add,
                      TOut* __restrict__ dx, float* __restrict__ partial, long long rows, int C) {
-  extern __shared__ float red[];  // [warps][2][C]
+  extern __shared__ float red[];  // [warps][rows per warp][2][C]
+  constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
   const int nvec = C >> 3;
-  float* mine = red + static_cast<long long>(warp) * 2 * C;
-  for (int i = lane; i < 2 * C; i += 32) mine[i] = 0.f;
+  float* mine = red + (static_cast<long long>(warp) * RPW + grp) * 2 * C;
+  for (int i = sub; i < 2 * C; i += LPR) mine[i] = 0.f;
   __syncwarp();
   const long long warp0 = blockIdx.x * static_cast<long long>(nw) + warp;
   const long long nwarps = static_cast<long long>(gridDim.x) * nw;
-  for (long long r = warp0; r < rows; r += nwarps) {
-    const float mu = mean[r], rs = rstd[r];
+  for (long long rb = warp0 * RPW; rb < rows; rb += nwarps * RPW) {
+    const long long r = rb + grp;
+    const bool live = r < rows;
+    const float mu = live ? mean[r] : 0.f, rs = live ? rstd[r] : 0.f;
     float xh[MAXV][8], dg[MAXV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
         float xv[8], dv[8], g[8];
         load_row8<TIn>(x + r * C + vi * 8, xv);
         unpack8(*reinterpret_cast<const uint4*>(dy + r * C + vi * 8), dv);
@@ -139,12 +155,12 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict
         ab[0] = b0; ab[1] = b1; ag[0] = g0; ag[1] = g1;
       }
     }
-    s1 = warp_sum(s1) / C;
-    s2 = warp_sum(s2) / C;
+    s1 = group_sum<LPR>(s1) / C;
+    s2 = group_sum<LPR>(s2) / C;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-      const int vi = i * 32 + lane;
-      if (vi < nvec) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = rs * (dg[i][j] - s1 - xh[i][j] * s2);
@@ -161,7 +177,7 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict
   __syncthreads();
   for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
     float s = 0.f;
-    for (int w = 0; w < nw; ++w) s += red[static_cast<long long>(w) * 2 * C + c];
+    for (int w = 0; w < nw * RPW; ++w) s += red[static_cast<long long>(w) * 2 * C + c];
     partial[static_cast<long long>(blockIdx.x) * 2 * C + c] = s;
   }
 }

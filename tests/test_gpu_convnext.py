@@ -24,7 +24,7 @@ def _close(a, b, rtol, atol, what):
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} bad, max abs err {float(err.max()):.4g} (ref max {float(b.abs().max()):.4g})"
 
 
-@pytest.mark.parametrize("B,H,W,C", [(2, 56, 56, 96), (3, 7, 7, 768), (2, 14, 9, 192)])
+@pytest.mark.parametrize("B,H,W,C", [(2, 56, 56, 96), (3, 28, 14, 192), (5, 14, 14, 384), (3, 7, 7, 768), (2, 14, 9, 192)])
 def test_dwconv7_fwd_bwd(B, H, W, C):
     ops = _ops()
     x = _rand(B, H, W, C, seed=1, dtype=torch.float32)

@@ -26,7 +26,7 @@ def _close(a, b, rtol, atol, what):
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} bad, max abs err {float(err.max()):.4g} (ref max {float(b.abs().max()):.4g})"
 
 
-@pytest.mark.parametrize("rows,C,dt", [(1000, 768, torch.float32), (513, 96, torch.bfloat16), (64, 1536, torch.float32), (300, 384, torch.float32)])
+@pytest.mark.parametrize("rows,C,dt", [(1000, 768, torch.float32), (513, 96, torch.bfloat16), (1001, 96, torch.float32), (777, 192, torch.float32), (64, 1536, torch.float32), (300, 384, torch.float32)])
 def test_layernorm_fwd_bwd(rows, C, dt):
     ops = _ops()
     x = (_rand(rows, C, seed=1, dtype=torch.float32) * 2 + 0.5).to(dt)

@@ -1,0 +1,83 @@
+"""Runs single ops at their BASELINE shapes inside a cudaProfilerStart/Stop range (for `ncu --profile-from-start off`).
+python tools/prof_ops.py attn_bwd|wattn_bwd|wattn_fwd|dwconv|dwconv_wgrad|ln96 ..."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from deeplearning_b200 import ops
+
+BF16 = torch.bfloat16
+dev = "cuda"
+
+
+def rnd(*shape, dtype=BF16, scale=1.0):
+    return (torch.randn(*shape, device=dev) * scale).to(dtype)
+
+
+def attn_bwd():
+    B, T, H = 256, 197, 12
+    qkv = rnd(B, T, 3 * H * 64, scale=0.5)
+    out, lse = ops.attention_fwd(qkv, H, 0.125)
+    dout = rnd(B, T, H * 64)
+    return lambda: ops.attention_bwd(qkv, out, dout, lse, H, 0.125)
+
+
+def _wattn():
+    B, Hh, W, nH = 128, 56, 56, 3
+    qkv = rnd(B, Hh, W, 3 * nH * 32, scale=0.5)
+    bias = torch.randn(nH, 49, 49, device=dev)
+    nW = 64
+    mask = torch.zeros(nW, 49, 49, device=dev)
+    return B, Hh, W, nH, qkv, bias, mask
+
+
+def wattn_fwd():
+    B, Hh, W, nH, qkv, bias, mask = _wattn()
+    return lambda: ops.window_attention_fwd(qkv, nH, bias, mask, 3, 32 ** -0.5)
+
+
+def wattn_bwd():
+    B, Hh, W, nH, qkv, bias, mask = _wattn()
+    out, lse = ops.window_attention_fwd(qkv, nH, bias, mask, 3, 32 ** -0.5)
+    dout = rnd(B, Hh, W, nH * 32)
+    return lambda: ops.window_attention_bwd(qkv, out, dout, bias, mask, lse, nH, 3, 32 ** -0.5)
+
+
+def dwconv():
+    x = rnd(256, 56, 56, 96, dtype=torch.float32)
+    wt = ops.dwconv7_pack(torch.randn(96, 1, 7, 7, device=dev))
+    b = torch.randn(96, device=dev)
+    return lambda: ops.dwconv7(x, wt, b)
+
+
+def dwconv_wgrad():
+    x = rnd(256, 56, 56, 96, dtype=torch.float32)
+    du = rnd(256, 56, 56, 96)
+    return lambda: ops.dwconv7_wgrad(du, x)
+
+
+def ln96():
+    x = rnd(256 * 56 * 56, 96, dtype=torch.float32)
+    g = torch.ones(96, device=dev)
+    b = torch.zeros(96, device=dev)
+    return lambda: ops.layernorm_fwd(x, g, b, 1e-6)
+
+
+if __name__ == "__main__":
+    fns = [(n, globals()[n]()) for n in sys.argv[1:]]
+    for _, f in fns:
+        f()
+        f()
+    torch.cuda.synchronize()
+    for n, f in fns:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            f()
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"{n}: {e0.elapsed_time(e1) / 5 * 1e3:.1f} us per call")
+    torch.cuda.profiler.start()
+    for _, f in fns:
+        f()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
