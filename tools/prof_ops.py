@@ -62,6 +62,39 @@ def ln96():
     return lambda: ops.layernorm_fwd(x, g, b, 1e-6)
 
 
+def _swin_gemm(kind):
+    M, C = 128 * 56 * 56, 96
+    if kind == "qkv":
+        a = rnd(M, C); wp = ops.pack_weight(torch.randn(3 * C, C, device=dev) * 0.1); b = torch.randn(3 * C, device=dev)
+        return lambda: ops.gemm(a, wp, bias=b)
+    if kind == "proj":
+        a = rnd(M, C); wp = ops.pack_weight(torch.randn(C, C, device=dev) * 0.1); b = torch.randn(C, device=dev)
+        res = rnd(M, C, dtype=torch.float32)
+        return lambda: ops.gemm(a, wp, bias=b, residual=res, out_f32=True)
+    if kind == "fc1":
+        a = rnd(M, C); wp = ops.pack_weight(torch.randn(4 * C, C, device=dev) * 0.1); b = torch.randn(4 * C, device=dev)
+        return lambda: ops.gemm(a, wp, bias=b, act=2, aux_out=True)
+    a = rnd(M, 4 * C); wp = ops.pack_weight(torch.randn(C, 4 * C, device=dev) * 0.05); b = torch.randn(C, device=dev)
+    res = rnd(M, C, dtype=torch.float32)
+    return lambda: ops.gemm(a, wp, bias=b, residual=res, out_f32=True)
+
+
+def swin_qkv():
+    return _swin_gemm("qkv")
+
+
+def swin_proj():
+    return _swin_gemm("proj")
+
+
+def swin_fc1():
+    return _swin_gemm("fc1")
+
+
+def swin_fc2():
+    return _swin_gemm("fc2")
+
+
 if __name__ == "__main__":
     fns = [(n, globals()[n]()) for n in sys.argv[1:]]
     for _, f in fns:
