@@ -72,10 +72,33 @@ struct ConvGemmCfg {
   static constexpr int THREADS = 64 + EPI_WARPS * 32;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// Exact-erf GELU (nn.GELU() of the reference: vit_model.py:121, swin_transformer.py:20, convNext/models/networks.py:84) with
+// erf from Abramowitz & Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the bf16 rounding of the stored activation):
+// one reciprocal, one exp2 and six FMAs instead of erff()'s two-range polynomial (~3x fewer epilogue instructions).
+//   t = 1 / (1 + p |z|),  erf(|z|) = 1 - (a1 t + a2 t^2 + a3 t^3 + a4 t^4 + a5 t^5) exp(-z^2),   z = x / sqrt(2)
+// Returns erfc(|z|) / 2 = (1 - erf|z|) / 2 in `tail` and exp(-x^2 / 2) in `e` so that value and derivative share the work.
+__device__ __forceinline__ void gelu_parts(float x, float& tail, float& e) {
+  const float az = fabsf(x) * 0.70710678118654752f;
+  float t;  // MUFU.RCP (1 ulp) - __frcp_rn would expand into a Newton iteration
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * az * az));  // MUFU.EX2 (2 ulp)
+  tail = 0.5f * poly * t * e;
+}
+__device__ __forceinline__ float gelu_erf(float x) {
+  float tail, e;
+  gelu_parts(x, tail, e);
+  // Phi(x) = 1 - tail for x >= 0, tail for x < 0
+  return x * (x >= 0.f ? 1.0f - tail : tail);
+}
 __device__ __forceinline__ float gelu_erf_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752f));
-  return cdf + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+  float tail, e;
+  gelu_parts(x, tail, e);
+  const float cdf = x >= 0.f ? 1.0f - tail : tail;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
 template <int BLOCK_N>
@@ -274,6 +297,33 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         for (int h = 0; h < nsub; ++h) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_acc + u * unit_cols + h * 32, v);
+          // Global operands of the epilogue (residual / saved pre-activation) are requested BEFORE waiting for the
+          // accumulator, so their DRAM latency overlaps the TMEM load instead of stalling the warp afterwards.
+          const int nc_pre = n0 + h * 32;
+          uint4 pre_b[4];   // bf16 residual or aux_in: 32 x bf16
+          float4 pre_f[8];  // fp32 residual: 32 x fp32
+          const bool pre_res = chunk_live && has_res && row_ok;
+          const bool pre_aux = chunk_live && act == 3 && row_ok;
+          if (pre_res) {
+            const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc_pre;
+            if (p.res_f32) {
+              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (full_cols || nc_pre + j * 4 < N) pre_f[j] = __ldg(rp + j);
+            } else {
+              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (full_cols || nc_pre + j * 8 < N) pre_b[j] = __ldg(rp + j);
+            }
+          }
+          if (pre_aux) {
+            const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + p3 * p.as3 + p2 * p.as2 + p1 * p.as1 + nc_pre);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (full_cols || nc_pre + j * 8 < N) pre_b[j] = __ldg(ap + j);
+          }
           tmem_ld_wait();
           if (u == last_unit && h == nsub - 1) {
             // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
@@ -317,12 +367,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
           } else if (act == 3 && row_ok) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + p3 * p.as3 + p2 * p.as2 + p1 * p.as1 + nc);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (full_cols || nc + j * 8 < N) {
                 float a[8];
-                unpack8(__ldg(ap + j), a);
+                unpack8(pre_b[j], a);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[j * 8 + i] *= gelu_erf_grad(a[i]);
               }
@@ -333,13 +382,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) f[j] *= (full_cols || nc + j < N) ? __ldg(colscale + nc + j) : 0.0f;
           }
           if (has_res && row_ok) {
-            const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc;
             if (p.res_f32) {
-              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 if (full_cols || nc + j * 4 < N) {
-                  const float4 r = __ldg(rp + j);
+                  const float4 r = pre_f[j];
                   f[j * 4 + 0] += r.x;
                   f[j * 4 + 1] += r.y;
                   f[j * 4 + 2] += r.z;
@@ -347,12 +394,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                 }
               }
             } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 if (full_cols || nc + j * 8 < N) {
                   float r[8];
-                  unpack8(__ldg(rp + j), r);
+                  unpack8(pre_b[j], r);
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[j * 8 + i] += r[i];
                 }
