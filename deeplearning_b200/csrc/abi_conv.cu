@@ -164,24 +164,64 @@ int conv_grid(int tiles, int n_tiles, bool stats) {
   return grid;
 }
 
-template <int BLOCK_N>
-int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
+template <int BLOCK_N, int EPI>
+int launch_conv_gemm_epi(const ConvGemmParams& q, int grid, cudaStream_t st) {
   using Cfg = ConvGemmCfg<BLOCK_N>;
   static bool configured = false;
   if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BLOCK_N, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
     configured = true;
   }
+  conv_gemm_kernel<BLOCK_N, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
+  B200_LAUNCHED();
+  return OK;
+}
+
+// Epilogue option set of a launch (bits of conv_gemm.cuh::kEpi*).
+int epilogue_flags(const ConvGemmParams& p) {
+  int f = 0;
+  if (p.bias) f |= kEpiBias;
+  if (p.colscale) f |= kEpiColscale;
+  f |= (p.act & 3) << kEpiActShift;
+  if (p.residual) f |= p.res_f32 ? kEpiResF32 : kEpiResBf16;
+  if (p.has_aux_out) f |= kEpiAux;
+  if (p.out_f32) f |= kEpiOutF32;
+  if (p.out_direct) f |= kEpiDirect;
+  if (p.stats) f |= kEpiStats;
+  return f;
+}
+
+// The layer types on the four training paths get a compile-time epilogue; anything else runs the generic kernel.
+#define B200_EPI_LIST(X)                                                                                  \
+  X(kEpiStats)                                            /* ResNet conv -> BN statistics            */  \
+  X(0)                                                    /* plain dgrad                             */  \
+  X(kEpiResBf16)                                          /* dgrad + identity-branch gradient        */  \
+  X(kEpiBias)                                             /* qkv / patch embedding                   */  \
+  X(kEpiBias | kEpiResF32 | kEpiOutF32)                   /* proj, fc2: + residual stream (fp32)     */  \
+  X(kEpiBias | kEpiColscale | kEpiResF32 | kEpiOutF32)    /* ConvNeXt pwconv2 * gamma + shortcut     */  \
+  X(kEpiBias | (2 << kEpiActShift) | kEpiAux)             /* fc1 + GELU, keeps the pre-activation    */  \
+  X(3 << kEpiActShift)                                    /* fc2 dgrad * GELU'(pre)                  */  \
+  X(kEpiOutF32)                                           /* Swin patch-merging reduction            */  \
+  X(kEpiBias | kEpiOutF32)                                /* ConvNeXt downsample conv                */
+
+template <int BLOCK_N>
+int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   const int tiles = p.tiles1 * p.tiles2 * p.tiles3 * p.n_tiles;
   const int grid = conv_grid(tiles, p.n_tiles, p.stats != nullptr);
   B200_REQUIRE(grid > 0, "conv_gemm: %d channel blocks exceed the SM count (BN statistics need grid %% n_tiles == 0)", p.n_tiles);
   ConvGemmParams q = p;
   q.desc_lbo = g_fwd_lbo;
   q.desc_sbo = g_fwd_sbo;
-  conv_gemm_kernel<BLOCK_N><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
-  B200_LAUNCHED();
-  return OK;
+  switch (epilogue_flags(p)) {
+#define B200_EPI_CASE(F) \
+  case (F):              \
+    return launch_conv_gemm_epi<BLOCK_N, (F)>(q, grid, st);
+    B200_EPI_LIST(B200_EPI_CASE)
+#undef B200_EPI_CASE
+    default:
+      return launch_conv_gemm_epi<BLOCK_N, kEpiGeneric>(q, grid, st);
+  }
 }
 
 int dispatch_conv_gemm(ConvGemmParams& p, int N, cudaStream_t st) {

@@ -101,7 +101,13 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
-template <int BLOCK_N>
+// Epilogue specialisation: EPI < 0 keeps every epilogue option a run-time flag (generic fallback); EPI >= 0 is a bit set
+// of compile-time options so that the hot layer types get a branch-free epilogue without the unused operand loads.
+constexpr int kEpiGeneric = -1;
+constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEpiResBf16 = 16, kEpiResF32 = 32,
+              kEpiAux = 64, kEpiOutF32 = 128, kEpiDirect = 256, kEpiStats = 512;
+
+template <int BLOCK_N, int EPI = kEpiGeneric>
 __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   using Cfg = ConvGemmCfg<BLOCK_N>;
   constexpr int STAGES = Cfg::STAGES;
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   const int num_kb = p.num_taps * p.k_blocks_per_tap;
   // Epilogue work units: 64 bf16 (or 32 fp32) channels x one warp's 32 rows. Two warps share a TMEM lane quadrant and
   // take alternate units; with a single unit per tile the second warp of each pair has nothing to do.
-  const int unit_cols = p.out_f32 ? 32 : 64;
+  const int unit_cols = ((EPI < 0) ? (p.out_f32 != 0) : ((EPI & kEpiOutF32) != 0)) ? 32 : 64;
   const int units = BLOCK_N / unit_cols;
   // (with one unit per tile the two warps of a pair alternate TILES instead: pair p drains accumulator buffer p)
   const int arrivals_per_acc = units >= 2 ? 8 : 4;
@@ -229,15 +235,17 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
     for (int m = 0; m < 8; ++m) stat_off[m] = m * 128 + ((((lane >> 2) ^ m) << 4) | ((lane & 3) << 2));
     // kernel parameters used in the inner loops, hoisted into registers
+    constexpr bool G = EPI < 0;
     const int N = p.N;
-    const float* const bias = p.bias;
-    const float* const colscale = p.colscale;
-    const int act = p.act;
-    const bool has_res = p.residual != nullptr;
-    const bool has_aux = p.has_aux_out != 0;
-    const bool out_f32 = p.out_f32 != 0;
-    float* const out_direct = p.out_direct;
-    float* const stats = p.stats;
+    const float* const bias = (G || (EPI & kEpiBias)) ? p.bias : nullptr;
+    const float* const colscale = (G || (EPI & kEpiColscale)) ? p.colscale : nullptr;
+    const int act = G ? p.act : ((EPI >> kEpiActShift) & 3);
+    const bool has_res = G ? (p.residual != nullptr) : ((EPI & (kEpiResBf16 | kEpiResF32)) != 0);
+    const bool res_f32 = G ? (p.res_f32 != 0) : ((EPI & kEpiResF32) != 0);
+    const bool has_aux = G ? (p.has_aux_out != 0) : ((EPI & kEpiAux) != 0);
+    const bool out_f32 = G ? (p.out_f32 != 0) : ((EPI & kEpiOutF32) != 0);
+    float* const out_direct = (G || (EPI & kEpiDirect)) ? p.out_direct : nullptr;
+    float* const stats = (G || (EPI & kEpiStats)) ? p.stats : nullptr;
     const bool need_rowmap = has_res || act == 3 || out_direct != nullptr || p.dim1 % p.box1 != 0 ||
                              p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0;
     const bool full_cols = (N % BLOCK_N) == 0;  // no partially valid 32-column group anywhere
@@ -306,7 +314,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           const bool pre_aux = chunk_live && act == 3 && row_ok;
           if (pre_res) {
             const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc_pre;
-            if (p.res_f32) {
+            if (res_f32) {
               const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
 #pragma unroll
               for (int j = 0; j < 8; ++j)
@@ -382,7 +390,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) f[j] *= (full_cols || nc + j < N) ? __ldg(colscale + nc + j) : 0.0f;
           }
           if (has_res && row_ok) {
-            if (p.res_f32) {
+            if (res_f32) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 if (full_cols || nc + j * 4 < N) {
