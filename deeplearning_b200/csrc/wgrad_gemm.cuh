@@ -37,10 +37,10 @@ struct WgradCfg {
   static constexpr int A_BYTES = 2 * 64 * 128;             // two 64-channel atoms of dY
   static constexpr int B_BYTES = (BLOCK_NG / 64) * 64 * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_NG == 128) ? 6 : 8;
+  static constexpr int STAGES = (BLOCK_NG == 256) ? 4 : ((BLOCK_NG == 128) ? 6 : 8);
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
-  static constexpr int TMEM_COLS = (2 * BLOCK_NG <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = (2 * BLOCK_NG <= 128) ? 128 : (2 * BLOCK_NG <= 256 ? 256 : 512);
 };
 
 template <int BLOCK_NG>
