@@ -66,9 +66,9 @@ SIGNATURES = {
     "b200_conv2d_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200_adamw_tick": (_I, [_P, _F, _F, _P]),
     "b200_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
-    "b200_window_attention_fwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
-    "b200_window_attention_bwd": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
-    "b200_window_bias_gather": (_I, [_P, _P, _P, _I, _P]),
+    "b200_window_attention_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "b200_window_attention_bwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
+    "b200_window_bias_gather": (_I, [_P, _P, _P, _I, _P, _I, _P]),
     "b200_window_bias_scatter": (_I, [_P, _P, _P, _I, _P]),
     "b200_window_partition": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_window_merge": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

@@ -318,18 +318,13 @@ int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, lo
 }
 
 // ---------------------------------------------------------------------------------------------------- Swin
-static int wattn_grid(int nH) {
-  int per_head = (device_sm_count() * 3 + nH - 1) / nH;
-  if (per_head < 1) per_head = 1;
-  return per_head * nH;
-}
 static int wattn_check(int B, int H, int W, int nH, int shift) {
   B200_REQUIRE(B > 0 && nH > 0 && H % 7 == 0 && W % 7 == 0, "window attention: H=%d W=%d must be multiples of the 7x7 window", H, W);
   B200_REQUIRE(shift >= 0 && shift < 7, "window attention: shift %d out of range", shift);
   return OK;
 }
 
-int b200_window_attention_fwd(const void* qkv, void* out, const float* bias, const float* mask, float* lse, int B, int H,
+int b200_window_attention_fwd(const void* qkv, void* out, const float* bias_tab, int masked, float* lse, int B, int H,
                               int W, int nH, int shift, float scale, void* stream) {
   int rc = wattn_check(B, H, W, nH, shift);
   if (rc) return rc;
@@ -337,22 +332,24 @@ int b200_window_attention_fwd(const void* qkv, void* out, const float* bias, con
   memset(&p, 0, sizeof(p));
   p.qkv = static_cast<const __nv_bfloat16*>(qkv);
   p.out = static_cast<__nv_bfloat16*>(out);
-  p.bias = bias, p.mask = mask, p.lse = lse;
+  p.bias = bias_tab, p.masked = masked, p.lse = lse;
   p.B = B, p.H = H, p.W = W, p.nH = nH, p.shift = shift, p.scale = scale;
   static bool cfg = false;
   if (!cfg) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(wattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWAttnFwdSmem));
     cfg = true;
   }
-  int grid = wattn_grid(nH);
+  // one persistent, internally pipelined CTA per SM; CTAs of a head share its window pairs round-robin
+  int grid = device_sm_count() / nH * nH;
+  if (grid < nH) grid = nH;
   const int total = B * (H / 7) * (W / 7);
-  if (grid > total * nH) grid = total * nH;
-  wattn_fwd_kernel<<<grid, 160, kWAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (grid > (total + 1) / 2 * nH) grid = (total + 1) / 2 * nH;
+  wattn_fwd_kernel<<<grid, kWAttnFwdThreads, kWAttnFwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
   B200_LAUNCHED();
   return OK;
 }
 
-int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* bias, const float* mask,
+int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* bias_tab, int masked,
                               const float* lse, void* dqkv, float* dbias, int B, int H, int W, int nH, int shift,
                               float scale, void* stream) {
   int rc = wattn_check(B, H, W, nH, shift);
@@ -363,23 +360,29 @@ int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout
   p.o = static_cast<const __nv_bfloat16*>(out);
   p.dout = static_cast<const __nv_bfloat16*>(dout);
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
-  p.bias = bias, p.mask = mask, p.lse = const_cast<float*>(lse), p.dbias = dbias;
+  p.bias = bias_tab, p.masked = masked, p.lse = const_cast<float*>(lse), p.dbias = dbias;
   p.B = B, p.H = H, p.W = W, p.nH = nH, p.shift = shift, p.scale = scale;
   static bool cfg = false;
   if (!cfg) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(wattn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWAttnBwdSmem));
     cfg = true;
   }
-  int grid = wattn_grid(nH);
+  int grid = device_sm_count() / nH * nH;
+  if (grid < nH) grid = nH;
   const int total = B * (H / 7) * (W / 7);
-  if (grid > total * nH) grid = total * nH;
-  wattn_bwd_kernel<<<grid, 160, kWAttnBwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
+  if (grid > (total + 1) / 2 * nH) grid = (total + 1) / 2 * nH;
+  wattn_bwd_kernel<<<grid, kWAttnFwdThreads, kWAttnBwdSmem, static_cast<cudaStream_t>(stream)>>>(p);
   B200_LAUNCHED();
   return OK;
 }
 
-int b200_window_bias_gather(const float* table, const long long* index, float* bias, int nH, void* stream) {
-  wattn_bias_gather_kernel<<<(nH * 49 * 49 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, index, bias, nH);
+int b200_window_bias_gather(const float* table, const long long* index, const float* mask, int nW, float* bias_tab, int nH,
+                            void* stream) {
+  const int nWm = mask != nullptr ? nW : 1;
+  B200_REQUIRE(nH > 0 && nWm > 0, "window_bias_gather: bad sizes nH=%d nW=%d", nH, nW);
+  const long long n = static_cast<long long>(nH) * nWm * 49 * 64;
+  wattn_bias_gather_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, index, mask, nWm, bias_tab,
+                                                                                           nH);
   B200_LAUNCHED();
   return OK;
 }

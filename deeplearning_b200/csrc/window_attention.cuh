@@ -22,8 +22,9 @@ namespace b200 {
 struct WAttnParams {
   const __nv_bfloat16* qkv;   // [B][H][W][3*C]
   __nv_bfloat16* out;         // fwd: [B][H][W][C]
-  const float* bias;          // dense [nH][49][49]
-  const float* mask;          // [nW][49][49] (0 / -100) or null
+  const float* bias;          // [nH][masked ? nW : 1][49 keys j][64 (query i, 49 used)]: bias[h][i][j] (+ mask[w][i][j]), see
+                              // wattn_bias_gather_kernel - transposed so that the 32 query rows of a warp read contiguously
+  int masked;                 // 1: the table holds one slice per window (shifted blocks)
   float* lse;                 // [B][nW][nH][49]
   int B, H, W, nH, shift;
   float scale;
@@ -62,92 +63,173 @@ __device__ __forceinline__ void wattn_gather(uint32_t tile_s, const __nv_bfloat1
   }
 }
 
-constexpr int kWAttnFwdSmem = 3 * 8192 + 16384 + 256 + 1024;
+// Two windows per step: rows 0..63 of every operand tile belong to window "A" of the pair, rows 64..127 to window "B"
+// (49 real tokens + 15 zero rows each). One M=128 x N=128 MMA produces both score blocks (the off-diagonal blocks are never
+// read), all four soft-max warps own real rows, and P is written block-diagonally (the off-diagonal halves of the P tile
+// are zeroed once and never touched) so that P V, P^T dO, dS K and dS^T Q of both windows are single M=128 MMAs as well.
+constexpr int kWAttnStages = 3;  // Q/K/V ring: the gathers run two steps ahead of the tensor core
+constexpr int kWAttnFwdSmem = kWAttnStages * 3 * 16384 + 2 * 32768 + 256 + 1024;
+constexpr int kWAttnFwdThreads = 11 * 32;  // 8 soft-max warps (two groups), 1 MMA warp, 2 gather warps
+constexpr int kWAttnGatherThreads = 64;
 
-__global__ void __launch_bounds__(160, 3) wattn_fwd_kernel(const WAttnParams p) {
+__device__ __forceinline__ void wattn_item(const WAttnParams& p, int item, int nW, int nWx, int& b, int& win, int& wy, int& wx) {
+  b = item / nW;
+  win = item - b * nW;
+  wy = win / nWx;
+  wx = win - wy * nWx;
+}
+
+// Forward, warp specialised and double buffered. A step = one PAIR of windows of this CTA's head (see above).
+//   gather warps (9, 10): tokens i and i+64 of the pair -> 12 cp.async (q, k, v x 4 chunks) into ring stage n%3, then arrive full
+//   MMA warp (8):         S(n) = Q K^T into TMEM buffer n&1 as soon as the stage is full; O(n-1) = P V once group (n-1)&1
+//                         has written P; the commit of O also releases the stage to the gather warps
+//   soft-max group g (warps 4g..4g+3) owns the steps with n&1 == g: S -> P (bf16, block diagonal) -> wait O -> write out
+// so the gathers of step n+1, the soft-max of step n and the P V product / output of step n-1 overlap.
+__global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;            // [64][128B] (the M=128 MMA also reads the 64 rows that follow: the K tile, harmless)
-  uint8_t* sK = smem + 8192;
-  uint8_t* sV = smem + 16384;
-  uint8_t* sP = smem + 24576;    // [128][128B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 24576 + 16384);
-  uint64_t* bar_s = bars;
-  uint64_t* bar_o = bars + 1;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2);
+  // stage s: Q | K | V tiles [128][128B] (rows 0..48: window A, 64..112: window B; 64 B used per row); then P[g]
+  constexpr int kStage = 3 * 16384;
+  constexpr int NS = kWAttnStages;
+  uint8_t* sP = smem + NS * kStage;   // [2 groups][2 key atoms][128][128B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * kStage + 2 * 32768);
+  uint64_t* full = bars;        // [NS] gather complete (128 arrivals)
+  uint64_t* empty = bars + 4;   // [NS] stage consumed (commit of P V)
+  uint64_t* bar_s = bars + 8;   // [2] S in TMEM
+  uint64_t* bar_p = bars + 10;  // [2] P in smem (4 warp arrivals)
+  uint64_t* bar_o = bars + 12;  // [2] O in TMEM
+  uint64_t* tfree = bars + 14;  // [2] group done with its TMEM buffers and P tile (4 warp arrivals)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.nH * 32;
   const int nWy = p.H / kWS, nWx = p.W / kWS, nW = nWy * nWx;
 
-  // zero the operand tiles once: pad rows (49..63) of K / V must be finite zeros for every item
-  for (int i = threadIdx.x; i < (24576 + 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (warp_idx == 4) {
+  // zero everything once: pad rows of K / V and the off-diagonal halves of P must be finite zeros for every step
+  for (int i = threadIdx.x; i < (NS * kStage + 2 * 32768) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp_idx == 8) {
     if (lane == 0) {
-      mbar_init(bar_s, 1);
-      mbar_init(bar_o, 1);
+      for (int i = 0; i < NS; ++i) {
+        mbar_init(&full[i], kWAttnGatherThreads);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_p[i], 4);
+        mbar_init(&bar_o[i], 1);
+        mbar_init(&tfree[i], 4);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<128>(tmem_ptr_smem);
+    tmem_alloc<512>(tmem_ptr_smem);
   }
+  fence_proxy_async_smem();   // the zero fill above must be visible to the tensor core (async proxy)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV), p_s = smem_u32(sP);
-  const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // S[128 x 64 keys] = Q K^T, both K-major, K = 32 (2 steps)
-  const uint32_t idesc_o = make_idesc_bf16(128, 32, 0, 1);   // O[128 x 32] = P (K-major) V (MN-major), K = 64 keys
+  constexpr uint32_t kColS = 0, kColO = 256;   // S[g] at g*128, O[g] at 256 + g*32
 
   const int head = blockIdx.x % p.nH;
   const int lanes = gridDim.x / p.nH;           // CTAs sharing this head
   const int total = p.B * nW;
-  uint32_t phase = 0;
-  for (int item = blockIdx.x / p.nH; item < total; item += lanes, phase ^= 1) {
-    const int b = item / nW, win = item - b * nW;
-    const int wy = win / nWx, wx = win - wy * nWx;
-    // ---- gather Q, K, V of this (window, head)
-    wattn_gather(q_s, p.qkv, 3 * C, head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    wattn_gather(k_s, p.qkv, 3 * C, C + head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    wattn_gather(v_s, p.qkv, 3 * C, 2 * C + head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp_idx == 4) {
-      if (lane == 0) {
-        tc_fence_after();
+  const int npairs = (total + 1) / 2;
+  const int first = blockIdx.x / p.nH;
+  const int nsteps = first < npairs ? (npairs - first + lanes - 1) / lanes : 0;
+
+  if (warp_idx >= 9) {
+    // ===================== gather warps: one thread per token of the pair =====================
+    const int i0 = threadIdx.x - 9 * 32;   // 0..63; tokens i0 and i0 + 64 of the 98
+    for (int n = 0; n < nsteps; ++n) {
+      const int s = n % NS;
+      const uint32_t ph = (n / NS) & 1;
+      mbar_wait(&empty[s], ph ^ 1);
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_f16(tmem_base, make_smem_desc_sw128(q_s + k * 32, 16, 1024), make_smem_desc_sw128(k_s + k * 32, 16, 1024),
-                   idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
+      for (int rep = 0; rep < 2; ++rep) {
+        const int i = i0 + rep * kWAttnGatherThreads;
+        const int slot = i / kWT, tok = i - slot * kWT;
+        const int item = 2 * (first + n * lanes) + slot;
+        if (i < 2 * kWT && item < total) {
+          int b, win, wy, wx;
+          wattn_item(p, item, nW, nWx, b, win, wy, wx);
+          const __nv_bfloat16* src = p.qkv + wattn_pixel(p, b, wy, wx, tok) * 3 * C + head * 32;
+          const int r = slot * 64 + tok;
+          const uint32_t dst = smem_u32(smem + s * kStage) + r * 128;
+#pragma unroll
+          for (int t = 0; t < 3; ++t)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) cp_async16(dst + t * 16384 + ((c ^ (r & 7)) << 4), src + t * C + c * 8);
+        }
       }
-    } else {
-      // ---- soft-max: thread = query row
-      const int row = warp_idx * 32 + lane;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
-      mbar_wait(bar_s, phase);
+      cp_async_wait_all();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
+    }
+  } else if (warp_idx == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S[128 x 128 keys] = Q K^T, both K-major, K = 32
+      const uint32_t idesc_o = make_idesc_bf16(128, 32, 0, 1);   // O[128 x 32] = P (K-major) V (MN-major), K = 128 keys
+      for (int n = 0; n <= nsteps; ++n) {
+        if (n < nsteps) {
+          const int s = n % NS, g = n & 1;
+          mbar_wait(&tfree[g], ((n >> 1) & 1) ^ 1);   // group g has drained S/O of step n-2
+          mbar_wait(&full[s], (n / NS) & 1);
+          tc_fence_after();
+          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 16384;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem_base + kColS + g * 128, make_smem_desc_sw128(q_s + k * 32, 16, 1024),
+                     make_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[g]);
+        }
+        if (n > 0) {
+          const int m = n - 1, s = m % NS, g = m & 1;
+          mbar_wait(&bar_p[g], (m >> 1) & 1);
+          tc_fence_after();
+          const uint32_t v_s = smem_u32(smem + s * kStage) + 32768, p_s = smem_u32(sP + g * 32768);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base + kColO + g * 32, make_smem_desc_sw128(p_s + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                     make_smem_desc_sw128(v_s + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
+          umma_commit(&bar_o[g]);
+          umma_commit(&empty[s]);
+        }
+      }
+    }
+  } else {
+    // ===================== soft-max groups: thread = query row of window `slot` =====================
+    const int g = warp_idx >> 2;
+    const int row = (warp_idx & 3) * 32 + lane;
+    const int slot = row >> 6, tok = row & 63;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp_idx & 3) * 32) << 16);
+    const uint32_t p_s = smem_u32(sP + g * 32768) + slot * 16384 + row * 128;  // this row's 64 keys (key atom `slot`)
+    for (int n = g; n < nsteps; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
+      const int item = 2 * (first + n * lanes) + slot;
+      const bool valid = tok < kWT && item < total;
+      int b = 0, win = 0, wy = 0, wx = 0;
+      if (item < total) wattn_item(p, item, nW, nWx, b, win, wy, wx);
+      const float* brow = p.bias + (static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * (kWT * 64) +
+                          (valid ? tok : 0);
+      mbar_wait(&bar_s[g], ph);
       tc_fence_after();
       uint32_t v[64];
       {
         uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
         uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32(taddr, lo);
-        tmem_ld_32x32(taddr + 32, hi);
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64, lo);
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + 32, hi);
         tmem_ld_wait();
       }
       float mx = -INFINITY;
-      const bool valid = row < kWT;
-      const float* brow = p.bias + (static_cast<long long>(head) * kWT + (valid ? row : 0)) * kWT;
-      const float* mrow = p.mask ? p.mask + (static_cast<long long>(win) * kWT + (valid ? row : 0)) * kWT : nullptr;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
-        float s = -INFINITY;
-        if (j < kWT) {
-          s = fmaf(__uint_as_float(v[j]), p.scale, __ldg(brow + j));
-          if (mrow) s += __ldg(mrow + j);
-        }
-        v[j] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+        float sc = -INFINITY;
+        if (j < kWT) sc = fmaf(__uint_as_float(v[j]), p.scale, __ldg(brow + j * 64));
+        v[j] = __float_as_uint(sc);
+        mx = fmaxf(mx, sc);
       }
       float sum = 0.f;
 #pragma unroll
@@ -159,28 +241,23 @@ __global__ void __launch_bounds__(160, 3) wattn_fwd_kernel(const WAttnParams p) 
         v[j >> 1] = w;  // in place: slot j/2 has already been consumed
       }
 #pragma unroll
-      for (int c = 0; c < 8; ++c)
-        sts128(p_s + row * 128 + ((c ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
-      if (valid) p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + row] = mx + __logf(sum);
+      for (int c = 0; c < 8; ++c) sts128(p_s + ((c ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+      if (valid) p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] = mx + __logf(sum);
       tc_fence_before();
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem_base + 64, make_smem_desc_sw128(p_s + ks * 32, 16, 1024),
-                   make_smem_desc_sw128(v_s + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
-        umma_commit(bar_o);
-      }
-      mbar_wait(bar_o, phase);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[g]);
+      mbar_wait(&bar_o[g], ph);
       tc_fence_after();
       uint32_t ov[32];
-      tmem_ld_32x32(taddr + 64, ov);
+      tmem_ld_32x32(taddr + kColO + g * 32, ov);
       tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tfree[g]);   // S / O columns and the P tile of this group may be reused
       if (valid) {
         const float inv = 1.0f / sum;
-        __nv_bfloat16* dst = p.out + wattn_pixel(p, b, wy, wx, row) * C + head * 32;
+        __nv_bfloat16* dst = p.out + wattn_pixel(p, b, wy, wx, tok) * C + head * 32;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           uint4 w;
@@ -191,176 +268,246 @@ __global__ void __launch_bounds__(160, 3) wattn_fwd_kernel(const WAttnParams p) 
           *reinterpret_cast<uint4*>(dst + c * 8) = w;
         }
       }
-      tc_fence_before();
     }
-    __syncthreads();  // tiles and TMEM are free for the next item
-    tc_fence_after();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Backward. Per (batch, window, head):
+// Backward. Per (batch, window, head), two windows per step as in the forward kernel:
 //   P = exp(scale*S + bias + mask - lse);  dP = dO V^T;  dS = P*(dP - delta), delta_i = <dO_i, O_i>;  dbias += dS
 //   dV = P^T dO;  dQ = scale * dS K;  dK = scale * dS^T Q          (dS is stored pre-multiplied by scale)
-constexpr int kWAttnBwdSmem = 5 * 8192 + 16384 + 256 + 1024;
+constexpr int kWAttnBwdSmem = 2 * 4 * 16384 + 2 * 32768 + 256 + 1024;
 
-__global__ void __launch_bounds__(160, 3) wattn_bwd_kernel(const WAttnParams p) {
+// Same warp-specialised pipeline as the forward kernel (two-stage Q/K/V/dO ring, two soft-max groups with their own TMEM
+// columns and P/dS tile). Per step m the MMA warp issues   A(m): S = Q K^T   B(m): dP = dO V^T, dV = P^T dO   C(m): dQ = dS K,
+// dK = dS^T Q   in the order  B(n-1), A(n), C(n-1)  so that one group computes P while the other computes dS / stores.
+__global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // order matters: the M=128 MMAs with a 64-row A tile read 64 further rows of whatever tile follows (finite data)
-  uint8_t* sQ = smem;
-  uint8_t* sK = smem + 8192;
-  uint8_t* sV = smem + 16384;
-  uint8_t* sdO = smem + 24576;
-  uint8_t* sO = smem + 32768;
-  uint8_t* sP = smem + 40960;  // [128][128B]: P, then dS in place
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 40960 + 16384);
-  uint64_t* bar_s = bars;
-  uint64_t* bar_dp = bars + 1;
-  uint64_t* bar_dq = bars + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
+  constexpr int kStage = 4 * 16384;   // Q | K | V | dO tiles [128][128B]
+  constexpr int NS = 2;
+  uint8_t* sP = smem + NS * kStage;   // [2 groups][2 key atoms][128][128B]: P, then dS in place (block diagonal)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * kStage + 2 * 32768);
+  uint64_t* full = bars;         // [NS]
+  uint64_t* empty = bars + 2;    // [NS]
+  uint64_t* bar_s = bars + 4;    // [2] S in TMEM
+  uint64_t* bar_p = bars + 6;    // [2] P in smem (4 warp arrivals)
+  uint64_t* bar_dp = bars + 8;   // [2] dP (and dV) in TMEM
+  uint64_t* bar_ds = bars + 10;  // [2] dS in smem (4 warp arrivals)
+  uint64_t* bar_dq = bars + 12;  // [2] dQ, dK in TMEM
+  uint64_t* tfree = bars + 14;   // [2] group done with its TMEM columns and P tile
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.nH * 32;
   const int nWy = p.H / kWS, nWx = p.W / kWS, nW = nWy * nWx;
 
-  for (int i = threadIdx.x; i < (40960 + 16384) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  if (warp_idx == 4) {
+  for (int i = threadIdx.x; i < (NS * kStage + 2 * 32768) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (warp_idx == 8) {
     if (lane == 0) {
-      mbar_init(bar_s, 1);
-      mbar_init(bar_dp, 1);
-      mbar_init(bar_dq, 1);
+      for (int i = 0; i < NS; ++i) {
+        mbar_init(&full[i], kWAttnGatherThreads);
+        mbar_init(&empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&bar_s[i], 1);
+        mbar_init(&bar_p[i], 4);
+        mbar_init(&bar_dp[i], 1);
+        mbar_init(&bar_ds[i], 4);
+        mbar_init(&bar_dq[i], 1);
+        mbar_init(&tfree[i], 4);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<128>(tmem_ptr_smem);
+    tmem_alloc<512>(tmem_ptr_smem);
   }
+  fence_proxy_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t q_s = smem_u32(sQ), k_s = smem_u32(sK), v_s = smem_u32(sV), do_s = smem_u32(sdO), o_s = smem_u32(sO),
-                 p_s = smem_u32(sP);
-  const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // [128 q] x [64 keys], K = 32
-  const uint32_t idesc_t = make_idesc_bf16(128, 32, 1, 1);   // A^T B: A, B both MN-major (P^T dO, dS^T Q), K = 64 query rows
-  const uint32_t idesc_q = make_idesc_bf16(128, 32, 0, 1);   // dS (K-major) x K (MN-major), K = 64 keys
-  constexpr uint32_t kColS = 0, kColDV = 64, kColDK = 96;
+  constexpr uint32_t kColS = 0, kColDV = 256, kColDK = 320;   // S[g] at g*128; dV[g] / dK[g] at +g*32
 
   const int head = blockIdx.x % p.nH;
   const int lanes = gridDim.x / p.nH;
   const int total = p.B * nW;
-  const int row = (warp_idx & 3) * 32 + lane;
-  const bool valid = warp_idx < 4 && row < kWT;
-  float db[kWT];  // gradient of bias[head][row][:] accumulated over this CTA's items
-#pragma unroll
-  for (int j = 0; j < kWT; ++j) db[j] = 0.f;
+  const int npairs = (total + 1) / 2;
+  const int first = blockIdx.x / p.nH;
+  const int nsteps = first < npairs ? (npairs - first + lanes - 1) / lanes : 0;
 
-  uint32_t phase = 0;
-  for (int item = blockIdx.x / p.nH; item < total; item += lanes, phase ^= 1) {
-    const int b = item / nW, win = item - b * nW;
-    const int wy = win / nWx, wx = win - wy * nWx;
-    wattn_gather(q_s, p.qkv, 3 * C, head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    wattn_gather(k_s, p.qkv, 3 * C, C + head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    wattn_gather(v_s, p.qkv, 3 * C, 2 * C + head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    wattn_gather(do_s, p.dout, C, head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    wattn_gather(o_s, p.o, C, head * 32, p, b, wy, wx, threadIdx.x, blockDim.x);
-    cp_async_wait_all();
-    fence_proxy_async_smem();
-    __syncthreads();
-    if (warp_idx == 4) {
-      if (lane == 0) {
-        tc_fence_after();
+  if (warp_idx >= 9) {
+    // ===================== gather warps: one thread per token of the pair (q, k, v, dO rows) =====================
+    const int i0 = threadIdx.x - 9 * 32;
+    for (int n = 0; n < nsteps; ++n) {
+      const int s = n % NS;
+      mbar_wait(&empty[s], ((n / NS) & 1) ^ 1);
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_f16(tmem_base + kColS, make_smem_desc_sw128(q_s + k * 32, 16, 1024),
-                   make_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
-      }
-      __syncwarp();
-    } else {
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp_idx * 32) << 16);
-      const long long pix = wattn_pixel(p, b, wy, wx, valid ? row : 0);
-      // delta_i = <dO_i, O_i> from the gathered tiles (64 B each)
-      float delta = 0.f;
-      if (valid) {
+      for (int rep = 0; rep < 2; ++rep) {
+        const int i = i0 + rep * kWAttnGatherThreads;
+        const int slot = i / kWT, tok = i - slot * kWT;
+        const int item = 2 * (first + n * lanes) + slot;
+        if (i < 2 * kWT && item < total) {
+          int b, win, wy, wx;
+          wattn_item(p, item, nW, nWx, b, win, wy, wx);
+          const long long pix = wattn_pixel(p, b, wy, wx, tok);
+          const __nv_bfloat16* src = p.qkv + pix * 3 * C + head * 32;
+          const __nv_bfloat16* dsrc = p.dout + pix * C + head * 32;
+          const int r = slot * 64 + tok;
+          const uint32_t dst = smem_u32(smem + s * kStage) + r * 128;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
-          float a[8], o[8];
-          unpack8(*reinterpret_cast<const uint4*>(sdO + off), a);
-          unpack8(*reinterpret_cast<const uint4*>(sO + off), o);
+          for (int t = 0; t < 3; ++t)
 #pragma unroll
-          for (int e = 0; e < 8; ++e) delta = fmaf(a[e], o[e], delta);
+            for (int c = 0; c < 4; ++c) cp_async16(dst + t * 16384 + ((c ^ (r & 7)) << 4), src + t * C + c * 8);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) cp_async16(dst + 3 * 16384 + ((c ^ (r & 7)) << 4), dsrc + c * 8);
         }
       }
-      const float lse = valid ? p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + row] : 0.f;
-      const float* brow = p.bias + (static_cast<long long>(head) * kWT + (valid ? row : 0)) * kWT;
-      const float* mrow = p.mask ? p.mask + (static_cast<long long>(win) * kWT + (valid ? row : 0)) * kWT : nullptr;
+      cp_async_wait_all();
+      fence_proxy_async_smem();
+      mbar_arrive(&full[s]);
+    }
+  } else if (warp_idx == 8) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // [128 q] x [128 keys], K = 32
+      const uint32_t idesc_t = make_idesc_bf16(128, 32, 1, 1);   // A^T B, both MN-major (P^T dO, dS^T Q), K = 128 query rows
+      const uint32_t idesc_q = make_idesc_bf16(128, 32, 0, 1);   // dS (K-major) x K (MN-major), K = 128 keys
+      for (int n = 0; n <= nsteps; ++n) {
+        if (n > 0) {  // B(n-1): dP = dO V^T (into the S columns) and dV = P^T dO
+          const int m = n - 1, s = m % NS, g = m & 1;
+          mbar_wait(&bar_p[g], (m >> 1) & 1);
+          tc_fence_after();
+          const uint32_t base = smem_u32(smem + s * kStage), v_s = base + 32768, do_s = base + 49152;
+          const uint32_t p_s = smem_u32(sP + g * 32768);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem_base + kColS + g * 128, make_smem_desc_sw128(do_s + k * 32, 16, 1024),
+                     make_smem_desc_sw128(v_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)  // 128 query rows = 8 steps of 16; A = P^T: two 64-key atoms 16384 B apart
+            umma_f16(tmem_base + kColDV + g * 32, make_smem_desc_sw128(p_s + ks * 2048, 16384, 1024),
+                     make_smem_desc_sw128(do_s + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
+          umma_commit(&bar_dp[g]);
+        }
+        if (n < nsteps) {  // A(n): S = Q K^T
+          const int s = n % NS, g = n & 1;
+          mbar_wait(&tfree[g], ((n >> 1) & 1) ^ 1);
+          mbar_wait(&full[s], (n / NS) & 1);
+          tc_fence_after();
+          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 16384;
+#pragma unroll
+          for (int k = 0; k < 2; ++k)
+            umma_f16(tmem_base + kColS + g * 128, make_smem_desc_sw128(q_s + k * 32, 16, 1024),
+                     make_smem_desc_sw128(k_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+          umma_commit(&bar_s[g]);
+        }
+        if (n > 0) {  // C(n-1): dQ = dS K (S columns again) and dK = dS^T Q
+          const int m = n - 1, s = m % NS, g = m & 1;
+          mbar_wait(&bar_ds[g], (m >> 1) & 1);
+          tc_fence_after();
+          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 16384;
+          const uint32_t p_s = smem_u32(sP + g * 32768);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base + kColS + g * 128, make_smem_desc_sw128(p_s + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                     make_smem_desc_sw128(k_s + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            umma_f16(tmem_base + kColDK + g * 32, make_smem_desc_sw128(p_s + ks * 2048, 16384, 1024),
+                     make_smem_desc_sw128(q_s + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
+          umma_commit(&bar_dq[g]);
+          umma_commit(&empty[s]);
+        }
+      }
+    }
+  } else {
+    // ===================== soft-max groups =====================
+    const int g = warp_idx >> 2;
+    const int row = (warp_idx & 3) * 32 + lane;
+    const int slot = row >> 6, tok = row & 63;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp_idx & 3) * 32) << 16);
+    uint8_t* const prow = sP + g * 32768 + slot * 16384 + row * 128;   // this row's 64 keys (key atom `slot`)
+    const uint32_t prow_s = smem_u32(prow);
+    float db[kWT];  // gradient of bias[head][tok][:] accumulated over this thread's steps
+#pragma unroll
+    for (int j = 0; j < kWT; ++j) db[j] = 0.f;
+    for (int n = g; n < nsteps; n += 2) {
+      const uint32_t ph = (n >> 1) & 1;
+      const int s = n % NS;
+      const int item = 2 * (first + n * lanes) + slot;
+      const bool valid = tok < kWT && item < total;
+      int b = 0, win = 0, wy = 0, wx = 0;
+      if (item < total) wattn_item(p, item, nW, nWx, b, win, wy, wx);
+      const long long pix = wattn_pixel(p, b, wy, wx, valid ? tok : 0);
+      const float lse = valid ? p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] : 0.f;
+      const float* brow = p.bias + (static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * (kWT * 64) +
+                          (valid ? tok : 0);
+      uint4 orow[4];  // forward output row (64 B), requested early: only needed for delta after the first MMA wait
+      if (valid) {
+        const uint4* op = reinterpret_cast<const uint4*>(p.o + pix * C + head * 32);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) orow[c] = __ldg(op + c);
+      }
       // ---- P
-      mbar_wait(bar_s, phase);
+      mbar_wait(&bar_s[g], ph);
       tc_fence_after();
       {
         uint32_t v[64];
         uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
         uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32(taddr + kColS, lo);
-        tmem_ld_32x32(taddr + kColS + 32, hi);
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64, lo);
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + 32, hi);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 64; j += 2) {
           float e0 = 0.f, e1 = 0.f;
-          if (valid && j < kWT) {
-            float s0 = fmaf(__uint_as_float(v[j]), p.scale, __ldg(brow + j));
-            if (mrow) s0 += __ldg(mrow + j);
-            e0 = __expf(s0 - lse);
-          }
-          if (valid && j + 1 < kWT) {
-            float s1 = fmaf(__uint_as_float(v[j + 1]), p.scale, __ldg(brow + j + 1));
-            if (mrow) s1 += __ldg(mrow + j + 1);
-            e1 = __expf(s1 - lse);
-          }
+          if (valid && j < kWT) e0 = __expf(fmaf(__uint_as_float(v[j]), p.scale, __ldg(brow + j * 64)) - lse);
+          if (valid && j + 1 < kWT) e1 = __expf(fmaf(__uint_as_float(v[j + 1]), p.scale, __ldg(brow + (j + 1) * 64)) - lse);
           v[j >> 1] = pack_bf16x2(e0, e1);
         }
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          sts128(p_s + row * 128 + ((c ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+          sts128(prow_s + ((c ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        // dP = dO V^T  (into the S columns)      and      dV = P^T dO
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_p[g]);
+      // delta_i = <dO_i, O_i>: dO from the gathered tile (stage s stays valid until C(n) retires)
+      float delta = 0.f;
+      if (valid) {
+        const uint8_t* drow = smem + s * kStage + 49152 + row * 128;
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
-          umma_f16(tmem_base + kColS, make_smem_desc_sw128(do_s + k * 32, 16, 1024),
-                   make_smem_desc_sw128(v_s + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+        for (int c = 0; c < 4; ++c) {
+          float a[8], o[8];
+          unpack8(*reinterpret_cast<const uint4*>(drow + ((c ^ (row & 7)) << 4)), a);
+          unpack8(orow[c], o);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // 64 query rows = 4 steps of 16
-          umma_f16(tmem_base + kColDV, make_smem_desc_sw128(p_s + ks * 2048, 8192, 1024),
-                   make_smem_desc_sw128(do_s + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
-        umma_commit(bar_dp);
+          for (int e = 0; e < 8; ++e) delta = fmaf(a[e], o[e], delta);
+        }
       }
       // ---- dS (in place over P)
-      mbar_wait(bar_dp, phase);
+      mbar_wait(&bar_dp[g], ph);
       tc_fence_after();
       {
         uint32_t v[64];
         uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
         uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32(taddr + kColS, lo);
-        tmem_ld_32x32(taddr + kColS + 32, hi);
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64, lo);
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + 32, hi);
         tmem_ld_wait();
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          const uint32_t off = row * 128 + ((c ^ (row & 7)) << 4);
+          const uint32_t off = (c ^ (row & 7)) << 4;
           float pv[8];
-          unpack8(*reinterpret_cast<const uint4*>(sP + off), pv);  // P of this row (bf16, as the tensor core saw it)
+          unpack8(*reinterpret_cast<const uint4*>(prow + off), pv);  // P of this row (bf16, as the tensor core saw it)
           float d[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
@@ -369,71 +516,76 @@ __global__ void __launch_bounds__(160, 3) wattn_bwd_kernel(const WAttnParams p) 
             if (j < kWT) db[j] += d[e];
             d[e] *= p.scale;
           }
-          sts128(p_s + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
+          sts128(prow_s + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (threadIdx.x == 0) {
-        tc_fence_after();
-        // dQ = dS K (S columns again) ;  dK = dS^T Q
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem_base + kColS, make_smem_desc_sw128(p_s + ks * 32, 16, 1024),
-                   make_smem_desc_sw128(k_s + ks * 2048, 8192, 1024), idesc_q, ks > 0 ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_f16(tmem_base + kColDK, make_smem_desc_sw128(p_s + ks * 2048, 8192, 1024),
-                   make_smem_desc_sw128(q_s + ks * 2048, 8192, 1024), idesc_t, ks > 0 ? 1u : 0u);
-        umma_commit(bar_dq);
-      }
-      mbar_wait(bar_dq, phase);
-      tc_fence_after();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar_ds[g]);
       // ---- write dq (row = query), dk / dv (row = key) of this token
-      uint32_t g[32];
-      __nv_bfloat16* dst = p.dqkv + pix * 3 * C + head * 32;
+      mbar_wait(&bar_dq[g], ph);
+      tc_fence_after();
+      uint32_t gq[32], gk[32], gv[32];
+      tmem_ld_32x32(taddr + kColS + g * 128, gq);
+      tmem_ld_32x32(taddr + kColDK + g * 32, gk);
+      tmem_ld_32x32(taddr + kColDV + g * 32, gv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tfree[g]);
+      if (valid) {
+        __nv_bfloat16* dst = p.dqkv + pix * 3 * C + head * 32;
 #pragma unroll
-      for (int which = 0; which < 3; ++which) {
-        tmem_ld_32x32(taddr + (which == 0 ? kColS : (which == 1 ? kColDK : kColDV)), g);
-        tmem_ld_wait();
-        if (valid) {
+        for (int which = 0; which < 3; ++which) {
+          const uint32_t* gg = which == 0 ? gq : (which == 1 ? gk : gv);
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 w;
-            w.x = pack_bf16x2(__uint_as_float(g[c * 8 + 0]), __uint_as_float(g[c * 8 + 1]));
-            w.y = pack_bf16x2(__uint_as_float(g[c * 8 + 2]), __uint_as_float(g[c * 8 + 3]));
-            w.z = pack_bf16x2(__uint_as_float(g[c * 8 + 4]), __uint_as_float(g[c * 8 + 5]));
-            w.w = pack_bf16x2(__uint_as_float(g[c * 8 + 6]), __uint_as_float(g[c * 8 + 7]));
+            w.x = pack_bf16x2(__uint_as_float(gg[c * 8 + 0]), __uint_as_float(gg[c * 8 + 1]));
+            w.y = pack_bf16x2(__uint_as_float(gg[c * 8 + 2]), __uint_as_float(gg[c * 8 + 3]));
+            w.z = pack_bf16x2(__uint_as_float(gg[c * 8 + 4]), __uint_as_float(gg[c * 8 + 5]));
+            w.w = pack_bf16x2(__uint_as_float(gg[c * 8 + 6]), __uint_as_float(gg[c * 8 + 7]));
             *reinterpret_cast<uint4*>(dst + which * C + c * 8) = w;
           }
         }
       }
-      tc_fence_before();
     }
-    __syncthreads();
-    tc_fence_after();
-  }
-  if (valid) {
-    float* dbp = p.dbias + (static_cast<long long>(head) * kWT + row) * kWT;
+    if (tok < kWT) {
+      float* dbp = p.dbias + (static_cast<long long>(head) * kWT + tok) * kWT;
 #pragma unroll
-    for (int j = 0; j < kWT; ++j) atomicAdd(dbp + j, db[j]);
+      for (int j = 0; j < kWT; ++j) atomicAdd(dbp + j, db[j]);
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp_idx == 4) {
+  if (warp_idx == 8) {
     tc_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<512>(tmem_base);
   }
 }
 
-// bias[h][i][j] = table[index[i][j]][h]      (WindowAttention.forward :131-134)
+// tab[h][w][j][i] = table[index[i][j]][h] (+ mask[w][i][j])      (WindowAttention.forward :131-141), i padded to 64
+// One launch per block and step folds the relative-position bias gather and the shift mask into one table whose innermost
+// index is the QUERY row, so that the soft-max threads of a warp (consecutive query rows) read consecutive floats.
 __global__ void wattn_bias_gather_kernel(const float* __restrict__ table, const long long* __restrict__ index,
-                                         float* __restrict__ bias, int nH) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= nH * kWT * kWT) return;
-  const int h = i / (kWT * kWT), ij = i - h * kWT * kWT;
-  bias[i] = table[index[ij] * nH + h];
+                                         const float* __restrict__ mask, int nWm, float* __restrict__ tab, int nH) {
+  const long long n = static_cast<long long>(nH) * nWm * kWT * 64;
+  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n;
+       e += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int i = static_cast<int>(e & 63);
+    long long t = e >> 6;
+    const int j = static_cast<int>(t % kWT);
+    t /= kWT;
+    const int w = static_cast<int>(t % nWm);
+    const int h = static_cast<int>(t / nWm);
+    float v = 0.f;
+    if (i < kWT) {
+      v = table[index[i * kWT + j] * nH + h];
+      if (mask != nullptr) v += mask[(static_cast<long long>(w) * kWT + i) * kWT + j];
+    }
+    tab[e] = v;
+  }
 }
 // dtable[index[i][j]][h] (+)= dbias[h][i][j]   (dtable zeroed / holding the running gradient)
 __global__ void wattn_bias_scatter_kernel(const float* __restrict__ dbias, const long long* __restrict__ index,

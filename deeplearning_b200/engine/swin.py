@@ -102,9 +102,9 @@ def forward(model, x, train, want_tape):
             nH = att_m.num_heads
             y1, m1, r1 = ops.layernorm_fwd(h, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
             qkv, _ = ops.gemm(y1, pack.get(att_m.qkv.weight, 0), bias=att_m.qkv.bias)
-            bias = ops.window_bias_gather(att_m.relative_position_bias_table.detach(), att_m.relative_position_index, nH)
-            att, lse = ops.window_attention_fwd(qkv.view(B, H, W, 3 * C), nH, bias, blk.attn_mask, blk.shift_size,
-                                                float(att_m.scale))
+            bias = ops.window_bias_gather(att_m.relative_position_bias_table.detach(), att_m.relative_position_index, nH,
+                                          blk.attn_mask)   # bias (+ shift mask) table, query index innermost
+            att, lse = ops.window_attention_fwd(qkv.view(B, H, W, 3 * C), nH, bias, blk.shift_size, float(att_m.scale))
             h2, _ = ops.gemm(att.view(B, H * W, C), pack.get(att_m.proj.weight, 0), bias=att_m.proj.bias, residual=h,
                              out_f32=True)
             y2, m2, r2 = ops.layernorm_fwd(h2, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
@@ -200,8 +200,8 @@ def backward(model, tape, dlogits, sink=None):
             g2 = g.view(M, C)
             _lin_grads(grads, att_m.proj, g2, att.view(M, C))
             d_att, _ = ops.gemm(g2, pack.get(att_m.proj.weight, 1))
-            dqkv, dbias = ops.window_attention_bwd(qkv.view(B, H, W, 3 * C), att, d_att.view(B, H, W, C), bias, blk.attn_mask,
-                                                   lse, nH, blk.shift_size, float(att_m.scale))
+            dqkv, dbias = ops.window_attention_bwd(qkv.view(B, H, W, 3 * C), att, d_att.view(B, H, W, C), bias, lse, nH,
+                                                   blk.shift_size, float(att_m.scale))
             table = att_m.relative_position_bias_table
             dt = grads.dest(table)
             dt = dt.zero_() if dt is not None else torch.zeros_like(table, dtype=F32)

@@ -695,12 +695,14 @@ def conv2d_fwd_f32(x, w_packed, ksize, stride, bias=None):
 
 
 # --------------------------------------------------------------------------------------------------------- Swin pieces
-def window_bias_gather(table, index, nH):
-    """relative_position_bias_table [(2*7-1)^2, nH] + relative_position_index [49,49] int64 -> dense fp32 [nH,49,49]."""
+def window_bias_gather(table, index, nH, mask=None):
+    """relative_position_bias_table [(2*7-1)^2, nH] + relative_position_index [49,49] int64 (+ attn_mask [nW,49,49]) ->
+    fp32 table [nH, nW or 1, 49 (key), 64 (query, 49 used)] read by the window-attention kernels."""
     lib = _lib.load()
-    bias = torch.empty(nH, 49, 49, dtype=F32, device=table.device)
-    _lib.check(lib.b200_window_bias_gather(_p(table), _p(index), _p(bias), nH, _stream()), "b200_window_bias_gather")
-    return bias
+    nW = mask.shape[0] if mask is not None else 1
+    tab = torch.empty(nH, nW, 49, 64, dtype=F32, device=table.device)
+    _lib.check(lib.b200_window_bias_gather(_p(table), _p(index), _p(mask), nW, _p(tab), nH, _stream()), "b200_window_bias_gather")
+    return tab
 
 
 def window_bias_scatter(dbias, index, dtable):
@@ -710,8 +712,16 @@ def window_bias_scatter(dbias, index, dtable):
     return dtable
 
 
-def window_attention_fwd(qkv, nH, bias, mask, shift, scale):
-    """qkv bf16 [B,H,W,3*nH*32] (natural pixel order) -> (out bf16 [B,H,W,nH*32], lse fp32 [B,nW,nH,49])."""
+def _wattn_masked(bias_tab, nW):
+    """1 when the table carries one (bias + mask) slice per window; with a single window slice 0 is the right one anyway."""
+    if bias_tab.shape[1] not in (1, nW):
+        raise ValueError(f"window attention: bias table holds {bias_tab.shape[1]} window slices, the image has {nW} windows")
+    return 1 if (bias_tab.shape[1] == nW and nW > 1) else 0
+
+
+def window_attention_fwd(qkv, nH, bias_tab, shift, scale):
+    """qkv bf16 [B,H,W,3*nH*32] (natural pixel order), bias_tab = window_bias_gather(...) ->
+    (out bf16 [B,H,W,nH*32], lse fp32 [B,nW,nH,49])."""
     lib = _lib.load()
     B, H, W, _ = qkv.shape
     C = nH * 32
@@ -719,14 +729,15 @@ def window_attention_fwd(qkv, nH, bias, mask, shift, scale):
     out = torch.empty(B, H, W, C, dtype=BF16, device=qkv.device)
     lse = torch.empty(B, nW, nH, 49, dtype=F32, device=qkv.device)
     sp = _span("window_attention_fwd", 4.0 * B * nW * nH * 49 * 49 * 32, _nb(qkv, out))
-    rc = lib.b200_window_attention_fwd(_p(qkv), _p(out), _p(bias), _p(mask), _p(lse), B, H, W, nH, shift, scale, _stream())
+    rc = lib.b200_window_attention_fwd(_p(qkv), _p(out), _p(bias_tab), _wattn_masked(bias_tab, nW), _p(lse), B, H, W, nH, shift,
+                                       scale, _stream())
     _lib.check(rc, "b200_window_attention_fwd")
     if sp:
         sp.end()
     return out, lse
 
 
-def window_attention_bwd(qkv, out, dout, bias, mask, lse, nH, shift, scale):
+def window_attention_bwd(qkv, out, dout, bias_tab, lse, nH, shift, scale):
     """Returns (dqkv bf16 like qkv, dbias fp32 [nH,49,49])."""
     lib = _lib.load()
     B, H, W, _ = qkv.shape
@@ -734,8 +745,8 @@ def window_attention_bwd(qkv, out, dout, bias, mask, lse, nH, shift, scale):
     dqkv = torch.empty_like(qkv)
     dbias = torch.zeros(nH, 49, 49, dtype=F32, device=qkv.device)
     sp = _span("window_attention_bwd", 10.0 * B * nW * nH * 49 * 49 * 32, _nb(qkv, out, dout, dqkv))
-    rc = lib.b200_window_attention_bwd(_p(qkv), _p(out), _p(dout), _p(bias), _p(mask), _p(lse), _p(dqkv), _p(dbias), B, H, W,
-                                       nH, shift, scale, _stream())
+    rc = lib.b200_window_attention_bwd(_p(qkv), _p(out), _p(dout), _p(bias_tab), _wattn_masked(bias_tab, nW), _p(lse), _p(dqkv),
+                                       _p(dbias), B, H, W, nH, shift, scale, _stream())
     _lib.check(rc, "b200_window_attention_bwd")
     if sp:
         sp.end()

@@ -134,16 +134,20 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
 /* ---- Swin (classification/swin_transformer/models/swin_transformer.py) -----------------------------------------------------
  * Shifted-window attention, 7x7 windows, head_dim 32, on tcgen05. qkv bf16 [B][H][W][3*nH*32] in natural (un-rolled) pixel
  * order; torch.roll / window_partition / window_reverse (:251-280) are folded into the gather / scatter addressing.
- * bias = dense [nH][49][49] (b200_window_bias_gather of relative_position_bias_table[relative_position_index], :131-134);
- * mask = attn_mask buffer [nW][49][49] (0 / -100, :215-238) for shifted blocks or NULL; lse fp32 [B][nW][nH][49].
- * backward: dqkv same layout as qkv; dbias dense [nH][49][49] must be zeroed by the caller (atomics), then
+ * bias_tab = b200_window_bias_gather(): fp32 [nH][masked ? nW : 1][49 (key j)][64 (query i, 49 used)] holding
+ *   relative_position_bias_table[relative_position_index[i][j]][h] (:131-134) plus, for shifted blocks, the attn_mask
+ *   buffer value mask[w][i][j] (0 / -100, :215-238, :142-147) - one small launch per block and step; the query index is
+ *   innermost so that the soft-max threads (one query row each) read it coalesced. masked = 1 when a mask was folded in.
+ * Two windows are processed per tensor-core step (block-diagonal 128x128 score tile). lse fp32 [B][nW][nH][49].
+ * backward: dqkv same layout as qkv; dbias dense [nH][49 i][49 j] must be zeroed by the caller (atomics), then
  * b200_window_bias_scatter adds it into the table gradient. */
-int b200_window_attention_fwd(const void* qkv, void* out, const float* bias, const float* mask, float* lse, int B, int H,
+int b200_window_attention_fwd(const void* qkv, void* out, const float* bias_tab, int masked, float* lse, int B, int H,
                               int W, int nH, int shift, float scale, void* stream);
-int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* bias, const float* mask,
+int b200_window_attention_bwd(const void* qkv, const void* out, const void* dout, const float* bias_tab, int masked,
                               const float* lse, void* dqkv, float* dbias, int B, int H, int W, int nH, int shift,
                               float scale, void* stream);
-int b200_window_bias_gather(const float* table, const long long* index, float* bias, int nH, void* stream);
+int b200_window_bias_gather(const float* table, const long long* index, const float* mask, int nW, float* bias_tab, int nH,
+                            void* stream);
 int b200_window_bias_scatter(const float* dbias, const long long* index, float* dtable, int nH, void* stream);
 /* The reference's own operator FFI (kernels/window_process/swin_window_process.cpp:70-131), any 2/4-byte element type:
  *   partition: out[B*nW][ws][ws][C] = window_partition(roll(in[B][H][W][C], shifts=(shift, shift)))   (forward)

@@ -97,7 +97,7 @@ def _shift_mask(H, W, shift):
     return m.masked_fill(m != 0, -100.0).masked_fill(m == 0, 0.0)
 
 
-@pytest.mark.parametrize("B,H,W,nH,shift", [(2, 56, 56, 3, 0), (2, 56, 56, 3, 3), (3, 14, 14, 12, 3), (4, 7, 7, 24, 0), (1, 28, 14, 6, 3)])
+@pytest.mark.parametrize("B,H,W,nH,shift", [(2, 56, 56, 3, 0), (2, 56, 56, 3, 3), (3, 14, 14, 12, 3), (4, 7, 7, 24, 0), (1, 28, 14, 6, 3), (3, 7, 7, 2, 0), (1, 7, 7, 1, 0), (5, 14, 7, 3, 3)])
 def test_window_attention_fwd_bwd(B, H, W, nH, shift):
     ops = _ops()
     C = nH * 32
@@ -106,16 +106,18 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift):
     table = (torch.randn(169, nH, device="cuda") * 0.5)
     index = _rel_index().cuda()
     mask = _shift_mask(H, W, shift).cuda() if shift > 0 else None
-    bias = ops.window_bias_gather(table, index, nH)
-    assert torch.equal(bias, table[index.view(-1)].view(49, 49, nH).permute(2, 0, 1).contiguous())
-    out, lse = ops.window_attention_fwd(qkv, nH, bias, mask, shift, scale)
+    bias = ops.window_bias_gather(table, index, nH, mask)   # [nH, nW or 1, 49 (j), 64 (i)]
+    dense = table[index.view(-1)].view(49, 49, nH).permute(2, 0, 1)           # [nH, i, j]
+    want = dense[:, None] + (mask[None] if mask is not None else 0)          # [nH, nW or 1, i, j]
+    assert torch.equal(bias[..., :49], want.transpose(-1, -2)) and float(bias[..., 49:].abs().max()) == 0.0
+    out, lse = ops.window_attention_fwd(qkv, nH, bias, shift, scale)
     qr = qkv.float().requires_grad_(True)
     tr = table.clone().requires_grad_(True)
     ref = _swin_attn_ref(qr, nH, tr, index, mask, shift, scale)
     _close(out, ref, 2e-2, 2e-2, "window attention fwd")
     dout = _rand(B, H, W, C, seed=2)
     gq, gt = torch.autograd.grad(ref, (qr, tr), dout.float())
-    dqkv, dbias = ops.window_attention_bwd(qkv, out, dout, bias, mask, lse, nH, shift, scale)
+    dqkv, dbias = ops.window_attention_bwd(qkv, out, dout, bias, lse, nH, shift, scale)
     sc = float(gq.abs().max())
     _close(dqkv / sc, gq / sc, 2e-2, 2e-2, "window attention dqkv")
     dtable = ops.window_bias_scatter(dbias, index, torch.zeros_like(table))

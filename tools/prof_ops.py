@@ -24,22 +24,22 @@ def attn_bwd():
 def _wattn():
     B, Hh, W, nH = 128, 56, 56, 3
     qkv = rnd(B, Hh, W, 3 * nH * 32, scale=0.5)
-    bias = torch.randn(nH, 49, 49, device=dev)
     nW = 64
-    mask = torch.zeros(nW, 49, 49, device=dev)
-    return B, Hh, W, nH, qkv, bias, mask
+    index = torch.randint(0, 169, (49, 49), device=dev)
+    bias = ops.window_bias_gather(torch.randn(169, nH, device=dev), index, nH, torch.zeros(nW, 49, 49, device=dev))
+    return B, Hh, W, nH, qkv, bias, None
 
 
 def wattn_fwd():
     B, Hh, W, nH, qkv, bias, mask = _wattn()
-    return lambda: ops.window_attention_fwd(qkv, nH, bias, mask, 3, 32 ** -0.5)
+    return lambda: ops.window_attention_fwd(qkv, nH, bias, 3, 32 ** -0.5)
 
 
 def wattn_bwd():
     B, Hh, W, nH, qkv, bias, mask = _wattn()
-    out, lse = ops.window_attention_fwd(qkv, nH, bias, mask, 3, 32 ** -0.5)
+    out, lse = ops.window_attention_fwd(qkv, nH, bias, 3, 32 ** -0.5)
     dout = rnd(B, Hh, W, nH * 32)
-    return lambda: ops.window_attention_bwd(qkv, out, dout, bias, mask, lse, nH, 3, 32 ** -0.5)
+    return lambda: ops.window_attention_bwd(qkv, out, dout, bias, lse, nH, 3, 32 ** -0.5)
 
 
 def dwconv():
