@@ -22,8 +22,8 @@ namespace b200 {
 struct WAttnParams {
   const __nv_bfloat16* qkv;   // [B][H][W][3*C]
   __nv_bfloat16* out;         // fwd: [B][H][W][C]
-  const float* bias;          // [nH][masked ? nW : 1][49 keys j][64 (query i, 49 used)]: bias[h][i][j] (+ mask[w][i][j]), see
-                              // wattn_bias_gather_kernel - transposed so that the 32 query rows of a warp read contiguously
+  const float* bias;          // [nH][masked ? nW : 1][49 queries i][64 (key j, 49 used)]: bias[h][i][j] (+ mask[w][i][j]), see
+                              // wattn_bias_gather_kernel - 256-byte rows so that a soft-max thread fetches its row as 13 float4
   int masked;                 // 1: the table holds one slice per window (shifted blocks)
   float* lse;                 // [B][nW][nH][49]
   int B, H, W, nH, shift;
@@ -211,8 +211,13 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
       const bool valid = tok < kWT && item < total;
       int b = 0, win = 0, wy = 0, wx = 0;
       if (item < total) wattn_item(p, item, nW, nWx, b, win, wy, wx);
-      const float* brow = p.bias + (static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * (kWT * 64) +
-                          (valid ? tok : 0);
+      // this row's bias (+ mask) values: requested before the wait so that their latency hides behind the gather / MMA
+      const float4* brow = reinterpret_cast<const float4*>(
+          p.bias + ((static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * kWT + (valid ? tok : 0)) * 64);
+      float4 bv[13];
+#pragma unroll
+      for (int c = 0; c < 13; ++c) bv[c] = __ldg(brow + c);
+      const float* bf = reinterpret_cast<const float*>(bv);
       mbar_wait(&bar_s[g], ph);
       tc_fence_after();
       uint32_t v[64];
@@ -227,7 +232,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         float sc = -INFINITY;
-        if (j < kWT) sc = fmaf(__uint_as_float(v[j]), p.scale, __ldg(brow + j * 64));
+        if (j < kWT) sc = fmaf(__uint_as_float(v[j]), p.scale, bf[j]);
         v[j] = __float_as_uint(sc);
         mx = fmaxf(mx, sc);
       }
@@ -447,8 +452,12 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
       if (item < total) wattn_item(p, item, nW, nWx, b, win, wy, wx);
       const long long pix = wattn_pixel(p, b, wy, wx, valid ? tok : 0);
       const float lse = valid ? p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] : 0.f;
-      const float* brow = p.bias + (static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * (kWT * 64) +
-                          (valid ? tok : 0);
+      const float4* brow = reinterpret_cast<const float4*>(
+          p.bias + ((static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * kWT + (valid ? tok : 0)) * 64);
+      float4 bv[13];  // this row's bias (+ mask) values, requested before the wait
+#pragma unroll
+      for (int c = 0; c < 13; ++c) bv[c] = __ldg(brow + c);
+      const float* bf = reinterpret_cast<const float*>(bv);
       uint4 orow[4];  // forward output row (64 B), requested early: only needed for delta after the first MMA wait
       if (valid) {
         const uint4* op = reinterpret_cast<const uint4*>(p.o + pix * C + head * 32);
@@ -458,23 +467,22 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
       // ---- P
       mbar_wait(&bar_s[g], ph);
       tc_fence_after();
-      {
-        uint32_t v[64];
-        uint32_t(&lo)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
-        uint32_t(&hi)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32]);
-        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64, lo);
-        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + 32, hi);
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {   // two 32-key halves keep the live register set small
+        uint32_t v[32];
+        tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + hf * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 64; j += 2) {
+        for (int jj = 0; jj < 32; jj += 2) {
+          const int j = hf * 32 + jj;
           float e0 = 0.f, e1 = 0.f;
-          if (valid && j < kWT) e0 = __expf(fmaf(__uint_as_float(v[j]), p.scale, __ldg(brow + j * 64)) - lse);
-          if (valid && j + 1 < kWT) e1 = __expf(fmaf(__uint_as_float(v[j + 1]), p.scale, __ldg(brow + (j + 1) * 64)) - lse);
-          v[j >> 1] = pack_bf16x2(e0, e1);
+          if (valid && j < kWT) e0 = __expf(fmaf(__uint_as_float(v[jj]), p.scale, bf[j]) - lse);
+          if (valid && j + 1 < kWT) e1 = __expf(fmaf(__uint_as_float(v[jj + 1]), p.scale, bf[j + 1 < 52 ? j + 1 : 51]) - lse);
+          v[jj >> 1] = pack_bf16x2(e0, e1);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          sts128(prow_s + ((c ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+        for (int c = 0; c < 4; ++c)
+          sts128(prow_s + (((hf * 4 + c) ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
       }
       tc_fence_before();
       fence_proxy_async_smem();
@@ -565,22 +573,22 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
   }
 }
 
-// tab[h][w][j][i] = table[index[i][j]][h] (+ mask[w][i][j])      (WindowAttention.forward :131-141), i padded to 64
-// One launch per block and step folds the relative-position bias gather and the shift mask into one table whose innermost
-// index is the QUERY row, so that the soft-max threads of a warp (consecutive query rows) read consecutive floats.
+// tab[h][w][i][j] = table[index[i][j]][h] (+ mask[w][i][j])      (WindowAttention.forward :131-147), j padded to 64
+// One launch per block and step folds the relative-position bias gather and the shift mask into one table of 256-byte
+// rows (one per query) that the soft-max threads read with 13 vector loads.
 __global__ void wattn_bias_gather_kernel(const float* __restrict__ table, const long long* __restrict__ index,
                                          const float* __restrict__ mask, int nWm, float* __restrict__ tab, int nH) {
   const long long n = static_cast<long long>(nH) * nWm * kWT * 64;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int i = static_cast<int>(e & 63);
+    const int j = static_cast<int>(e & 63);
     long long t = e >> 6;
-    const int j = static_cast<int>(t % kWT);
+    const int i = static_cast<int>(t % kWT);
     t /= kWT;
     const int w = static_cast<int>(t % nWm);
     const int h = static_cast<int>(t / nWm);
     float v = 0.f;
-    if (i < kWT) {
+    if (j < kWT) {
       v = table[index[i * kWT + j] * nH + h];
       if (mask != nullptr) v += mask[(static_cast<long long>(w) * kWT + i) * kWT + j];
     }

@@ -697,7 +697,7 @@ def conv2d_fwd_f32(x, w_packed, ksize, stride, bias=None):
 # --------------------------------------------------------------------------------------------------------- Swin pieces
 def window_bias_gather(table, index, nH, mask=None):
     """relative_position_bias_table [(2*7-1)^2, nH] + relative_position_index [49,49] int64 (+ attn_mask [nW,49,49]) ->
-    fp32 table [nH, nW or 1, 49 (key), 64 (query, 49 used)] read by the window-attention kernels."""
+    fp32 table [nH, nW or 1, 49 (query), 64 (key, 49 used)] read by the window-attention kernels."""
     lib = _lib.load()
     nW = mask.shape[0] if mask is not None else 1
     tab = torch.empty(nH, nW, 49, 64, dtype=F32, device=table.device)
