@@ -67,8 +67,8 @@ __device__ __forceinline__ void wattn_gather(uint32_t tile_s, const __nv_bfloat1
 // (49 real tokens + 15 zero rows each). One M=128 x N=128 MMA produces both score blocks (the off-diagonal blocks are never
 // read), all four soft-max warps own real rows, and P is written block-diagonally (the off-diagonal halves of the P tile
 // are zeroed once and never touched) so that P V, P^T dO, dS K and dS^T Q of both windows are single M=128 MMAs as well.
-constexpr int kWAttnStages = 3;  // Q/K/V ring: the gathers run two steps ahead of the tensor core
-constexpr int kWAttnFwdSmem = kWAttnStages * 3 * 16384 + 2 * 32768 + 256 + 1024;
+constexpr int kWAttnStages = 4;  // operand ring: the gathers run up to three steps ahead of the tensor core
+constexpr int kWAttnFwdSmem = kWAttnStages * 2 * 16384 + 2 * 32768 + 256 + 1024;
 constexpr int kWAttnFwdThreads = 11 * 32;  // 8 soft-max warps (two groups), 1 MMA warp, 2 gather warps
 constexpr int kWAttnGatherThreads = 64;
 
@@ -88,8 +88,10 @@ __device__ __forceinline__ void wattn_item(const WAttnParams& p, int item, int n
 __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // stage s: Q | K | V tiles [128][128B] (rows 0..48: window A, 64..112: window B; 64 B used per row); then P[g]
-  constexpr int kStage = 3 * 16384;
+  // stage s: two tiles [128][128B] (rows 0..48: window A, 64..112: window B). A head row is only 64 B, so Q and K share
+  // a tile (Q = 16-byte chunks 0..3 of a row, K = chunks 4..7: the K descriptor simply starts 64 B later) and V takes the
+  // first half of the second tile; then P[g]
+  constexpr int kStage = 2 * 16384;
   constexpr int NS = kWAttnStages;
   uint8_t* sP = smem + NS * kStage;   // [2 groups][2 key atoms][128][128B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * kStage + 2 * 32768);
@@ -157,9 +159,11 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
           const int r = slot * 64 + tok;
           const uint32_t dst = smem_u32(smem + s * kStage) + r * 128;
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) cp_async16(dst + t * 16384 + ((c ^ (r & 7)) << 4), src + t * C + c * 8);
+          for (int c = 0; c < 4; ++c) {
+            cp_async16(dst + ((c ^ (r & 7)) << 4), src + c * 8);                        // q
+            cp_async16(dst + (((4 + c) ^ (r & 7)) << 4), src + C + c * 8);              // k
+            cp_async16(dst + 16384 + ((c ^ (r & 7)) << 4), src + 2 * C + c * 8);        // v
+          }
         }
       }
       cp_async_wait_all();
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
           mbar_wait(&tfree[g], ((n >> 1) & 1) ^ 1);   // group g has drained S/O of step n-2
           mbar_wait(&full[s], (n / NS) & 1);
           tc_fence_after();
-          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 16384;
+          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 64;
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_f16(tmem_base + kColS + g * 128, make_smem_desc_sw128(q_s + k * 32, 16, 1024),
@@ -188,7 +192,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
           const int m = n - 1, s = m % NS, g = m & 1;
           mbar_wait(&bar_p[g], (m >> 1) & 1);
           tc_fence_after();
-          const uint32_t v_s = smem_u32(smem + s * kStage) + 32768, p_s = smem_u32(sP + g * 32768);
+          const uint32_t v_s = smem_u32(smem + s * kStage) + 16384, p_s = smem_u32(sP + g * 32768);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
             umma_f16(tmem_base + kColO + g * 32, make_smem_desc_sw128(p_s + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
 // Backward. Per (batch, window, head), two windows per step as in the forward kernel:
 //   P = exp(scale*S + bias + mask - lse);  dP = dO V^T;  dS = P*(dP - delta), delta_i = <dO_i, O_i>;  dbias += dS
 //   dV = P^T dO;  dQ = scale * dS K;  dK = scale * dS^T Q          (dS is stored pre-multiplied by scale)
-constexpr int kWAttnBwdSmem = 2 * 4 * 16384 + 2 * 32768 + 256 + 1024;
+constexpr int kWAttnBwdSmem = kWAttnStages * 2 * 16384 + 2 * 32768 + 256 + 1024;
 
 // Same warp-specialised pipeline as the forward kernel (two-stage Q/K/V/dO ring, two soft-max groups with their own TMEM
 // columns and P/dS tile). Per step m the MMA warp issues   A(m): S = Q K^T   B(m): dP = dO V^T, dV = P^T dO   C(m): dQ = dS K,
@@ -295,19 +299,19 @@ constexpr int kWAttnBwdSmem = 2 * 4 * 16384 + 2 * 32768 + 256 + 1024;
 __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WAttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  constexpr int kStage = 4 * 16384;   // Q | K | V | dO tiles [128][128B]
-  constexpr int NS = 2;
+  constexpr int kStage = 2 * 16384;   // tile 0: Q (chunks 0..3 of a row) | K (chunks 4..7); tile 1: V | dO
+  constexpr int NS = kWAttnStages;
   uint8_t* sP = smem + NS * kStage;   // [2 groups][2 key atoms][128][128B]: P, then dS in place (block diagonal)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NS * kStage + 2 * 32768);
   uint64_t* full = bars;         // [NS]
-  uint64_t* empty = bars + 2;    // [NS]
-  uint64_t* bar_s = bars + 4;    // [2] S in TMEM
-  uint64_t* bar_p = bars + 6;    // [2] P in smem (4 warp arrivals)
-  uint64_t* bar_dp = bars + 8;   // [2] dP (and dV) in TMEM
-  uint64_t* bar_ds = bars + 10;  // [2] dS in smem (4 warp arrivals)
-  uint64_t* bar_dq = bars + 12;  // [2] dQ, dK in TMEM
-  uint64_t* tfree = bars + 14;   // [2] group done with its TMEM columns and P tile
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* empty = bars + 4;    // [NS]
+  uint64_t* bar_s = bars + 8;    // [2] S in TMEM
+  uint64_t* bar_p = bars + 10;   // [2] P in smem (4 warp arrivals)
+  uint64_t* bar_dp = bars + 12;  // [2] dP (and dV) in TMEM
+  uint64_t* bar_ds = bars + 14;  // [2] dS in smem (4 warp arrivals)
+  uint64_t* bar_dq = bars + 16;  // [2] dQ, dK in TMEM
+  uint64_t* tfree = bars + 18;   // [2] group done with its TMEM columns and P tile
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
   const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = p.nH * 32;
   const int nWy = p.H / kWS, nWx = p.W / kWS, nW = nWy * nWx;
@@ -367,11 +371,12 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           const int r = slot * 64 + tok;
           const uint32_t dst = smem_u32(smem + s * kStage) + r * 128;
 #pragma unroll
-          for (int t = 0; t < 3; ++t)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) cp_async16(dst + t * 16384 + ((c ^ (r & 7)) << 4), src + t * C + c * 8);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) cp_async16(dst + 3 * 16384 + ((c ^ (r & 7)) << 4), dsrc + c * 8);
+          for (int c = 0; c < 4; ++c) {
+            cp_async16(dst + ((c ^ (r & 7)) << 4), src + c * 8);                          // q
+            cp_async16(dst + (((4 + c) ^ (r & 7)) << 4), src + C + c * 8);                // k
+            cp_async16(dst + 16384 + ((c ^ (r & 7)) << 4), src + 2 * C + c * 8);          // v
+            cp_async16(dst + 16384 + (((4 + c) ^ (r & 7)) << 4), dsrc + c * 8);           // dO
+          }
         }
       }
       cp_async_wait_all();
@@ -389,7 +394,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           const int m = n - 1, s = m % NS, g = m & 1;
           mbar_wait(&bar_p[g], (m >> 1) & 1);
           tc_fence_after();
-          const uint32_t base = smem_u32(smem + s * kStage), v_s = base + 32768, do_s = base + 49152;
+          const uint32_t base = smem_u32(smem + s * kStage), v_s = base + 16384, do_s = v_s + 64;
           const uint32_t p_s = smem_u32(sP + g * 32768);
 #pragma unroll
           for (int k = 0; k < 2; ++k)
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           mbar_wait(&tfree[g], ((n >> 1) & 1) ^ 1);
           mbar_wait(&full[s], (n / NS) & 1);
           tc_fence_after();
-          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 16384;
+          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 64;
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_f16(tmem_base + kColS + g * 128, make_smem_desc_sw128(q_s + k * 32, 16, 1024),
@@ -417,7 +422,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           const int m = n - 1, s = m % NS, g = m & 1;
           mbar_wait(&bar_ds[g], (m >> 1) & 1);
           tc_fence_after();
-          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 16384;
+          const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 64;
           const uint32_t p_s = smem_u32(sP + g * 32768);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks)
@@ -491,11 +496,11 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
       // delta_i = <dO_i, O_i>: dO from the gathered tile (stage s stays valid until C(n) retires)
       float delta = 0.f;
       if (valid) {
-        const uint8_t* drow = smem + s * kStage + 49152 + row * 128;
+        const uint8_t* drow = smem + s * kStage + 16384 + row * 128;   // dO = chunks 4..7 of the V|dO tile row
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           float a[8], o[8];
-          unpack8(*reinterpret_cast<const uint4*>(drow + ((c ^ (row & 7)) << 4)), a);
+          unpack8(*reinterpret_cast<const uint4*>(drow + (((4 + c) ^ (row & 7)) << 4)), a);
           unpack8(orow[c], o);
 #pragma unroll
           for (int e = 0; e < 8; ++e) delta = fmaf(a[e], o[e], delta);
