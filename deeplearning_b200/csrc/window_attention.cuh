@@ -25,7 +25,7 @@ struct WAttnParams {
   const float* bias;          // [nH][masked ? nW : 1][49 queries i][64 (key j, 49 used)]: bias[h][i][j] (+ mask[w][i][j]), see
                               // wattn_bias_gather_kernel - 256-byte rows so that a soft-max thread fetches its row as 13 float4
   int masked;                 // 1: the table holds one slice per window (shifted blocks)
-  float* lse;                 // [B][nW][nH][49]
+  float* lse;                 // [B][nW][nH][49], base-2 log-sum-exp of the scaled, biased scores
   int B, H, W, nH, shift;
   float scale;
   // backward only
@@ -37,6 +37,20 @@ struct WAttnParams {
 
 constexpr int kWS = 7, kWT = 49;
 
+// Optional phase timers (-DWATTN_PROFILE): CTA 0 prints the average cycles per step of every wait / compute phase.
+#ifdef WATTN_PROFILE
+#define WPROF_DECL(N) long long wp_t[N] = {}; long long wp_0 = clock64(), wp_1;
+#define WPROF_TICK(i) { wp_1 = clock64(); wp_t[i] += wp_1 - wp_0; wp_0 = wp_1; }
+#else
+#define WPROF_DECL(N)
+#define WPROF_TICK(i)
+#endif
+
+__device__ __forceinline__ float wattn_ex2(float x) {  // MUFU.EX2 without the denormal-range fix-up of exp2f / __expf
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gptr) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
 }
@@ -232,26 +246,28 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WA
         tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + 32, hi);
         tmem_ld_wait();
       }
+      // log2 domain, branch free: rows outside the window (zero Q rows -> finite scores) get max = +inf -> all-zero P
+      const float scale2 = p.scale * 1.4426950408889634f;
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        float sc = -INFINITY;
-        if (j < kWT) sc = fmaf(__uint_as_float(v[j]), p.scale, bf[j]);
+      for (int j = 0; j < kWT; ++j) {
+        const float sc = fmaf(__uint_as_float(v[j]), scale2, bf[j]);
         v[j] = __float_as_uint(sc);
         mx = fmaxf(mx, sc);
       }
+      const float mxe = valid ? mx : INFINITY;
       float sum = 0.f;
 #pragma unroll
       for (int j = 0; j < 64; j += 2) {
-        const float e0 = valid ? __expf(__uint_as_float(v[j]) - mx) : 0.f;
-        const float e1 = valid ? __expf(__uint_as_float(v[j + 1]) - mx) : 0.f;
+        const float e0 = j < kWT ? wattn_ex2(__uint_as_float(v[j]) - mxe) : 0.f;
+        const float e1 = j + 1 < kWT ? wattn_ex2(__uint_as_float(v[j + 1]) - mxe) : 0.f;
         const uint32_t w = pack_bf16x2(e0, e1);
         sum += bf16_lo(w) + bf16_hi(w);
         v[j >> 1] = w;  // in place: slot j/2 has already been consumed
       }
 #pragma unroll
       for (int c = 0; c < 8; ++c) sts128(p_s + ((c ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
-      if (valid) p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] = mx + __logf(sum);
+      if (valid) p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] = mx + __log2f(sum);  // log2 units
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
@@ -354,9 +370,12 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
   if (warp_idx >= 9) {
     // ===================== gather warps: one thread per token of the pair (q, k, v, dO rows) =====================
     const int i0 = threadIdx.x - 9 * 32;
+    WPROF_DECL(3)
     for (int n = 0; n < nsteps; ++n) {
       const int s = n % NS;
+      WPROF_TICK(2)
       mbar_wait(&empty[s], ((n / NS) & 1) ^ 1);
+      WPROF_TICK(0)
 #pragma unroll
       for (int rep = 0; rep < 2; ++rep) {
         const int i = i0 + rep * kWAttnGatherThreads;
@@ -379,20 +398,28 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           }
         }
       }
+      WPROF_TICK(1)
       cp_async_wait_all();
       fence_proxy_async_smem();
       mbar_arrive(&full[s]);
     }
+#ifdef WATTN_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 9 * 32 && nsteps > 0)
+      printf("bwd gather : wait_empty %lld  issue %lld  wait_data %lld\n", wp_t[0] / nsteps, wp_t[1] / nsteps, wp_t[2] / nsteps);
+#endif
   } else if (warp_idx == 8) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // [128 q] x [128 keys], K = 32
       const uint32_t idesc_t = make_idesc_bf16(128, 32, 1, 1);   // A^T B, both MN-major (P^T dO, dS^T Q), K = 128 query rows
       const uint32_t idesc_q = make_idesc_bf16(128, 32, 0, 1);   // dS (K-major) x K (MN-major), K = 128 keys
+      WPROF_DECL(5)
       for (int n = 0; n <= nsteps; ++n) {
         if (n > 0) {  // B(n-1): dP = dO V^T (into the S columns) and dV = P^T dO
           const int m = n - 1, s = m % NS, g = m & 1;
+          WPROF_TICK(4)
           mbar_wait(&bar_p[g], (m >> 1) & 1);
+          WPROF_TICK(0)
           tc_fence_after();
           const uint32_t base = smem_u32(smem + s * kStage), v_s = base + 16384, do_s = v_s + 64;
           const uint32_t p_s = smem_u32(sP + g * 32768);
@@ -408,8 +435,11 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
         }
         if (n < nsteps) {  // A(n): S = Q K^T
           const int s = n % NS, g = n & 1;
+          WPROF_TICK(4)
           mbar_wait(&tfree[g], ((n >> 1) & 1) ^ 1);
+          WPROF_TICK(1)
           mbar_wait(&full[s], (n / NS) & 1);
+          WPROF_TICK(2)
           tc_fence_after();
           const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 64;
 #pragma unroll
@@ -420,7 +450,9 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
         }
         if (n > 0) {  // C(n-1): dQ = dS K (S columns again) and dK = dS^T Q
           const int m = n - 1, s = m % NS, g = m & 1;
+          WPROF_TICK(4)
           mbar_wait(&bar_ds[g], (m >> 1) & 1);
+          WPROF_TICK(3)
           tc_fence_after();
           const uint32_t q_s = smem_u32(smem + s * kStage), k_s = q_s + 64;
           const uint32_t p_s = smem_u32(sP + g * 32768);
@@ -436,6 +468,11 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           umma_commit(&empty[s]);
         }
       }
+#ifdef WATTN_PROFILE
+      if (blockIdx.x == 0 && nsteps > 0)
+        printf("bwd mma    : wait_p %lld  wait_tfree %lld  wait_full %lld  wait_ds %lld  issue %lld\n", wp_t[0] / nsteps,
+               wp_t[1] / nsteps, wp_t[2] / nsteps, wp_t[3] / nsteps, wp_t[4] / nsteps);
+#endif
     }
   } else {
     // ===================== soft-max groups =====================
@@ -445,6 +482,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp_idx & 3) * 32) << 16);
     uint8_t* const prow = sP + g * 32768 + slot * 16384 + row * 128;   // this row's 64 keys (key atom `slot`)
     const uint32_t prow_s = smem_u32(prow);
+    WPROF_DECL(14)
     float db[kWT];  // gradient of bias[head][tok][:] accumulated over this thread's steps
 #pragma unroll
     for (int j = 0; j < kWT; ++j) db[j] = 0.f;
@@ -456,7 +494,9 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
       int b = 0, win = 0, wy = 0, wx = 0;
       if (item < total) wattn_item(p, item, nW, nWx, b, win, wy, wx);
       const long long pix = wattn_pixel(p, b, wy, wx, valid ? tok : 0);
-      const float lse = valid ? p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] : 0.f;
+      // log2-domain row log-sum-exp; +inf for rows outside the window makes their P exactly zero without a branch
+      const float lse = valid ? p.lse[((static_cast<long long>(b) * nW + win) * p.nH + head) * kWT + tok] : INFINITY;
+      const float scale2 = p.scale * 1.4426950408889634f;
       const float4* brow = reinterpret_cast<const float4*>(
           p.bias + ((static_cast<long long>(head) * (p.masked ? nW : 1) + (p.masked ? win : 0)) * kWT + (valid ? tok : 0)) * 64);
       float4 bv[13];  // this row's bias (+ mask) values, requested before the wait
@@ -470,29 +510,35 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
         for (int c = 0; c < 4; ++c) orow[c] = __ldg(op + c);
       }
       // ---- P
+      WPROF_TICK(13)
       mbar_wait(&bar_s[g], ph);
+      WPROF_TICK(0)
       tc_fence_after();
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {   // two 32-key halves keep the live register set small
         uint32_t v[32];
         tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + hf * 32, v);
         tmem_ld_wait();
+        WPROF_TICK(1)
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 2) {
           const int j = hf * 32 + jj;
           float e0 = 0.f, e1 = 0.f;
-          if (valid && j < kWT) e0 = __expf(fmaf(__uint_as_float(v[jj]), p.scale, bf[j]) - lse);
-          if (valid && j + 1 < kWT) e1 = __expf(fmaf(__uint_as_float(v[jj + 1]), p.scale, bf[j + 1 < 52 ? j + 1 : 51]) - lse);
+          if (j < kWT) e0 = wattn_ex2(fmaf(__uint_as_float(v[jj]), scale2, bf[j]) - lse);
+          if (j + 1 < kWT) e1 = wattn_ex2(fmaf(__uint_as_float(v[jj + 1]), scale2, bf[j + 1 < 52 ? j + 1 : 51]) - lse);
           v[jj >> 1] = pack_bf16x2(e0, e1);
         }
+        WPROF_TICK(2)
 #pragma unroll
         for (int c = 0; c < 4; ++c)
           sts128(prow_s + (((hf * 4 + c) ^ (row & 7)) << 4), v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+        WPROF_TICK(3)
       }
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_p[g]);
+      WPROF_TICK(4)
       // delta_i = <dO_i, O_i>: dO from the gathered tile (stage s stays valid until C(n) retires)
       float delta = 0.f;
       if (valid) {
@@ -507,7 +553,9 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
         }
       }
       // ---- dS (in place over P)
+      WPROF_TICK(5)
       mbar_wait(&bar_dp[g], ph);
+      WPROF_TICK(6)
       tc_fence_after();
       {
         uint32_t v[64];
@@ -516,6 +564,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
         tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64, lo);
         tmem_ld_32x32(taddr + kColS + g * 128 + slot * 64 + 32, hi);
         tmem_ld_wait();
+        WPROF_TICK(7)
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           const uint32_t off = (c ^ (row & 7)) << 4;
@@ -525,25 +574,29 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = c * 8 + e;
-            d[e] = valid ? pv[e] * (__uint_as_float(v[j]) - delta) : 0.f;
+            d[e] = pv[e] * (__uint_as_float(v[j]) - delta);   // rows outside the window have P == 0 (and finite dP)
             if (j < kWT) db[j] += d[e];
             d[e] *= p.scale;
           }
           sts128(prow_s + off, pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]), pack_bf16x2(d[6], d[7]));
         }
       }
+      WPROF_TICK(8)
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar_ds[g]);
       // ---- write dq (row = query), dk / dv (row = key) of this token
+      WPROF_TICK(9)
       mbar_wait(&bar_dq[g], ph);
+      WPROF_TICK(10)
       tc_fence_after();
       uint32_t gq[32], gk[32], gv[32];
       tmem_ld_32x32(taddr + kColS + g * 128, gq);
       tmem_ld_32x32(taddr + kColDK + g * 32, gk);
       tmem_ld_32x32(taddr + kColDV + g * 32, gv);
       tmem_ld_wait();
+      WPROF_TICK(11)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tfree[g]);
@@ -563,7 +616,17 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
           }
         }
       }
+      WPROF_TICK(12)
     }
+#ifdef WATTN_PROFILE
+    WPROF_TICK(12)
+    if (blockIdx.x == 0 && lane == 0 && (warp_idx & 3) == 0 && nsteps > 1) {
+      const int ns = (nsteps - g + 1) / 2;
+      printf("bwd softmax g%d: wait_s %lld | P: ld %lld math %lld sts %lld fence %lld | delta %lld wait_dp %lld | dS: ld %lld math %lld fence %lld | "
+             "wait_dq %lld | epi: ld %lld store %lld | prologue %lld\n", g, wp_t[0] / ns, wp_t[1] / ns, wp_t[2] / ns, wp_t[3] / ns, wp_t[4] / ns,
+             wp_t[5] / ns, wp_t[6] / ns, wp_t[7] / ns, wp_t[8] / ns, wp_t[9] / ns, wp_t[10] / ns, wp_t[11] / ns, wp_t[12] / ns, wp_t[13] / ns);
+    }
+#endif
     if (tok < kWT) {
       float* dbp = p.dbias + (static_cast<long long>(head) * kWT + tok) * kWT;
 #pragma unroll
@@ -578,7 +641,7 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
   }
 }
 
-// tab[h][w][i][j] = table[index[i][j]][h] (+ mask[w][i][j])      (WindowAttention.forward :131-147), j padded to 64
+// tab[h][w][i][j] = log2(e) * (table[index[i][j]][h] (+ mask[w][i][j]))      (WindowAttention.forward :131-147), j padded to 64
 // One launch per block and step folds the relative-position bias gather and the shift mask into one table of 256-byte
 // rows (one per query) that the soft-max threads read with 13 vector loads.
 __global__ void wattn_bias_gather_kernel(const float* __restrict__ table, const long long* __restrict__ index,
@@ -596,6 +659,7 @@ __global__ void wattn_bias_gather_kernel(const float* __restrict__ table, const 
     if (j < kWT) {
       v = table[index[i * kWT + j] * nH + h];
       if (mask != nullptr) v += mask[(static_cast<long long>(w) * kWT + i) * kWT + j];
+      v *= 1.4426950408889634f;   // the kernels work in the log2 domain: p = 2^(s*scale*log2e + tab - lse2)
     }
     tab[e] = v;
   }

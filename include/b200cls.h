@@ -135,10 +135,11 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
  * Shifted-window attention, 7x7 windows, head_dim 32, on tcgen05. qkv bf16 [B][H][W][3*nH*32] in natural (un-rolled) pixel
  * order; torch.roll / window_partition / window_reverse (:251-280) are folded into the gather / scatter addressing.
  * bias_tab = b200_window_bias_gather(): fp32 [nH][masked ? nW : 1][49 (query i)][64 (key j, 49 used)] holding
- *   relative_position_bias_table[relative_position_index[i][j]][h] (:131-134) plus, for shifted blocks, the attn_mask
- *   buffer value mask[w][i][j] (0 / -100, :215-238, :142-147) - one small launch per block and step; a soft-max thread
+ *   log2(e) x ( relative_position_bias_table[relative_position_index[i][j]][h] (:131-134) plus, for shifted blocks, the
+ *   attn_mask buffer value mask[w][i][j] (0 / -100, :215-238, :142-147) ) - one small launch per block and step; a soft-max thread
  *   (one query row) fetches its 256-byte row with 13 vector loads. masked = 1 when a mask was folded in.
- * Two windows are processed per tensor-core step (block-diagonal 128x128 score tile). lse fp32 [B][nW][nH][49].
+ * Two windows are processed per tensor-core step (block-diagonal 128x128 score tile). lse fp32 [B][nW][nH][49] is the
+ * base-2 log-sum-exp of the (scaled, biased) score rows - an opaque hand-over from forward to backward.
  * backward: dqkv same layout as qkv; dbias dense [nH][49 i][49 j] must be zeroed by the caller (atomics), then
  * b200_window_bias_scatter adds it into the table gradient. */
 int b200_window_attention_fwd(const void* qkv, void* out, const float* bias_tab, int masked, float* lse, int B, int H,

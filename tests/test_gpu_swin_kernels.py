@@ -109,7 +109,8 @@ def test_window_attention_fwd_bwd(B, H, W, nH, shift):
     bias = ops.window_bias_gather(table, index, nH, mask)   # [nH, nW or 1, 49 (i), 64 (j)]
     dense = table[index.view(-1)].view(49, 49, nH).permute(2, 0, 1)           # [nH, i, j]
     want = dense[:, None] + (mask[None] if mask is not None else 0)          # [nH, nW or 1, i, j]
-    assert torch.equal(bias[..., :49], want.expand_as(bias[..., :49])) and float(bias[..., 49:].abs().max()) == 0.0
+    _close(bias[..., :49], want.expand_as(bias[..., :49]) * 1.4426950408889634, 1e-6, 1e-5, "bias table (log2 units)")
+    assert float(bias[..., 49:].abs().max()) == 0.0
     out, lse = ops.window_attention_fwd(qkv, nH, bias, shift, scale)
     qr = qkv.float().requires_grad_(True)
     tr = table.clone().requires_grad_(True)
