@@ -16,6 +16,12 @@
 
 namespace b200 {
 
+__device__ __forceinline__ float attn_ex2(float x) {  // MUFU.EX2; exp2f() adds a denormal-range fix-up per element
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct alignas(64) AttnFwdParams {
   CUtensorMap q_map;    // qkv as (3*H*64, T, B), box (64, 128, 1)
   CUtensorMap kv_map;   // same tensor, box (64, Tpad, 1)
@@ -111,9 +117,14 @@ __global__ void __launch_bounds__(160, 2) attn_fwd_kernel(const __grid_constant_
       uint32_t v[32];
       tmem_ld_32x32(taddr + c * 32, v);
       tmem_ld_wait();
+      if (c * 32 + 32 <= p.T) {   // warp-uniform: only the chunk that crosses T needs per-column masks
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (c * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
     }
     if (tail16) {
       uint32_t v[16];
@@ -129,13 +140,15 @@ __global__ void __launch_bounds__(160, 2) attn_fwd_kernel(const __grid_constant_
     // (Q and K are dead once bar_s has fired, so P may overwrite them.)
     auto emit = [&](const uint32_t* v, int col0, int n) {
       // n is 32 or 16; col0 multiple of 16
+      const bool crosses = col0 + n > p.T;   // warp-uniform
       for (int g = 0; g < n / 8; ++g) {
         float e[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int col = col0 + g * 8 + j;
-          const float x = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), p.scale_log2e, -mxs));
-          e[j] = (col < p.T) ? x : 0.f;
+        for (int j = 0; j < 8; ++j) e[j] = attn_ex2(fmaf(__uint_as_float(v[g * 8 + j]), p.scale_log2e, -mxs));
+        if (crosses) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (col0 + g * 8 + j >= p.T) e[j] = 0.f;
         }
         uint4 w;
         w.x = pack_bf16x2(e[0], e[1]);
@@ -358,19 +371,22 @@ __global__ void __launch_bounds__(288, 1) attn_bwd_kernel(const __grid_constant_
       const uint32_t ph = mb & 1;
       const int t = mb * 128 + row;
       const bool valid = t < p.T;
-      const float lse2 = valid ? p.lse[bh * p.T + t] * 1.4426950408889634f : 0.f;
+      // +inf for rows beyond T (their scores are exact zeros from the TMA zero fill) makes P vanish without a select
+      const float lse2 = valid ? p.lse[bh * p.T + t] * 1.4426950408889634f : INFINITY;
       const float delta = valid ? p.delta[bh * p.T + t] : 0.f;
       // ---- P = exp2(S*scale*log2e - lse*log2e)
       mbar_wait(bar_s, ph);
       tc_fence_after();
       auto emit_p = [&](const uint32_t* v, int col0, int n) {
+        const bool crosses = col0 + n > p.T;   // warp-uniform
         for (int g = 0; g < n / 8; ++g) {
           float e[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = col0 + g * 8 + j;
-            const float x = exp2f(fmaf(__uint_as_float(v[g * 8 + j]), p.scale_log2e, -lse2));
-            e[j] = (valid && col < p.T) ? x : 0.f;
+          for (int j = 0; j < 8; ++j) e[j] = attn_ex2(fmaf(__uint_as_float(v[g * 8 + j]), p.scale_log2e, -lse2));
+          if (crosses) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (col0 + g * 8 + j >= p.T) e[j] = 0.f;
           }
           const int col = col0 + g * 8;
           *reinterpret_cast<uint4*>(sP + (col >> 6) * 16384 + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)) = pack8(e);
