@@ -614,9 +614,17 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
     rc = launch_wgrad<256>(p, st);
   if (rc) return rc;
   const long long total = static_cast<long long>(Cout) * Cin * pl.taps;
-  int blocks = static_cast<int>((total + 255) / 256);
-  if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
-  wgrad_reduce_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale);
+  if (pl.splits >= 16) {
+    long long nb = (total + 31) / 32;   // 32 elements per block, 8 split slices each
+    if (nb > device_sm_count() * 32ll) nb = device_sm_count() * 32ll;
+    wgrad_reduce_kernel<<<static_cast<int>(nb), 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate,
+                                                              g_wgrad_rowscale);
+  } else {
+    int blocks = static_cast<int>((total + 255) / 256);
+    if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
+    wgrad_reduce_flat_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate,
+                                                     g_wgrad_rowscale);
+  }
   g_wgrad_rowscale = nullptr;
   B200_LAUNCHED();
   return OK;

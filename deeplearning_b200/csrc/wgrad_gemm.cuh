@@ -210,7 +210,47 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
 }
 
 // grad[cout][cin][tap] (OIHW, fp32) (+)= sum_s partial[s][cout][tap*Cin + cin]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
+// Block = 32 consecutive elements (coalesced) x 8 slices of the split range, folded through shared memory in a fixed order:
+// layers with few output tiles run with ~150 splits, and a single thread walking them serially is pure load latency.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
+                                                           int splits, int Cout, int Cin, int taps, int accumulate,
+                                                           const float* __restrict__ rowscale) {
+  __shared__ float red[8][33];
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  const long long slice = total;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (long long base = static_cast<long long>(blockIdx.x) * 32; base < total; base += static_cast<long long>(gridDim.x) * 32) {
+    // i indexes the partial layout (coalesced reads): [cout][tap][cin]
+    const long long i = base + tx;
+    float s0 = 0.f, s1 = 0.f;
+    if (i < total) {
+      int k = ty;
+      for (; k + 8 < splits; k += 16) {
+        s0 += __ldcs(partial + k * slice + i);
+        s1 += __ldcs(partial + (k + 8) * slice + i);
+      }
+      if (k < splits) s0 += __ldcs(partial + k * slice + i);
+    }
+    red[ty][tx] = s0 + s1;
+    __syncthreads();
+    if (ty == 0 && i < total) {
+      float s = red[0][tx];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) s += red[y][tx];
+      const int cin = static_cast<int>(i % Cin);
+      const long long t = i / Cin;
+      const int tap = static_cast<int>(t % taps);
+      const int cout = static_cast<int>(t / taps);
+      if (rowscale != nullptr) s *= __ldg(rowscale + cout);
+      const long long o = (static_cast<long long>(cout) * Cin + cin) * taps + tap;
+      grad[o] = accumulate ? grad[o] + s : s;
+    }
+    __syncthreads();
+  }
+}
+
+// Same reduction, one thread per element walking the splits: used when there are only a few splits (large weight matrices).
+__global__ void wgrad_reduce_flat_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
                                     int Cin, int taps, int accumulate, const float* __restrict__ rowscale) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   const long long slice = total;
@@ -228,5 +268,6 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     grad[o] = accumulate ? grad[o] + s : s;
   }
 }
+
 
 }  // namespace b200
