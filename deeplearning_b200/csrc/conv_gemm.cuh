@@ -15,6 +15,7 @@
 // Replaces the cuDNN/cuBLAS calls behind nn.Conv2d / nn.Linear on the reference's hot path
 // (classification/resnet/models/networks.py:27-35,104-124; classification/vision_transformer/vit_model.py:95,109,127-133).
 #pragma once
+#include <cstdio>
 #include "common.cuh"
 
 namespace b200 {
@@ -101,6 +102,15 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
+// Optional phase timers (-DCONV_PROFILE): CTA 0 prints average cycles per tile of every wait / work phase of each role.
+#ifdef CONV_PROFILE
+#define CPROF_DECL(N) long long cp_t[N] = {}; long long cp_0 = clock64(), cp_1;
+#define CPROF_TICK(i) { cp_1 = clock64(); cp_t[i] += cp_1 - cp_0; cp_0 = cp_1; }
+#else
+#define CPROF_DECL(N)
+#define CPROF_TICK(i)
+#endif
+
 // Epilogue specialisation: EPI < 0 keeps every epilogue option a run-time flag (generic fallback); EPI >= 0 is a bit set
 // of compile-time options so that the hot layer types get a branch-free epilogue without the unused operand loads.
 constexpr int kEpiGeneric = -1;
@@ -161,6 +171,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      CPROF_DECL(2)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
@@ -168,10 +179,15 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         const int t2 = (m_tile / p.tiles1) % p.tiles2;
         const int t3 = m_tile / (p.tiles1 * p.tiles2);
         const int c1 = t1 * p.box1, c2 = t2 * p.box2, c3 = t3 * p.box3;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          const int tap = kb / p.k_blocks_per_tap;
-          const int cb = kb - tap * p.k_blocks_per_tap;
+        int tap = 0, cb = 0;   // running (tap, channel block) of k-block kb: no division in the single-thread issue loop
+        for (int kb = 0; kb < num_kb; ++kb, ++cb) {
+          if (cb == p.k_blocks_per_tap) {
+            cb = 0;
+            ++tap;
+          }
+          CPROF_TICK(1)
           mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
+          CPROF_TICK(0)
           uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
@@ -184,30 +200,43 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           }
         }
       }
+#ifdef CONV_PROFILE
+      if (blockIdx.x == 0) {
+        const int nt = (num_tiles - 1) / gridDim.x + 1;
+        printf("conv producer: wait_empty %lld issue %lld  (cycles/tile, %d tiles, %d k-blocks)\n", cp_t[0] / nt, cp_t[1] / nt, nt, num_kb);
+      }
+#endif
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+      // The shared-memory descriptors of all stages / K steps differ only in the 14-bit (address >> 4) field, so they are
+      // derived from two base descriptors with 64-bit adds: the one thread that issues every MMA of the CTA spends
+      // ~3 instructions per MMA instead of rebuilding two descriptors (what bounds the small-N tiles).
+      const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(stage_base), p.desc_lbo, p.desc_sbo);
+      const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(stage_base) + Cfg::A_BYTES, p.desc_lbo, p.desc_sbo);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      CPROF_DECL(3)
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        CPROF_TICK(2)
         mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1);
+        CPROF_TICK(0)
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < num_kb; ++kb) {
+          CPROF_TICK(2)
           mbar_wait_backoff(&full_bar[stage], phase);
+          CPROF_TICK(1)
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(stage_base + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          const uint64_t soff = static_cast<uint64_t>(stage) * (Cfg::STAGE_BYTES >> 4);
+          const uint64_t da = desc_a0 + soff, db = desc_b0 + soff;
+          umma_f16(tmem_d, da, db, idesc, kb > 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, p.desc_lbo, p.desc_sbo);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, p.desc_lbo, p.desc_sbo);
-            umma_f16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 1; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);   // +32 B per 16-element K step
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == STAGES) {
             stage = 0;
@@ -220,6 +249,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           acc_phase ^= 1;
         }
       }
+#ifdef CONV_PROFILE
+      if (blockIdx.x == 0) {
+        const int nt = (num_tiles - 1) / gridDim.x + 1;
+        printf("conv mma     : wait_tmem_empty %lld wait_full %lld issue %lld  (cycles/tile)\n", cp_t[0] / nt, cp_t[1] / nt, cp_t[2] / nt);
+      }
+#endif
     }
   } else {
     // ===================== Epilogue: 8 independent warps, no CTA-level barriers =====================
@@ -263,6 +298,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
     for (int k = 0; k < UN; ++k) run_s[k] = 0, run_q[k] = 0;
     int it = 0;
+    CPROF_DECL(2)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       if (split_tiles && (it & 1) != pair) continue;
       const int acc = it & 1;
@@ -284,7 +320,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       }
       const int s1 = c1 + p.qoff1[q], s2 = c2 + p.qoff2[q], s3 = c3 + p.qoff3[q];
 
+      CPROF_TICK(1)
       mbar_wait(&tmem_full[acc], acc_phase);
+      CPROF_TICK(0)
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
 
@@ -483,6 +521,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         store_counter += has_aux ? 2 : 1;
       }
     }
+#ifdef CONV_PROFILE
+    CPROF_TICK(1)
+    if (blockIdx.x == 0 && lane == 0 && (ew == 0 || ew == 4)) {
+      const int nt = (num_tiles - 1) / gridDim.x + 1;
+      printf("conv epilogue warp %d: wait_tmem_full %lld work %lld  (cycles/tile)\n", ew, cp_t[0] / nt, cp_t[1] / nt);
+    }
+#endif
     if (stats != nullptr) {
       const int n_tile = blockIdx.x % p.n_tiles, grp = blockIdx.x / p.n_tiles;
       const int srow = split_tiles ? (grp * 4 + q) * 2 + pair : grp * 4 + q;

@@ -120,6 +120,10 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
   } else if (warp_idx == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_NG, 1, 1);  // both operands MN-major
+      // descriptors of all stages / K steps by 64-bit adds on two base descriptors (see conv_gemm.cuh)
+      const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(smem), p.desc_lbo, p.desc_sbo);
+      const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(smem) + Cfg::A_BYTES, p.desc_lbo, p.desc_sbo);
+      const uint64_t kstep = p.desc_kstep >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -134,15 +138,12 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+          // 16 pixel rows per MMA = 2048 B; LBO = next 64-channel atom (8192 B); SBO = next 8 pixel rows (1024 B)
+          const uint64_t soff = static_cast<uint64_t>(stage) * (Cfg::STAGE_BYTES >> 4);
+          const uint64_t da = desc_a0 + soff, db = desc_b0 + soff;
+          umma_f16(tmem_d, da, db, idesc, kb > kb0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            // 16 pixel rows per MMA = 2048 B; LBO = next 64-channel atom (8192 B); SBO = next 8 pixel rows (1024 B)
-            const uint64_t da = make_smem_desc_sw128(a_addr + k * p.desc_kstep, p.desc_lbo, p.desc_sbo);
-            const uint64_t db = make_smem_desc_sw128(b_addr + k * p.desc_kstep, p.desc_lbo, p.desc_sbo);
-            umma_f16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 1; k < 4; ++k) umma_f16(tmem_d, da + k * kstep, db + k * kstep, idesc, 1u);
           umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) {
             stage = 0;

@@ -95,6 +95,24 @@ def swin_fc2():
     return _swin_gemm("fc2")
 
 
+def res_l1_conv3():   # ResNet layer1 conv3: 1x1 64 -> 256 at 56x56 (+BN statistics)
+    x = rnd(256, 56, 56, 64)
+    wp = ops.pack_weight(torch.randn(256, 64, 1, 1, device=dev) * 0.1)
+    return lambda: ops.conv2d_fwd(x, wp, want_stats=True)
+
+
+def res_l1_conv2():   # ResNet layer1 conv2: 3x3 64 -> 64
+    x = rnd(256, 56, 56, 64)
+    wp = ops.pack_weight(torch.randn(64, 64, 3, 3, device=dev) * 0.1)
+    return lambda: ops.conv2d_fwd(x, wp, 3, 1, want_stats=True)
+
+
+def res_l3_conv2():   # ResNet layer3 conv2: 3x3 256 -> 256 at 14x14
+    x = rnd(256, 14, 14, 256)
+    wp = ops.pack_weight(torch.randn(256, 256, 3, 3, device=dev) * 0.05)
+    return lambda: ops.conv2d_fwd(x, wp, 3, 1, want_stats=True)
+
+
 if __name__ == "__main__":
     fns = [(n, globals()[n]()) for n in sys.argv[1:]]
     for _, f in fns:
