@@ -170,7 +170,9 @@ def run_b200(args):
 
         # convnext_tiny(1000) with stochastic depth off
         model = ConvNeXt(depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], num_classes=1000, drop_path_rate=0.0).to(dev).train()
-    if args.model in ADAMW_MODELS:      # AdamW(lr 5e-4, wd 5e-2) with the reference's decay groups
+    if args.model == "swin_tiny":       # Swin recipe: AdamW + clip_grad_norm_(5.0) (main.py:197, config.py TRAIN.CLIP_GRAD)
+        trainer = TrainStep(model, lr=5e-4, weight_decay=5e-2, optimizer="adamw", clip_grad=5.0)
+    elif args.model in ADAMW_MODELS:    # AdamW(lr 5e-4, wd 5e-2) with the reference's decay groups
         trainer = TrainStep(model, lr=5e-4, weight_decay=5e-2, optimizer="adamw")
     else:                               # SGD(momentum 0.9, wd 5e-5) (resnet/train.py:96, vision_transformer/train.py:94)
         trainer = TrainStep(model, lr=0.01, momentum=0.9, weight_decay=5e-5)
@@ -260,7 +262,9 @@ def run_b200(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": spec["workload"],
                        "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "optimizer": "AdamW(lr=5e-4, wd=5e-2, decay groups)" if args.model in ADAMW_MODELS else "SGD(momentum=0.9, weight_decay=5e-5)",
+                       "optimizer": ("AdamW(lr=5e-4, wd=5e-2, decay groups, clip_grad_norm 5.0)" if args.model == "swin_tiny" else
+                                     "AdamW(lr=5e-4, wd=5e-2, decay groups)" if args.model in ADAMW_MODELS else
+                                     "SGD(momentum=0.9, weight_decay=5e-5)"),
                        "step": "fwd+CE+bwd+allreduce+optimizer",
                        "launch": "eager" if args.eager else "CUDA graph replay",
                        "l2": "working set (~14 GB of activations per step) is far larger than the 126 MB L2; no flush needed"},

@@ -65,7 +65,9 @@ SIGNATURES = {
     "b200_layerscale_grads": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _P]),
     "b200_conv2d_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200_adamw_tick": (_I, [_P, _F, _F, _P]),
-    "b200_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P]),
+    "b200_adamw": (_I, [_P, _P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _P, _P]),
+    "b200_grad_clip_blocks": (_I, []),
+    "b200_grad_clip_coef": (_I, [_P, _L, _F, _F, _P, _P, _P]),
     "b200_window_attention_fwd": (_I, [_P, _P, _P, _I, _P, _I, _I, _I, _I, _I, _F, _P]),
     "b200_window_attention_bwd": (_I, [_P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _F, _P]),
     "b200_window_bias_gather": (_I, [_P, _P, _P, _I, _P, _I, _P]),
@@ -96,7 +98,7 @@ SIGNATURES = {
     "b200_im2col_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_debug_set_desc": (_I, [_I, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
     "b200_stem_wgrad_relayout": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
-    "b200_sgd_momentum": (_I, [_P, _P, _P, _L, _F, _P, _F, _F, _F, _I, _P]),
+    "b200_sgd_momentum": (_I, [_P, _P, _P, _L, _F, _P, _F, _F, _F, _I, _P, _P]),
 }
 
 

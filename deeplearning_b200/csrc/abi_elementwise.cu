@@ -239,9 +239,9 @@ int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, in
 }
 
 int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
-                      float weight_decay, float gscale, int first_step, void* stream) {
+                      float weight_decay, float gscale, int first_step, const float* clip_coef, void* stream) {
   sgd_momentum_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, buf, n, lr, lr_dev, momentum,
-                                                                               weight_decay, gscale, first_step);
+                                                                               weight_decay, gscale, first_step, clip_coef);
   B200_LAUNCHED();
   return OK;
 }

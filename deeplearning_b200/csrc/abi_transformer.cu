@@ -310,9 +310,24 @@ int b200_adamw_tick(float* hyper, float beta1, float beta2, void* stream) {
 }
 
 int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, long long n, const float* hyper,
-               float beta1, float beta2, float eps, float gscale, void* stream) {
+               float beta1, float beta2, float eps, float gscale, const float* clip_coef, void* stream) {
   adamw_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, wd, n, hyper, beta1, beta2,
-                                                                               eps, gscale);
+                                                                               eps, gscale, clip_coef);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_grad_clip_blocks(void) { return device_sm_count() * 4; }
+
+int b200_grad_clip_coef(const float* g, long long n, float gscale, float max_norm, float* partial, float* clip,
+                        void* stream) {
+  B200_REQUIRE(n > 0 && max_norm > 0.f, "grad_clip_coef: bad arguments n=%lld max_norm=%f", n, max_norm);
+  B200_REQUIRE((reinterpret_cast<uintptr_t>(g) & 15) == 0, "grad_clip_coef: the gradient arena must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = b200_grad_clip_blocks();
+  grad_sumsq_partial_kernel<<<blocks, 256, 0, st>>>(g, n, partial);
+  B200_LAUNCHED();
+  grad_clip_coef_kernel<<<1, 256, 0, st>>>(partial, blocks, gscale, max_norm, clip);
   B200_LAUNCHED();
   return OK;
 }

@@ -422,9 +422,57 @@ __global__ void adamw_tick_kernel(float* __restrict__ hyper, float beta1, float 
   }
 }
 
+// Global-norm gradient clipping (torch.nn.utils.clip_grad_norm_, used by the Swin recipe:
+// classification/swin_transformer/utils/torch_utils.py:303-317, main.py:197) without a pass that rewrites the gradients:
+//   pass 1: per-block sums of squares of the flat gradient arena;  pass 2 (one block): total_norm = gscale * sqrt(sum),
+//   clip[0] = min(1, max_norm / (total_norm + 1e-6)), clip[1] = total_norm;  the optimizer kernels multiply by clip[0].
+__global__ void __launch_bounds__(256) grad_sumsq_partial_kernel(const float* __restrict__ g, long long n,
+                                                                 float* __restrict__ partial) {
+  __shared__ float red[8];
+  float s = 0.f;
+  const long long n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 x = __ldg(g4 + i);
+    s = fmaf(x.x, x.x, fmaf(x.y, x.y, fmaf(x.z, x.z, fmaf(x.w, x.w, s))));
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float x = g[(n4 << 2) + threadIdx.x];
+    s = fmaf(x, x, s);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(256) grad_clip_coef_kernel(const float* __restrict__ partial, int nblocks, float gscale,
+                                                             float max_norm, float* __restrict__ clip) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) s += static_cast<double>(partial[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    const float norm = gscale * static_cast<float>(sqrt(t));
+    clip[0] = fminf(1.0f, max_norm / (norm + 1e-6f));
+    clip[1] = norm;
+  }
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, const float* __restrict__ wd, long long n,
-                             const float* __restrict__ hyper, float beta1, float beta2, float eps, float gscale) {
+                             const float* __restrict__ hyper, float beta1, float beta2, float eps, float gscale,
+                             const float* __restrict__ clip) {
+  if (clip != nullptr) gscale *= __ldg(clip);
   const float lr = __ldg(hyper), bc1 = __ldg(hyper + 1), bc2 = __ldg(hyper + 2);
   const float step = lr / bc1, rsq = rsqrtf(bc2);
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;

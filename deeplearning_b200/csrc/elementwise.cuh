@@ -701,8 +701,9 @@ __global__ void stem_wgrad_relayout_kernel(const float* __restrict__ src, float*
 //   g' = g*gscale + wd*p ; buf = first ? g' : mu*buf + g' ; p -= lr*buf
 __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                     long long n, float lr, const float* __restrict__ lr_dev, float momentum, float wd,
-                                    float gscale, int first_step) {
+                                    float gscale, int first_step, const float* __restrict__ clip) {
   if (lr_dev != nullptr) lr = __ldg(lr_dev);  // device-resident learning rate: lets a captured CUDA graph follow a schedule
+  if (clip != nullptr) gscale *= __ldg(clip);  // global-norm clipping coefficient (b200_grad_clip_coef)
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float pv = p[i];

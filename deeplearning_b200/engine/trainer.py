@@ -44,6 +44,12 @@ def _engine_for(model):
     raise NotImplementedError(f"no B200 engine schedule for {type(model).__name__}")
 
 
+def ops_clip_blocks():
+    from .. import _lib
+
+    return _lib.load().b200_grad_clip_blocks()
+
+
 class FlatArena:
     """Parameters, gradients and optimizer state of a model as three contiguous fp32 buffers (device agnostic host logic).
 
@@ -118,10 +124,12 @@ def model_no_decay_rule(model):
 
 class TrainStep:
     def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
-                 broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None):
+                 broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None, clip_grad=None):
         """optimizer="sgd": torch.optim.SGD(momentum, weight_decay on every parameter) - resnet/vit train.py:96,94.
         optimizer="adamw": torch.optim.AdamW(betas, eps, weight_decay) with the reference's decay / no-decay groups
-        (``no_decay(name, param) -> bool``, default ``no_decay_rule``) - convNext/train.py:96,102."""
+        (``no_decay(name, param) -> bool``, default ``no_decay_rule``) - convNext/train.py:96,102.
+        clip_grad: max global L2 norm of the (all-reduced, averaged) gradient, ``clip_grad_norm_`` of the Swin recipe
+        (swin_transformer/main.py:197, config TRAIN.CLIP_GRAD = 5.0); the norm of the last step is ``self.grad_norm``."""
         self.model = model
         self.engine = _engine_for(model)
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
@@ -133,6 +141,12 @@ class TrainStep:
             raise RuntimeError("TrainStep needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
         self.world = self.arena.world
         self.steps = 0
+        self.clip_grad = clip_grad
+        self._clip = None
+        if clip_grad is not None:
+            dev = self.arena.flat_p.device
+            self._clip = torch.ones(2, dtype=torch.float32, device=dev)   # {coefficient, total norm}
+            self._clip_scratch = torch.empty(ops_clip_blocks(), dtype=torch.float32, device=dev)
         if optimizer == "adamw":
             arena = self.arena
             rule = no_decay or model_no_decay_rule(model)
@@ -156,19 +170,26 @@ class TrainStep:
         self.engine.backward(model, tape, dlogits, sink=arena.grad_view)
         return loss, correct
 
+    @property
+    def grad_norm(self):
+        """Total gradient norm of the last step (device scalar), when clip_grad is set."""
+        return None if self._clip is None else self._clip[1]
+
     def _update(self, lr, lr_dev=None):
         arena = self.arena
+        if self._clip is not None:
+            ops.grad_clip_coef(arena.flat_g, self.clip_grad, gscale=arena.grad_scale, out=self._clip, scratch=self._clip_scratch)
         if self.optimizer == "adamw":
             if lr != self._hyper_lr():
                 self._hyper[0:1].fill_(float(lr))
                 self._hyper_lr_value = float(lr)
             ops.adamw_(arena.flat_p, arena.flat_g, arena.flat_m, arena.flat_v, arena.flat_wd, self._hyper, self.betas[0],
-                       self.betas[1], self.eps, gscale=arena.grad_scale)
+                       self.betas[1], self.eps, gscale=arena.grad_scale, clip=self._clip)
             weight_cache.bump()
             return
         # momentum buffer starts at zero, so "buf = mu*buf + g" already equals torch's first-step "buf = g"
         ops.sgd_momentum_(arena.flat_p, arena.flat_g, arena.flat_m, lr, self.momentum, self.weight_decay,
-                          gscale=arena.grad_scale, first_step=False, lr_dev=lr_dev)
+                          gscale=arena.grad_scale, first_step=False, lr_dev=lr_dev, clip=self._clip)
         weight_cache.bump()  # parameters changed behind autograd's back -> repack bf16 operands on next use
 
     def _hyper_lr(self):

@@ -383,11 +383,12 @@ def colsum(m, cols=None, out=None, accumulate=False):
     return out
 
 
-def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=False, lr_dev=None):
-    """lr_dev: optional 1-element fp32 CUDA tensor holding the learning rate (read by the kernel; graph friendly)."""
+def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=False, lr_dev=None, clip=None):
+    """lr_dev: optional 1-element fp32 CUDA tensor holding the learning rate (read by the kernel; graph friendly).
+    clip: optional output of grad_clip_coef (the gradient is additionally scaled by clip[0])."""
     lib = _lib.load()
     rc = lib.b200_sgd_momentum(_p(p), _p(g), _p(buf), p.numel(), float(lr), _p(lr_dev), momentum, weight_decay, gscale,
-                               1 if first_step else 0, _stream())
+                               1 if first_step else 0, _p(clip), _stream())
     _lib.check(rc, "b200_sgd_momentum")
 
 
@@ -658,13 +659,27 @@ def colsum_prod(a, b=None, out=None):
     return out
 
 
-def adamw_(p, g, m, v, wd, hyper, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0, tick=True):
-    """hyper: fp32 CUDA tensor {lr, 1-beta1^t, 1-beta2^t, beta1^t, beta2^t} (init {lr, 0, 0, 1, 1}); tick advances t first."""
+def adamw_(p, g, m, v, wd, hyper, beta1=0.9, beta2=0.999, eps=1e-8, gscale=1.0, tick=True, clip=None):
+    """hyper: fp32 CUDA tensor {lr, 1-beta1^t, 1-beta2^t, beta1^t, beta2^t} (init {lr, 0, 0, 1, 1}); tick advances t first.
+    clip: optional output of grad_clip_coef (the gradient is additionally scaled by clip[0])."""
     lib = _lib.load()
     if tick:
         _lib.check(lib.b200_adamw_tick(_p(hyper), beta1, beta2, _stream()), "b200_adamw_tick")
-    rc = lib.b200_adamw(_p(p), _p(g), _p(m), _p(v), _p(wd), p.numel(), _p(hyper), beta1, beta2, eps, gscale, _stream())
+    rc = lib.b200_adamw(_p(p), _p(g), _p(m), _p(v), _p(wd), p.numel(), _p(hyper), beta1, beta2, eps, gscale, _p(clip),
+                        _stream())
     _lib.check(rc, "b200_adamw")
+
+
+def grad_clip_coef(g, max_norm, gscale=1.0, out=None, scratch=None):
+    """clip_grad_norm_ without touching the gradients: returns fp32 [2] = {min(1, max_norm / (gscale*||g|| + 1e-6)), norm}."""
+    lib = _lib.load()
+    if out is None:
+        out = torch.empty(2, dtype=F32, device=g.device)
+    if scratch is None:
+        scratch = torch.empty(lib.b200_grad_clip_blocks(), dtype=F32, device=g.device)
+    rc = lib.b200_grad_clip_coef(_p(g), g.numel(), float(gscale), float(max_norm), _p(scratch), _p(out), _stream())
+    _lib.check(rc, "b200_grad_clip_coef")
+    return out
 
 
 def layerscale_grads(G, W2, b2, gsum, gamma, dW2=None, db2=None, dgamma=None):

@@ -188,7 +188,13 @@ int b200_layerscale_grads(const float* G, const float* W2, const float* b2, cons
  * (initialise hyper to {lr, 0, 0, 1, 1}), so the whole update is CUDA-graph replayable. */
 int b200_adamw_tick(float* hyper, float beta1, float beta2, void* stream);
 int b200_adamw(float* p, const float* g, float* m, float* v, const float* wd, long long n, const float* hyper,
-               float beta1, float beta2, float eps, float gscale, void* stream);
+               float beta1, float beta2, float eps, float gscale, const float* clip_coef, void* stream);
+/* Global-norm gradient clipping of the Swin recipe (torch.nn.utils.clip_grad_norm_: swin_transformer/utils/torch_utils.py:303-317,
+ * main.py:197) without rewriting the gradients: clip[0] = min(1, max_norm / (gscale*||g||_2 + 1e-6)), clip[1] = the norm.
+ * The optimizer entries multiply their gradient scale by clip_coef[0] when the pointer is non-null.
+ * partial: fp32 scratch of b200_grad_clip_blocks() floats; g must be 16-byte aligned. */
+int b200_grad_clip_blocks(void);
+int b200_grad_clip_coef(const float* g, long long n, float gscale, float max_norm, float* partial, float* clip, void* stream);
 
 /* ---- BatchNorm2d (train: batch statistics, eval: running statistics) ----------------------------------------------------
  * replaces nn.BatchNorm2d + nn.ReLU (+ residual add) of Bottleneck.forward, classification/resnet/models/networks.py:108-124 */
@@ -254,7 +260,7 @@ int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, in
 /* fused SGD(momentum) over a flat fp32 arena; torch.optim.SGD semantics (classification/resnet/train.py:96).
  * lr_dev (optional device float*) overrides lr, so a captured CUDA graph can follow the reference's LambdaLR schedule. */
 int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
-                      float weight_decay, float gscale, int first_step, void* stream);
+                      float weight_decay, float gscale, int first_step, const float* clip_coef, void* stream);
 
 /* bring-up only: override the UMMA shared-memory descriptor strides (which: 0 = forward K-major, 1 = wgrad MN-major) */
 int b200_debug_set_desc(int which, unsigned lbo, unsigned sbo, unsigned kstep);

@@ -42,6 +42,39 @@ def test_fused_optimizer_matches_torch(opt):
             assert torch.allclose(p.detach(), named[n].detach(), rtol=2e-4, atol=2e-6), (opt, step, n)
 
 
+@pytest.mark.parametrize("opt,max_norm", [("adamw", 0.05), ("adamw", 1e6), ("sgd", 0.05)])
+def test_grad_clipping_matches_clip_grad_norm(opt, max_norm):
+    """TrainStep(clip_grad=...) == torch.nn.utils.clip_grad_norm_ + torch optimizer (the Swin recipe,
+    classification/swin_transformer/utils/torch_utils.py:303-317): clipped (small max_norm) and not clipped (huge)."""
+    from deeplearning_b200.engine.trainer import TrainStep, no_decay_rule
+
+    m = _small_resnet(3)
+    ref = copy.deepcopy(m)
+    tr = TrainStep(m, lr=0.02, momentum=0.9, weight_decay=5e-2, optimizer=opt, clip_grad=max_norm)
+    named = dict(ref.named_parameters())
+    if opt == "sgd":
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.02, momentum=0.9, weight_decay=5e-2)
+    else:
+        decay = [p for n, p in named.items() if not no_decay_rule(n, p)]
+        nodecay = [p for n, p in named.items() if no_decay_rule(n, p)]
+        ropt = torch.optim.AdamW([{"params": decay, "weight_decay": 5e-2}, {"params": nodecay, "weight_decay": 0.0}], lr=0.02)
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 16, (8,), device="cuda")
+    for step in range(2):
+        before = [p.detach().clone() for p in m.parameters()]
+        tr.step_eager(x, y)
+        for (n, p), b in zip(m.named_parameters(), before):
+            named[n].data.copy_(b)
+            named[n].grad = p.grad.detach().clone()
+        total = torch.nn.utils.clip_grad_norm_(list(named.values()), max_norm)
+        assert abs(float(tr.grad_norm) - float(total)) <= 1e-4 * float(total)
+        if max_norm < 1:
+            assert float(total) > max_norm   # the clipped branch is really exercised
+        ropt.step()
+        for (n, p) in m.named_parameters():
+            assert torch.allclose(p.detach(), named[n].detach(), rtol=3e-4, atol=3e-6), (opt, step, n)
+
+
 def test_graph_replay_equals_eager():
     from deeplearning_b200.engine.trainer import TrainStep
 
