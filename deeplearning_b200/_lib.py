@@ -98,6 +98,11 @@ SIGNATURES = {
     "b200_im2col_nchw": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_debug_set_desc": (_I, [_I, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
     "b200_stem_wgrad_relayout": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
+    "b200_stem_s2d": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200_stem_s2d_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "b200_stem_s2d_conv_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I]),
+    "b200_stem_s2d_conv_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _P]),
+    "b200_stem_s2d_wgrad_relayout": (_I, [_P, _P, _I, _P]),
     "b200_sgd_momentum": (_I, [_P, _P, _P, _L, _F, _P, _F, _F, _F, _I, _P, _P]),
 }
 

@@ -258,20 +258,15 @@ struct WgradPlan {
   int Ho, Wo;
 };
 
-WgradPlan plan_wgrad(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+WgradPlan plan_wgrad_geom(long long d1, long long d2, long long d3, int Cin, int Cout, int taps) {
   WgradPlan pl;
-  pl.taps = ksize * ksize;
-  pl.Ho = out_dim(H, ksize, stride);
-  pl.Wo = out_dim(W, ksize, stride);
+  pl.taps = taps;
+  pl.Ho = static_cast<int>(d2), pl.Wo = static_cast<int>(d1);
   // 128 x 256 tiles halve the dY re-reads per Cin block (48 KB of operands per 2*128*256*64 flops instead of 32 KB per
   // 2*128*128*64): used whenever the padded operand traffic is lower than with 128-wide tiles.
   pl.block_ng = Cin <= 64 ? 64 : (((Cin + 255) / 256) * 48 < ((Cin + 127) / 128) * 32 ? 256 : 128);
   pl.mg_tiles = (Cout + 127) / 128;
   pl.ng_tiles = (Cin + pl.block_ng - 1) / pl.block_ng;
-  const bool flat = (ksize == 1 && stride == 1);
-  const long long d1 = flat ? static_cast<long long>(B) * H * W : pl.Wo;
-  const long long d2 = flat ? 1 : pl.Ho;
-  const long long d3 = flat ? 1 : B;
   pl.box = choose_box(d1, d2, d3, 64);
   pl.tiles1 = static_cast<int>((d1 + pl.box.b1 - 1) / pl.box.b1);
   pl.tiles2 = static_cast<int>((d2 + pl.box.b2 - 1) / pl.box.b2);
@@ -286,6 +281,30 @@ WgradPlan plan_wgrad(int B, int H, int W, int Cin, int Cout, int ksize, int stri
   pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
   pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
   return pl;
+}
+
+WgradPlan plan_wgrad(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+  const int Ho = out_dim(H, ksize, stride), Wo = out_dim(W, ksize, stride);
+  const bool flat = (ksize == 1 && stride == 1);
+  WgradPlan pl = plan_wgrad_geom(flat ? static_cast<long long>(B) * H * W : Wo, flat ? 1 : Ho, flat ? 1 : B, Cin, Cout,
+                                 ksize * ksize);
+  pl.Ho = Ho, pl.Wo = Wo;
+  return pl;
+}
+
+// Space-to-depth stem (conv 7x7 / stride 2 / pad 3 on 3 channels, classification/resnet/models/networks.py:150,206):
+// z[B][Ho+3][Wo+3][16] holds the zero-padded input with the 2x2 pixel phase folded into the channels (12 real + 4 zero), so
+// the conv becomes a 4x4 / stride-1 conv. The four x-taps of a pixel are 64 CONTIGUOUS elements of z, therefore a tensor map
+// whose rows overlap (row pitch 16 elements, row length 64) presents every k-block (one y-tap) as an ordinary 64-channel
+// activation row: the implicit-GEMM kernels run unchanged with Cin = 64 and four taps (0, ky).
+View stem_s2d_view(const void* z, int B, int Ho, int Wo) {
+  const int Hz = Ho + 3, Wz = Wo + 3;
+  View v;
+  v.base = z;
+  v.dims[0] = 64, v.dims[1] = Wo, v.dims[2] = Hz, v.dims[3] = B;
+  v.strides[0] = 1, v.strides[1] = 16, v.strides[2] = static_cast<uint64_t>(Wz) * 16;
+  v.strides[3] = static_cast<uint64_t>(Hz) * Wz * 16;
+  return v;
 }
 
 }  // namespace
@@ -626,6 +645,71 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
                                                      g_wgrad_rowscale);
   }
   g_wgrad_rowscale = nullptr;
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_stem_s2d_conv_fwd(const void* z, const void* w, void* y, float* stats, int B, int Ho, int Wo, void* stream) {
+  B200_REQUIRE(B > 0 && Ho > 0 && Wo > 0, "stem_s2d_conv_fwd: empty output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Cout = 64;
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = setup_output(p, make_view(y, B, Ho, Wo, Cout, 1, 0, 0), Cout, 0, nullptr))) return rc;
+  const Box3 bx = box_of(p);
+  p.k_per_tap = 64;
+  p.k_blocks_per_tap = 1;
+  p.num_taps = 4;
+  if ((rc = encode_view(&p.a_maps[0], stem_s2d_view(z, B, Ho, Wo), bx))) return rc;
+  for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+  for (int ky = 0; ky < 4; ++ky) {
+    p.tap_map[ky] = 0, p.tap_o1[ky] = 0, p.tap_o2[ky] = static_cast<int8_t>(ky), p.tap_w[ky] = static_cast<int8_t>(ky);
+  }
+  {
+    uint64_t dims[2] = {256, static_cast<uint64_t>(Cout)};
+    uint64_t strides[2] = {1, 256};
+    uint32_t box[2] = {64, 64};
+    if ((rc = encode_tmap_bf16(&p.b_map, w, 2, dims, strides, box))) return rc;
+  }
+  p.stats = stats;
+  return dispatch_conv_gemm(p, Cout, st);
+}
+
+size_t b200_stem_s2d_conv_wgrad_workspace_bytes(int B, int Ho, int Wo) {
+  const WgradPlan pl = plan_wgrad_geom(Wo, Ho, B, 64, 64, 4);
+  return static_cast<size_t>(pl.splits) * 64 * 4 * 64 * sizeof(float);
+}
+
+int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* workspace, size_t workspace_bytes, int B, int Ho,
+                             int Wo, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int Cout = 64, Cin = 64, taps = 4;
+  const WgradPlan pl = plan_wgrad_geom(Wo, Ho, B, Cin, Cout, taps);
+  const size_t need = static_cast<size_t>(pl.splits) * Cout * taps * Cin * sizeof(float);
+  B200_REQUIRE(workspace != nullptr && workspace_bytes >= need, "stem_s2d_conv_wgrad: workspace too small (%zu < %zu)",
+               workspace_bytes, need);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_taps = taps;
+  p.Cout = Cout, p.Cin = Cin;
+  p.mg_tiles = pl.mg_tiles, p.ng_tiles = pl.ng_tiles;
+  p.tiles1 = pl.tiles1, p.tiles2 = pl.tiles2, p.tiles3 = pl.tiles3;
+  p.box1 = pl.box.b1, p.box2 = pl.box.b2, p.box3 = pl.box.b3;
+  p.splits = pl.splits, p.kb_per_split = pl.kb_per_split, p.kb_total = pl.kb_total;
+  p.ld_partial = static_cast<long long>(taps) * Cin;
+  p.partial = static_cast<float*>(workspace);
+  int rc;
+  if ((rc = encode_view(&p.dy_map, make_view(dy, B, Ho, Wo, Cout, 1, 0, 0), pl.box))) return rc;
+  if ((rc = encode_view(&p.x_maps[0], stem_s2d_view(z, B, Ho, Wo), pl.box))) return rc;
+  for (int i = 1; i < 4; ++i) p.x_maps[i] = p.x_maps[0];
+  for (int ky = 0; ky < 4; ++ky) p.tap_map[ky] = 0, p.tap_o1[ky] = 0, p.tap_o2[ky] = static_cast<int8_t>(ky);
+  if ((rc = launch_wgrad<64>(p, st))) return rc;
+  // g[cout][k64][ky] (the generic "OIHW" layout of a 64-channel, 4-tap conv); b200_stem_s2d_wgrad_relayout maps it to [64,3,7,7]
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  long long nb = (total + 31) / 32;
+  if (nb > device_sm_count() * 32ll) nb = device_sm_count() * 32ll;
+  wgrad_reduce_kernel<<<static_cast<int>(nb), 256, 0, st>>>(p.partial, g, pl.splits, Cout, Cin, taps, 0, nullptr);
   B200_LAUNCHED();
   return OK;
 }

@@ -246,4 +246,18 @@ int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float l
   return OK;
 }
 
+int b200_stem_s2d(const float* x, void* z, int B, int H, int W, void* stream) {
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "stem_s2d: H=%d W=%d must be even", H, W);
+  const long long total = static_cast<long long>(B) * (H / 2 + 3) * (W / 2 + 3);
+  stem_s2d_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, static_cast<uint4*>(z), B, H, W);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_stem_s2d_wgrad_relayout(const float* g, float* dw, int accumulate, void* stream) {
+  stem_s2d_wgrad_relayout_kernel<<<(64 * 3 * 49 + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, dw, accumulate);
+  B200_LAUNCHED();
+  return OK;
+}
+
 }  // extern "C"

@@ -663,7 +663,18 @@ __global__ void pack_weights_multi_kernel(const long long* __restrict__ table, i
     const long long r = idx / ld;
     const long long k = idx % ld;
     float v = 0.f;
-    if (r < rows_src) {
+    if (mode == 2) {
+      // space-to-depth stem operand: src [O][3][7][7] -> dst [O][256], k = ky4*64 + kx4*16 + (dy*2+dx)*3 + c with
+      // kernel row 2*ky4+dy and column 2*kx4+dx (taps that fall outside the 7x7 kernel and channels 12..15 are zero)
+      if (r < O && k < 256) {
+        const int ky4 = static_cast<int>(k >> 6), kx4 = static_cast<int>((k >> 4) & 3), q = static_cast<int>(k & 15);
+        if (q < 12) {
+          const int d = q / 3, c = q - d * 3;
+          const int kh = 2 * ky4 + (d >> 1), kw = 2 * kx4 + (d & 1);
+          if (kh < 7 && kw < 7) v = src[((r * 3 + c) * 7 + kh) * 7 + kw];
+        }
+      }
+    } else if (r < rows_src) {
       if (mode == 0) {
         if (k < static_cast<long long>(taps) * I) {
           const int tap = static_cast<int>(k / I), i = static_cast<int>(k % I);
@@ -712,6 +723,49 @@ __global__ void sgd_momentum_kernel(float* __restrict__ p, const float* __restri
     buf[i] = bv;
     p[i] = pv - lr * bv;
   }
+}
+
+// Space-to-depth input of the stem: x fp32 NCHW [B][3][H][W] (H, W even) -> z bf16 [B][H/2+3][W/2+3][16],
+// z[b][Y][X][(dy*2+dx)*3 + c] = xpad[b][c][2Y+dy][2X+dx] with xpad = x zero-padded by 3 pixels; channels 12..15 = 0.
+__global__ void stem_s2d_kernel(const float* __restrict__ x, uint4* __restrict__ z, int B, int H, int W) {
+  const int Hz = H / 2 + 3, Wz = W / 2 + 3;
+  const long long total = static_cast<long long>(B) * Hz * Wz;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(i % Wz);
+    const int Y = static_cast<int>((i / Wz) % Hz);
+    const long long b = i / (static_cast<long long>(Wz) * Hz);
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int h = 2 * Y + dy - 3;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int w = 2 * X + dx - 3;
+        if (w < 0 || w >= W) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = __ldg(x + ((b * 3 + c) * H + h) * W + w);
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lo[q] = v[q], hi[q] = v[8 + q];
+    z[2 * i] = pack8(lo);
+    z[2 * i + 1] = pack8(hi);
+  }
+}
+
+// Weight gradient of the space-to-depth stem: g[64][k64 = kx4*16 + (dy*2+dx)*3 + c][ky4] -> dW [64][3][7][7] (OIHW).
+__global__ void stem_s2d_wgrad_relayout_kernel(const float* __restrict__ g, float* __restrict__ dw, int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 3 * 49) return;
+  const int kw = i % 7, kh = (i / 7) % 7, c = (i / 49) % 3, o = i / 147;
+  const int ky4 = kh >> 1, dy = kh & 1, kx4 = kw >> 1, dx = kw & 1;
+  const float v = g[(o * 64 + kx4 * 16 + (dy * 2 + dx) * 3 + c) * 4 + ky4];
+  dw[i] = accumulate ? dw[i] + v : v;
 }
 
 }  // namespace b200

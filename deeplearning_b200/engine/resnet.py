@@ -44,7 +44,7 @@ class _PackSpec:
                 w = mod.weight
                 O, I, kh, kw = w.shape
                 if name == "conv1":
-                    specs.append((w, 0, 160, O))  # stem patch-matrix layout, K padded 147 -> 160
+                    specs.append((w, 2, 256, O, (O, I, kh * kw)))  # space-to-depth stem operand [64][256]
                     continue
                 specs.append((w, 0, kh * kw * I, O))
                 specs.append((w, 1, kh * kw * O, I))
@@ -100,16 +100,17 @@ def forward(model, x, train, want_tape):
         raise NotImplementedError("model.fc must be an nn.Linear")
     pack = weight_cache.model_pack(model, _pack_spec)  # one launch repacks every bf16 operand if parameters changed
     tape = {"stem": None, "blocks": [], "head": None, "pack": pack} if want_tape else None
-    # ---- stem: 7x7/2 conv as patch-matrix GEMM, BN statistics in the epilogue, BN+ReLU+max-pool in one pass
+    # ---- stem: 7x7/2 conv as a space-to-depth implicit GEMM, BN statistics in the epilogue, BN+ReLU+max-pool in one pass
     conv1, bn1 = model.conv1, model.bn1
     _check_bn(bn1, "bn1")
     if conv1.kernel_size != (7, 7) or conv1.stride != (2, 2) or conv1.padding != (3, 3) or conv1.bias is not None:
         raise NotImplementedError("stem must be the 7x7/2 pad-3 bias-free convolution of the reference")
-    kpad = 160
-    a, Ho, Wo = ops.im2col_nchw(x, 7, 7, 2, 3, kpad)
-    wp = pack.get(conv1.weight, 0)
-    c1, st = ops.conv2d_fwd(a.view(-1, 1, 1, kpad), wp, want_stats=train)
-    c1 = c1.view(B, Ho, Wo, 64)
+    if conv1.out_channels != 64 or x.shape[2] % 2 or x.shape[3] % 2:
+        raise NotImplementedError("stem: 64 output channels and an even input size are required")
+    # space-to-depth operand (108 MB at bs 256 instead of a 1 GB patch matrix); the conv reads it through overlapping TMA rows
+    a = ops.stem_s2d(x)
+    Ho, Wo = a.shape[1] - 3, a.shape[2] - 3
+    c1, st = ops.stem_s2d_conv_fwd(a, pack.get(conv1.weight, 2), want_stats=train)
     if train:
         co1 = ops.bn_finalize(st, B * Ho * Wo, bn1.weight, bn1.bias, bn1.eps, bn1.momentum, bn1.running_mean,
                               bn1.running_var, bn1.num_batches_tracked)
@@ -243,9 +244,7 @@ def backward(model, tape, dlogits, sink=None):
                                            dbeta=grads.dest(model.bn1.bias))
     grads.put(model.bn1.weight, dgamma)
     grads.put(model.bn1.bias, dbeta)
-    kpad = a.shape[1]
-    gw = ops.conv2d_wgrad(dc.view(-1, 1, 1, 64), a.view(-1, 1, 1, kpad))  # [64, kpad, 1, 1], k = (kh*7+kw)*3 + c
-    grads.put(model.conv1.weight, ops.stem_wgrad_relayout(gw.view(64, kpad), 64, 3, 49, out=grads.dest(model.conv1.weight)))
+    grads.put(model.conv1.weight, ops.stem_s2d_conv_wgrad(dc, a, out=grads.dest(model.conv1.weight)))
     return grads
 
 

@@ -392,6 +392,55 @@ def sgd_momentum_(p, g, buf, lr, momentum, weight_decay, gscale=1.0, first_step=
     _lib.check(rc, "b200_sgd_momentum")
 
 
+def stem_s2d(x):
+    """fp32 NCHW [B,3,H,W] -> bf16 [B, H/2+3, W/2+3, 16] space-to-depth operand of the ResNet stem (see b200cls.h)."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    if C != 3:
+        raise ValueError("stem_s2d expects 3 input channels")
+    z = torch.empty(B, H // 2 + 3, W // 2 + 3, 16, dtype=BF16, device=x.device)
+    sp = _span("stem_s2d", 0.0, _nb(x, z))
+    _lib.check(lib.b200_stem_s2d(_p(x), _p(z), B, H, W, _stream()), "b200_stem_s2d")
+    if sp:
+        sp.end()
+    return z
+
+
+def stem_s2d_conv_fwd(z, w_packed, want_stats=False):
+    """conv 7x7/2/pad 3 from the space-to-depth operand: returns (y bf16 [B,Ho,Wo,64], BN statistics partials or None)."""
+    lib = _lib.load()
+    B, Hz, Wz, _ = z.shape
+    Ho, Wo = Hz - 3, Wz - 3
+    y = torch.empty(B, Ho, Wo, 64, dtype=BF16, device=z.device)
+    stats = None
+    if want_stats:
+        stats = torch.empty(lib.b200_conv2d_fwd_stats_rows(B, Ho, Wo, 64, 3, 1), 2, 64, dtype=F32, device=z.device)
+    sp = _span("conv_gemm_fwd", 2.0 * B * Ho * Wo * 64 * 147, _nb(z, w_packed, y))
+    rc = lib.b200_stem_s2d_conv_fwd(_p(z), _p(w_packed), _p(y), _p(stats), B, Ho, Wo, _stream())
+    _lib.check(rc, "b200_stem_s2d_conv_fwd")
+    if sp:
+        sp.end()
+    return y, stats
+
+
+def stem_s2d_conv_wgrad(dy, z, out=None, accumulate=False):
+    """Weight gradient [64,3,7,7] fp32 of the stem conv from dy bf16 [B,Ho,Wo,64] and the space-to-depth operand z."""
+    lib = _lib.load()
+    B, Ho, Wo, _ = dy.shape
+    ws = _workspace(lib.b200_stem_s2d_conv_wgrad_workspace_bytes(B, Ho, Wo), dy.device)
+    g = torch.empty(64, 64, 4, dtype=F32, device=dy.device)
+    sp = _span("wgrad_gemm", 2.0 * dy.numel() * 147, _nb(dy, z))
+    rc = lib.b200_stem_s2d_conv_wgrad(_p(dy), _p(z), _p(g), _p(ws), ws.numel() * ws.element_size(), B, Ho, Wo, _stream())
+    _lib.check(rc, "b200_stem_s2d_conv_wgrad")
+    if out is None:
+        out = torch.empty(64, 3, 7, 7, dtype=F32, device=dy.device)
+        accumulate = False
+    _lib.check(lib.b200_stem_s2d_wgrad_relayout(_p(g), _p(out), 1 if accumulate else 0, _stream()), "b200_stem_s2d_wgrad_relayout")
+    if sp:
+        sp.end()
+    return out
+
+
 def stem_wgrad_relayout(src, cout, cin, taps, out=None, accumulate=False):
     """[Cout][ldk] patch-matrix weight gradient (k = tap*Cin + c) -> OIHW [Cout, Cin, kh, kw] fp32."""
     lib = _lib.load()

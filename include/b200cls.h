@@ -245,13 +245,27 @@ int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, floa
 /* weight packing fp32 OIHW -> bf16 GEMM operand; mode 0: [O][taps*I] (pitch ld_dst), mode 1: [I][taps*O] */
 int b200_pack_weight(const float* src, void* dst, int O, int I, int taps, int mode, long long ld_dst, void* stream);
 /* all weights of a model in one launch: table[n][10] int64 {src, dst, O, I, taps, mode, ld_dst, first_block, rows_out,
- * oscale (optional fp32 [O] multiplier per output channel, 0 = none)} */
+ * oscale (optional fp32 [O] multiplier per output channel, 0 = none)}; mode 0 = forward / wgrad operand [O][tap*I+i],
+ * 1 = dgrad operand [I][tap*O+o], 2 = space-to-depth stem operand [O][256] of a [O][3][7][7] kernel */
 int b200_pack_weights_multi(const void* table, int n_entries, int total_blocks, void* stream);
 int b200_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
 int b200_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
 /* stem im2col from the user's NCHW fp32 batch: a bf16 [B*Ho*Wo][ldk], k=(kh*KW+kw)*Cin+c (networks.py:206 conv1 7x7/2) */
 int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int KH, int KW, int stride, int pad,
                      int ldk, void* stream);
+
+/* Space-to-depth stem - the conv1 7x7 / stride 2 / pad 3 of ResNet (classification/resnet/models/networks.py:150,206) without a
+ * patch matrix: b200_stem_s2d writes z bf16 [B][H/2+3][W/2+3][16] (zero-padded input, 2x2 pixel phase folded into 12 + 4
+ * zero channels); the conv is then a 4x4 / stride-1 conv whose four x-taps are 64 contiguous elements of z, presented to the
+ * implicit-GEMM kernels through a tensor map with overlapping rows. w = b200_pack_weights_multi mode 2 ([64][256]).
+ * y bf16 [B][Ho][Wo][64] (Ho = H/2), stats as for b200_conv2d_fwd (rows: b200_conv2d_fwd_stats_rows(B, Ho, Wo, 64, 3, 1)).
+ * wgrad: g fp32 [64][64][4] scratch gradient in the operand layout -> b200_stem_s2d_wgrad_relayout -> dW [64][3][7][7]. */
+int b200_stem_s2d(const float* x, void* z, int B, int H, int W, void* stream);
+int b200_stem_s2d_conv_fwd(const void* z, const void* w, void* y, float* stats, int B, int Ho, int Wo, void* stream);
+size_t b200_stem_s2d_conv_wgrad_workspace_bytes(int B, int Ho, int Wo);
+int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* workspace, size_t workspace_bytes, int B, int Ho,
+                             int Wo, void* stream);
+int b200_stem_s2d_wgrad_relayout(const float* g, float* dw, int accumulate, void* stream);
 
 /* stem weight gradient [Cout][ldk] (k = tap*Cin + c, as produced by b200_conv2d_wgrad on the patch matrix) -> OIHW */
 int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, int taps, int ldk, int accumulate,

@@ -219,3 +219,40 @@ def test_stem_im2col():
     y, _ = ops.conv2d_fwd(a.reshape(-1, 1, 1, 160), wp)
     ref = F.conv2d(x.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=3).permute(0, 2, 3, 1)
     _close(y.reshape(2, Ho, Wo, 64), ref, 1e-2, 1e-2, "stem conv")
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 224, 224), (3, 64, 96), (1, 32, 32)])
+def test_stem_space_to_depth_conv(B, H, W):
+    """conv1 7x7/2/pad3 (3 -> 64) through the space-to-depth operand and overlapping TMA rows: forward, BN statistics
+    partials and weight gradient against F.conv2d on the bf16-rounded operands."""
+    ops = _ops()
+    from deeplearning_b200 import _lib
+
+    x = torch.randn(B, 3, H, W, device="cuda")
+    w = torch.randn(64, 3, 7, 7, device="cuda") * 0.1
+    z = ops.stem_s2d(x)
+    assert z.shape == (B, H // 2 + 3, W // 2 + 3, 16)
+    xp = F.pad(x, (3, 3, 3, 3)).to(torch.bfloat16)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                assert torch.equal(z[..., (dy * 2 + dx) * 3 + c], xp[:, c, dy::2, dx::2][:, :H // 2 + 3, :W // 2 + 3])
+    assert float(z[..., 12:].abs().max()) == 0.0
+    # pack through the multi-tensor packer (mode 2)
+    lib = _lib.load()
+    wp = torch.empty(64, 256, dtype=torch.bfloat16, device="cuda")
+    table = torch.tensor([[w.data_ptr(), wp.data_ptr(), 64, 3, 49, 2, 256, 0, 64, 0]], dtype=torch.int64, device="cuda")
+    _lib.check(lib.b200_pack_weights_multi(table.data_ptr(), 1, 64, torch.cuda.current_stream().cuda_stream), "pack")
+    y, stats = ops.stem_s2d_conv_fwd(z, wp, want_stats=True)
+    xr = x.to(torch.bfloat16).float().requires_grad_(True)
+    wr = w.to(torch.bfloat16).float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=2, padding=3)
+    _close(y, ref.permute(0, 2, 3, 1), 1e-2, 2e-2, "stem conv fwd")
+    yf = y.float().reshape(-1, 64)
+    _close(stats[:, 0].sum(0), yf.sum(0), 1e-3, 1e-1, "stem stats sum")
+    _close(stats[:, 1].sum(0), (yf * yf).sum(0), 1e-3, 1e-1, "stem stats sumsq")
+    dy_ = _rand(B, H // 2, W // 2, 64, seed=5)
+    (gw,) = torch.autograd.grad(ref, wr, dy_.float().permute(0, 3, 1, 2))
+    dw = ops.stem_s2d_conv_wgrad(dy_, z)
+    sc = float(gw.abs().max())
+    _close(dw / sc, gw / sc, 2e-3, 2e-3, "stem conv wgrad")
