@@ -154,15 +154,17 @@ int b200_copy_rows(const void* src, long long src_pitch_bytes, void* dst, long l
 }
 
 int b200_colsum_partial_slices(long long rows) {
-  long long s = rows / 64;
+  long long s = rows / 256;   // >= 256 rows per slice, up to ~4 blocks per SM
   if (s < 1) s = 1;
-  if (s > 64) s = 64;
+  if (s > 592) s = 592;
   return static_cast<int>(s);
 }
 
 int b200_colsum_partial(const void* m, long long rows, long long ld, int cols, float* partial, void* stream) {
+  B200_REQUIRE(cols % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(m) & 15) == 0,
+               "colsum_partial: cols=%d / ld=%lld must be multiples of 8 and the matrix 16-byte aligned", cols, ld);
   const int S = b200_colsum_partial_slices(rows);
-  colsum_partial_kernel<<<dim3((cols + 63) / 64, S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  colsum_partial_kernel<<<dim3((cols / 8 + 255) / 256, S), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(m), rows, ld, cols, partial);
   B200_LAUNCHED();
   return OK;

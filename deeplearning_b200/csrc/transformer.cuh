@@ -373,24 +373,61 @@ __global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long long src_
   }
 }
 
-// Column-sum partials of a bf16 matrix [rows][ld]: partial[slice][2][cols] (second plane zero), folded by the BN finalize
-// machinery.  Block = 64 columns x 4 row lanes.
-__global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ m, long long rows, long long ld, int cols,
-                                      float* __restrict__ partial) {
-  __shared__ float sh[4][64];
-  const int cx = threadIdx.x & 63, ry = threadIdx.x >> 6;
-  const int c = blockIdx.x * 64 + cx;
+// Column-sum partials of a bf16 matrix [rows][ld] (bias gradients): partial[slice][2][cols] (second plane zero), folded by
+// the BN finalize machinery. 16-byte loads: a thread owns ONE 8-column vector (vector v = tid % vpr of column block
+// blockIdx.x) and walks the rows of its slice with 4 independent loads in flight; 256/vpr row lanes per block are folded
+// through shared memory. (The first version read one bf16 per thread from ~128 blocks: 1 TB/s; this one is HBM bound.)
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ m, long long rows, long long ld,
+                                                             int cols, float* __restrict__ partial) {
+  __shared__ float sh[256 * 8];
+  const int nvec = cols >> 3;                        // cols is a multiple of 8
+  const int vpr = min(nvec - static_cast<int>(blockIdx.x) * 256, 256);   // vectors of this column block
+  const int rpi = 256 / vpr;                         // row lanes
+  const int v = threadIdx.x % vpr, lane_r = threadIdx.x / vpr;
+  const bool active = lane_r < rpi;
   const int S = gridDim.y;
   const long long chunk = (rows + S - 1) / S;
   const long long r0 = blockIdx.y * chunk, r1 = min(rows, r0 + chunk);
-  float s = 0.f;
-  if (c < cols)
-    for (long long r = r0 + ry; r < r1; r += 4) s += __bfloat162float(m[r * ld + c]);
-  sh[ry][cx] = s;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (active) {
+    const uint4* base = reinterpret_cast<const uint4*>(m) + blockIdx.x * 256 + v;
+    const long long ldv = ld >> 3;
+    long long r = r0 + lane_r;
+    for (; r + 3 * rpi < r1; r += 4 * rpi) {
+      const uint4 x0 = __ldg(base + r * ldv), x1 = __ldg(base + (r + rpi) * ldv), x2 = __ldg(base + (r + 2 * rpi) * ldv),
+                  x3 = __ldg(base + (r + 3 * rpi) * ldv);
+      float f0[8], f1[8], f2[8], f3[8];
+      unpack8(x0, f0);
+      unpack8(x1, f1);
+      unpack8(x2, f2);
+      unpack8(x3, f3);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+    }
+    for (; r < r1; r += rpi) {
+      float f[8];
+      unpack8(__ldg(base + r * ldv), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sh[threadIdx.x * 8 + j] = active ? acc[j] : 0.f;
   __syncthreads();
-  if (ry == 0 && c < cols) {
-    partial[(static_cast<long long>(blockIdx.y) * 2 + 0) * cols + c] = sh[0][cx] + sh[1][cx] + sh[2][cx] + sh[3][cx];
-    partial[(static_cast<long long>(blockIdx.y) * 2 + 1) * cols + c] = 0.f;
+  if (lane_r == 0) {
+    for (int k = 1; k < rpi; ++k)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += sh[(k * vpr + v) * 8 + j];
+    const int c = (blockIdx.x * 256 + v) * 8;
+    float* p0 = partial + (static_cast<long long>(blockIdx.y) * 2 + 0) * cols + c;
+    float* p1 = partial + (static_cast<long long>(blockIdx.y) * 2 + 1) * cols + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      p0[j] = acc[j];
+      p1[j] = 0.f;
+    }
   }
 }
 

@@ -13,6 +13,8 @@ Backward folds the layer scale into the dgrad operand of pwconv2 (packed copy sc
 epilogue, and derives dgamma / dW2 / db2 from the *unscaled* weight gradient G = g^T post (dgamma_c = <W2_c, G_c> + b2_c sum(g_c)),
 so the pre-scale activation is never stored.  Stochastic depth (drop_path) must be 0 in training mode.
 """
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -76,10 +78,13 @@ class _DwCache:
     def get(self, param):
         stamp = (param._version, param.data_ptr(), weight_cache.generation)
         hit = self.store.get(id(param))
-        if hit is not None and hit[0] == stamp:
+        # id() and the device address of a freed parameter can both be recycled by a NEW model: the entry is only valid
+        # while the very same parameter object is alive
+        if hit is not None and hit[0] == stamp and hit[2]() is param:
             return hit[1]
         wt = ops.dwconv7_pack(param)
-        self.store[id(param)] = (stamp, wt)
+        key = id(param)
+        self.store[key] = (stamp, wt, weakref.ref(param, lambda _r, k=key, st=self.store: st.pop(k, None)))
         return wt
 
 
