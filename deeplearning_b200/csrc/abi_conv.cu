@@ -202,6 +202,7 @@ int epilogue_flags(const ConvGemmParams& p) {
   X(kEpiBias | kEpiColscale | kEpiResF32 | kEpiOutF32)    /* ConvNeXt pwconv2 * gamma + shortcut     */  \
   X(kEpiBias | (2 << kEpiActShift) | kEpiAux)             /* fc1 + GELU, keeps the pre-activation    */  \
   X(3 << kEpiActShift)                                    /* fc2 dgrad * GELU'(pre)                  */  \
+  X((3 << kEpiActShift) | kEpiStats)                      /* ... + column sums = fc1 bias gradient   */  \
   X(kEpiOutF32)                                           /* Swin patch-merging reduction            */  \
   X(kEpiBias | kEpiOutF32)                                /* ConvNeXt downsample conv                */
 

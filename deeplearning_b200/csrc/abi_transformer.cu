@@ -489,7 +489,7 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     const long long rows = static_cast<long long>(B) * T * H;
-    attn_delta_kernel<<<static_cast<int>((rows * 32 + 255) / 256), 256, 0, st>>>(
+    attn_delta_kernel<<<grid_for(rows, 256), 256, 0, st>>>(
         static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out), delta, B, T, H);
     B200_LAUNCHED();
   }

@@ -147,14 +147,17 @@ def forward(model, x, train, want_tape):
     return (logits[:, :n_cls] if n_pad != n_cls else logits), tape
 
 
-def _lin_wgrad(grads, lin, dy2d, x2d):
+def _lin_wgrad(grads, lin, dy2d, x2d, dy_stats=None):
     M, N = dy2d.shape
     K = x2d.shape[1]
     dst = grads.dest(lin.weight)
     gw = ops.conv2d_wgrad(dy2d.view(M, 1, 1, N), x2d.view(M, 1, 1, K), out=dst.view(N, K, 1, 1) if dst is not None else None)
     grads.put(lin.weight, gw)
     if lin.bias is not None:
-        grads.put(lin.bias, ops.colsum_tall(dy2d, out=grads.dest(lin.bias)))
+        if dy_stats is not None:   # column sums already produced by the epilogue of the GEMM that wrote dy
+            grads.put(lin.bias, ops.stats_colsum(dy_stats, out=grads.dest(lin.bias)))
+        else:
+            grads.put(lin.bias, ops.colsum_tall(dy2d, out=grads.dest(lin.bias)))
 
 
 def backward(model, tape, dlogits, sink=None):
@@ -202,8 +205,9 @@ def backward(model, tape, dlogits, sink=None):
             grads.put(blk.pwconv2.bias, db2)
             if blk.gamma is not None:
                 grads.put(blk.gamma, dgam)
-            d_pre, _ = ops.gemm(g2, pack.get(blk.pwconv2.weight, 1), act=3, aux_in=pre)   # (g*gamma) W2, times GELU'(pre)
-            _lin_wgrad(grads, blk.pwconv1, d_pre, y.view(M, C))
+            # (g*gamma) W2, times GELU'(pre); the epilogue also sums the columns of d_pre (= pwconv1 bias gradient)
+            d_pre, _, st_pre = ops.gemm(g2, pack.get(blk.pwconv2.weight, 1), act=3, aux_in=pre, want_stats=True)
+            _lin_wgrad(grads, blk.pwconv1, d_pre, y.view(M, C), dy_stats=st_pre)
             d_y, _ = ops.gemm(d_pre, pack.get(blk.pwconv1.weight, 1))
             du, dgl, dbl = ops.layernorm_bwd(d_y, u.view(M, C), m, r, blk.norm.weight, dx_dtype=BF16,
                                              dgamma=grads.dest(blk.norm.weight), dbeta=grads.dest(blk.norm.bias))

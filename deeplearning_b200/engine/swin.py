@@ -190,8 +190,8 @@ def backward(model, tape, dlogits, sink=None):
             nH = att_m.num_heads
             g2 = g.view(M, C)
             _lin_grads(grads, mlp.fc2, g2, post.view(M, -1))
-            d_pre, _ = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1))
-            _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, C))
+            d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1), want_stats=True)
+            _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, C), dy_stats=st_pre)
             d_y2, _ = ops.gemm(d_pre, pack.get(mlp.fc1.weight, 1))
             g, dg2, db2 = ops.layernorm_bwd(d_y2, h2, m2, r2, blk.norm2.weight, add=g, dx_dtype=BF16,
                                             dgamma=grads.dest(blk.norm2.weight), dbeta=grads.dest(blk.norm2.bias))

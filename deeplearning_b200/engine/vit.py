@@ -129,15 +129,19 @@ def forward(model, x, train, want_tape):
     return (logits[:, :n_cls] if n_pad != n_cls else logits), tape
 
 
-def _lin_grads(grads, lin, dy2d, x2d):
-    """Weight / bias gradient of a Linear layer from dy [M, N] and its input x [M, K] (both bf16)."""
+def _lin_grads(grads, lin, dy2d, x2d, dy_stats=None):
+    """Weight / bias gradient of a Linear layer from dy [M, N] and its input x [M, K] (both bf16).
+    dy_stats: epilogue column-sum partials of dy when the GEMM that produced dy already summed its columns."""
     M, N = dy2d.shape
     K = x2d.shape[1]
     dst = grads.dest(lin.weight)
     gw = ops.conv2d_wgrad(dy2d.view(M, 1, 1, N), x2d.view(M, 1, 1, K), out=dst.view(N, K, 1, 1) if dst is not None else None)
     grads.put(lin.weight, gw)
     if lin.bias is not None:
-        grads.put(lin.bias, ops.colsum_tall(dy2d, out=grads.dest(lin.bias)))
+        if dy_stats is not None:
+            grads.put(lin.bias, ops.stats_colsum(dy_stats, out=grads.dest(lin.bias)))
+        else:
+            grads.put(lin.bias, ops.colsum_tall(dy2d, out=grads.dest(lin.bias)))
 
 
 def backward(model, tape, dlogits, sink=None):
@@ -177,8 +181,9 @@ def backward(model, tape, dlogits, sink=None):
         g2 = g.view(M, D)
         # h3 = h2 + fc2(gelu(fc1(LN2(h2))))
         _lin_grads(grads, mlp.fc2, g2, post.view(M, -1))
-        d_pre, _ = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1))   # dgrad + GELU' in the epilogue
-        _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, D))
+        # dgrad + GELU' in the epilogue, which also sums the columns of d_pre (= fc1 bias gradient) on the way out
+        d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1), want_stats=True)
+        _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, D), dy_stats=st_pre)
         d_y2, _ = ops.gemm(d_pre, pack.get(mlp.fc1.weight, 1))
         g, dg2, db2 = ops.layernorm_bwd(d_y2, h2, m2, r2, blk.norm2.weight, add=g, dx_dtype=BF16,
                                         dgamma=grads.dest(blk.norm2.weight), dbeta=grads.dest(blk.norm2.bias))

@@ -509,12 +509,34 @@ def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, 
         iv = _view(aux_in, N)
         keep.append(iv)
         args.aux_in = ctypes.pointer(iv)
+    stats = None
+    if want_stats:
+        # per-CTA column sums / sums of squares of the stored output (the BN-statistics epilogue): plane 0 summed over the
+        # rows is e.g. the bias gradient of the layer whose output gradient this GEMM produces (see stats_colsum)
+        if out_f32 or a_view is not None or out_view is not None:
+            raise ValueError("gemm: want_stats needs a plain bf16 [rows, N] output")
+        stats = torch.empty(lib.b200_conv2d_fwd_stats_rows(rows, 1, 1, N, 1, 1), 2, N, dtype=F32, device=a.device)
+        args.stats = _p(stats)
     sp = _span("conv_gemm_fwd", 2.0 * rows * N * K, _nb(a, w_packed, out, residual, aux, aux_in))
     rc = lib.b200_gemm_ex(ctypes.byref(av), ctypes.byref(ov), ctypes.byref(args), _stream())
     _lib.check(rc, "b200_gemm_ex")
     if sp:
         sp.end()
+    if want_stats:
+        return out, aux, stats
     return out, aux
+
+
+def stats_colsum(stats, out=None):
+    """Column sums from epilogue statistics partials [T, 2, C] (plane 0): fp32 [C]."""
+    lib = _lib.load()
+    T, _, C = stats.shape
+    if out is None:
+        out = torch.empty(C, dtype=F32, device=stats.device)
+    sc = _reduce_scratch(stats.device)
+    rc = lib.b200_bn_bwd_finalize(_p(stats), T, C, 1.0, None, _p(out), 0, None, None, None, None, _p(sc), sc.numel(), _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------- layer norm
