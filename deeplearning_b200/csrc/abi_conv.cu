@@ -639,6 +639,13 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
     if (nb > device_sm_count() * 32ll) nb = device_sm_count() * 32ll;
     wgrad_reduce_kernel<<<static_cast<int>(nb), 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate,
                                                               g_wgrad_rowscale);
+  } else if (pl.taps == 1 && Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) {
+    const long long n4 = total / 4;
+    long long nb = (n4 + 255) / 256;
+    if (nb > device_sm_count() * 16ll) nb = device_sm_count() * 16ll;
+    wgrad_reduce_vec4_kernel<<<static_cast<int>(nb), 256, 0, st>>>(reinterpret_cast<const float4*>(p.partial),
+                                                                   reinterpret_cast<float4*>(dw), pl.splits, n4, Cin / 4,
+                                                                   accumulate, g_wgrad_rowscale);
   } else {
     int blocks = static_cast<int>((total + 255) / 256);
     if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;

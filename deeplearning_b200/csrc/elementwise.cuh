@@ -659,6 +659,32 @@ __global__ void pack_weights_multi_kernel(const long long* __restrict__ table, i
   const long long nblk = next_first - first;
   const long long total = rows_out * ld;
   const long long rows_src = mode == 0 ? O : I;
+  if (mode == 1 && taps == 1) {
+    // dgrad operand of a linear layer = transpose of the [O][I] parameter: 32 x 32 tiles through shared memory so that both
+    // the fp32 reads (along I) and the bf16 writes (along O) are coalesced (the generic loop below reads with stride I)
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const long long tiles_k = (ld + 31) / 32, tiles_r = (rows_out + 31) / 32;
+    for (long long t = blockIdx.x - first; t < tiles_k * tiles_r; t += nblk) {
+      const long long r0 = (t / tiles_k) * 32, k0 = (t % tiles_k) * 32;
+      for (int j = ty; j < 32; j += 8) {
+        const long long o = k0 + j, i = r0 + tx;
+        float v = 0.f;
+        if (o < O && i < I) {
+          v = src[o * I + i];
+          if (oscale) v *= oscale[o];
+        }
+        tile[j][tx] = v;
+      }
+      __syncthreads();
+      for (int j = ty; j < 32; j += 8) {
+        const long long r = r0 + j, k = k0 + tx;
+        if (r < rows_out && k < ld) dst[r * ld + k] = __float2bfloat16_rn(tile[tx][j]);
+      }
+      __syncthreads();
+    }
+    return;
+  }
   for (long long idx = (blockIdx.x - first) * blockDim.x + threadIdx.x; idx < total; idx += nblk * blockDim.x) {
     const long long r = idx / ld;
     const long long k = idx % ld;

@@ -271,4 +271,28 @@ __global__ void wgrad_reduce_flat_kernel(const float* __restrict__ partial, floa
 }
 
 
+// Linear layers (taps == 1, Cin % 4 == 0): the partial layout equals the gradient layout, so the reduction is a plain
+// element-wise sum over the splits - four elements per thread, all splits' loads independent.
+__global__ void __launch_bounds__(256) wgrad_reduce_vec4_kernel(const float4* __restrict__ partial, float4* __restrict__ grad,
+                                                                int splits, long long n4, int cin4, int accumulate,
+                                                                const float* __restrict__ rowscale) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 s = __ldcs(partial + i);
+    for (int k = 1; k < splits; ++k) {
+      const float4 x = __ldcs(partial + k * n4 + i);
+      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
+    }
+    if (rowscale != nullptr) {
+      const float r = __ldg(rowscale + i / cin4);
+      s.x *= r; s.y *= r; s.z *= r; s.w *= r;
+    }
+    if (accumulate) {
+      const float4 g = grad[i];
+      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+    }
+    grad[i] = s;
+  }
+}
+
 }  // namespace b200
