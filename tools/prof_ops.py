@@ -113,6 +113,51 @@ def res_l3_conv2():   # ResNet layer3 conv2: 3x3 256 -> 256 at 14x14
     return lambda: ops.conv2d_fwd(x, wp, 3, 1, want_stats=True)
 
 
+def vit_fc1():        # ViT-B/16 fc1: [50432, 768] x [3072, 768]^T + bias, GELU, keeps the pre-activation
+    a = rnd(256 * 197, 768, scale=0.5)
+    wp = ops.pack_weight(torch.randn(3072, 768, device=dev) * 0.03)
+    b = torch.randn(3072, device=dev) * 0.1
+    return lambda: ops.gemm(a, wp, bias=b, act=2, aux_out=True)
+
+
+def vit_qkv():
+    a = rnd(256 * 197, 768, scale=0.5)
+    wp = ops.pack_weight(torch.randn(2304, 768, device=dev) * 0.03)
+    b = torch.randn(2304, device=dev) * 0.1
+    return lambda: ops.gemm(a, wp, bias=b)
+
+
+def vit_fc2_dgrad():  # d_pre = (g W2) * GELU'(pre) with column sums (fc1 bias gradient)
+    g = rnd(256 * 197, 768, scale=0.1)
+    wd = ops.pack_weight(torch.randn(768, 3072, device=dev) * 0.03, mode=1)
+    pre = rnd(256 * 197, 3072)
+    return lambda: ops.gemm(g, wd, act=3, aux_in=pre, want_stats=True)
+
+
+def vit_fc1_wgrad():
+    dy = rnd(256 * 197, 1, 1, 3072, scale=0.1)
+    x = rnd(256 * 197, 1, 1, 768)
+    return lambda: ops.conv2d_wgrad(dy, x)
+
+
+def vit_attn_fwd():
+    qkv = rnd(256, 197, 3 * 768, scale=0.5)
+    return lambda: ops.attention_fwd(qkv, 12, 0.125)
+
+
+def res_l3_wgrad():   # ResNet layer3 conv2 weight gradient: 3x3 256 -> 256 at 14x14
+    x = rnd(256, 14, 14, 256)
+    dy = rnd(256, 14, 14, 256, scale=0.1)
+    return lambda: ops.conv2d_wgrad(dy, x, 3, 1)
+
+
+def res_l2_dgrad_res():   # ResNet layer2 conv1 dgrad (1x1 512 <- 128) + identity-branch gradient
+    dy = rnd(256, 28, 28, 128, scale=0.1)
+    wd = ops.pack_weight(torch.randn(128, 512, 1, 1, device=dev) * 0.05, mode=1)
+    res = rnd(256, 28, 28, 512, scale=0.1)
+    return lambda: ops.conv2d_dgrad(dy, wd, (28, 28), residual=res)
+
+
 if __name__ == "__main__":
     fns = [(n, globals()[n]()) for n in sys.argv[1:]]
     for _, f in fns:
