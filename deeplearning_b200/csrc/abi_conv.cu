@@ -254,6 +254,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
 
 struct WgradPlan {
   int block_ng, mg_tiles, ng_tiles, taps;
+  int merge_atoms;  // > 0: merged-tap mode (wgrad_gemm.cuh), the taps are columns of one N = 192 / 256 tile
   Box3 box;
   int tiles1, tiles2, tiles3, kb_total, splits, kb_per_split;
   int Ho, Wo;
@@ -268,14 +269,21 @@ WgradPlan plan_wgrad_geom(long long d1, long long d2, long long d3, int Cin, int
   pl.block_ng = Cin <= 64 ? 64 : (((Cin + 255) / 256) * 48 < ((Cin + 127) / 128) * 32 ? 256 : 128);
   pl.mg_tiles = (Cout + 127) / 128;
   pl.ng_tiles = (Cin + pl.block_ng - 1) / pl.block_ng;
+  pl.merge_atoms = 0;
+  if (Cin == 64 && taps > 1 && (taps % 4 == 0 || taps % 3 == 0)) {
+    pl.merge_atoms = 1;
+    pl.block_ng = taps % 4 == 0 ? 256 : 192;
+    pl.ng_tiles = taps * 64 / pl.block_ng;
+  }
   pl.box = choose_box(d1, d2, d3, 64);
   pl.tiles1 = static_cast<int>((d1 + pl.box.b1 - 1) / pl.box.b1);
   pl.tiles2 = static_cast<int>((d2 + pl.box.b2 - 1) / pl.box.b2);
   pl.tiles3 = static_cast<int>((d3 + pl.box.b3 - 1) / pl.box.b3);
   pl.kb_total = pl.tiles1 * pl.tiles2 * pl.tiles3;
-  const int items_per_split = pl.mg_tiles * pl.ng_tiles * pl.taps;
+  const int items_per_split = pl.mg_tiles * pl.ng_tiles * (pl.merge_atoms ? 1 : pl.taps);
   const int target = 2 * device_sm_count();
   int splits = (target + items_per_split - 1) / items_per_split;
+  if (pl.merge_atoms && splits > 1 && splits * items_per_split > target) --splits;  // no one-item third wave
   const int max_splits = pl.kb_total / 4 > 0 ? pl.kb_total / 4 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -585,7 +593,9 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
                workspace_bytes, need);
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.num_taps = pl.taps;
+  p.num_taps = pl.merge_atoms ? 1 : pl.taps;
+  p.merge_atoms = pl.merge_atoms;
+  p.n_cols = pl.merge_atoms ? pl.taps * Cin : Cin;
   p.Cout = Cout, p.Cin = Cin;
   p.mg_tiles = pl.mg_tiles, p.ng_tiles = pl.ng_tiles;
   p.tiles1 = pl.tiles1, p.tiles2 = pl.tiles2, p.tiles3 = pl.tiles3;
@@ -630,6 +640,8 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
     rc = launch_wgrad<64>(p, st);
   else if (pl.block_ng == 128)
     rc = launch_wgrad<128>(p, st);
+  else if (pl.block_ng == 192)
+    rc = launch_wgrad<192>(p, st);
   else
     rc = launch_wgrad<256>(p, st);
   if (rc) return rc;
@@ -699,7 +711,9 @@ int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* work
                workspace_bytes, need);
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  p.num_taps = taps;
+  p.num_taps = pl.merge_atoms ? 1 : taps;
+  p.merge_atoms = pl.merge_atoms;
+  p.n_cols = pl.merge_atoms ? taps * Cin : Cin;
   p.Cout = Cout, p.Cin = Cin;
   p.mg_tiles = pl.mg_tiles, p.ng_tiles = pl.ng_tiles;
   p.tiles1 = pl.tiles1, p.tiles2 = pl.tiles2, p.tiles3 = pl.tiles3;
@@ -712,7 +726,7 @@ int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* work
   if ((rc = encode_view(&p.x_maps[0], stem_s2d_view(z, B, Ho, Wo), pl.box))) return rc;
   for (int i = 1; i < 4; ++i) p.x_maps[i] = p.x_maps[0];
   for (int ky = 0; ky < 4; ++ky) p.tap_map[ky] = 0, p.tap_o1[ky] = 0, p.tap_o2[ky] = static_cast<int8_t>(ky);
-  if ((rc = launch_wgrad<64>(p, st))) return rc;
+  if ((rc = launch_wgrad<256>(p, st))) return rc;  // merged-tap mode: the four y-taps are the four 64-column atoms
   // g[cout][k64][ky] (the generic "OIHW" layout of a 64-channel, 4-tap conv); b200_stem_s2d_wgrad_relayout maps it to [64,3,7,7]
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   long long nb = (total + 31) / 32;

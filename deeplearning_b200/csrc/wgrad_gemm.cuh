@@ -6,6 +6,10 @@
 // The pixel range is split across CTAs (split-K); each CTA writes its fp32 partial tile to a workspace which
 // wgrad_reduce_kernel sums deterministically (no atomics) into the OIHW gradient.
 //
+// 64-channel inputs with several taps (ResNet layer1 3x3, the space-to-depth stem) run in MERGED-TAP mode: the 64-column
+// atoms of one B tile belong to DIFFERENT taps (same pixels, shifted TMA coordinates), so one dY tile feeds an N = 192 / 256
+// MMA instead of one N = 64 MMA per tap (tcgen05.mma costs ~100 cycles however small N is).
+//
 // Replaces the cuDNN backward-filter / cuBLAS calls autograd issues for nn.Conv2d / nn.Linear in the reference
 // (loss.backward(): classification/resnet/utils.py:43).
 #pragma once
@@ -17,7 +21,9 @@ namespace b200 {
 struct alignas(64) WgradParams {
   CUtensorMap dy_map;     // 4-D (Cout, d1, d2, d3), box (64, b1, b2, b3), b1*b2*b3 = 64 pixels
   CUtensorMap x_maps[4];  // 4-D (Cin, ...), same box
-  int num_taps;
+  int num_taps;     // taps that are separate work items (1 in merged-tap mode)
+  int merge_atoms;  // merged-tap mode: 64-channel atoms per tap (Cin / 64); 0 = one tap per work item
+  int n_cols;       // valid columns of one partial row segment: Cin, or taps * Cin in merged-tap mode
   int Cout, Cin;
   int mg_tiles, ng_tiles;
   int tiles1, tiles2, tiles3;
@@ -37,7 +43,7 @@ struct WgradCfg {
   static constexpr int A_BYTES = 2 * 64 * 128;             // two 64-channel atoms of dY
   static constexpr int B_BYTES = (BLOCK_NG / 64) * 64 * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_NG == 256) ? 4 : ((BLOCK_NG == 128) ? 6 : 8);
+  static constexpr int STAGES = (BLOCK_NG == 256) ? 4 : (BLOCK_NG == 192 ? 5 : (BLOCK_NG == 128 ? 6 : 8));
   static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;
   static constexpr int TMEM_COLS = (2 * BLOCK_NG <= 128) ? 128 : (2 * BLOCK_NG <= 256 ? 256 : 512);
@@ -94,8 +100,20 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
         const int mg = r / p.ng_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const CUtensorMap* xm = &p.x_maps[p.tap_map[tap]];
-        const int o1 = p.tap_o1[tap], o2 = p.tap_o2[tap];
+        // per 64-column atom of the B tile: tensor map, channel offset and tap shift
+        const CUtensorMap* xm[BLOCK_NG / 64];
+        int ch0[BLOCK_NG / 64], o1[BLOCK_NG / 64], o2[BLOCK_NG / 64];
+#pragma unroll
+        for (int j = 0; j < BLOCK_NG / 64; ++j) {
+          int tp = tap, ca = ng * (BLOCK_NG / 64) + j;
+          if (p.merge_atoms) {
+            tp = ca / p.merge_atoms;
+            ca -= tp * p.merge_atoms;
+          }
+          xm[j] = &p.x_maps[p.tap_map[tp]];
+          ch0[j] = ca * 64;
+          o1[j] = p.tap_o1[tp], o2[j] = p.tap_o2[tp];
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           const int t1 = kb % p.tiles1;
           const int t2 = (kb / p.tiles1) % p.tiles2;
@@ -109,7 +127,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
           tma_load_4d(a_dst + 8192, &p.dy_map, &full_bar[stage], mg * 128 + 64, c1, c2, c3);
 #pragma unroll
           for (int j = 0; j < BLOCK_NG / 64; ++j)
-            tma_load_4d(b_dst + j * 8192, xm, &full_bar[stage], ng * BLOCK_NG + j * 64, c1 + o1, c2 + o2, c3);
+            tma_load_4d(b_dst + j * 8192, xm[j], &full_bar[stage], ch0[j], c1 + o1[j], c2 + o2[j], c3);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
           const int cin0 = ng * BLOCK_NG + ch * 32;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (cin0 + j * 4 < p.Cin) {  // Cin is a multiple of 8
+            if (cin0 + j * 4 < p.n_cols) {  // a multiple of 8
               uint4 w = make_uint4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
               *reinterpret_cast<uint4*>(out_row + ch * 32 + j * 4) = w;
             }
