@@ -252,6 +252,27 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   return OK;
 }
 
+// partial[splits][Cout][taps*Cin] -> grad[Cout][Cin][taps] (+)=, see wgrad_gemm.cuh
+void launch_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, int Cin, int taps, int accumulate,
+                         const float* rowscale, cudaStream_t st) {
+  const long long total = static_cast<long long>(Cout) * Cin * taps;
+  if (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
+    int chunk = taps == 1 ? 256 : 64;
+    while (chunk > 16 && chunk / 2 >= Cin) chunk /= 2;  // (stays a multiple of 16: vector loads need 16 B alignment)
+    while (chunk > 16 && static_cast<long long>(Cout) * ((Cin + chunk - 1) / chunk) < 2ll * device_sm_count()) chunk /= 2;
+    const int SL = splits < 8 ? splits : 8;
+    const size_t smem = static_cast<size_t>(SL) * taps * chunk * sizeof(float);
+    if (smem <= 48 * 1024 && Cout <= 65535 * 32) {
+      dim3 grid(Cout, (Cin + chunk - 1) / chunk);
+      wgrad_reduce_rows_kernel<<<grid, 256, smem, st>>>(partial, dw, splits, Cout, Cin, taps, chunk, SL, accumulate, rowscale);
+      return;
+    }
+  }
+  int blocks = static_cast<int>((total + 255) / 256);
+  if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
+  wgrad_reduce_flat_kernel<<<blocks, 256, 0, st>>>(partial, dw, splits, Cout, Cin, taps, accumulate, rowscale);
+}
+
 struct WgradPlan {
   int block_ng, mg_tiles, ng_tiles, taps;
   int merge_atoms;  // > 0: merged-tap mode (wgrad_gemm.cuh), the taps are columns of one N = 192 / 256 tile
@@ -280,13 +301,24 @@ WgradPlan plan_wgrad_geom(long long d1, long long d2, long long d3, int Cin, int
   pl.tiles2 = static_cast<int>((d2 + pl.box.b2 - 1) / pl.box.b2);
   pl.tiles3 = static_cast<int>((d3 + pl.box.b3 - 1) / pl.box.b3);
   pl.kb_total = pl.tiles1 * pl.tiles2 * pl.tiles3;
+  // Split-K factor: minimise (waves x pixel blocks per item x time per block) + the fp32 partial traffic it causes. The
+  // per-block times are the measured, L2-operand-bandwidth-bound rates of the kernel (us per 64-pixel block and tile width).
   const int items_per_split = pl.mg_tiles * pl.ng_tiles * (pl.merge_atoms ? 1 : pl.taps);
-  const int target = 2 * device_sm_count();
-  int splits = (target + items_per_split - 1) / items_per_split;
-  if (pl.merge_atoms && splits > 1 && splits * items_per_split > target) --splits;  // no one-item third wave
+  const int sms = device_sm_count();
+  const double t_kb = pl.block_ng == 256 ? 0.45 : (pl.block_ng == 192 ? 0.36 : (pl.block_ng == 128 ? 0.30 : 0.25));
+  const double part_us = static_cast<double>(Cout) * Cin * taps * 4.0 * 2.0 / 3.0e6;  // write + read of one split at ~3 TB/s
   const int max_splits = pl.kb_total / 4 > 0 ? pl.kb_total / 4 : 1;
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
+  int splits = 1;
+  double best = 1e30;
+  for (int s = 1; s <= max_splits; ++s) {
+    const int kps = (pl.kb_total + s - 1) / s;
+    const int s2 = (pl.kb_total + kps - 1) / kps;
+    if (s2 != s) continue;
+    const int waves = (items_per_split * s + sms - 1) / sms;
+    const double cost = waves * (kps * t_kb + 2.0) + s * part_us;
+    if (cost < best) best = cost, splits = s;
+    if (waves > 4 && s > 8) break;
+  }
   pl.kb_per_split = (pl.kb_total + splits - 1) / splits;
   pl.splits = (pl.kb_total + pl.kb_per_split - 1) / pl.kb_per_split;
   return pl;
@@ -645,25 +677,7 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   else
     rc = launch_wgrad<256>(p, st);
   if (rc) return rc;
-  const long long total = static_cast<long long>(Cout) * Cin * pl.taps;
-  if (pl.splits >= 16) {
-    long long nb = (total + 31) / 32;   // 32 elements per block, 8 split slices each
-    if (nb > device_sm_count() * 32ll) nb = device_sm_count() * 32ll;
-    wgrad_reduce_kernel<<<static_cast<int>(nb), 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate,
-                                                              g_wgrad_rowscale);
-  } else if (pl.taps == 1 && Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0) {
-    const long long n4 = total / 4;
-    long long nb = (n4 + 255) / 256;
-    if (nb > device_sm_count() * 16ll) nb = device_sm_count() * 16ll;
-    wgrad_reduce_vec4_kernel<<<static_cast<int>(nb), 256, 0, st>>>(reinterpret_cast<const float4*>(p.partial),
-                                                                   reinterpret_cast<float4*>(dw), pl.splits, n4, Cin / 4,
-                                                                   accumulate, g_wgrad_rowscale);
-  } else {
-    int blocks = static_cast<int>((total + 255) / 256);
-    if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
-    wgrad_reduce_flat_kernel<<<blocks, 256, 0, st>>>(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate,
-                                                     g_wgrad_rowscale);
-  }
+  launch_wgrad_reduce(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale, st);
   g_wgrad_rowscale = nullptr;
   B200_LAUNCHED();
   return OK;
@@ -728,10 +742,7 @@ int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* work
   for (int ky = 0; ky < 4; ++ky) p.tap_map[ky] = 0, p.tap_o1[ky] = 0, p.tap_o2[ky] = static_cast<int8_t>(ky);
   if ((rc = launch_wgrad<256>(p, st))) return rc;  // merged-tap mode: the four y-taps are the four 64-column atoms
   // g[cout][k64][ky] (the generic "OIHW" layout of a 64-channel, 4-tap conv); b200_stem_s2d_wgrad_relayout maps it to [64,3,7,7]
-  const long long total = static_cast<long long>(Cout) * Cin * taps;
-  long long nb = (total + 31) / 32;
-  if (nb > device_sm_count() * 32ll) nb = device_sm_count() * 32ll;
-  wgrad_reduce_kernel<<<static_cast<int>(nb), 256, 0, st>>>(p.partial, g, pl.splits, Cout, Cin, taps, 0, nullptr);
+  launch_wgrad_reduce(p.partial, g, pl.splits, Cout, Cin, taps, 0, nullptr, st);
   B200_LAUNCHED();
   return OK;
 }

@@ -4,7 +4,7 @@
 // (64 rows of 128 B, 128B swizzle) is exactly one canonical MN-major SWIZZLE_128B atom column (K = pixel rows). The same
 // NHWC activation tensors and the same tap/phase tensor maps as the forward kernel are used - no transposes, no im2col.
 // The pixel range is split across CTAs (split-K); each CTA writes its fp32 partial tile to a workspace which
-// wgrad_reduce_kernel sums deterministically (no atomics) into the OIHW gradient.
+// wgrad_reduce_rows_kernel sums deterministically (no atomics) into the OIHW gradient.
 //
 // 64-channel inputs with several taps (ResNet layer1 3x3, the space-to-depth stem) run in MERGED-TAP mode: the 64-column
 // atoms of one B tile belong to DIFFERENT taps (same pixels, shifted TMA coordinates), so one dY tile feeds an N = 192 / 256
@@ -229,46 +229,57 @@ __global__ void __launch_bounds__(192, 1) wgrad_gemm_kernel(const __grid_constan
 }
 
 // grad[cout][cin][tap] (OIHW, fp32) (+)= sum_s partial[s][cout][tap*Cin + cin]
-// Block = 32 consecutive elements (coalesced) x 8 slices of the split range, folded through shared memory in a fixed order:
-// layers with few output tiles run with ~150 splits, and a single thread walking them serially is pure load latency.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ grad,
-                                                           int splits, int Cout, int Cin, int taps, int accumulate,
-                                                           const float* __restrict__ rowscale) {
-  __shared__ float red[8][33];
-  const long long total = static_cast<long long>(Cout) * Cin * taps;
-  const long long slice = total;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  for (long long base = static_cast<long long>(blockIdx.x) * 32; base < total; base += static_cast<long long>(gridDim.x) * 32) {
-    // i indexes the partial layout (coalesced reads): [cout][tap][cin]
-    const long long i = base + tx;
-    float s0 = 0.f, s1 = 0.f;
-    if (i < total) {
-      int k = ty;
-      for (; k + 8 < splits; k += 16) {
-        s0 += __ldcs(partial + k * slice + i);
-        s1 += __ldcs(partial + (k + 8) * slice + i);
-      }
-      if (k < splits) s0 += __ldcs(partial + k * slice + i);
+// Row-block reduction: one block owns `chunk` input channels of one output channel for ALL taps, i.e. a contiguous run of
+// chunk * taps gradient elements. The split range is folded by `SL` thread slices with float4 loads (coalesced along cin in
+// the partial layout, two independent loads in flight per thread), staged in shared memory as [slice][tap][cin] and written
+// out tap-innermost, so that both the partial reads and the OIHW gradient writes are fully coalesced. Fixed summation order.
+__global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ grad,
+                                                                int splits, int Cout, int Cin, int taps, int chunk, int SL,
+                                                                int accumulate, const float* __restrict__ rowscale) {
+  extern __shared__ float4 rows_sm4[];
+  const int cout = blockIdx.x;
+  const int c0 = blockIdx.y * chunk;
+  const int cw = min(chunk, Cin - c0);
+  const int vpt = cw >> 2;          // float4 vectors per tap
+  const int nvec = taps * vpt;
+  const long long slice4 = static_cast<long long>(Cout) * taps * Cin / 4;
+  const float4* row4 = reinterpret_cast<const float4*>(partial + static_cast<long long>(cout) * taps * Cin + c0);
+  const int cin4 = Cin >> 2;
+  for (int w = threadIdx.x; w < nvec * SL; w += blockDim.x) {
+    const int sl = w / nvec;
+    const int v = w - sl * nvec;
+    const int tap = v / vpt;
+    const int cv = v - tap * vpt;
+    const float4* src = row4 + tap * cin4 + cv;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    int k = sl;
+    for (; k + SL < splits; k += 2 * SL) {
+      const float4 x = __ldcs(src + k * slice4);
+      const float4 y = __ldcs(src + (k + SL) * slice4);
+      a.x += x.x, a.y += x.y, a.z += x.z, a.w += x.w;
+      b.x += y.x, b.y += y.y, b.z += y.z, b.w += y.w;
     }
-    red[ty][tx] = s0 + s1;
-    __syncthreads();
-    if (ty == 0 && i < total) {
-      float s = red[0][tx];
-#pragma unroll
-      for (int y = 1; y < 8; ++y) s += red[y][tx];
-      const int cin = static_cast<int>(i % Cin);
-      const long long t = i / Cin;
-      const int tap = static_cast<int>(t % taps);
-      const int cout = static_cast<int>(t / taps);
-      if (rowscale != nullptr) s *= __ldg(rowscale + cout);
-      const long long o = (static_cast<long long>(cout) * Cin + cin) * taps + tap;
-      grad[o] = accumulate ? grad[o] + s : s;
+    if (k < splits) {
+      const float4 x = __ldcs(src + k * slice4);
+      a.x += x.x, a.y += x.y, a.z += x.z, a.w += x.w;
     }
-    __syncthreads();
+    rows_sm4[w] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  }
+  __syncthreads();
+  const float* sm = reinterpret_cast<const float*>(rows_sm4);
+  const float rs = rowscale != nullptr ? __ldg(rowscale + cout) : 1.f;
+  float* out = grad + (static_cast<long long>(cout) * Cin + c0) * taps;
+  for (int e = threadIdx.x; e < cw * taps; e += blockDim.x) {
+    const int cin = e / taps;
+    const int tap = e - cin * taps;
+    float s = 0.f;
+    for (int sl = 0; sl < SL; ++sl) s += sm[(sl * nvec) * 4 + tap * cw + cin];
+    s *= rs;
+    out[e] = accumulate ? out[e] + s : s;
   }
 }
 
-// Same reduction, one thread per element walking the splits: used when there are only a few splits (large weight matrices).
+// Same reduction, one thread per element walking the splits: fallback for shapes the row kernel does not take.
 __global__ void wgrad_reduce_flat_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
                                     int Cin, int taps, int accumulate, const float* __restrict__ rowscale) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
@@ -288,29 +299,5 @@ __global__ void wgrad_reduce_flat_kernel(const float* __restrict__ partial, floa
   }
 }
 
-
-// Linear layers (taps == 1, Cin % 4 == 0): the partial layout equals the gradient layout, so the reduction is a plain
-// element-wise sum over the splits - four elements per thread, all splits' loads independent.
-__global__ void __launch_bounds__(256) wgrad_reduce_vec4_kernel(const float4* __restrict__ partial, float4* __restrict__ grad,
-                                                                int splits, long long n4, int cin4, int accumulate,
-                                                                const float* __restrict__ rowscale) {
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    float4 s = __ldcs(partial + i);
-    for (int k = 1; k < splits; ++k) {
-      const float4 x = __ldcs(partial + k * n4 + i);
-      s.x += x.x; s.y += x.y; s.z += x.z; s.w += x.w;
-    }
-    if (rowscale != nullptr) {
-      const float r = __ldg(rowscale + i / cin4);
-      s.x *= r; s.y *= r; s.z *= r; s.w *= r;
-    }
-    if (accumulate) {
-      const float4 g = grad[i];
-      s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
-    }
-    grad[i] = s;
-  }
-}
 
 }  // namespace b200
