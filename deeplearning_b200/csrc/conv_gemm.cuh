@@ -320,6 +320,37 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       }
       const int s1 = c1 + p.qoff1[q], s2 = c2 + p.qoff2[q], s3 = c3 + p.qoff3[q];
 
+      // Global operands of the epilogue (residual / saved pre-activation) run ONE 32-column group ahead: the group's loads
+      // are issued while the previous group is converted and stored (the first one before the accumulator is even
+      // complete), so every epilogue warp always has 64-128 B per lane in flight towards HBM.
+      uint4 nx_b[4];   // bf16 residual or aux_in: 32 x bf16
+      float4 nx_f[8];  // fp32 residual: 32 x fp32
+      auto issue_pre = [&](int u, int h) {
+        const int ncp = n_tile * BLOCK_N + u * unit_cols + h * 32;
+        if (n_tile * BLOCK_N + u * unit_cols >= N || !row_ok) return;
+        if (has_res) {
+          const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + ncp;
+          if (res_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (full_cols || ncp + j * 4 < N) nx_f[j] = __ldg(rp + j);
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (full_cols || ncp + j * 8 < N) nx_b[j] = __ldg(rp + j);
+          }
+        }
+        if (act == 3) {
+          const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + p3 * p.as3 + p2 * p.as2 + p1 * p.as1 + ncp);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (full_cols || ncp + j * 8 < N) nx_b[j] = __ldg(ap + j);
+        }
+      };
+      if (has_res || act == 3) issue_pre(u_first, 0);
+
       CPROF_TICK(1)
       mbar_wait(&tmem_full[acc], acc_phase);
       CPROF_TICK(0)
@@ -343,32 +374,17 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         for (int h = 0; h < nsub; ++h) {
           uint32_t v[32];
           tmem_ld_32x32(tmem_acc + u * unit_cols + h * 32, v);
-          // Global operands of the epilogue (residual / saved pre-activation) are requested BEFORE waiting for the
-          // accumulator, so their DRAM latency overlaps the TMEM load instead of stalling the warp afterwards.
-          const int nc_pre = n0 + h * 32;
-          uint4 pre_b[4];   // bf16 residual or aux_in: 32 x bf16
-          float4 pre_f[8];  // fp32 residual: 32 x fp32
-          const bool pre_res = chunk_live && has_res && row_ok;
-          const bool pre_aux = chunk_live && act == 3 && row_ok;
-          if (pre_res) {
-            const long long off = p3 * p.rs3 + p2 * p.rs2 + p1 * p.rs1 + nc_pre;
-            if (res_f32) {
-              const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + off);
+          uint4 pre_b[4];
+          float4 pre_f[8];
+          if (has_res || act == 3) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (full_cols || nc_pre + j * 4 < N) pre_f[j] = __ldg(rp + j);
-            } else {
-              const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.residual) + off);
+            for (int j = 0; j < 4; ++j) pre_b[j] = nx_b[j];
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (full_cols || nc_pre + j * 8 < N) pre_b[j] = __ldg(rp + j);
-            }
-          }
-          if (pre_aux) {
-            const uint4* ap = reinterpret_cast<const uint4*>(p.aux_in + p3 * p.as3 + p2 * p.as2 + p1 * p.as1 + nc_pre);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (full_cols || nc_pre + j * 8 < N) pre_b[j] = __ldg(ap + j);
+            for (int j = 0; j < 8; ++j) pre_f[j] = nx_f[j];
+            if (h + 1 < nsub)
+              issue_pre(u, h + 1);
+            else if (u + 2 < units)
+              issue_pre(u + 2, 0);
           }
           tmem_ld_wait();
           if (u == last_unit && h == nsub - 1) {
