@@ -302,7 +302,7 @@ def run_b200(args):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(top["kernel"])
+                traffic = json.load(f).get(args.model, {}).get(top["kernel"])
         flops_bound = a["flops"] > 0 and (a["flops"] / (peaks["bf16_tflops_sustained"] * 1e12)) > (a["bytes"] / (peaks["hbm_gbs"] * 1e9))
         if flops_bound:
             ach, peak, unit = a["flops"] / a["ms"] / 1e9, peaks["bf16_tflops_sustained"], "TFLOP/s"

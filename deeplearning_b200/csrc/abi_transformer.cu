@@ -154,7 +154,7 @@ int b200_copy_rows(const void* src, long long src_pitch_bytes, void* dst, long l
 }
 
 int b200_colsum_partial_slices(long long rows) {
-  long long s = rows / 256;   // >= 256 rows per slice, up to ~4 blocks per SM
+  long long s = rows / 64;    // >= 64 rows per slice, up to 4 blocks per SM
   if (s < 1) s = 1;
   if (s > 592) s = 592;
   return static_cast<int>(s);

@@ -375,7 +375,7 @@ __global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long long src_
 
 // Column-sum partials of a bf16 matrix [rows][ld] (bias gradients): partial[slice][2][cols] (second plane zero), folded by
 // the BN finalize machinery. 16-byte loads: a thread owns ONE 8-column vector (vector v = tid % vpr of column block
-// blockIdx.x) and walks the rows of its slice with 4 independent loads in flight; 256/vpr row lanes per block are folded
+// blockIdx.x) and walks the rows of its slice with 8 independent loads in flight; 256/vpr row lanes per block are folded
 // through shared memory. (The first version read one bf16 per thread from ~128 blocks: 1 TB/s; this one is HBM bound.)
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ m, long long rows, long long ld,
                                                              int cols, float* __restrict__ partial) {
@@ -395,16 +395,18 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
     const uint4* base = reinterpret_cast<const uint4*>(m) + blockIdx.x * 256 + v;
     const long long ldv = ld >> 3;
     long long r = r0 + lane_r;
-    for (; r + 3 * rpi < r1; r += 4 * rpi) {
-      const uint4 x0 = __ldg(base + r * ldv), x1 = __ldg(base + (r + rpi) * ldv), x2 = __ldg(base + (r + 2 * rpi) * ldv),
-                  x3 = __ldg(base + (r + 3 * rpi) * ldv);
-      float f0[8], f1[8], f2[8], f3[8];
-      unpack8(x0, f0);
-      unpack8(x1, f1);
-      unpack8(x2, f2);
-      unpack8(x3, f3);
+    for (; r + 7 * rpi < r1; r += 8 * rpi) {
+      uint4 x[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] += (f0[j] + f1[j]) + (f2[j] + f3[j]);
+      for (int k = 0; k < 8; ++k) x[k] = __ldg(base + (r + k * rpi) * ldv);
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        float f0[8], f1[8];
+        unpack8(x[k], f0);
+        unpack8(x[k + 1], f1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f0[j] + f1[j];
+      }
     }
     for (; r < r1; r += rpi) {
       float f[8];

@@ -151,6 +151,18 @@ def res_l3_wgrad():   # ResNet layer3 conv2 weight gradient: 3x3 256 -> 256 at 1
     return lambda: ops.conv2d_wgrad(dy, x, 3, 1)
 
 
+def res_l1_wgrad():   # ResNet layer1 conv2 weight gradient: 3x3 64 -> 64 at 56x56 (merged-tap mode, N = 192)
+    x = rnd(256, 56, 56, 64)
+    dy = rnd(256, 56, 56, 64, scale=0.1)
+    return lambda: ops.conv2d_wgrad(dy, x, 3, 1)
+
+
+def res_l4_wgrad():   # ResNet layer4 conv2 weight gradient: 3x3 512 -> 512 at 7x7 (72 output tiles x 2 splits: one wave)
+    x = rnd(256, 7, 7, 512)
+    dy = rnd(256, 7, 7, 512, scale=0.1)
+    return lambda: ops.conv2d_wgrad(dy, x, 3, 1)
+
+
 def res_l2_dgrad_res():   # ResNet layer2 conv1 dgrad (1x1 512 <- 128) + identity-branch gradient
     dy = rnd(256, 28, 28, 128, scale=0.1)
     wd = ops.pack_weight(torch.randn(128, 512, 1, 1, device=dev) * 0.05, mode=1)

@@ -20,7 +20,10 @@ elif which == "swin_tiny":
 else:
     from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
     m = vit_base_patch16_224_in21k(num_classes=1000, has_logits=False).cuda().train()
-tr = TrainStep(m, lr=5e-4, weight_decay=5e-2, optimizer="adamw") if which in ("convnext_tiny", "swin_tiny") else TrainStep(m)
+if which in ("convnext_tiny", "swin_tiny"):
+    tr = TrainStep(m, lr=5e-4, weight_decay=5e-2, optimizer="adamw", clip_grad=5.0 if which == "swin_tiny" else None)
+else:
+    tr = TrainStep(m)
 x = torch.randn(B, 3, 224, 224, device="cuda")
 y = torch.randint(0, 1000, (B,), device="cuda")
 for _ in range(2):
