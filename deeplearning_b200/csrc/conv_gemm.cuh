@@ -102,6 +102,41 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return fmaf(x * 0.3989422804014327f, e, cdf);
 }
 
+// Two GELUs at once with packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: same IEEE fp32 results per lane, half the issue
+// slots): 10 instructions per element instead of 18 - the epilogue of the MLP GEMMs is instruction-issue bound.
+// cdf = 0.5 + sign(x) * (0.5 - tail) replaces the compare / select of the scalar version.
+__device__ __forceinline__ void gelu_parts2(float x0, float x1, uint64_t& cdf, uint64_t& e) {
+  const uint64_t az = f2_pack(fabsf(x0) * 0.70710678118654752f, fabsf(x1) * 0.70710678118654752f);
+  float d0, d1, t0, t1, g0, g1, e0, e1, h0, h1;
+  f2_unpack(f2_fma(f2_bcast(0.3275911f), az, f2_bcast(1.0f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(d1));
+  const uint64_t t = f2_pack(t0, t1);
+  uint64_t poly = f2_fma(f2_bcast(1.061405429f), t, f2_bcast(-1.453152027f));
+  poly = f2_fma(poly, t, f2_bcast(1.421413741f));
+  poly = f2_fma(poly, t, f2_bcast(-0.284496736f));
+  poly = f2_fma(poly, t, f2_bcast(0.254829592f));
+  f2_unpack(f2_mul(f2_mul(az, az), f2_bcast(-1.4426950408889634f)), g0, g1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(g0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(g1));
+  e = f2_pack(e0, e1);
+  // 0.5 - tail = 0.5 - 0.5 * poly * t * e  (>= 0), then the sign of x
+  f2_unpack(f2_fma(f2_mul(f2_mul(poly, t), e), f2_bcast(-0.5f), f2_bcast(0.5f)), h0, h1);
+  cdf = f2_add(f2_pack(copysignf(h0, x0), copysignf(h1, x1)), f2_bcast(0.5f));
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  uint64_t cdf, e;
+  gelu_parts2(x0, x1, cdf, e);
+  f2_unpack(f2_mul(f2_pack(x0, x1), cdf), x0, x1);
+}
+// f0 *= GELU'(a0), f1 *= GELU'(a1)
+__device__ __forceinline__ void gelu_erf_grad_mul2(float a0, float a1, float& f0, float& f1) {
+  uint64_t cdf, e;
+  gelu_parts2(a0, a1, cdf, e);
+  const uint64_t g = f2_fma(f2_mul(f2_pack(a0, a1), f2_bcast(0.3989422804014327f)), e, cdf);
+  f2_unpack(f2_mul(f2_pack(f0, f1), g), f0, f1);
+}
+
 // Optional phase timers (-DCONV_PROFILE): CTA 0 prints average cycles per tile of every wait / work phase of each role.
 #ifdef CONV_PROFILE
 #define CPROF_DECL(N) long long cp_t[N] = {}; long long cp_0 = clock64(), cp_1;
@@ -427,7 +462,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           } else if (act == 2) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
           } else if (act == 3 && row_ok) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -435,7 +470,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                 float a[8];
                 unpack8(pre_b[j], a);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) f[j * 8 + i] *= gelu_erf_grad(a[i]);
+                for (int i = 0; i < 8; i += 2) gelu_erf_grad_mul2(a[i], a[i + 1], f[j * 8 + i], f[j * 8 + i + 1]);
               }
             }
           }
