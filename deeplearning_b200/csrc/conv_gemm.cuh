@@ -438,10 +438,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + nc) + j);
-                f[j * 4 + 0] += b4.x;
-                f[j * 4 + 1] += b4.y;
-                f[j * 4 + 2] += b4.z;
-                f[j * 4 + 3] += b4.w;
+                f2_unpack(f2_add(f2_pack(f[j * 4 + 0], f[j * 4 + 1]), f2_pack(b4.x, b4.y)), f[j * 4 + 0], f[j * 4 + 1]);
+                f2_unpack(f2_add(f2_pack(f[j * 4 + 2], f[j * 4 + 3]), f2_pack(b4.z, b4.w)), f[j * 4 + 2], f[j * 4 + 3]);
               }
             } else {
 #pragma unroll
@@ -450,12 +448,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           }
           if (has_aux) {
             // pre-activation copy (bf16) for the backward pass
-            const float z = row_ok ? 1.f : 0.f;
+            const uint32_t z = row_ok ? 0xffffffffu : 0u;
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              sts128(aux_s + row_s + ((((h * 4 + j) << 4)) ^ sw), pack_bf16x2(f[j * 8 + 0] * z, f[j * 8 + 1] * z),
-                     pack_bf16x2(f[j * 8 + 2] * z, f[j * 8 + 3] * z), pack_bf16x2(f[j * 8 + 4] * z, f[j * 8 + 5] * z),
-                     pack_bf16x2(f[j * 8 + 6] * z, f[j * 8 + 7] * z));
+              sts128(aux_s + row_s + ((((h * 4 + j) << 4)) ^ sw), pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]) & z,
+                     pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]) & z, pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]) & z,
+                     pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]) & z);
           }
           if (act == 1) {
 #pragma unroll
@@ -484,10 +482,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               for (int j = 0; j < 8; ++j) {
                 if (full_cols || nc + j * 4 < N) {
                   const float4 r = pre_f[j];
-                  f[j * 4 + 0] += r.x;
-                  f[j * 4 + 1] += r.y;
-                  f[j * 4 + 2] += r.z;
-                  f[j * 4 + 3] += r.w;
+                  f2_unpack(f2_add(f2_pack(f[j * 4 + 0], f[j * 4 + 1]), f2_pack(r.x, r.y)), f[j * 4 + 0], f[j * 4 + 1]);
+                  f2_unpack(f2_add(f2_pack(f[j * 4 + 2], f[j * 4 + 3]), f2_pack(r.z, r.w)), f[j * 4 + 2], f[j * 4 + 3]);
                 }
               }
             } else {
@@ -497,7 +493,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                   float r[8];
                   unpack8(pre_b[j], r);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[j * 8 + i] += r[i];
+                  for (int i = 0; i < 8; i += 2)
+                    f2_unpack(f2_add(f2_pack(f[j * 8 + i], f[j * 8 + i + 1]), f2_pack(r[i], r[i + 1])), f[j * 8 + i],
+                              f[j * 8 + i + 1]);
                 }
               }
             }
