@@ -256,3 +256,36 @@ def test_stem_space_to_depth_conv(B, H, W):
     dw = ops.stem_s2d_conv_wgrad(dy_, z)
     sc = float(gw.abs().max())
     _close(dw / sc, gw / sc, 2e-3, 2e-3, "stem conv wgrad")
+
+
+@pytest.mark.parametrize("O,I,kh,mode,ld_pad,rows_pad,scaled", [
+    (64, 64, 3, 0, 0, 0, False), (64, 64, 3, 1, 0, 0, False), (192, 96, 1, 0, 0, 0, False), (192, 96, 1, 1, 0, 0, True),
+    (40, 72, 1, 1, 8, 0, False), (1000, 2048, 1, 0, 0, 24, False), (128, 128, 3, 1, 16, 0, True), (96, 48, 2, 0, 8, 32, True),
+    (96, 48, 2, 1, 0, 0, False), (33, 17, 3, 1, 7, 3, False), (24, 3, 7, 0, 13, 0, False), (24, 3, 7, 1, 0, 0, False)])
+def test_pack_weights_multi_matches_single(O, I, kh, mode, ld_pad, rows_pad, scaled):
+    """The one-launch model packer (shared-memory tiled layouts) == the plain per-tensor packer, padding zeroed."""
+    from deeplearning_b200 import _lib
+    ops = _ops()
+    lib = _lib.load()
+    torch.manual_seed(O * 131 + I)
+    ws = [torch.randn(O, I, kh, kh, device="cuda"), torch.randn(O + 8, I, kh, kh, device="cuda")]
+    scales = [torch.rand(w.shape[0], device="cuda") + 0.5 for w in ws]
+    rows, outs, first = [], [], 0
+    for w, sc in zip(ws, scales):
+        o = w.shape[0]
+        taps = kh * kh
+        nrow = (o if mode == 0 else I) + rows_pad
+        ld = taps * (I if mode == 0 else o) + ld_pad
+        dst = torch.full((nrow, ld), 7.0, dtype=torch.bfloat16, device="cuda")
+        outs.append(dst)
+        rows.append([w.data_ptr(), dst.data_ptr(), o, I, taps, mode, ld, first, nrow, sc.data_ptr() if scaled else 0])
+        first += 5
+    table = torch.tensor(rows, dtype=torch.int64, device="cuda")
+    _lib.check(lib.b200_pack_weights_multi(table.data_ptr(), len(rows), first, torch.cuda.current_stream().cuda_stream), "pack")
+    for w, sc, dst in zip(ws, scales, outs):
+        o = w.shape[0]
+        ref = ops.pack_weight(w * sc.view(-1, 1, 1, 1) if scaled else w, mode=mode)
+        nrow, ncol = ref.shape
+        assert torch.equal(dst[:nrow, :ncol], ref)
+        assert float(dst[nrow:].float().abs().max() if dst.shape[0] > nrow else 0.0) == 0.0
+        assert float(dst[:, ncol:].float().abs().max() if dst.shape[1] > ncol else 0.0) == 0.0

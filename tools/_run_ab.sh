@@ -1,0 +1,4 @@
+tag=$1; shift
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for m in "$@"; do timeout 300 python bench.py --model $m --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${tag}_$m.json 2> gpurun_out/bench_${tag}_$m.err; python -c "
+import json;d=json.load(open('gpurun_out/bench_${tag}_$m.json'));print('$m',round(d['ms_per_step'],3),round(d['value'],1),d['clocks']['sm_mhz'])"; done
