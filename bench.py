@@ -116,6 +116,20 @@ def cpu_reference_run(steps, warmup, batch=16, budget_s=150.0):
             "ms_per_step": dt / steps * 1e3, "batch": batch}
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract goes to the real stdout; everything else a library prints while the bench runs
+    (e.g. NCCL's version banner) was redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -129,7 +143,7 @@ def run_reference(args):
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------- B200 arm
@@ -317,7 +331,7 @@ def run_b200(args):
         if world == 1 and not args.no_cpu_baseline and args.model == "resnet50":
             cb = cpu_reference_run(3, 1, batch=16, budget_s=30.0)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -334,6 +348,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into CUDA graphs")
     args = ap.parse_args()
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)  # stdout of this process (and of native libraries) -> stderr; emit() writes the JSON line to the saved fd
     if args.impl == "reference":
         run_reference(args)
     else:
