@@ -54,15 +54,18 @@ struct alignas(64) ConvGemmParams {
   uint32_t desc_lbo, desc_sbo;  // K-major smem descriptor strides (bytes): 16 / 1024
   float* out_direct;        // direct fp32 output ([pixels][ld_out]) for tiny N (logits) or null
   long long ld_out;
+  // --- CTA-pair bring-up (kPair kernels only; appended so that the layout seen by the other kernels does not move)
+  CUtensorMap b_map_half;   // weights with a 128-row box: each CTA of a pair stages half of the 256-column tile
+  int pair;                 // host-side: launch the kPair kernel
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool kPair = false>
 struct ConvGemmCfg {
   static constexpr int BLOCK_M = 128;
   static constexpr int BLOCK_K = 64;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 6);
+  static constexpr int B_BYTES = (kPair ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;   // a pair member stages half of B
+  static constexpr int STAGES = kPair ? 4 : ((BLOCK_N == 256) ? 3 : (BLOCK_N == 128 ? 4 : 6));
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_WARPS = 8;
   static constexpr int SLAB_BYTES = 32 * 128;                       // one warp's 32 rows x 128 B
@@ -152,9 +155,15 @@ constexpr int kEpiGeneric = -1;
 constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEpiResBf16 = 16, kEpiResF32 = 32,
               kEpiAux = 64, kEpiOutF32 = 128, kEpiDirect = 256, kEpiStats = 512;
 
-template <int BLOCK_N, int EPI = kEpiGeneric>
+// kPair (BRING-UP, not yet run on hardware; default off, see abi_conv.cu gemm_pair_enabled()): the two CTAs of a cluster
+// compute one 256-pixel x 256-channel tile with tcgen05.mma.cta_group::2. Each CTA stages its own 128 pixels of A and HALF
+// of the B tile (32 KB instead of 48 KB of operands per k-block and SM), the leader (cluster rank 0) issues the MMAs for
+// both and commits to the barriers of both; every CTA drains its own 128 accumulator rows with the unchanged epilogue.
+template <int BLOCK_N, int EPI = kEpiGeneric, bool kPair = false>
 __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using Cfg = ConvGemmCfg<BLOCK_N>;
+  static_assert(!kPair || (BLOCK_N == 256 && EPI >= 0 && !(EPI & kEpiStats) && !(EPI & kEpiDirect)),
+                "pair mode: 256-wide tiles of the linear layers only");
+  using Cfg = ConvGemmCfg<BLOCK_N, kPair>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -170,7 +179,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles1 * p.tiles2 * p.tiles3;
-  const int num_tiles = m_tiles * p.n_tiles;
+  // pair mode: a work item is a PAIR of pixel tiles (2g, 2g + 1) x one channel block; CTA `cta_rank` owns pixel tile 2g + rank
+  const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+  const int num_tiles = (kPair ? (m_tiles + 1) / 2 : m_tiles) * p.n_tiles;
+  // (first work item / stride of this CTA: written as constant-folded ternaries in the loop headers so that the kPair = false
+  //  instantiations compile to exactly the code they had before the pair mode existed - checked by diffing the SASS)
+#define B200_TILE_FIRST (kPair ? (blockIdx.x >> 1) : blockIdx.x)
+#define B200_TILE_STEP (kPair ? (gridDim.x >> 1) : gridDim.x)
   const int num_kb = p.num_taps * p.k_blocks_per_tap;
   // Epilogue work units: 64 bf16 (or 32 fp32) channels x one warp's 32 rows. Two warps share a TMEM lane quadrant and
   // take alternate units; with a single unit per tile the second warp of each pair has nothing to do.
@@ -189,15 +204,22 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], arrivals_per_acc);  // one arrive per epilogue warp that drains this buffer
+      // one arrive per epilogue warp that drains this buffer (pair mode: the leader's barrier also counts the peer's warps)
+      mbar_init(&tmem_empty[i], kPair ? 2 * arrivals_per_acc : arrivals_per_acc);
     }
     fence_mbar_init();
   }
   if (warp_idx == 1) {
-    tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    if constexpr (kPair)
+      tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_ptr_smem);
+    else
+      tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr_smem);
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair)
+    cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / cross-CTA TMA completion
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
@@ -207,12 +229,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       CPROF_DECL(2)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = B200_TILE_FIRST; tile < num_tiles; tile += B200_TILE_STEP) {
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        const int m_tile = kPair ? (tile / p.n_tiles) * 2 + static_cast<int>(cta_rank) : tile / p.n_tiles;
         const int t1 = m_tile % p.tiles1;
         const int t2 = (m_tile / p.tiles1) % p.tiles2;
-        const int t3 = m_tile / (p.tiles1 * p.tiles2);
+        const int t3 = m_tile / (p.tiles1 * p.tiles2);   // (an odd tile count leaves the last peer tile past the tensor: zero fill)
         const int c1 = t1 * p.box1, c2 = t2 * p.box2, c3 = t3 * p.box3;
         int tap = 0, cb = 0;   // running (tap, channel block) of k-block kb: no division in the single-thread issue loop
         for (int kb = 0; kb < num_kb; ++kb, ++cb) {
@@ -225,10 +247,19 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           CPROF_TICK(0)
           uint8_t* a_dst = stage_base + stage * Cfg::STAGE_BYTES;
           uint8_t* b_dst = a_dst + Cfg::A_BYTES;
+          if constexpr (kPair) {
+            // the bytes of both CTAs complete on the LEADER's barrier, which alone gates the MMAs
+            const uint32_t full_leader = mapa_leader(smem_u32(&full_bar[stage]));
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+            tma_load_4d_2cta(a_dst, &p.a_maps[p.tap_map[tap]], full_leader, cb * 64, c1 + p.tap_o1[tap], c2 + p.tap_o2[tap], c3);
+            tma_load_2d_2cta(b_dst, &p.b_map_half, full_leader, p.tap_w[tap] * p.k_per_tap + cb * 64,
+                             n_tile * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
+          } else {
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(a_dst, &p.a_maps[p.tap_map[tap]], &full_bar[stage], cb * 64, c1 + p.tap_o1[tap],
                       c2 + p.tap_o2[tap], c3);
           tma_load_2d(b_dst, &p.b_map, &full_bar[stage], p.tap_w[tap] * p.k_per_tap + cb * 64, n_tile * BLOCK_N);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -244,8 +275,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     }
   } else if (warp_idx == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kPair ? 256 : 128, BLOCK_N, 0, 0);
       // The shared-memory descriptors of all stages / K steps differ only in the 14-bit (address >> 4) field, so they are
       // derived from two base descriptors with 64-bit adds: the one thread that issues every MMA of the CTA spends
       // ~3 instructions per MMA instead of rebuilding two descriptors (what bounds the small-N tiles).
@@ -256,7 +287,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       int acc = 0;
       uint32_t acc_phase = 0;
       CPROF_DECL(3)
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = B200_TILE_FIRST; tile < num_tiles; tile += B200_TILE_STEP) {
         CPROF_TICK(2)
         mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1);
         CPROF_TICK(0)
@@ -269,16 +300,26 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           tc_fence_after();
           const uint64_t soff = static_cast<uint64_t>(stage) * (Cfg::STAGE_BYTES >> 4);
           const uint64_t da = desc_a0 + soff, db = desc_b0 + soff;
+          if constexpr (kPair) {
+            umma_f16_2cta(tmem_d, da, db, idesc, kb > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 1; k < 4; ++k) umma_f16_2cta(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);
+            umma_commit_2cta(&empty_bar[stage]);  // frees the slot in BOTH CTAs
+          } else {
           umma_f16(tmem_d, da, db, idesc, kb > 0 ? 1u : 0u);
 #pragma unroll
           for (int k = 1; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, 1u);   // +32 B per 16-element K step
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if constexpr (kPair)
+          umma_commit_2cta(&tmem_full[acc]);  // wakes the epilogue warps of both CTAs
+        else
+          umma_commit(&tmem_full[acc]);  // accumulator complete
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -316,8 +357,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const bool out_f32 = G ? (p.out_f32 != 0) : ((EPI & kEpiOutF32) != 0);
     float* const out_direct = (G || (EPI & kEpiDirect)) ? p.out_direct : nullptr;
     float* const stats = (G || (EPI & kEpiStats)) ? p.stats : nullptr;
+    // (pair mode with an odd number of pixel tiles: the last peer tile lies past the tensor and must not touch memory)
     const bool need_rowmap = has_res || act == 3 || out_direct != nullptr || p.dim1 % p.box1 != 0 ||
-                             p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0;
+                             p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0 || (kPair && (m_tiles & 1) != 0);
     const bool full_cols = (N % BLOCK_N) == 0;  // no partially valid 32-column group anywhere
     uint32_t store_counter = 0;
     const int nsub = out_f32 ? 1 : 2;  // 32-column TMEM loads per unit
@@ -334,12 +376,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     for (int k = 0; k < UN; ++k) run_s[k] = 0, run_q[k] = 0;
     int it = 0;
     CPROF_DECL(2)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = B200_TILE_FIRST; tile < num_tiles; tile += B200_TILE_STEP, ++it) {
       if (split_tiles && (it & 1) != pair) continue;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = kPair ? (tile / p.n_tiles) * 2 + static_cast<int>(cta_rank) : tile / p.n_tiles;
       const int t1 = m_tile % p.tiles1;
       const int t2 = (m_tile / p.tiles1) % p.tiles2;
       const int t3 = m_tile / (p.tiles1 * p.tiles2);
@@ -426,7 +468,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             // all TMEM reads of this accumulator by this warp are done -> hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) {
+              if constexpr (kPair)
+                mbar_arrive_cluster(mapa_leader(smem_u32(&tmem_empty[acc])));   // the leader's barrier gates the next MMAs
+              else
+                mbar_arrive(&tmem_empty[acc]);
+            }
           }
           if (!chunk_live) continue;
           const int nc = n0 + h * 32;  // first channel of this 32-column group
@@ -598,11 +645,19 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair)
+    cluster_sync_all();   // neither CTA frees TMEM or exits while its peer can still reach its barriers / shared memory
+  else
+    __syncthreads();
   if (warp_idx == 1) {
     tc_fence_after();
-    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+    if constexpr (kPair)
+      tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+    else
+      tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+#undef B200_TILE_FIRST
+#undef B200_TILE_STEP
 }
 
 }  // namespace b200
