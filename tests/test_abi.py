@@ -60,3 +60,38 @@ def test_missing_library_fails_loudly(monkeypatch):
         assert "no CPU" in str(e)
     else:
         raise AssertionError("load() must raise when the CUDA extension is missing")
+
+
+def test_wgrad_split_plan_is_one_wave_and_bounded():
+    """Split-K plan of the weight-gradient GEMM (abi_conv.cu: plan_wgrad_geom), read back through the workspace size:
+    workspace = splits * Cout * taps * Cin * 4 bytes. The cost model must keep (output tiles x splits) within one or two
+    waves of the 148 SMs (no third, mostly empty wave) and never ask for an absurd amount of fp32 partials."""
+    from deeplearning_b200 import _lib
+
+    lib = _lib.load()
+
+    def splits(B, H, W, Cin, Cout, k, s):
+        nbytes = lib.b200_conv2d_wgrad_workspace_bytes(B, H, W, Cin, Cout, k, s)
+        unit = Cout * k * k * Cin * 4
+        assert nbytes % unit == 0
+        return nbytes // unit
+
+    def tiles(Cin, Cout, taps, merged=False):
+        bn = 64 if Cin <= 64 else (256 if -(-Cin // 256) * 48 < -(-Cin // 128) * 32 else 128)
+        if merged:
+            return -(-Cout // 128) * (taps * 64 // (256 if taps % 4 == 0 else 192))
+        return -(-Cout // 128) * -(-Cin // bn) * taps
+
+    cases = [  # B, H, W, Cin, Cout, k, s, merged-tap mode
+        (256, 56, 56, 64, 64, 3, 1, True), (256, 28, 28, 128, 128, 3, 1, False), (256, 14, 14, 256, 256, 3, 1, False),
+        (256, 7, 7, 512, 512, 3, 1, False), (256, 7, 7, 512, 2048, 1, 1, False), (256, 56, 56, 64, 256, 1, 1, False),
+        (256 * 197, 1, 1, 768, 3072, 1, 1, False), (256 * 197, 1, 1, 3072, 768, 1, 1, False), (256 * 197, 1, 1, 768, 2304, 1, 1, False),
+        (128 * 3136, 1, 1, 96, 384, 1, 1, False), (256, 1, 1, 2048, 1000, 1, 1, False)]
+    for B, H, W, Cin, Cout, k, s, merged in cases:
+        sp = splits(B, H, W, Cin, Cout, k, s)
+        pixel_blocks = -(-(B * (H // s) * (W // s)) // 64)
+        assert 1 <= sp <= max(1, pixel_blocks // 4), (B, H, W, Cin, Cout, k, sp)
+        items = tiles(Cin, Cout, k * k, merged) * sp
+        if tiles(Cin, Cout, k * k, merged) <= 148:
+            assert items <= 2 * 148, ("more than two waves", B, H, W, Cin, Cout, k, sp, items)
+        assert sp * Cout * k * k * Cin * 4 <= 256 << 20   # at most 256 MB of partials per layer
