@@ -2,12 +2,15 @@
 """Headline benchmark: images/sec of the ResNet-50 training step (bf16, synthetic 3x224x224, bs=256 per GPU).
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torch.distributed.run, one rank per GPU)
-  python bench.py --impl reference --steps K --warmup W     (the reference's CPU path, oracle port, on the host cores)
+  python bench.py --impl reference --steps K --warmup W     (the reference's own CPU train_one_epoch on the host cores)
 
 One step = forward + soft-max cross-entropy + backward + gradient all-reduce + SGD(momentum) update, i.e. the body of the
 reference's train_one_epoch (classification/resnet/utils.py:35-55) in the DDP pattern of others/train_with_DDP.
 Prints ONE JSON line (rank 0).  `value` times the step with the batch already resident in HBM; `e2e` times the same public
 API call with the batch copied from pinned host memory every step and the loss read back to the host.
+BASELINE.json's metric names ResNet-50 AND ViT-B/16: the line's `value` is ResNet-50 (configs[1]) and its `secondary` block
+holds the same measurements (value / ms_per_step / e2e / step_roofline / roofline / kernels) of ViT-B/16 bs 256 (configs[2]),
+taken in the same invocation.
 """
 import argparse
 import json
@@ -23,15 +26,22 @@ sys.path.insert(0, ROOT)
 
 # per-image algorithmic work, fwd+bwd = 3 x forward: GFLOP (GEMM-like ops) and MB of HBM traffic
 MODELS = {
-    "resnet50": {"gflop": 24.53, "mb": 3 * 43.8, "batch": 256,
+    "resnet50": {"gflop": 24.53, "mb": 3 * 43.8, "batch": 256, "label": "ResNet-50",
                  "workload": "classification/resnet ResNet-50 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[1])"},
-    "vit_b16": {"gflop": 105.38, "mb": 3 * 73.9, "batch": 256,
+    "vit_b16": {"gflop": 105.38, "mb": 3 * 73.9, "batch": 256, "label": "ViT-B/16",
                 "workload": "classification/vision_transformer ViT-B/16 bf16, synthetic 3x224x224, bs=256/GPU (BASELINE.json configs[2])"},
-    "convnext_tiny": {"gflop": 26.73, "mb": 3 * 54.2, "batch": 256,
+    "convnext_tiny": {"gflop": 26.73, "mb": 3 * 54.2, "batch": 256, "label": "ConvNeXt-T",
                       "workload": "classification/convNext ConvNeXt-T bf16, synthetic 3x224x224, bs=256/GPU, drop_path 0 (BASELINE.json configs[4])"},
-    "swin_tiny": {"gflop": 26.94, "mb": 3 * 60.1, "batch": 128,
+    "swin_tiny": {"gflop": 26.94, "mb": 3 * 60.1, "batch": 128, "label": "Swin-T",
                   "workload": "classification/swin_transformer Swin-T bf16, synthetic 3x224x224, bs=128/GPU, drop_path 0 (BASELINE.json configs[3])"},
 }
+
+
+def metric_label(model):
+    """ONE metric string per model, shared by the B200 arm and the reference arm (the driver matches the two lines on it)."""
+    return f"images/sec ({MODELS[model]['label']} training step)"
+
+
 ADAMW_MODELS = ("convnext_tiny", "swin_tiny")   # AdamW(lr 5e-4, wd 5e-2): convNext/train.py:96,102; swin config.py:133-162
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -83,36 +93,64 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_run(steps, warmup, batch=16, budget_s=150.0):
-    """Reference CPU path (oracle port of torchvision.resnet50 + train_one_epoch + SGD), fp32, all host threads."""
+REF_BATCH = 16   # fixed per-step sample of the bs-256 workload (bs 16, fp32, all host cores)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_reference_run(steps, warmup, batch=REF_BATCH):
+    """The reference's CPU training path on `batch` synthetic images per step, fp32, ALL host cores (whatever
+    OMP_NUM_THREADS torchrun exported).  kind "reference": the unmodified reference module + its own train_one_epoch
+    (classification/resnet/{models/networks.py,utils.py}, staged under oracle/_ref by oracle/build_ref.py); kind "port": the
+    oracle restatement (bit-identical to the reference, tests/golden/make_golden.py) when oracle/_ref is absent."""
     import torch
 
-    from deeplearning_b200.classification.resnet.models.networks import resnet50
-    from oracle.resnet import resnet_forward
-    from oracle.train_loop import CpuSgdTrainer
-
-    torch.manual_seed(0)
-    state = {k: v.clone() for k, v in resnet50().state_dict().items()}
-    tr = CpuSgdTrainer(resnet_forward, state, lr=0.01, momentum=0.9, weight_decay=5e-5)
-    cores = torch.get_num_threads()
+    cores = host_cores()
+    torch.set_num_threads(cores)
     g = torch.Generator().manual_seed(1234)
     x = torch.randn(batch, 3, 224, 224, generator=g)
     y = torch.randint(0, 1000, (batch,), generator=g)
+    from oracle import build_ref
+
+    if build_ref.available():
+        kind = "reference"
+        net = build_ref.load("resnet", "models/networks")
+        utils = build_ref.load("resnet", "utils")
+        torch.manual_seed(0)
+        model = net.resnet50()
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-5)   # resnet/train.py:96
+        loss_fn = torch.nn.CrossEntropyLoss()
+        dev = torch.device("cpu")
+
+        def run(n):   # one "epoch" of n steps through the reference's own loop (it prints per step: stdout -> stderr here)
+            utils.train_one_epoch(model, [(x, y)] * n, dev, opt, loss_fn, 0)
+        what = "the reference's train_one_epoch on its own resnet50()"
+    else:
+        kind = "port"
+        from deeplearning_b200.classification.resnet.models.networks import resnet50
+        from oracle.resnet import resnet_forward
+        from oracle.train_loop import CpuSgdTrainer
+
+        torch.manual_seed(0)
+        state = {k: v.clone() for k, v in resnet50().state_dict().items()}
+        tr = CpuSgdTrainer(resnet_forward, state, lr=0.01, momentum=0.9, weight_decay=5e-5)
+
+        def run(n):
+            for _ in range(n):
+                tr.step(x, y)
+        what = "the oracle port of the reference ResNet-50 loop"
+    if warmup:
+        run(warmup)
     t0 = time.time()
-    tr.step(x, y)  # first warm-up step doubles as the cost probe
-    probe = time.time() - t0
-    # bound the whole run: shrink the per-step sample if K+W steps would not fit in the budget
-    while batch > 2 and probe * (steps + warmup) * (batch / x.shape[0]) > budget_s:
-        batch //= 2
-    x, y = x[:batch].contiguous(), y[:batch].contiguous()
-    for _ in range(max(0, warmup - 1)):
-        tr.step(x, y)
-    t0 = time.time()
-    for _ in range(steps):
-        tr.step(x, y)
+    run(steps)
     dt = time.time() - t0
-    return {"value": batch * steps / dt, "unit": "images/sec", "cores": cores, "kind": "port",
-            "sample": f"{steps} SGD steps of the oracle ResNet-50 (fp32, CPU) on {batch} synthetic 3x224x224 images each",
+    return {"value": batch * steps / dt, "unit": "images/sec", "cores": cores, "kind": kind,
+            "sample": f"{steps} SGD steps of {what} (fp32, CPU, {cores} threads) on {batch} synthetic 3x224x224 images each",
             "ms_per_step": dt / steps * 1e3, "batch": batch}
 
 
@@ -121,7 +159,7 @@ _JSON_FD = None
 
 def emit(line):
     """The ONE JSON line of the contract goes to the real stdout; everything else a library prints while the bench runs
-    (e.g. NCCL's version banner) was redirected to stderr by main()."""
+    (e.g. NCCL's version banner, the reference loop's per-step prints) was redirected to stderr by main()."""
     data = (json.dumps(line) + "\n").encode()
     if _JSON_FD is None:
         sys.stdout.write(data.decode())
@@ -135,10 +173,11 @@ def run_reference(args):
     if rank != 0:
         return
     cb = cpu_reference_run(args.steps, args.warmup)
-    line = {"impl": "reference", "metric": "images/sec (ResNet-50 training step)", "value": cb["value"], "unit": "images/sec",
+    line = {"impl": "reference", "metric": metric_label("resnet50"), "value": cb["value"], "unit": "images/sec",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "classification/resnet ResNet-50, synthetic 3x224x224, CPU fp32 (reference's own device default)",
+            "config": {"workload": MODELS["resnet50"]["workload"],
+                       "device": "CPU fp32 (the reference's own device default, resnet/train.py:151)",
                        "per_step_batch": cb["batch"], "optimizer": "SGD(momentum=0.9, weight_decay=5e-5)"},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -147,48 +186,49 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------------- B200 arm
-def run_b200(args):
+def build_model(name, dev):
+    if name == "resnet50":
+        from deeplearning_b200.classification.resnet.models.networks import resnet50
+
+        return resnet50().to(dev).train()
+    if name == "vit_b16":
+        from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
+
+        return vit_base_patch16_224_in21k(num_classes=1000, has_logits=False).to(dev).train()
+    if name == "swin_tiny":
+        from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer
+
+        return SwinTransformer(drop_path_rate=0.0).to(dev).train()   # Swin-T defaults, stochastic depth off
+    from deeplearning_b200.classification.convNext.models.networks import ConvNeXt
+
+    # convnext_tiny(1000) with stochastic depth off
+    return ConvNeXt(depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], num_classes=1000, drop_path_rate=0.0).to(dev).train()
+
+
+def optimizer_desc(name):
+    return ("AdamW(lr=5e-4, wd=5e-2, decay groups, clip_grad_norm 5.0)" if name == "swin_tiny" else
+            "AdamW(lr=5e-4, wd=5e-2, decay groups)" if name in ADAMW_MODELS else "SGD(momentum=0.9, weight_decay=5e-5)")
+
+
+def measure(name, args, dev, world, rank, local_rank, batch=None):
+    """All measurements of one model: device-resident throughput, e2e, per-kernel spans.  Returns the JSON dict (every rank
+    runs everything; only rank 0's dict carries the roofline / kernel table)."""
     import torch
     import torch.distributed as dist
 
     from deeplearning_b200 import ops
     from deeplearning_b200.engine.trainer import TrainStep
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a B200: no CUDA device visible (there is no CPU fallback; use --impl reference)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    spec = MODELS[args.model]
-    B = args.batch or spec["batch"]
+    spec = MODELS[name]
+    B = batch or spec["batch"]
+    warmup = max(args.warmup, 3)   # the timing rules ask for >= 3 warm-up steps; the line reports the number actually run
     torch.manual_seed(0)  # identical init on every rank (and broadcast from rank 0 inside TrainStep)
-    if args.model == "resnet50":
-        from deeplearning_b200.classification.resnet.models.networks import resnet50
-
-        model = resnet50().to(dev).train()
-    elif args.model == "vit_b16":
-        from deeplearning_b200.classification.vision_transformer.vit_model import vit_base_patch16_224_in21k
-
-        model = vit_base_patch16_224_in21k(num_classes=1000, has_logits=False).to(dev).train()
-    elif args.model == "swin_tiny":
-        from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer
-
-        model = SwinTransformer(drop_path_rate=0.0).to(dev).train()   # Swin-T defaults, stochastic depth off
-    else:
-        from deeplearning_b200.classification.convNext.models.networks import ConvNeXt
-
-        # convnext_tiny(1000) with stochastic depth off
-        model = ConvNeXt(depths=[3, 3, 9, 3], dims=[96, 192, 384, 768], num_classes=1000, drop_path_rate=0.0).to(dev).train()
-    if args.model == "swin_tiny":       # Swin recipe: AdamW + clip_grad_norm_(5.0) (main.py:197, config.py TRAIN.CLIP_GRAD)
+    model = build_model(name, dev)
+    if name == "swin_tiny":       # Swin recipe: AdamW + clip_grad_norm_(5.0) (main.py:197, config.py TRAIN.CLIP_GRAD)
         trainer = TrainStep(model, lr=5e-4, weight_decay=5e-2, optimizer="adamw", clip_grad=5.0)
-    elif args.model in ADAMW_MODELS:    # AdamW(lr 5e-4, wd 5e-2) with the reference's decay groups
+    elif name in ADAMW_MODELS:    # AdamW(lr 5e-4, wd 5e-2) with the reference's decay groups
         trainer = TrainStep(model, lr=5e-4, weight_decay=5e-2, optimizer="adamw")
-    else:                               # SGD(momentum 0.9, wd 5e-5) (resnet/train.py:96, vision_transformer/train.py:94)
+    else:                         # SGD(momentum 0.9, wd 5e-5) (resnet/train.py:96, vision_transformer/train.py:94)
         trainer = TrainStep(model, lr=0.01, momentum=0.9, weight_decay=5e-5)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     images = torch.randn(B, 3, 224, 224, device=dev, generator=g)
@@ -212,8 +252,8 @@ def run_b200(args):
     trainer.step_eager(images, labels)          # one eager step: counts this library's kernel launches per step
     launches_per_step = ops.launch_count() - launches0
     if not args.eager:
-        trainer.capture(images, labels)         # whole step (fwd+CE+bwd+SGD; all-reduce between two graphs if N>1)
-    for _ in range(max(args.warmup, 3)):
+        trainer.capture(images, labels)         # whole step (fwd+CE+bwd+all-reduce+update)
+    for _ in range(warmup):
         loss, _ = trainer.step(images, labels)
     sync_all()
     sampler = ClockSampler(local_rank)
@@ -271,17 +311,15 @@ def run_b200(args):
     e2e_value = world * B * args.steps / (e2e_ms / 1e3)
     h2d = B * 3 * 224 * 224 * 4 + B * 8
 
-    line = {"metric": f"images/sec ({args.model} training step)", "value": value, "unit": "images/sec", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+    line = {"metric": metric_label(name), "value": value, "unit": "images/sec", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": spec["workload"],
                        "per_gpu_batch": B, "global_batch": world * B, "parallelism": f"dp{world}",
-                       "optimizer": ("AdamW(lr=5e-4, wd=5e-2, decay groups, clip_grad_norm 5.0)" if args.model == "swin_tiny" else
-                                     "AdamW(lr=5e-4, wd=5e-2, decay groups)" if args.model in ADAMW_MODELS else
-                                     "SGD(momentum=0.9, weight_decay=5e-5)"),
+                       "optimizer": optimizer_desc(name),
                        "step": "fwd+CE+bwd+allreduce+optimizer",
                        "launch": "eager" if args.eager else "CUDA graph replay",
-                       "l2": "working set (~14 GB of activations per step) is far larger than the 126 MB L2; no flush needed"},
+                       "l2": "working set (>10 GB of activations per step) is far larger than the 126 MB L2; no flush needed"},
             "e2e": {"value": e2e_value, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "final_loss": final_loss}
@@ -298,7 +336,6 @@ def run_b200(args):
     sync_all()
     if rank == 0:
         peaks = load_peaks()
-        # whole-step roofline: the step is HBM-bound on this design; both fractions are reported
         per_gpu = value / world
         line["step_roofline"] = {
             "hbm_frac": per_gpu * spec["mb"] * 1e6 / (peaks["hbm_gbs"] * 1e9),
@@ -307,8 +344,8 @@ def run_b200(args):
         agg = prof.summary()
         tot = sum(a["ms"] for a in agg.values())
         kernels = []
-        for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
-            kernels.append({"kernel": name, "calls": a["calls"], "ms": round(a["ms"], 3), "share": round(a["ms"] / tot, 4),
+        for kname, a in sorted(agg.items(), key=lambda kv: -kv[1]["ms"]):
+            kernels.append({"kernel": kname, "calls": a["calls"], "ms": round(a["ms"], 3), "share": round(a["ms"] / tot, 4),
                             "GBps": round(a["bytes"] / a["ms"] / 1e6, 1), "TFLOPs": round(a["flops"] / a["ms"] / 1e9, 1)})
         top = kernels[0]
         a = agg[top["kernel"]]
@@ -316,7 +353,7 @@ def run_b200(args):
         tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(args.model, {}).get(top["kernel"])
+                traffic = json.load(f).get(name, {}).get(top["kernel"])
         flops_bound = a["flops"] > 0 and (a["flops"] / (peaks["bf16_tflops_sustained"] * 1e12)) > (a["bytes"] / (peaks["hbm_gbs"] * 1e9))
         if flops_bound:
             ach, peak, unit = a["flops"] / a["ms"] / 1e9, peaks["bf16_tflops_sustained"], "TFLOP/s"
@@ -328,8 +365,39 @@ def run_b200(args):
                             "how": "CUDA-event spans on the launching stream over one extra eager step after the timed region (host enqueues ahead of the device behind a spin kernel, so spans hold no launch gaps); "
                                    "algorithmic bytes = tensors read+written once per launch"}
         line["kernels"] = kernels
+    # release this model's activations / graphs before the next one is measured
+    del trainer, model, images, labels, host_imgs, host_lbls, dev_imgs, dev_lbls
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200: no CUDA device visible (there is no CPU fallback; use --impl reference)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    line = measure(args.model, args, dev, world, rank, local_rank, args.batch or None)
+    if args.model == "resnet50" and not args.no_secondary:
+        # BASELINE.json's metric is quoted on ResNet-50 AND ViT-B/16: same measurements, same invocation, as a sub-block
+        sec = measure("vit_b16", args, dev, world, rank, local_rank)
+        line["secondary"] = {k: sec[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "e2e", "gpu_launches",
+                                                  "clocks", "final_loss", "step_roofline", "roofline", "kernels") if k in sec}
+        line["gpu_launches"] += sec["gpu_launches"]
+    if rank == 0:
         if world == 1 and not args.no_cpu_baseline and args.model == "resnet50":
-            cb = cpu_reference_run(3, 1, batch=16, budget_s=30.0)
+            cb = cpu_reference_run(3, 1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         emit(line)
     if world > 1:
@@ -346,6 +414,7 @@ def main():
     ap.add_argument("--model", default="resnet50", choices=sorted(MODELS), help="resnet50 = BASELINE configs[1] (headline)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the ViT-B/16 block of the default (resnet50) line")
     ap.add_argument("--eager", action="store_true", help="do not capture the step into CUDA graphs")
     args = ap.parse_args()
     global _JSON_FD

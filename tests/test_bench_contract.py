@@ -28,9 +28,23 @@ def test_reference_arm_prints_one_json_line():
                 "config", "e2e", "cpu_baseline", "gpu_launches"):
         assert key in d, key
     assert d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["per_step_batch"] == 16          # fixed sample: the denominator must not move between runs
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+
+
+def test_both_arms_share_the_metric_string():
+    """The driver divides the two arms only when their metric strings are equal (round-1 lost its anchor to a one-word
+    difference)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    r = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][0])
+    assert d["metric"] == bench.metric_label("resnet50") == "images/sec (ResNet-50 training step)"
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"metric": metric_label(') == 2      # both arms take the label from the one shared helper
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
