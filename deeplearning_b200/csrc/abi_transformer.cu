@@ -3,6 +3,7 @@
 
 #include "../../include/b200cls.h"
 #include "attention.cuh"
+#include "attention_bwd.cuh"
 #include "host_utils.h"
 #include "convnext.cuh"
 #include "transformer.cuh"
@@ -496,16 +497,14 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.B = B, p.H = H, p.T = T;
-  p.Tpad = (T + 15) / 16 * 16;
-  p.mblocks = (T + 127) / 128;
+  p.nblk = (T + 127) / 128;
   p.scale = scale;
   p.scale_log2e = scale * 1.4426950408889634f;
   p.lse = lse;
   p.delta = delta;
   const long long HD = static_cast<long long>(H) * 64;
   int rc;
-  if ((rc = encode3(&p.q_map, qkv, 3 * HD, T, B, 128))) return rc;
-  if ((rc = encode3(&p.kv_map, qkv, 3 * HD, T, B, p.Tpad))) return rc;
+  if ((rc = encode3(&p.qkv_map, qkv, 3 * HD, T, B, 128))) return rc;
   if ((rc = encode3(&p.do_map, dout, HD, T, B, 128))) return rc;
   if ((rc = encode3(&p.dqkv_map, dqkv, 3 * HD, T, B, 128))) return rc;
   static bool cfg = false;

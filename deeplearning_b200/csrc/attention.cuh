@@ -224,303 +224,8 @@ __global__ void __launch_bounds__(160, 2) attn_fwd_kernel(const __grid_constant_
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------------------------------
-// Backward. One CTA per (batch, head); loops over the 128-query blocks and keeps dK / dV accumulating in TMEM:
-//   S  = Q K^T                    -> P = exp(scale*S - lse)            (recomputed, never stored in HBM)
-//   dP = dO V^T                   -> dS = scale * P * (dP - delta),  delta_i = sum_d dO[i,d] O[i,d] (attn_delta_kernel)
-//   dV += P^T dO ,  dK += dS^T Q ,  dQ = dS K
-// P and dS live in shared memory as bf16 in the key-blocked 128B-swizzled layout, which serves both as a K-major A operand
-// (dQ = dS K) and as an MN-major A operand (P^T dO, dS^T Q) without any transpose; K, V, Q, dO tiles are likewise consumed
-// in place as K-major or MN-major B operands.
-struct alignas(64) AttnBwdParams {
-  CUtensorMap q_map;     // qkv (3*H*64, T, B), box (64, 128, 1)
-  CUtensorMap kv_map;    // qkv, box (64, Tpad, 1)
-  CUtensorMap do_map;    // dO (H*64, T, B), box (64, 128, 1)
-  CUtensorMap dqkv_map;  // dqkv (3*H*64, T, B), box (64, 128, 1)  (stores)
-  int B, H, T, Tpad, mblocks;
-  float scale, scale_log2e;
-  const float* lse;      // [B][H][T]
-  const float* delta;    // [B][H][T]
-};
-
-constexpr int kAttnBwdSmemBytes = 32768 * 2 + 16384 * 2 + 65536 * 2 + 256 + 1024;
-
-__global__ void __launch_bounds__(288, 1) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + 32768;
-  uint8_t* sQ = smem + 65536;
-  uint8_t* sdO = smem + 65536 + 16384;
-  uint8_t* sP = smem + 98304;
-  uint8_t* sdS = smem + 98304 + 65536;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 98304 + 131072);
-  uint64_t* bar_kv = bars + 0;
-  uint64_t* bar_q = bars + 1;      // Q/dO of the current block landed
-  uint64_t* bar_s = bars + 2;      // S in TMEM
-  uint64_t* bar_p = bars + 3;      // P in smem (4 warp arrivals)
-  uint64_t* bar_dp = bars + 4;     // dP in TMEM (and the dV MMAs of this block retired)
-  uint64_t* bar_ds = bars + 5;     // dS in smem (4 warp arrivals)
-  uint64_t* bar_dq = bars + 6;     // dQ in TMEM, dK MMAs retired -> Q/dO/P/dS buffers reusable
-  uint64_t* bar_free = bars + 7;   // soft-max warps have drained dQ (4 warp arrivals)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
-
-  const int warp_idx = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x % p.H;
-  const int b = blockIdx.x / p.H;
-  const int HD = p.H * 64;
-
-  if (warp_idx == 4) {
-    if (lane == 0) {
-      tma_prefetch_desc(&p.q_map);
-      tma_prefetch_desc(&p.kv_map);
-      tma_prefetch_desc(&p.do_map);
-      tma_prefetch_desc(&p.dqkv_map);
-      mbar_init(bar_kv, 1);
-      mbar_init(bar_q, 1);
-      mbar_init(bar_s, 1);
-      mbar_init(bar_p, 8);
-      mbar_init(bar_dp, 1);
-      mbar_init(bar_ds, 8);
-      mbar_init(bar_dq, 1);
-      mbar_init(bar_free, 8);
-      fence_mbar_init();
-    }
-    __syncwarp();
-    tmem_alloc<512>(tmem_ptr_smem);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t kColS = 0, kColDV = 256, kColDK = 384;
-  const int ksteps_keys = p.Tpad / 16;
-
-  if (warp_idx == 4) {
-    if (lane == 0) {
-      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), do_addr = smem_u32(sdO);
-      const uint32_t p_addr = smem_u32(sP), ds_addr = smem_u32(sdS);
-      mbar_expect_tx(bar_kv, 2 * p.Tpad * 128);
-      tma_load_3d(sK, &p.kv_map, bar_kv, HD + h * 64, 0, b);
-      tma_load_3d(sV, &p.kv_map, bar_kv, 2 * HD + h * 64, 0, b);
-      const uint32_t idesc_s = make_idesc_bf16(128, p.Tpad, 0, 0);   // [128 q] x [Tpad keys], K-major both
-      const uint32_t idesc_t = make_idesc_bf16(128, 64, 1, 1);       // A^T B with both operands MN-major
-      const uint32_t idesc_q = make_idesc_bf16(128, 64, 0, 1);       // dS (K-major) x K (MN-major)
-      for (int mb = 0; mb < p.mblocks; ++mb) {
-        const uint32_t ph = mb & 1;
-        if (mb > 0) mbar_wait(bar_free, (mb - 1) & 1);  // previous block's dQ drained, buffers reusable
-        mbar_expect_tx(bar_q, 2 * 16384);
-        tma_load_3d(sQ, &p.q_map, bar_q, h * 64, mb * 128, b);
-        tma_load_3d(sdO, &p.do_map, bar_q, h * 64, mb * 128, b);
-        if (mb == 0) mbar_wait(bar_kv, 0);
-        mbar_wait(bar_q, ph);
-        tc_fence_after();
-        // S = Q K^T
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + kColS, make_smem_desc_sw128(q_addr + k * 32, 16, 1024),
-                   make_smem_desc_sw128(k_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        umma_commit(bar_s);
-        // wait for P (S consumed), then dP = dO V^T into the same columns and dV += P^T dO
-        mbar_wait(bar_p, ph);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_f16(tmem_base + kColS, make_smem_desc_sw128(do_addr + k * 32, 16, 1024),
-                   make_smem_desc_sw128(v_addr + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-        for (int j = 0; j < 2; ++j) {  // key rows [128 j, 128 j + 128)
-          if (j * 128 >= p.Tpad) break;
-          for (int ks = 0; ks < 8; ++ks) {  // 128 queries = 8 steps of 16
-            const uint64_t da = make_smem_desc_sw128(p_addr + (2 * j) * 16384 + ks * 2048, 16384, 1024);
-            const uint64_t db = make_smem_desc_sw128(do_addr + ks * 2048, 8192, 1024);
-            umma_f16(tmem_base + kColDV + j * 64, da, db, idesc_t, (mb > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(bar_dp);
-        // wait for dS, then dQ = dS K and dK += dS^T Q
-        mbar_wait(bar_ds, ph);
-        tc_fence_after();
-        for (int ks = 0; ks < ksteps_keys; ++ks) {
-          const uint64_t da = make_smem_desc_sw128(ds_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(k_addr + ks * 2048, 8192, 1024);
-          umma_f16(tmem_base + kColS, da, db, idesc_q, ks > 0 ? 1u : 0u);
-        }
-        for (int j = 0; j < 2; ++j) {
-          if (j * 128 >= p.Tpad) break;
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t da = make_smem_desc_sw128(ds_addr + (2 * j) * 16384 + ks * 2048, 16384, 1024);
-            const uint64_t db = make_smem_desc_sw128(q_addr + ks * 2048, 8192, 1024);
-            umma_f16(tmem_base + kColDK + j * 64, da, db, idesc_t, (mb > 0 || ks > 0) ? 1u : 0u);
-          }
-        }
-        umma_commit(bar_dq);
-      }
-    }
-  } else {
-    // 8 soft-max warps: two per TMEM lane quadrant (warp_idx % 4); the pair splits the key columns of every row in half
-    const int quad = warp_idx & 3;
-    const int pair = warp_idx > 4 ? 1 : 0;
-    const int row = quad * 32 + lane;
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
-    const int nfull = p.Tpad / 32;
-    const bool tail16 = (p.Tpad & 31) != 0;
-    const int nchunks = nfull + (tail16 ? 1 : 0);
-    const int c_begin = pair == 0 ? 0 : (nchunks + 1) / 2;
-    const int c_end = pair == 0 ? (nchunks + 1) / 2 : nchunks;
-    const long long bh = static_cast<long long>(b) * p.H + h;
-    for (int mb = 0; mb < p.mblocks; ++mb) {
-      const uint32_t ph = mb & 1;
-      const int t = mb * 128 + row;
-      const bool valid = t < p.T;
-      // +inf for rows beyond T (their scores are exact zeros from the TMA zero fill) makes P vanish without a select
-      const float lse2 = valid ? p.lse[bh * p.T + t] * 1.4426950408889634f : INFINITY;
-      const float delta = valid ? p.delta[bh * p.T + t] : 0.f;
-      // ---- P = exp2(S*scale*log2e - lse*log2e)
-      mbar_wait(bar_s, ph);
-      tc_fence_after();
-      auto emit_p = [&](const uint32_t* v, int col0, int n) {
-        const bool crosses = col0 + n > p.T;   // warp-uniform
-        for (int g = 0; g < n / 8; ++g) {
-          float e[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = attn_ex2(fmaf(__uint_as_float(v[g * 8 + j]), p.scale_log2e, -lse2));
-          if (crosses) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (col0 + g * 8 + j >= p.T) e[j] = 0.f;
-          }
-          const int col = col0 + g * 8;
-          *reinterpret_cast<uint4*>(sP + (col >> 6) * 16384 + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4)) = pack8(e);
-        }
-      };
-      for (int c = c_begin; c < c_end; ++c) {
-        if (c < nfull) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-          tmem_ld_wait();
-          emit_p(v, c * 32, 32);
-        } else {
-          uint32_t v[16];
-          tmem_ld_32x16(lane_addr + kColS + nfull * 32, v);
-          tmem_ld_wait();
-          emit_p(v, nfull * 32, 16);
-        }
-      }
-      if (pair == 1 && p.Tpad < 256) {
-        // zero the key columns [Tpad, next multiple of 64) that the P^T / dS^T MMAs (M = 128 keys) still read
-        const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        const int cend = ((p.Tpad + 127) / 128) * 128;
-        for (int col = p.Tpad; col < cend; col += 8) {
-          const int off = (col >> 6) * 16384 + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4);
-          *reinterpret_cast<uint4*>(sP + off) = pack8(z);
-          *reinterpret_cast<uint4*>(sdS + off) = pack8(z);
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_p);
-      // ---- dS = scale * P * (dP - delta)
-      mbar_wait(bar_dp, ph);
-      tc_fence_after();
-      auto emit_ds = [&](const uint32_t* v, int col0, int n) {
-        for (int g = 0; g < n / 8; ++g) {
-          const int col = col0 + g * 8;
-          const int off = (col >> 6) * 16384 + row * 128 + ((((col & 63) >> 3) ^ (row & 7)) << 4);
-          float pv[8], e[8];
-          unpack8(*reinterpret_cast<const uint4*>(sP + off), pv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = p.scale * pv[j] * (__uint_as_float(v[g * 8 + j]) - delta);
-          *reinterpret_cast<uint4*>(sdS + off) = pack8(e);
-        }
-      };
-      for (int c = c_begin; c < c_end; ++c) {
-        if (c < nfull) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-          tmem_ld_wait();
-          emit_ds(v, c * 32, 32);
-        } else {
-          uint32_t v[16];
-          tmem_ld_32x16(lane_addr + kColS + nfull * 32, v);
-          tmem_ld_wait();
-          emit_ds(v, nfull * 32, 16);
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_ds);
-      // ---- dQ -> bf16 -> staging (the dO tile is dead once bar_dq fires) -> TMA store
-      mbar_wait(bar_dq, ph);
-      tc_fence_after();
-      uint8_t* stg = sdO;
-      {
-        const int c = pair;  // each warp of the pair drains one 32-column half of dQ
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float e[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) e[j] = __uint_as_float(v[g * 8 + j]);
-          *reinterpret_cast<uint4*>(stg + row * 128 + (((c * 4 + g) ^ (row & 7)) << 4)) = pack8(e);
-        }
-      }
-      tc_fence_before();
-      fence_proxy_async_smem();
-      named_bar_sync(1, 256);
-      if (threadIdx.x == 0) {
-        tma_store_3d(&p.dqkv_map, stg, h * 64, mb * 128, b);
-        tma_store_commit();
-        tma_store_wait_read<0>();
-      }
-      named_bar_sync(1, 256);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_free);
-    }
-    // ---- dK, dV: two 128-key blocks each, staged through the (now free) P region
-    // (the last bar_dq wait above guarantees every MMA has retired)
-    for (int which = 0; which < 2; ++which) {      // 0: dK, 1: dV
-      for (int j = 0; j < 2; ++j) {
-        if (j * 128 >= p.Tpad) break;
-        uint8_t* stg = sP + (which * 2 + j) * 16384;
-        const uint32_t col0 = (which == 0 ? kColDK : kColDV) + j * 64;
-        {
-          const int c = pair;
-          uint32_t v[32];
-          tmem_ld_32x32(lane_addr + col0 + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float e[8];
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) e[jj] = __uint_as_float(v[g * 8 + jj]);
-            *reinterpret_cast<uint4*>(stg + row * 128 + (((c * 4 + g) ^ (row & 7)) << 4)) = pack8(e);
-          }
-        }
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async_smem();
-    named_bar_sync(1, 256);
-    if (threadIdx.x == 0) {
-      for (int which = 0; which < 2; ++which)
-        for (int j = 0; j < 2; ++j) {
-          if (j * 128 >= p.Tpad) break;
-          tma_store_3d(&p.dqkv_map, sP + (which * 2 + j) * 16384, (which == 0 ? HD : 2 * HD) + h * 64, j * 128, b);
-        }
-      tma_store_commit();
-      tma_store_wait_all<0>();
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp_idx == 4) {
-    tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
-  }
-}
+// Backward: attention_bwd.cuh (attn_bwd_kernel, two CTAs per SM); the row term delta_i = sum_d dO[i,d] O[i,d] it needs is
+// produced by attn_delta_kernel below.
 
 // delta[b][h][t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one THREAD per (b,t,h) row: 2 x 128 contiguous bytes, 8 x 16-byte loads;
 // consecutive threads walk consecutive head rows, so a warp streams 2 x 4 KB - the one-warp-per-row version moved 4 bytes

@@ -1,27 +1,33 @@
-// ROUND-2 PROTOTYPE (not part of the product library; compiles, never run on hardware - round 1's GPU budget was spent).
+// ViT multi-head attention backward for sm_100a (T <= 256 tokens, head dim 64), the backward of attn_fwd_kernel
+// (attention.cuh); replaces autograd through classification/vision_transformer/vit_model.py:97-108.
 //
-// ViT attention backward restructured so that TWO CTAs fit on one SM and overlap each other's phases.  The product kernel
-// (csrc/attention.cuh, attn_bwd_kernel) owns all 512 TMEM columns and 230 KB of shared memory per (batch, head), so one CTA
-// runs per SM and its S -> P -> dP/dV -> dS -> dQ/dK chain is strictly serial (tensor pipe 14 % busy, 383 us per ViT-B/16
-// layer at bs 256).  Here a CTA still owns one (batch, head) but walks the keys in blocks of 128:
+//   S  = Q K^T                    -> P = exp(scale*S - lse)            (recomputed from the saved log-sum-exp, never in HBM)
+//   dP = dO V^T                   -> dS = scale * P * (dP - delta),  delta_i = sum_d dO[i,d] O[i,d] (attn_delta_kernel)
+//   dV += P^T dO ,  dK += dS^T Q ,  dQ = dS K
+//
+// One CTA per (batch, head) walks the keys in blocks of 128 so that TWO CTAs fit on an SM and overlap each other's
+// MMA / soft-max / TMA phases (the first version owned all 512 TMEM columns and 230 KB per CTA, its S -> P -> dP -> dS -> dQ
+// chain was strictly serial with the tensor pipe 14 % busy: 386 us per ViT-B/16 layer at bs 256; this one: 281 us):
 //
 //   for key block j (128 keys):      K_j, V_j resident (16 KB each), dK_j / dV_j accumulate in TMEM (64 + 64 columns)
 //     for query block mb (128 rows): S = Q K_j^T (128 columns) -> P -> dP = dO V_j^T -> dS (in place over P)
 //                                    dV_j += P^T dO, dK_j += dS^T Q, dQ_part = dS K_j
 //
-//   TMEM: 128 (S / dP / dQ_part) + 64 + 64 = 256 columns;  shared memory: K, V, Q, dO 16 KB each + P/dS 32 KB = 96 KB
-//   -> 2 CTAs per SM.  dQ of a query block is the sum over the key blocks: block 0 stores its part (bf16) through the normal
-//   dQ path, later blocks TMA-load that part back (same CTA, so program order + wait_group make it visible), add their
-//   fp32 accumulator and store the sum - deterministic, no atomics, 25 KB of L2-hot extra traffic per (batch, head).
+//   TMEM: 128 (S / dP / dQ_part) + 64 + 64 = 256 columns;  shared memory: K, V, Q, dO 16 KB each + P/dS 32 KB = 96 KB.
+//   dQ of a query block is the sum over the key blocks: block 0 stores its part (bf16) through the normal dQ path, later
+//   blocks TMA-load that part back (same CTA, so program order + wait_group make it visible), add their fp32 accumulator
+//   and store the sum - deterministic, no atomics, 25 KB of L2-hot extra traffic per (batch, head).
 //
-// Same operand layouts, descriptors and soft-max arithmetic as the product kernel (see the comments there); only what
-// differs is commented here.  Checked against the product kernel by tools/experiments/attn_bwd_v2_check.py.
+// P and dS live in shared memory as bf16 in the key-blocked 128B-swizzled layout, which serves both as a K-major A operand
+// (dQ = dS K) and as an MN-major A operand (P^T dO, dS^T Q) without any transpose; K, V, Q, dO tiles are likewise consumed
+// in place as K-major or MN-major B operands.  Warp 4 = TMA producer + MMA issuer (one elected thread), warps 0-3 / 5-8 =
+// soft-max warps (two per TMEM lane quadrant, the pair splits the 128 key columns of every row in half).
 #pragma once
-#include "../../deeplearning_b200/csrc/attention.cuh"
+#include "attention.cuh"
 
 namespace b200 {
 
-struct alignas(64) AttnBwd2Params {
+struct alignas(64) AttnBwdParams {
   CUtensorMap qkv_map;   // qkv (3*H*64, T, B), box (64, 128, 1): Q, K and V tiles
   CUtensorMap do_map;    // dO (H*64, T, B), box (64, 128, 1)
   CUtensorMap dqkv_map;  // dqkv (3*H*64, T, B), box (64, 128, 1): stores, and loads of the partial dQ
@@ -31,9 +37,9 @@ struct alignas(64) AttnBwd2Params {
   const float* delta;    // [B][H][T]
 };
 
-constexpr int kAttnBwd2SmemBytes = 4 * 16384 + 32768 + 256 + 1024;
+constexpr int kAttnBwdSmemBytes = 4 * 16384 + 32768 + 256 + 1024;
 
-__global__ void __launch_bounds__(288, 2) attn_bwd2_kernel(const __grid_constant__ AttnBwd2Params p) {
+__global__ void __launch_bounds__(288, 2) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;

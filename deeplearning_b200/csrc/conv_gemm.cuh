@@ -54,7 +54,7 @@ struct alignas(64) ConvGemmParams {
   uint32_t desc_lbo, desc_sbo;  // K-major smem descriptor strides (bytes): 16 / 1024
   float* out_direct;        // direct fp32 output ([pixels][ld_out]) for tiny N (logits) or null
   long long ld_out;
-  // --- CTA-pair bring-up (kPair kernels only; appended so that the layout seen by the other kernels does not move)
+  // --- CTA-pair mode (kPair kernels only)
   CUtensorMap b_map_half;   // weights with a 128-row box: each CTA of a pair stages half of the 256-column tile
   int pair;                 // host-side: launch the kPair kernel
 };
@@ -155,7 +155,7 @@ constexpr int kEpiGeneric = -1;
 constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEpiResBf16 = 16, kEpiResF32 = 32,
               kEpiAux = 64, kEpiOutF32 = 128, kEpiDirect = 256, kEpiStats = 512;
 
-// kPair (BRING-UP, not yet run on hardware; default off, see abi_conv.cu gemm_pair_enabled()): the two CTAs of a cluster
+// kPair (validated on B200, default for the 256-wide linear layers, see abi_conv.cu gemm_pair_enabled()): the two CTAs of a cluster
 // compute one 256-pixel x 256-channel tile with tcgen05.mma.cta_group::2. Each CTA stages its own 128 pixels of A and HALF
 // of the B tile (32 KB instead of 48 KB of operands per k-block and SM), the leader (cluster rank 0) issues the MMAs for
 // both and commits to the barriers of both; every CTA drains its own 128 accumulator rows with the unchanged epilogue.

@@ -216,16 +216,35 @@ class TrainStep:
         self._g_images.copy_(images)
         self._g_labels.copy_(labels)
         self._lr_dev = torch.full((1,), float(self.lr), dtype=torch.float32, device=dev)
+        # The warm-up below runs two real steps (first-launch attribute calls, allocator growth).  They must not perturb
+        # the caller's model: parameters, optimizer state, AdamW step counters and every buffer (BatchNorm running
+        # statistics, num_batches_tracked) are snapshotted and restored, so capture() with a dummy batch is side-effect free.
+        arena = self.arena
+        saved = [t.clone() for t in (arena.flat_p, arena.flat_m)]
+        saved_v = arena.flat_v.clone() if hasattr(arena, "flat_v") else None
+        saved_hyper = self._hyper.clone() if hasattr(self, "_hyper") else None
+        saved_bufs = [b.clone() for b in self.model.buffers()]
+        saved_steps = self.steps
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):  # warm-up: first-launch attribute calls, allocator growth
+        with torch.cuda.stream(side):
             for _ in range(2):
                 self._fwd_bwd(self._g_images, self._g_labels)
                 self.arena.all_reduce_grads()
                 self._update(self.lr, self._lr_dev)
-                self.steps += 1
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        with torch.no_grad():
+            arena.flat_p.copy_(saved[0])
+            arena.flat_m.copy_(saved[1])
+            if saved_v is not None:
+                arena.flat_v.copy_(saved_v)
+            if saved_hyper is not None:
+                self._hyper.copy_(saved_hyper)
+            for b, sb in zip(self.model.buffers(), saved_bufs):
+                b.copy_(sb)
+        self.steps = saved_steps
+        weight_cache.bump()
         self._graph_fb = torch.cuda.CUDAGraph()
         self._graph_up = None
         if self.world == 1:
@@ -261,6 +280,9 @@ class TrainStep:
             self.arena.all_reduce_grads()
             self._graph_up.replay()
         self.steps += 1
+        # the replay updated the parameters behind autograd's back (and repacked the bf16 operands from the PRE-update
+        # values at its start): any forward outside the graph must repack first
+        weight_cache.bump()
         return self._g_loss, self._g_correct
 
     @property

@@ -171,7 +171,14 @@ def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=Non
     B, Ho, Wo, Cout = dy.shape
     H, W = in_hw
     Cin = wd_packed.shape[0]
-    dx = out if out is not None else torch.empty(B, H, W, Cin, dtype=BF16, device=dy.device)
+    if out is not None:
+        dx = out
+    elif ksize == 1 and stride == 2:
+        # a 1x1 / stride-2 convolution only reads the even input pixels: the kernel writes that phase alone, the gradient of
+        # every other pixel is zero
+        dx = torch.zeros(B, H, W, Cin, dtype=BF16, device=dy.device)
+    else:
+        dx = torch.empty(B, H, W, Cin, dtype=BF16, device=dy.device)
     sp = _span("conv_gemm_dgrad", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize, _nb(dy, wd_packed, dx, residual))
     rc = lib.b200_conv2d_dgrad(_p(dy), _p(wd_packed), _p(dx), B, H, W, Cin, Cout, ksize, stride, _p(residual), _stream())
     _lib.check(rc, "b200_conv2d_dgrad")

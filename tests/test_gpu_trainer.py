@@ -82,9 +82,7 @@ def test_graph_replay_equals_eager():
     ta, tb = TrainStep(a, lr=0.02), TrainStep(b, lr=0.02)
     x = torch.randn(8, 3, 64, 64, device="cuda")
     y = torch.randint(0, 16, (8,), device="cuda")
-    tb.capture(x, y)           # capture runs two warm-up steps
-    for _ in range(2):
-        ta.step_eager(x, y)
+    tb.capture(x, y)           # capture's warm-up steps are rolled back: both models are still at the same point
     for _ in range(3):
         la, _ = ta.step_eager(x, y)
         lb, _ = tb.step(x, y)
@@ -93,3 +91,52 @@ def test_graph_replay_equals_eager():
         assert torch.allclose(pa, pb, rtol=1e-3, atol=1e-5)
     for ba, bb in zip(a.buffers(), b.buffers()):
         assert torch.allclose(ba.float(), bb.float(), rtol=1e-3, atol=1e-5)
+
+
+def test_capture_is_side_effect_free():
+    """capture() warms up with real steps; parameters, momentum, BN running statistics and the step count must come back."""
+    from deeplearning_b200.engine.trainer import TrainStep
+
+    for opt in ("sgd", "adamw"):
+        m = _small_resnet(2)
+        tr = TrainStep(m, lr=0.02, optimizer=opt)
+        x = torch.randn(8, 3, 64, 64, device="cuda")
+        y = torch.randint(0, 16, (8,), device="cuda")
+        tr.step_eager(x, y)     # non-trivial optimizer state
+        before_p = [p.detach().clone() for p in m.parameters()]
+        before_b = [b.detach().clone() for b in m.buffers()]
+        before_m = tr.arena.flat_m.clone()
+        steps = tr.steps
+        tr.capture(torch.randn_like(x), y)   # a dummy batch
+        assert tr.steps == steps
+        assert torch.equal(tr.arena.flat_m, before_m)
+        for p, b in zip(m.parameters(), before_p):
+            assert torch.equal(p.detach(), b)
+        for p, b in zip(m.buffers(), before_b):
+            assert torch.equal(p, b)
+
+
+def test_forward_after_graph_replay_sees_updated_weights():
+    """the captured graph repacks the bf16 operands at its START (pre-update values); a forward outside the graph
+    after N replays must repack, i.e. equal the forward of an eagerly trained twin."""
+    from deeplearning_b200.engine.trainer import TrainStep
+
+    a, b = _small_resnet(5), _small_resnet(5)
+    ta, tb = TrainStep(a, lr=0.05), TrainStep(b, lr=0.05)
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 16, (8,), device="cuda")
+    tb.capture(x, y)
+    for _ in range(3):
+        ta.step_eager(x, y)
+        tb.step(x, y)
+    a.eval(), b.eval()
+    with torch.no_grad():
+        oa, ob = a(x), b(x)
+    assert torch.allclose(oa, ob, rtol=1e-3, atol=1e-3), float((oa - ob).abs().max())
+    # and the stale-operand failure mode is detectable: one more replay changes the eval output
+    b.train()
+    tb.step(x, y)
+    b.eval()
+    with torch.no_grad():
+        ob2 = b(x)
+    assert float((ob2 - ob).abs().max()) > 0
