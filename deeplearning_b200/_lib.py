@@ -28,7 +28,7 @@ class GemmArgs(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("N", c_int), ("K", c_int), ("bias", c_void_p), ("colscale", c_void_p), ("act", c_int),
                 ("out_f32", c_int),
                 ("residual", ctypes.POINTER(View)), ("residual_f32", c_int), ("aux_out", ctypes.POINTER(View)),
-                ("aux_in", ctypes.POINTER(View)), ("stats", c_void_p)]
+                ("aux_in", ctypes.POINTER(View)), ("stats", c_void_p), ("rowscale", c_void_p), ("rows_per_sample", c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol of include/b200cls.h (tests/test_abi.py checks this).
@@ -103,6 +103,9 @@ SIGNATURES = {
     "b200_stem_s2d_conv_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "b200_stem_s2d_conv_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _P]),
     "b200_stem_s2d_wgrad_relayout": (_I, [_P, _P, _I, _P]),
+    "b200_rowscale_bf16": (_I, [_P, _P, _P, _L, _L, _P]),
+    "b200_tanh_fwd": (_I, [_P, _P, _P, _L, _P]),
+    "b200_tanh_bwd": (_I, [_P, _P, _P, _L, _P]),
     "b200_sgd_momentum": (_I, [_P, _P, _P, _L, _F, _P, _F, _F, _F, _I, _P, _P]),
 }
 

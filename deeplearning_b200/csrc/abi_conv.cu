@@ -190,6 +190,7 @@ int epilogue_flags(const ConvGemmParams& p) {
   if (p.out_f32) f |= kEpiOutF32;
   if (p.out_direct) f |= kEpiDirect;
   if (p.stats) f |= kEpiStats;
+  if (p.rowscale) f |= kEpiRowscale;
   return f;
 }
 
@@ -666,6 +667,12 @@ int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_a
     p.residual = g->residual->base;
     p.res_f32 = g->residual_f32;
     p.rs1 = g->residual->stride[0], p.rs2 = g->residual->stride[1], p.rs3 = g->residual->stride[2];
+  }
+  if (g->rowscale != nullptr) {
+    B200_REQUIRE(g->rows_per_sample > 0, "gemm_ex: rowscale needs rows_per_sample > 0");
+    p.rowscale = g->rowscale;
+    p.rows_per_sample = g->rows_per_sample;
+    p.pair = 0;   // the per-sample multiplier lives in the generic single-CTA epilogue
   }
   if (g->act == B200_ACT_GELU_GRAD) {
     B200_REQUIRE(g->aux_in != nullptr, "gemm_ex: B200_ACT_GELU_GRAD needs aux_in");

@@ -260,4 +260,30 @@ int b200_stem_s2d_wgrad_relayout(const float* g, float* dw, int accumulate, void
   return OK;
 }
 
+int b200_rowscale_bf16(const void* x, const float* scale, void* y, long long n_samples, long long elems_per_sample,
+                       void* stream) {
+  B200_REQUIRE(n_samples > 0 && elems_per_sample > 0 && elems_per_sample % 8 == 0,
+               "rowscale_bf16: elems_per_sample=%lld must be a positive multiple of 8", elems_per_sample);
+  const long long nvec = n_samples * (elems_per_sample / 8);
+  rowscale_bf16_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), scale, static_cast<uint4*>(y), nvec, elems_per_sample / 8);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_tanh_fwd(const float* u, float* t, void* t_bf16, long long n, void* stream) {
+  B200_REQUIRE(n > 0, "tanh_fwd: empty input");
+  tanh_fwd_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(u, t, static_cast<__nv_bfloat16*>(t_bf16), n);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_tanh_bwd(const void* dt_bf16, const float* t, void* du_bf16, long long n, void* stream) {
+  B200_REQUIRE(n > 0, "tanh_bwd: empty input");
+  tanh_bwd_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dt_bf16), t, static_cast<__nv_bfloat16*>(du_bf16), n);
+  B200_LAUNCHED();
+  return OK;
+}
+
 }  // extern "C"

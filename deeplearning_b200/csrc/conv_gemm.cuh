@@ -57,6 +57,10 @@ struct alignas(64) ConvGemmParams {
   // --- CTA-pair mode (kPair kernels only)
   CUtensorMap b_map_half;   // weights with a 128-row box: each CTA of a pair stages half of the 256-column tile
   int pair;                 // host-side: launch the kPair kernel
+  // --- stochastic depth (generic epilogue only): per-SAMPLE multiplier applied after bias / act / colscale, before the
+  // residual add: sample = flat output pixel / rows_per_sample  (drop_path of the reference: convNext/models/networks.py:11-26)
+  const float* rowscale;
+  int rows_per_sample;
 };
 
 template <int BLOCK_N, bool kPair = false>
@@ -153,7 +157,8 @@ __device__ __forceinline__ void gelu_erf_grad_mul2(float a0, float a1, float& f0
 // of compile-time options so that the hot layer types get a branch-free epilogue without the unused operand loads.
 constexpr int kEpiGeneric = -1;
 constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEpiResBf16 = 16, kEpiResF32 = 32,
-              kEpiAux = 64, kEpiOutF32 = 128, kEpiDirect = 256, kEpiStats = 512;
+              kEpiAux = 64, kEpiOutF32 = 128, kEpiDirect = 256, kEpiStats = 512,
+              kEpiRowscale = 1024 /* never specialised: selects the generic kernel */;
 
 // kPair (validated on B200, default for the 256-wide linear layers, see abi_conv.cu gemm_pair_enabled()): the two CTAs of a cluster
 // compute one 256-pixel x 256-channel tile with tcgen05.mma.cta_group::2. Each CTA stages its own 128 pixels of A and HALF
@@ -357,8 +362,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const bool out_f32 = G ? (p.out_f32 != 0) : ((EPI & kEpiOutF32) != 0);
     float* const out_direct = (G || (EPI & kEpiDirect)) ? p.out_direct : nullptr;
     float* const stats = (G || (EPI & kEpiStats)) ? p.stats : nullptr;
+    const float* const rowscale = G ? p.rowscale : nullptr;
     // (pair mode with an odd number of pixel tiles: the last peer tile lies past the tensor and must not touch memory)
-    const bool need_rowmap = has_res || act == 3 || out_direct != nullptr || p.dim1 % p.box1 != 0 ||
+    const bool need_rowmap = has_res || act == 3 || out_direct != nullptr || rowscale != nullptr || p.dim1 % p.box1 != 0 ||
                              p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0 || (kPair && (m_tiles & 1) != 0);
     const bool full_cols = (N % BLOCK_N) == 0;  // no partially valid 32-column group anywhere
     uint32_t store_counter = 0;
@@ -522,6 +528,12 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           if (colscale != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= (full_cols || nc + j < N) ? __ldg(colscale + nc + j) : 0.0f;
+          }
+          if (rowscale != nullptr && row_ok) {
+            const long long pix = (static_cast<long long>(p3) * p.dim2 + p2) * p.dim1 + p1;
+            const float rs = __ldg(rowscale + pix / p.rows_per_sample);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= rs;
           }
           if (has_res && row_ok) {
             if (res_f32) {

@@ -888,4 +888,45 @@ __global__ void stem_s2d_wgrad_relayout_kernel(const float* __restrict__ g, floa
   dw[i] = accumulate ? dw[i] + v : v;
 }
 
+// Stochastic depth (drop_path of the reference: classification/convNext/models/networks.py:11-26, vision_transformer/
+// vit_model.py:12-40, timm DropPath in swin_transformer.py:282,285): y[b, ...] = x[b, ...] * scale[b], scale[b] =
+// floor(keep + U_b) / keep.  Used on the BACKWARD side (the gradient entering a dropped residual branch); the forward side
+// lives in the GEMM epilogue (ConvGemmParams::rowscale).  vec_per_sample = elements per sample / 8.
+__global__ void __launch_bounds__(256) rowscale_bf16_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
+                                                            uint4* __restrict__ y, long long nvec, long long vec_per_sample) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float s = __ldg(scale + i / vec_per_sample);
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (s != 0.f) {   // a dropped sample: no read of x at all
+      float f[8];
+      unpack8(__ldg(x + i), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] *= s;
+      o = pack8(f);
+    }
+    y[i] = o;
+  }
+}
+
+// ViT pre_logits activation (vit_model.py:218-221: Linear -> Tanh on the class-token row).  t = tanh(u) (fp32, kept for the
+// backward) and its bf16 copy for the classifier GEMM;  backward: du = dt * (1 - t^2)  (bf16 in / out).
+__global__ void __launch_bounds__(256) tanh_fwd_kernel(const float* __restrict__ u, float* __restrict__ t,
+                                                       __nv_bfloat16* __restrict__ t16, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = tanhf(u[i]);
+    t[i] = v;
+    t16[i] = __float2bfloat16(v);
+  }
+}
+__global__ void __launch_bounds__(256) tanh_bwd_kernel(const __nv_bfloat16* __restrict__ dt, const float* __restrict__ t,
+                                                       __nv_bfloat16* __restrict__ du, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = t[i];
+    du[i] = __float2bfloat16(__bfloat162float(dt[i]) * (1.0f - v * v));
+  }
+}
+
 }  // namespace b200

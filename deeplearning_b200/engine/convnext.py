@@ -11,7 +11,9 @@ Mirrors ``ConvNeXt.forward_features`` / ``Block.forward`` of the reference (clas
 
 Backward folds the layer scale into the dgrad operand of pwconv2 (packed copy scaled by gamma), applies GELU' in that GEMM's
 epilogue, and derives dgamma / dW2 / db2 from the *unscaled* weight gradient G = g^T post (dgamma_c = <W2_c, G_c> + b2_c sum(g_c)),
-so the pre-scale activation is never stored.  Stochastic depth (drop_path) must be 0 in training mode.
+so the pre-scale activation is never stored.  Stochastic depth (``drop_path``, reference :11-26,104): the per-sample
+multiplier of engine/droppath.py scales the branch in the pwconv2 epilogue (before the shortcut add) and the gradient
+entering the branch in the backward pass.
 """
 import weakref
 
@@ -19,6 +21,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import droppath
 from .packing import weight_cache
 from .resnet import _Grads
 
@@ -60,11 +63,6 @@ _pack_spec = _PackSpec()
 
 
 def _check(model):
-    for stage in model.stages:
-        for blk in stage:
-            if not isinstance(blk.drop_path, nn.Identity) and model.training and (blk.drop_path.drop_prob or 0) > 0:
-                raise NotImplementedError("stochastic depth > 0 is not implemented on the B200 engine: build the model with "
-                                          "drop_path_rate=0 (or call eval()); SURVEY.md 8(c) parity protocol does the same")
     if not isinstance(model.head, nn.Linear):
         raise NotImplementedError("model.head must be an nn.Linear")
 
@@ -121,10 +119,11 @@ def forward(model, x, train, want_tape):
             u = ops.dwconv7(h, _dw_cache.get(blk.dwconv.weight), blk.dwconv.bias)       # bf16 NHWC
             y, m, r = ops.layernorm_fwd(u, blk.norm.weight, blk.norm.bias, blk.norm.eps)
             post, pre = ops.gemm(y.view(-1, C), pack.get(blk.pwconv1.weight, 0), bias=blk.pwconv1.bias, act=2, aux_out=want_tape)
+            dps = droppath.sample_scale(droppath.drop_prob_of(blk, train), Bb, 4, h.device)   # x = shortcut + drop_path(x)
             h_new, _ = ops.gemm(post, pack.get(blk.pwconv2.weight, 0), bias=blk.pwconv2.bias, colscale=blk.gamma,
-                                residual=h, out_f32=True)
+                                residual=h, out_f32=True, rowscale=None if dps is None else (dps, H * W))
             if want_tape:
-                rec["blocks"].append((blk, h, u, m, r, y, pre, post))
+                rec["blocks"].append((blk, h, u, m, r, y, pre, post, dps))
             h = h_new.view(Bb, H, W, C)
         if want_tape:
             tape["stages"].append(rec)
@@ -191,10 +190,11 @@ def backward(model, tape, dlogits, sink=None):
     g = ops.avgpool_bwd(d_pool, (Hf, Wf))                          # bf16 [B, Hf, Wf, Cf]: gradient of the stream
     for i in range(3, -1, -1):
         rec = tape["stages"][i]
-        for (blk, h, u, m, r, y, pre, post) in reversed(rec["blocks"]):
+        for (blk, h, u, m, r, y, pre, post, dps) in reversed(rec["blocks"]):
             Bb, H, W, C = h.shape
             M = Bb * H * W
-            g2 = g.view(M, C)
+            # the gradient entering the residual branch carries the sample's stochastic-depth multiplier; the identity path keeps g
+            g2 = (g if dps is None else ops.rowscale(g, dps)).view(M, C)
             # x' = x + gamma * (post W2^T + b2)
             gsum = ops.colsum_tall(g2)
             G = ops.conv2d_wgrad(g2.view(M, 1, 1, C), post.view(M, 1, 1, 4 * C)).view(C, 4 * C)   # unscaled g^T post

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import droppath
 from .packing import weight_cache
 from .resnet import _Grads
 from .vit import _lin_grads
@@ -70,8 +71,6 @@ def _check(model):
             if isinstance(m, nn.Dropout) and m.p != 0:
                 raise NotImplementedError("dropout > 0 is not implemented on the B200 engine")
     for blk in _blocks(model):
-        if not isinstance(blk.drop_path, nn.Identity) and model.training and blk.drop_path.drop_prob:
-            raise NotImplementedError("stochastic depth > 0 is not implemented on the B200 engine (build with drop_path_rate=0)")
         if blk.window_size != 7 or blk.dim // blk.num_heads != 32:
             raise NotImplementedError("the window-attention kernel is built for window_size 7 and head_dim 32")
         if not isinstance(blk.mlp.act, nn.GELU):
@@ -105,13 +104,17 @@ def forward(model, x, train, want_tape):
             bias = ops.window_bias_gather(att_m.relative_position_bias_table.detach(), att_m.relative_position_index, nH,
                                           blk.attn_mask)   # bias (+ shift mask) table, query index innermost
             att, lse = ops.window_attention_fwd(qkv.view(B, H, W, 3 * C), nH, bias, blk.shift_size, float(att_m.scale))
+            dp = droppath.drop_prob_of(blk, train)
+            dp1 = droppath.sample_scale(dp, B, 3, x.device)   # x = shortcut + drop_path(x)         (swin_transformer.py:282)
             h2, _ = ops.gemm(att.view(B, H * W, C), pack.get(att_m.proj.weight, 0), bias=att_m.proj.bias, residual=h,
-                             out_f32=True)
+                             out_f32=True, rowscale=None if dp1 is None else (dp1, H * W))
             y2, m2, r2 = ops.layernorm_fwd(h2, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
             post, pre = ops.gemm(y2, pack.get(mlp.fc1.weight, 0), bias=mlp.fc1.bias, act=2, aux_out=want_tape)
-            h3, _ = ops.gemm(post, pack.get(mlp.fc2.weight, 0), bias=mlp.fc2.bias, residual=h2, out_f32=True)
+            dp2 = droppath.sample_scale(dp, B, 3, x.device)   # x = x + drop_path(mlp(norm2(x)))    (swin_transformer.py:285)
+            h3, _ = ops.gemm(post, pack.get(mlp.fc2.weight, 0), bias=mlp.fc2.bias, residual=h2, out_f32=True,
+                             rowscale=None if dp2 is None else (dp2, H * W))
             if want_tape:
-                recs.append((blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, pre, post))
+                recs.append((blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2))
             h = h3
         merge = None
         if layer.downsample is not None:
@@ -185,10 +188,11 @@ def backward(model, tape, dlogits, sink=None):
             grads.put(ds.norm.bias, dbm)
         M = B * H * W
         g = g.view(B, H * W, C)
-        for (blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, pre, post) in reversed(recs):
+        for (blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2) in reversed(recs):
             att_m, mlp = blk.attn, blk.mlp
             nH = att_m.num_heads
-            g2 = g.view(M, C)
+            # (stochastic depth: the branch sees the per-sample scaled gradient, the identity path - `add=g` - the full one)
+            g2 = (g if dp2 is None else ops.rowscale(g, dp2)).view(M, C)
             _lin_grads(grads, mlp.fc2, g2, post.view(M, -1))
             d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1), want_stats=True)
             _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, C), dy_stats=st_pre)
@@ -197,7 +201,7 @@ def backward(model, tape, dlogits, sink=None):
                                             dgamma=grads.dest(blk.norm2.weight), dbeta=grads.dest(blk.norm2.bias))
             grads.put(blk.norm2.weight, dg2)
             grads.put(blk.norm2.bias, db2)
-            g2 = g.view(M, C)
+            g2 = (g if dp1 is None else ops.rowscale(g, dp1)).view(M, C)
             _lin_grads(grads, att_m.proj, g2, att.view(M, C))
             d_att, _ = ops.gemm(g2, pack.get(att_m.proj.weight, 1))
             dqkv, dbias = ops.window_attention_bwd(qkv.view(B, H, W, 3 * C), att, d_att.view(B, H, W, C), bias, lse, nH,

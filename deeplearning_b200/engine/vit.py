@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
+from . import droppath
 from .packing import weight_cache
 from .resnet import _Grads  # same gradient-sink protocol as the ResNet engine
 
@@ -25,13 +26,15 @@ def _linears(model):
     out = [model.head]
     for blk in model.blocks:
         out += [blk.attn.qkv, blk.attn.proj, blk.mlp.fc1, blk.mlp.fc2]
+    if model.has_logits:
+        out.append(model.pre_logits.fc)   # Linear + Tanh on the class-token row (vit_model.py:218-221)
     return out
 
 
 class _PackSpec:
     @staticmethod
     def key(model):
-        return (len(model.blocks), id(model.head), model.head.out_features)
+        return (len(model.blocks), id(model.head), model.head.out_features, bool(model.has_logits))
 
     def __call__(self, model):
         specs = []
@@ -55,17 +58,15 @@ _pack_spec = _PackSpec()
 def _check(model):
     if model.dist_token is not None:
         raise NotImplementedError("distilled ViT (dist_token) is not implemented on the B200 engine")
-    if model.has_logits:
-        raise NotImplementedError("pre_logits (representation_size) is not implemented yet; build the model with has_logits=False "
-                                  "as classification/vision_transformer/train.py:66 does")
+    if model.has_logits and not (isinstance(getattr(model.pre_logits, "fc", None), nn.Linear)
+                                 and isinstance(getattr(model.pre_logits, "act", None), nn.Tanh)):
+        raise NotImplementedError("pre_logits must be the reference's Sequential(fc=Linear, act=Tanh) (vit_model.py:218-221)")
     if not isinstance(model.head, nn.Linear):
         raise NotImplementedError("model.head must be an nn.Linear (num_classes > 0)")
     for m in model.modules():
         if isinstance(m, nn.Dropout) and m.p != 0 and model.training:
             raise NotImplementedError("dropout > 0 is not implemented on the B200 engine")
     for blk in model.blocks:
-        if not isinstance(blk.drop_path, nn.Identity) and model.training:
-            raise NotImplementedError("stochastic depth > 0 is not implemented on the B200 engine")
         if blk.attn.qkv.in_features // blk.attn.num_heads != 64:
             raise NotImplementedError("the attention kernel is built for head_dim 64")
         if not isinstance(blk.mlp.act, nn.GELU):
@@ -103,18 +104,29 @@ def forward(model, x, train, want_tape):
         y1, m1, r1 = ops.layernorm_fwd(h, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
         qkv, _ = ops.gemm(y1, pack.get(att_m.qkv.weight, 0), bias=att_m.qkv.bias)
         att, lse = ops.attention_fwd(qkv, H, float(att_m.scale))
-        h2, _ = ops.gemm(att, pack.get(att_m.proj.weight, 0), bias=att_m.proj.bias, residual=h, out_f32=True)
+        dp = droppath.drop_prob_of(blk, train)
+        dp1 = droppath.sample_scale(dp, B, 3, x.device)     # x = x + drop_path(attn(norm1(x)))   (vit_model.py:159)
+        h2, _ = ops.gemm(att, pack.get(att_m.proj.weight, 0), bias=att_m.proj.bias, residual=h, out_f32=True,
+                         rowscale=None if dp1 is None else (dp1, T))
         y2, m2, r2 = ops.layernorm_fwd(h2, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
         post, pre = ops.gemm(y2, pack.get(mlp.fc1.weight, 0), bias=mlp.fc1.bias, act=2, aux_out=want_tape)
-        h3, _ = ops.gemm(post, pack.get(mlp.fc2.weight, 0), bias=mlp.fc2.bias, residual=h2, out_f32=True)
+        dp2 = droppath.sample_scale(dp, B, 3, x.device)     # x = x + drop_path(mlp(norm2(x)))    (vit_model.py:160)
+        h3, _ = ops.gemm(post, pack.get(mlp.fc2.weight, 0), bias=mlp.fc2.bias, residual=h2, out_f32=True,
+                         rowscale=None if dp2 is None else (dp2, T))
         if want_tape:
-            tape["blocks"].append((blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, pre, post))
+            tape["blocks"].append((blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2))
         h = h3
     # ---- head: final LayerNorm on the class-token rows only, then the classifier (fp32 logits)
     cls_rows = torch.empty(B, D, dtype=F32, device=x.device)
     ops.copy_rows(h, 0, T * D, cls_rows, 0, D, B, D)
     yc, mc, rc = ops.layernorm_fwd(cls_rows, model.norm.weight, model.norm.bias, model.norm.eps)
     head = model.head
+    feat, t32 = yc, None          # classifier input (bf16 [B, R])
+    if model.has_logits:          # pre_logits: tanh(fc(cls row))  (vit_model.py:218-221,254)
+        fc = model.pre_logits.fc
+        u, _ = ops.gemm(yc, pack.get(fc.weight, 0), bias=fc.bias, out_f32=True)
+        t32, feat = ops.tanh_fwd(u)
+    R = feat.shape[1]
     n_cls = head.out_features
     n_pad = (n_cls + 7) // 8 * 8
     bias = None
@@ -122,10 +134,10 @@ def forward(model, x, train, want_tape):
         bias = head.bias.detach()
         if n_pad != n_cls:
             bias = torch.cat([bias, bias.new_zeros(n_pad - n_cls)])
-    logits, _ = ops.conv2d_fwd(yc.view(B, 1, 1, D), pack.get(head.weight, 0), bias=bias, out_f32=True)
+    logits, _ = ops.conv2d_fwd(feat.view(B, 1, 1, R), pack.get(head.weight, 0), bias=bias, out_f32=True)
     logits = logits.view(B, n_pad)
     if want_tape:
-        tape["head"] = (cls_rows, yc, mc, rc, n_cls, n_pad, (B, T, D, P))
+        tape["head"] = (cls_rows, yc, mc, rc, n_cls, n_pad, (B, T, D, P), feat, t32)
     return (logits[:, :n_cls] if n_pad != n_cls else logits), tape
 
 
@@ -147,8 +159,9 @@ def _lin_grads(grads, lin, dy2d, x2d, dy_stats=None):
 def backward(model, tape, dlogits, sink=None):
     grads = _Grads(sink)
     pack = tape["pack"]
-    cls_rows, yc, mc, rc, n_cls, n_pad, (B, T, D, P) = tape["head"]
+    cls_rows, yc, mc, rc, n_cls, n_pad, (B, T, D, P), feat, t32 = tape["head"]
     head = model.head
+    R = feat.shape[1]
     if dlogits.dtype == BF16 and dlogits.shape[1] == n_pad and dlogits.is_contiguous():
         dl16 = dlogits
     else:
@@ -158,16 +171,21 @@ def backward(model, tape, dlogits, sink=None):
         dl16 = ops.cast_bf16(dl)
     dst = grads.dest(head.weight)
     if dst is not None and n_pad == n_cls:
-        grads.put(head.weight, ops.conv2d_wgrad(dl16.view(B, 1, 1, n_pad), yc.view(B, 1, 1, D), out=dst.view(n_cls, D, 1, 1)))
+        grads.put(head.weight, ops.conv2d_wgrad(dl16.view(B, 1, 1, n_pad), feat.view(B, 1, 1, R), out=dst.view(n_cls, R, 1, 1)))
     else:
-        gw = ops.conv2d_wgrad(dl16.view(B, 1, 1, n_pad), yc.view(B, 1, 1, D)).view(n_pad, D)[:n_cls]
+        gw = ops.conv2d_wgrad(dl16.view(B, 1, 1, n_pad), feat.view(B, 1, 1, R)).view(n_pad, R)[:n_cls]
         if dst is not None:
             dst.copy_(gw)
             gw = dst
         grads.put(head.weight, gw)
     if head.bias is not None:
         grads.put(head.bias, ops.colsum(dl16, cols=n_cls, out=grads.dest(head.bias)))
-    d_yc = ops.conv2d_dgrad(dl16.view(B, 1, 1, n_pad), pack.get(head.weight, 1), (1, 1)).view(B, D)
+    d_yc = ops.conv2d_dgrad(dl16.view(B, 1, 1, n_pad), pack.get(head.weight, 1), (1, 1)).view(B, R)
+    if model.has_logits:
+        fc = model.pre_logits.fc
+        du = ops.tanh_bwd(d_yc, t32)                      # bf16 [B, R]: d tanh
+        _lin_grads(grads, fc, du, yc)
+        d_yc, _ = ops.gemm(du, pack.get(fc.weight, 1))    # bf16 [B, D]
     d_cls, dgn, dbn = ops.layernorm_bwd(d_yc, cls_rows, mc, rc, model.norm.weight, dx_dtype=BF16,
                                         dgamma=grads.dest(model.norm.weight), dbeta=grads.dest(model.norm.bias))
     grads.put(model.norm.weight, dgn)
@@ -175,10 +193,11 @@ def backward(model, tape, dlogits, sink=None):
     g = torch.zeros(B, T, D, dtype=BF16, device=d_cls.device)   # gradient of the residual stream
     ops.copy_rows(d_cls, 0, D, g, 0, T * D, B, D)
     M = B * T
-    for (blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, pre, post) in reversed(tape["blocks"]):
+    for (blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2) in reversed(tape["blocks"]):
         att_m, mlp = blk.attn, blk.mlp
         H = att_m.num_heads
-        g2 = g.view(M, D)
+        # (stochastic depth: the branch sees the per-sample scaled gradient, the identity path - `add=g` below - the full one)
+        g2 = (g if dp2 is None else ops.rowscale(g, dp2)).view(M, D)
         # h3 = h2 + fc2(gelu(fc1(LN2(h2))))
         _lin_grads(grads, mlp.fc2, g2, post.view(M, -1))
         # dgrad + GELU' in the epilogue, which also sums the columns of d_pre (= fc1 bias gradient) on the way out
@@ -190,7 +209,7 @@ def backward(model, tape, dlogits, sink=None):
         grads.put(blk.norm2.weight, dg2)
         grads.put(blk.norm2.bias, db2)
         # h2 = h + proj(attention(qkv(LN1(h))))
-        g2 = g.view(M, D)
+        g2 = (g if dp1 is None else ops.rowscale(g, dp1)).view(M, D)
         _lin_grads(grads, att_m.proj, g2, att.view(M, D))
         d_att, _ = ops.gemm(g2, pack.get(att_m.proj.weight, 1))
         dqkv = ops.attention_bwd(qkv, att, d_att.view(B, T, D), lse, H, float(att_m.scale))

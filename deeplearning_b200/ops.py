@@ -481,9 +481,10 @@ def _view(t, channels, pix_dims=None, pix_strides=None, offset=0):
 
 
 def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, aux_out=False, aux_in=None,
-         a_view=None, out_view=None, residual_view=None, out_offset=0, want_stats=False, colscale=None):
+         a_view=None, out_view=None, residual_view=None, out_offset=0, want_stats=False, colscale=None, rowscale=None):
     """out[rows, N] = epilogue(a[rows, K] @ w_packed[N, K]^T). `*_view` = (pix_dims, pix_strides) for strided layouts.
-    Returns (out, aux) where aux is the bf16 pre-activation copy when aux_out=True."""
+    rowscale = (fp32 [n_samples] tensor, rows_per_sample): stochastic-depth multiplier of every sample's rows, applied
+    before the residual add.  Returns (out, aux) where aux is the bf16 pre-activation copy when aux_out=True."""
     import ctypes
 
     lib = _lib.load()
@@ -498,6 +499,8 @@ def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, 
     args.w, args.N, args.K = w_packed.data_ptr(), N, K
     args.bias = _p(bias)
     args.colscale = _p(colscale)
+    if rowscale is not None:
+        args.rowscale, args.rows_per_sample = _p(rowscale[0]), int(rowscale[1])
     args.act = act
     args.out_f32 = 1 if out_f32 else 0
     keep = []
@@ -544,6 +547,34 @@ def stats_colsum(stats, out=None):
     rc = lib.b200_bn_bwd_finalize(_p(stats), T, C, 1.0, None, _p(out), 0, None, None, None, None, _p(sc), sc.numel(), _stream())
     _lib.check(rc, "b200_bn_bwd_finalize")
     return out
+
+
+# --------------------------------------------------------------------------------------------------------- stochastic depth
+def rowscale(x, scale):
+    """y[b] = x[b] * scale[b] for a bf16 tensor whose first dim is the sample dim (scale fp32 [B])."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    B = scale.numel()
+    per = x.numel() // B
+    y = torch.empty_like(x)
+    _lib.check(lib.b200_rowscale_bf16(_p(x), _p(scale), _p(y), B, per, _stream()), "b200_rowscale_bf16")
+    return y
+
+
+def tanh_fwd(u):
+    """fp32 u -> (t fp32, t bf16)."""
+    lib = _lib.load()
+    t = torch.empty_like(u)
+    t16 = torch.empty(u.shape, dtype=BF16, device=u.device)
+    _lib.check(lib.b200_tanh_fwd(_p(u), _p(t), _p(t16), u.numel(), _stream()), "b200_tanh_fwd")
+    return t, t16
+
+
+def tanh_bwd(dt16, t):
+    lib = _lib.load()
+    du = torch.empty(t.shape, dtype=BF16, device=t.device)
+    _lib.check(lib.b200_tanh_bwd(_p(dt16), _p(t), _p(du), t.numel(), _stream()), "b200_tanh_bwd")
+    return du
 
 
 # --------------------------------------------------------------------------------------------------------- layer norm

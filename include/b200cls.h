@@ -97,6 +97,10 @@ typedef struct {
   const b200_view_t* aux_out;  /* bf16 copy of the pre-activation (act == GELU), or NULL */
   const b200_view_t* aux_in;   /* act == B200_ACT_GELU_GRAD: pre-activation tensor */
   float* stats;                /* optional per-32-row-slab column sum / sum of squares, or NULL */
+  const float* rowscale;       /* stochastic depth: per-SAMPLE multiplier [n_samples] applied after bias/act/colscale and
+                                  before the residual (drop_path: convNext/models/networks.py:11-26, vit_model.py:12-40,
+                                  swin_transformer.py:282,285), or NULL */
+  int rows_per_sample;         /* output pixels per sample (sample = flat pixel index / rows_per_sample) */
 } b200_gemm_args_t;
 
 int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_args_t* args, void* stream);
@@ -275,6 +279,17 @@ int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, in
  * lr_dev (optional device float*) overrides lr, so a captured CUDA graph can follow the reference's LambdaLR schedule. */
 int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
                       float weight_decay, float gscale, int first_step, const float* clip_coef, void* stream);
+
+/* ---- stochastic depth / pre_logits helpers -------------------------------------------------------------------------------
+ * y[b, :] = x[b, :] * scale[b] over bf16 samples of elems_per_sample elements: the gradient entering a residual branch whose
+ * forward was scaled per sample by drop_path (convNext/models/networks.py:11-26, vit_model.py:12-40, swin_transformer.py:282,285;
+ * the forward scaling itself is b200_gemm_args_t::rowscale).  Samples with scale 0 are not read. */
+int b200_rowscale_bf16(const void* x, const float* scale, void* y, long long n_samples, long long elems_per_sample,
+                       void* stream);
+/* ViT pre_logits = Linear + Tanh on the class-token row (vit_model.py:218-221): t = tanh(u) fp32 (kept for the backward) and
+ * its bf16 copy (operand of the classifier GEMM); backward du = dt * (1 - t^2), bf16 in / out. */
+int b200_tanh_fwd(const float* u, float* t, void* t_bf16, long long n, void* stream);
+int b200_tanh_bwd(const void* dt_bf16, const float* t, void* du_bf16, long long n, void* stream);
 
 /* bring-up only: override the UMMA shared-memory descriptor strides (which: 0 = forward K-major, 1 = wgrad MN-major) */
 int b200_debug_set_desc(int which, unsigned lbo, unsigned sbo, unsigned kstep);

@@ -3,7 +3,9 @@
 SwinTransformerBlock (:241-287): LN -> roll(-s) -> window_partition (:38-50) -> WindowAttention (:118-149: qkv, q*scale,
 q k^T + relative_position_bias_table[relative_position_index] + attn_mask (0/-100), softmax, @v, proj) -> window_reverse
 (:53-67) -> roll(+s) -> residual; LN -> Mlp (fc1, exact GELU, fc2) -> residual; PatchMerging (:324-345): 2x2 gather-concat
-[x0,x1,x2,x3] -> LN(4C) -> Linear(4C,2C, no bias); head: LN -> mean over tokens -> Linear (:590-597)."""
+[x0,x1,x2,x3] -> LN(4C) -> Linear(4C,2C, no bias); head: LN -> mean over tokens -> Linear (:590-597).
+Stochastic depth (timm 0.4.12 ``DropPath`` = the rand/floor ``drop_path`` function, applied to both branches :282,285) takes
+its per-sample masks from ``drop``: two entries per block in forward order, each None or ``(random_tensor [B], keep_prob)``."""
 import torch
 import torch.nn.functional as F
 
@@ -18,8 +20,16 @@ def _reverse(w, ws, H, W):
     return w.view(B, H // ws, W // ws, ws, ws, -1).permute(0, 1, 3, 2, 4, 5).contiguous().view(B, H, W, -1)
 
 
-def swin_forward(s, x, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), patch=4, eps=1e-5, train=False):
+def _drop_path(y, entry):
+    if entry is None:
+        return y
+    r, keep = entry
+    return y.div(keep) * r.to(y.dtype).view((-1,) + (1,) * (y.dim() - 1))
+
+
+def swin_forward(s, x, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), patch=4, eps=1e-5, train=False, drop=None):
     B = x.shape[0]
+    drop = list(drop) if (drop is not None and train) else None
     h = F.conv2d(x, s["patch_embed.proj.weight"], s["patch_embed.proj.bias"], stride=patch)
     H, W = h.shape[2], h.shape[3]
     h = h.flatten(2).transpose(1, 2)
@@ -53,10 +63,11 @@ def swin_forward(s, x, depths=(2, 2, 6, 2), num_heads=(3, 6, 12, 24), patch=4, e
             y = _reverse(yw.view(-1, ws, ws, C), ws, H, W)
             if shift > 0:
                 y = torch.roll(y, shifts=(shift, shift), dims=(1, 2))
-            h = h + y.view(B, H * W, C)
+            y = y.view(B, H * W, C)
+            h = h + (_drop_path(y, drop.pop(0)) if drop is not None else y)
             y = F.layer_norm(h, (C,), s[p + "norm2.weight"], s[p + "norm2.bias"], eps)
             y = F.linear(F.gelu(F.linear(y, s[p + "mlp.fc1.weight"], s[p + "mlp.fc1.bias"])), s[p + "mlp.fc2.weight"], s[p + "mlp.fc2.bias"])
-            h = h + y
+            h = h + (_drop_path(y, drop.pop(0)) if drop is not None else y)
         p = f"layers.{li}.downsample."
         if (p + "reduction.weight") in s:
             y = h.view(B, H, W, C)

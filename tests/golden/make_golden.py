@@ -214,8 +214,121 @@ def swin_fixture():
             "train_loss": float(loss.detach()), "grad_norms": _grad_norms(ref.named_parameters())}
 
 
+class _ScriptedRand:
+    """Replays a fixed sequence of uniforms through ``torch.rand`` (the only RNG call of the reference's drop_path)."""
+
+    def __init__(self, us):
+        self.us, self.i = us, 0
+
+    def __enter__(self):
+        self._orig = torch.rand
+
+        def fake(*shape, **kw):
+            shape = shape[0] if len(shape) == 1 and isinstance(shape[0], (tuple, list, torch.Size)) else shape
+            u = self.us[self.i]
+            self.i += 1
+            return u.to(kw.get("dtype") or torch.float32).view(*shape)
+
+        torch.rand = fake
+        return self
+
+    def __exit__(self, *exc):
+        torch.rand = self._orig
+
+
+def drop_entries(blocks_probs, us, per_block):
+    """Oracle ``drop`` list for blocks with the given drop probabilities (``per_block`` drop_path applications each)."""
+    out, i = [], 0
+    for p in blocks_probs:
+        for _ in range(per_block):
+            if p and p > 0:
+                keep = 1.0 - p
+                out.append(((keep + us[i]).floor(), keep))
+                i += 1
+            else:
+                out.append(None)
+    return out, i
+
+
+def _timm_drop_path_shim():
+    """timm 0.4.12 ``DropPath`` (the version classification/swin_transformer/README.md:7-13 pins): the published rand/floor
+    algorithm, identical to the drop_path function the ConvNeXt / ViT sub-projects carry."""
+
+    class DropPath(torch.nn.Module):
+        def __init__(self, drop_prob=None):
+            super().__init__()
+            self.drop_prob = drop_prob
+
+        def forward(self, x):
+            if self.drop_prob == 0. or not self.training:
+                return x
+            keep_prob = 1 - self.drop_prob
+            shape = (x.shape[0],) + (1,) * (x.ndim - 1)
+            random_tensor = keep_prob + torch.rand(shape, dtype=x.dtype, device=x.device)
+            random_tensor.floor_()
+            return x.div(keep_prob) * random_tensor
+
+    return DropPath
+
+
+def droppath_fixture():
+    """Stochastic depth ON (the reference's real recipes: convnext_tiny 0.2, SwinTransformer() 0.1, ViT 0.1): the reference's
+    train-mode forward/backward with torch.rand scripted == the oracle fed the same per-sample masks, bit for bit."""
+    from oracle import convnext as oc, swin as osw, vit as ov
+
+    B = 4
+    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(11))
+    y = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(12))
+    us = [torch.rand(B, generator=torch.Generator().manual_seed(100 + i)) for i in range(64)]
+    out = {"seeds": {"x": 11, "labels": 12, "u0": 100}, "batch": B}
+
+    def run(ref, probs, per_block, oracle_grads, **kw):
+        sr = {k: v.clone() for k, v in ref.state_dict().items()}
+        ref.train()
+        with _ScriptedRand(us) as sc:
+            lt = ref(x)
+            used = sc.i
+        loss = F.cross_entropy(lt, y)
+        loss.backward()
+        drop, n = drop_entries(probs, us, per_block)
+        assert n == used and used > 0, (n, used)
+        assert any(e is not None and float(e[0].min()) == 0.0 for e in drop), "no sample was dropped: pick other seeds"
+        lg, lo, grads = oracle_grads(sr, x, y, drop=drop, **kw)
+        assert torch.equal(lg, lt.detach()) and float(lo) == float(loss.detach())
+        for n_, p in ref.named_parameters():
+            assert torch.equal(p.grad, grads[n_]), n_
+        return {"train_loss": float(loss.detach()), "train_logits": lt.detach().clone(), "grad_norms": _grad_norms(ref.named_parameters()),
+                "rand_calls": used}
+
+    ref_mod = _load(f"{REF}/classification/convNext/models/networks.py", "ref_convnext_networks_dp")
+    torch.manual_seed(0)
+    ref = ref_mod.convnext_tiny(1000)          # drop_path_rate 0.2 hard-coded (networks.py:178)
+    probs = [getattr(b.drop_path, "drop_prob", 0.0) for st in ref.stages for b in st]
+    out["convnext_tiny"] = run(ref, probs, 1, oc.train_step_grads)
+
+    ref_mod = _load(f"{REF}/classification/vision_transformer/vit_model.py", "ref_vit_model_dp")
+    torch.manual_seed(0)
+    ref = ref_mod.VisionTransformer(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, representation_size=768,
+                                    num_classes=1000, drop_path_ratio=0.1)
+    probs = [getattr(b.drop_path, "drop_prob", 0.0) for b in ref.blocks]
+    out["vit_b16"] = run(ref, probs, 2, ov.train_step_grads)
+
+    sys.modules.pop("timm.models.layers", None)
+    _shim("timm")
+    _shim("timm.models")
+    _shim("timm.models.layers", DropPath=_timm_drop_path_shim(), trunc_normal_=torch.nn.init.trunc_normal_,
+          to_2tuple=lambda v: tuple(v) if isinstance(v, (tuple, list)) else (v, v))
+    ref_mod = _load(f"{REF}/classification/swin_transformer/models/swin_transformer.py", "ref_swin_transformer_dp")
+    torch.manual_seed(0)
+    ref = ref_mod.SwinTransformer()            # class default drop_path_rate 0.1
+    probs = [getattr(b.drop_path, "drop_prob", 0.0) for l in ref.layers for b in l.blocks]
+    out["swin_tiny"] = run(ref, probs, 2, osw.train_step_grads)
+    sys.modules.pop("timm.models.layers", None)
+    return out
+
+
 FIXTURES = {"resnet50": resnet50_fixture, "mnist": mnist_fixture, "vit_b16": vit_fixture, "convnext_tiny": convnext_fixture,
-            "swin_tiny": swin_fixture}
+            "swin_tiny": swin_fixture, "droppath": droppath_fixture}
 
 if __name__ == "__main__":
     torch.set_num_threads(8)

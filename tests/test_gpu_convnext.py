@@ -152,11 +152,14 @@ def test_convnext_train_step_parity(depths, std, gamma):
     print(f"worst grad rel-L2 error {worst[0]:.3g} at {worst[1]}")
 
 
-def test_convnext_drop_path_training_raises():
+def test_convnext_tiny_default_ctor_runs_in_train_and_eval():
+    """convnext_tiny(n) keeps the reference's hard-coded drop_path_rate 0.2 (:178) and trains (tests/test_gpu_droppath.py
+    checks the numbers against the oracle with shared masks)."""
     from deeplearning_b200.classification.convNext.models.networks import convnext_tiny
 
-    m = convnext_tiny(10).cuda().train()  # hard-coded drop_path_rate 0.2 (reference :178)
-    with pytest.raises(NotImplementedError):
-        m(torch.randn(2, 3, 224, 224, device="cuda"))
+    m = convnext_tiny(10).cuda().train()
+    out = m(torch.randn(2, 3, 224, 224, device="cuda"))
+    out.sum().backward()
+    assert out.shape == (2, 10) and torch.isfinite(out).all() and torch.isfinite(m.head.weight.grad).all()
     m.eval()
     assert m(torch.randn(2, 3, 224, 224, device="cuda")).shape == (2, 10)

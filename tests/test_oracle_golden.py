@@ -135,3 +135,58 @@ def test_swin_tiny_init_and_oracle_match_reference():
     for n, g in grads.items():
         ref = fx["grad_norms"][n]
         assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
+
+
+def _drop_entries(probs, per_block, batch, u0):
+    """The oracle's ``drop`` list from the scripted uniforms of make_golden.droppath_fixture (seed u0 + call index)."""
+    out, i = [], 0
+    for p in probs:
+        for _ in range(per_block):
+            if p and p > 0:
+                keep = 1.0 - p
+                u = torch.rand(batch, generator=torch.Generator().manual_seed(u0 + i))
+                out.append(((keep + u).floor(), keep))
+                i += 1
+            else:
+                out.append(None)
+    return out, i
+
+
+@pytest.mark.parametrize("name", ["convnext_tiny", "vit_b16", "swin_tiny"])
+def test_droppath_oracle_matches_reference(name):
+    """Stochastic depth at the reference's own default rates (convnext_tiny 0.2, VisionTransformer(drop_path_ratio=0.1) with
+    pre_logits, SwinTransformer() 0.1): the oracle fed the scripted per-sample masks reproduces the reference's loss /
+    logits / gradient norms recorded by make_golden.py (there: bit-identical to the reference with torch.rand scripted)."""
+    fx = FX["droppath"]
+    B = fx["batch"]
+    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(fx["seeds"]["x"]))
+    y = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(fx["seeds"]["labels"]))
+    torch.manual_seed(0)
+    if name == "convnext_tiny":
+        from deeplearning_b200.classification.convNext.models.networks import convnext_tiny
+        from oracle.convnext import train_step_grads
+
+        m = convnext_tiny(1000)
+        probs, per = [getattr(b.drop_path, "drop_prob", 0.0) for st in m.stages for b in st], 1
+    elif name == "vit_b16":
+        from deeplearning_b200.classification.vision_transformer.vit_model import VisionTransformer
+        from oracle.vit import train_step_grads
+
+        m = VisionTransformer(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, representation_size=768,
+                              num_classes=1000, drop_path_ratio=0.1)
+        probs, per = [getattr(b.drop_path, "drop_prob", 0.0) for b in m.blocks], 2
+    else:
+        from deeplearning_b200.classification.swin_transformer.models.swin_transformer import SwinTransformer
+        from oracle.swin import train_step_grads
+
+        m = SwinTransformer()
+        probs, per = [getattr(b.drop_path, "drop_prob", 0.0) for l in m.layers for b in l.blocks], 2
+    drop, calls = _drop_entries(probs, per, B, fx["seeds"]["u0"])
+    assert calls == fx[name]["rand_calls"]
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    logits, loss, grads = train_step_grads(state, x, y, drop=drop)
+    _close(logits, fx[name]["train_logits"])
+    assert abs(float(loss) - fx[name]["train_loss"]) < 1e-3
+    for n, g in grads.items():
+        ref = fx[name]["grad_norms"][n]
+        assert abs(float(g.double().norm()) - ref) <= 2e-3 * (ref + 1e-6), n
