@@ -4,6 +4,7 @@
 #include <string.h>
 #include "../../include/b200cls.h"
 #include "conv_gemm.cuh"
+#include "conv1x1_stream.cuh"
 #include "host_utils.h"
 #include "wgrad_gemm.cuh"
 
@@ -191,6 +192,8 @@ int epilogue_flags(const ConvGemmParams& p) {
   if (p.out_direct) f |= kEpiDirect;
   if (p.stats) f |= kEpiStats;
   if (p.rowscale) f |= kEpiRowscale;
+  if (p.affine) f = (f & ~(kEpiBias | kEpiColscale)) | kEpiAffine;   // colscale / bias carry the BatchNorm scale / shift
+  if (p.mask_in) f |= kEpiMask;
   return f;
 }
 
@@ -206,7 +209,9 @@ int epilogue_flags(const ConvGemmParams& p) {
   X(3 << kEpiActShift)                                    /* fc2 dgrad * GELU'(pre)                  */  \
   X((3 << kEpiActShift) | kEpiStats)                      /* ... + column sums = fc1 bias gradient   */  \
   X(kEpiOutF32)                                           /* Swin patch-merging reduction            */  \
-  X(kEpiBias | kEpiOutF32)                                /* ConvNeXt downsample conv                */
+  X(kEpiBias | kEpiOutF32)                                /* ConvNeXt downsample conv                */  \
+  X(kEpiAffine | kEpiResBf16 | (1 << kEpiActShift))       /* bottleneck conv3: relu(bn(conv) + identity) */ \
+  X(kEpiMask | kEpiResBf16 | kEpiStats)                   /* dgrad + identity gradient, ReLU mask, sum dz */
 
 // ---- CTA-pair GEMM (tcgen05 cta_group::2): the 256-wide linear layers of the transformer / ConvNeXt paths run as pairs
 // of CTAs on one 256-pixel x 256-channel tile (each CTA stages half of the B tile).  Validated on B200 in round 2 (bit-exact
@@ -291,6 +296,75 @@ int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
     default:
       return launch_conv_gemm_epi<BLOCK_N, kEpiGeneric>(q, grid, st);
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Streaming kernel for the narrow-K -> wide-N 1x1 layers (conv1x1_stream.cuh): K in {64, 128}, N % 256 == 0, pixels % 128 == 0.
+bool stream_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_STREAM");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+bool stream_ok(long long pixels, int K, int N) {
+  return stream_enabled() && (K == 64 || K == 128) && N % 256 == 0 && pixels % 128 == 0 && pixels / 128 < (1LL << 30);
+}
+int stream_grid(long long pixels, int N) {
+  const int n_tiles = N / 256;
+  const long long items = pixels / 128 * n_tiles;
+  int grid = items < device_sm_count() ? static_cast<int>(items) : device_sm_count();
+  return grid / n_tiles * n_tiles;
+}
+
+template <int KB, int MODE>
+int launch_stream(const StreamParams& q, int grid, cudaStream_t st) {
+  using Cfg = StreamCfg<KB, MODE>;
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv1x1_stream_kernel<KB, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  conv1x1_stream_kernel<KB, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
+  B200_LAUNCHED();
+  return OK;
+}
+
+// a: [pixels][K], w: [N][K], out / res / mask: [pixels][N]
+int run_stream(int mode, const void* a, const void* w, void* out, const void* res, const void* mask, const float* scale,
+               const float* shift, float* stats, long long pixels, int K, int N, cudaStream_t st) {
+  StreamParams q;
+  memset(&q, 0, sizeof(q));
+  int rc;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(pixels)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(K)};
+    uint32_t box[2] = {64, 128};
+    if ((rc = encode_tmap_bf16(&q.a_map, a, 2, dims, strides, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K), static_cast<uint64_t>(N)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(K)};
+    uint32_t box[2] = {64, 256};
+    if ((rc = encode_tmap_bf16(&q.b_map, w, 2, dims, strides, box))) return rc;
+  }
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(N), static_cast<uint64_t>(pixels)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(N)};
+    uint32_t box[2] = {64, 32};
+    if ((rc = encode_tmap_bf16(&q.out_map, out, 2, dims, strides, box))) return rc;
+    if ((rc = encode_tmap_bf16(&q.res_map, res, 2, dims, strides, box))) return rc;
+    if (mask != nullptr && (rc = encode_tmap_bf16(&q.mask_map, mask, 2, dims, strides, box))) return rc;
+  }
+  q.m_tiles = static_cast<int>(pixels / 128);
+  q.n_tiles = N / 256;
+  q.N = N;
+  q.scale = scale, q.shift = shift, q.stats = stats;
+  const int grid = stream_grid(pixels, N);
+  if (mode == kStreamBnRelu) return K == 64 ? launch_stream<1, kStreamBnRelu>(q, grid, st) : launch_stream<2, kStreamBnRelu>(q, grid, st);
+  return K == 64 ? launch_stream<1, kStreamMask>(q, grid, st) : launch_stream<2, kStreamMask>(q, grid, st);
 }
 
 int dispatch_conv_gemm(ConvGemmParams& p, int N, cudaStream_t st) {
@@ -824,6 +898,114 @@ int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* work
   launch_wgrad_reduce(p.partial, g, pl.splits, Cout, Cin, taps, 0, nullptr, st);
   B200_LAUNCHED();
   return OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BatchNorm folded through a 1x1 convolution (ResNet bottleneck conv3, engine/resnet.py "algebra" path).
+
+int b200_conv1x1_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
+                            void* y, long long pixels, int Cin, int Cout, int relu, void* stream) {
+  B200_REQUIRE(pixels > 0 && Cin % 64 == 0 && Cout % 64 == 0, "conv1x1_bn_act_fwd: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+  B200_REQUIRE(scale != nullptr && shift != nullptr && residual != nullptr && relu == 1,
+               "conv1x1_bn_act_fwd: implemented for relu(bn(conv) + residual)");
+  if (stream_ok(pixels, Cin, Cout))
+    return run_stream(kStreamBnRelu, x, w, y, residual, nullptr, scale, shift, nullptr, pixels, Cin, Cout,
+                      static_cast<cudaStream_t>(stream));
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  View dv = make_flat_view(y, pixels, Cout);
+  if ((rc = setup_output(p, dv, Cout, 0, nullptr))) return rc;
+  const Box3 bx = box_of(p);
+  p.k_per_tap = Cin;
+  p.k_blocks_per_tap = Cin / 64;
+  p.num_taps = 1;
+  if ((rc = encode_view(&p.a_maps[0], make_flat_view(x, pixels, Cin), bx))) return rc;
+  for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Cin), static_cast<uint64_t>(Cout)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(Cin)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(block_n_for(Cout))};
+    if ((rc = encode_tmap_bf16(&p.b_map, w, 2, dims, strides, box))) return rc;
+  }
+  p.affine = 1;
+  p.colscale = scale;
+  p.bias = shift;
+  p.act = 1;
+  p.residual = residual;
+  p.rs1 = static_cast<long long>(dv.strides[1]);
+  p.rs2 = static_cast<long long>(dv.strides[2]);
+  p.rs3 = static_cast<long long>(dv.strides[3]);
+  return dispatch_conv_gemm(p, Cout, static_cast<cudaStream_t>(stream));
+}
+
+int b200_conv1x1_dgrad_masked_stats_rows(long long pixels, int Cin) {
+  // (the streaming kernel and the generic one write the same number of partial rows: one per CTA group and TMEM quadrant)
+  return b200_conv2d_fwd_stats_rows(1, 1, static_cast<int>(pixels), Cin, 1, 1);
+}
+
+int b200_conv1x1_dgrad_masked(const void* dy, const void* wd, void* dx, long long pixels, int Cin, int Cout,
+                              const void* residual, const void* mask_src, float* stats, void* stream) {
+  B200_REQUIRE(pixels > 0 && Cin % 64 == 0 && Cout % 64 == 0, "conv1x1_dgrad_masked: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+  B200_REQUIRE(residual != nullptr && mask_src != nullptr && stats != nullptr, "conv1x1_dgrad_masked: residual, mask and stats are required");
+  if (stream_ok(pixels, Cout, Cin))
+    return run_stream(kStreamMask, dy, wd, dx, residual, mask_src, nullptr, nullptr, stats, pixels, Cout, Cin,
+                      static_cast<cudaStream_t>(stream));
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  View dv = make_flat_view(dx, pixels, Cin);
+  if ((rc = setup_output(p, dv, Cin, 0, nullptr))) return rc;
+  const Box3 bx = box_of(p);
+  p.k_per_tap = Cout;
+  p.k_blocks_per_tap = Cout / 64;
+  p.num_taps = 1;
+  if ((rc = encode_view(&p.a_maps[0], make_flat_view(dy, pixels, Cout), bx))) return rc;
+  for (int i = 1; i < 4; ++i) p.a_maps[i] = p.a_maps[0];
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(Cout), static_cast<uint64_t>(Cin)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(Cout)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(block_n_for(Cin))};
+    if ((rc = encode_tmap_bf16(&p.b_map, wd, 2, dims, strides, box))) return rc;
+  }
+  p.residual = residual;
+  p.rs1 = static_cast<long long>(dv.strides[1]);
+  p.rs2 = static_cast<long long>(dv.strides[2]);
+  p.rs3 = static_cast<long long>(dv.strides[3]);
+  p.mask_in = static_cast<const __nv_bfloat16*>(mask_src);
+  p.ms1 = p.rs1, p.ms2 = p.rs2, p.ms3 = p.rs3;
+  p.stats = stats;
+  return dispatch_conv_gemm(p, Cin, static_cast<cudaStream_t>(stream));
+}
+
+int b200_gemm_dual(const void* a0, int K0, const void* a1, int K1, const void* wcat, const float* bias, void* out,
+                   long long pixels, int N, void* stream) {
+  B200_REQUIRE(pixels > 0 && K0 % 64 == 0 && K1 % 64 == 0 && N % 8 == 0, "gemm_dual: K0=%d / K1=%d must be multiples of 64", K0, K1);
+  ConvGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  View dv = make_flat_view(out, pixels, N);
+  if ((rc = setup_output(p, dv, N, 0, nullptr))) return rc;
+  const Box3 bx = box_of(p);
+  if ((rc = encode_view(&p.a_maps[0], make_flat_view(a0, pixels, K0), bx))) return rc;
+  if ((rc = encode_view(&p.a_maps[1], make_flat_view(a1, pixels, K1), bx))) return rc;
+  p.a_maps[2] = p.a_maps[0], p.a_maps[3] = p.a_maps[0];
+  p.num_taps = 2;
+  p.k_per_tap = K0;
+  p.k_blocks_per_tap = K0 / 64;
+  p.var_taps = 1;
+  p.tap_map[0] = 0, p.tap_map[1] = 1;
+  p.tap_kb[0] = static_cast<int16_t>(K0 / 64), p.tap_kb[1] = static_cast<int16_t>(K1 / 64);
+  p.tap_k0[0] = 0, p.tap_k0[1] = K0;
+  p.kb_total = (K0 + K1) / 64;
+  {
+    uint64_t dims[2] = {static_cast<uint64_t>(K0 + K1), static_cast<uint64_t>(N)};
+    uint64_t strides[2] = {1, static_cast<uint64_t>(K0 + K1)};
+    uint32_t box[2] = {64, static_cast<uint32_t>(block_n_for(N))};
+    if ((rc = encode_tmap_bf16(&p.b_map, wcat, 2, dims, strides, box))) return rc;
+  }
+  p.bias = bias;
+  return dispatch_conv_gemm(p, N, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

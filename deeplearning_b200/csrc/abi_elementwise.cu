@@ -3,6 +3,7 @@
 
 #include "../../include/b200cls.h"
 #include "elementwise.cuh"
+#include "bn_algebra.cuh"
 #include "host_utils.h"
 
 using namespace b200;
@@ -282,6 +283,35 @@ int b200_tanh_bwd(const void* dt_bf16, const float* t, void* du_bf16, long long 
   B200_REQUIRE(n > 0, "tanh_bwd: empty input");
   tanh_bwd_kernel<<<ew_grid(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(dt_bf16), t, static_cast<__nv_bfloat16*>(du_bf16), n);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_bn_gram_stats(const float* G, const float* s, const void* w_bf16, int N, int K, double count, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift, void* stream) {
+  B200_REQUIRE(N > 0 && K >= 32 && K <= 256 && K % 32 == 0 && count > 0, "bn_gram_stats: N=%d K=%d (K must be 32..256, multiple of 32)", N, K);
+  const size_t smem = static_cast<size_t>(5) * K * sizeof(float);
+  bn_gram_stats_kernel<<<(N + 3) / 4, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      G, s, static_cast<const __nv_bfloat16*>(w_bf16), N, K, count, gamma, beta, eps, momentum, running_mean, running_var,
+      num_batches_tracked, mean, invstd, scale, shift);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_bn_conv1x1_bwd(const float* dz_partial, int T, const float* D, const float* G, const float* s, const void* w_bf16,
+                        const float* w_f32, int N, int K, double count, const float* gamma, const float* mean,
+                        const float* invstd, float* dgamma, float* dbeta, float* dW, int accumulate, void* wcat, float* bias,
+                        void* coef_scratch, void* stream) {
+  B200_REQUIRE(N > 0 && T > 0 && K >= 32 && K <= 256 && K % 32 == 0 && count > 0, "bn_conv1x1_bwd: N=%d K=%d T=%d unsupported", N, K, T);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  bn_conv1x1_bwd_rows_kernel<<<(N + 3) / 4, 128, static_cast<size_t>(4) * K * sizeof(float), st>>>(
+      dz_partial, T, D, G, s, static_cast<const __nv_bfloat16*>(w_bf16), w_f32, N, K, count, gamma, mean, invstd, dgamma, dbeta,
+      dW, accumulate, static_cast<__nv_bfloat16*>(wcat), static_cast<float2*>(coef_scratch));
+  B200_LAUNCHED();
+  bn_conv1x1_bwd_m_kernel<<<dim3(K / 32, K / 32), 256, 0, st>>>(
+      static_cast<const float2*>(coef_scratch), static_cast<const __nv_bfloat16*>(w_bf16), w_f32, N, K,
+      static_cast<__nv_bfloat16*>(wcat), bias);
   B200_LAUNCHED();
   return OK;
 }

@@ -1,0 +1,244 @@
+// Train-mode BatchNorm folded THROUGH a 1x1 convolution (ResNet bottleneck conv3 -> bn3 -> (+identity) -> ReLU,
+// classification/resnet/models/networks.py:116-124), so that the wide conv output c = y2 W^T is never written to HBM.
+//
+// With y2 [P x K] (the narrow input, K = 64..256 channels), W [N x K], c[p,o] = sum_j y2[p,j] W[o,j]:
+//
+//   forward statistics   sum_p c[p,o]   = W[o,:] . s            s = colsum(y2)          [K]
+//                        sum_p c[p,o]^2 = W[o,:] G W[o,:]^T     G = y2^T y2             [K x K]  (one small tensor-core GEMM)
+//     -> mean / invstd / scale / shift without a pass over c; the conv then applies  relu(acc * scale + shift + identity)
+//        in its epilogue (conv_gemm.cuh kEpiAffine) and writes the block output directly.
+//
+//   backward  (dz = relu mask * upstream gradient,  dc = a dz + b c + k  per channel, the BatchNorm backward formula with
+//              a = gamma invstd,  b = -a invstd mean(dz xhat),  k = -a mean(dz) - b mu)
+//     D = dz^T y2 [N x K]   (the ordinary wgrad GEMM, on dz instead of dc)
+//     sum_p dz c  = rowsum(W .* D)                      -> dgamma, dbeta, a, b, k        (no pass over c)
+//     dW = a D + b (W G) + k s^T                         (weight gradient of the conv)
+//     g2 = dc W = dz (diag(a) W) + y2 (W^T diag(b) W) + k W   -> ONE GEMM over [dz | y2] with the packed operand
+//          Wcat[i][0..N) = a_o W[o,i],  Wcat[i][N + j] = M[j][i] = sum_o b_o W[o,j] W[o,i],  bias[i] = sum_o k_o W[o,i]
+//
+// c enters only through exact (fp32-accumulated) products of y2 and the bf16 weights the tensor cores used, i.e. the
+// un-rounded conv output: closer to the fp32 reference than statistics of a bf16-rounded c.  Small-matrix work below runs
+// in fp64 / fp32 on the CUDA cores (N K^2 MACs: 1 M for layer1 ... 67 M for layer3).
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per output channel o (4 per block).  G fp32 [K][K] (symmetric), s fp32 [K], Wb bf16 [N][K] (the forward operand).
+// Writes mean / invstd / scale / shift and updates the running statistics like nn.BatchNorm2d (momentum, unbiased var).
+// The row loop is unrolled by 8 so that 8 x K/32 independent loads are in flight per lane (the loop is latency-bound).
+__global__ void __launch_bounds__(128) bn_gram_stats_kernel(const float* __restrict__ G, const float* __restrict__ s,
+                                                            const __nv_bfloat16* __restrict__ Wb, int N, int K, double count,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, float momentum, float* running_mean,
+                                                            float* running_var, long long* num_batches, float* mean_out,
+                                                            float* invstd_out, float* scale_out, float* shift_out) {
+  extern __shared__ float sm_gs[];   // [4 warps][K] weights of the warp's channel, then [K] column means
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 4 + warp;
+  float* w = sm_gs + warp * K;
+  float* m = sm_gs + 4 * K;
+  const double inv_n = 1.0 / count;
+  const float inv_nf = static_cast<float>(inv_n);
+  for (int j = threadIdx.x; j < K; j += blockDim.x) m[j] = static_cast<float>(static_cast<double>(s[j]) * inv_n);
+  if (o < N)
+    for (int j = lane; j < K; j += 32) w[j] = __bfloat162float(Wb[static_cast<long long>(o) * K + j]);
+  __syncthreads();
+  if (o >= N) return;
+  // acc_j = sum_i w_i Cov[i][j],  Cov = G / count - m m^T   (lane owns columns j = lane + 32 q; fp32 products, fp64 sums)
+  double acc[8];   // K <= 256
+  float mj[8];
+  const int nq = K / 32;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    acc[q] = 0.0;
+    mj[q] = q < nq ? m[lane + 32 * q] : 0.f;
+  }
+  for (int i0 = 0; i0 < K; i0 += 8) {
+    float gv[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < nq) gv[r][q] = __ldg(G + static_cast<long long>(i0 + r) * K + lane + 32 * q);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float wi = w[i0 + r], mi = m[i0 + r];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < nq) acc[q] += static_cast<double>(wi * fmaf(gv[r][q], inv_nf, -mi * mj[q]));
+    }
+  }
+  double var = 0.0, mean = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    if (q < nq) {
+      const int j = lane + 32 * q;
+      var += acc[q] * static_cast<double>(w[j]);
+      mean += static_cast<double>(w[j]) * static_cast<double>(m[j]);
+    }
+  }
+  var = warp_sum_d(var);
+  mean = warp_sum_d(mean);
+  if (lane == 0) {
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + static_cast<double>(eps));
+    const float g = gamma ? gamma[o] : 1.0f, b = beta ? beta[o] : 0.0f;
+    mean_out[o] = static_cast<float>(mean);
+    invstd_out[o] = static_cast<float>(invstd);
+    scale_out[o] = static_cast<float>(g * invstd);
+    shift_out[o] = static_cast<float>(b - mean * g * invstd);
+    if (running_mean) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      running_mean[o] = static_cast<float>((1.0 - momentum) * running_mean[o] + momentum * mean);
+      running_var[o] = static_cast<float>((1.0 - momentum) * running_var[o] + momentum * unbiased);
+    }
+    if (num_batches && o == 0) *num_batches += 1;
+  }
+}
+
+// Backward, per output channel o (one warp each, 4 per block):
+//   sum_dz from the partial rows dz_partial[T][2][N] (plane 0), D fp32 [N][K] (raw dz^T y2), G, s, Wb as above, W fp32 [N][K]
+//   (the master weights, for the data-gradient operand), mean / invstd / gamma of the BatchNorm.
+// Writes dgamma[o], dbeta[o] (optionally accumulating), dW[o][:] = a D + b (Wb G) + k s (optionally accumulating),
+// the bf16 column o of the dgrad operand wcat[i][o] = a_o W[o][i] (ld = N + K) and coef[o] = {b_o, k_o} for the M kernel.
+__global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
+    const float* __restrict__ dz_partial, int T, const float* __restrict__ D, const float* __restrict__ G,
+    const float* __restrict__ s, const __nv_bfloat16* __restrict__ Wb, const float* __restrict__ W, int N, int K, double count,
+    const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma,
+    float* dbeta, float* dW, int accumulate, __nv_bfloat16* __restrict__ wcat, float2* __restrict__ coef) {
+  extern __shared__ float sm_f[];   // [4 warps][K] bf16 weights (as float) of the warp's channel
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 4 + warp;
+  if (o >= N) return;
+  float* wb = sm_f + warp * K;
+  const long long row = static_cast<long long>(o) * K;
+  const int nq = K / 32;
+  float dv[8], wv[8];
+  double t = 0.0;   // sum_j Wb[o][j] D[o][j] = sum_p dz[p,o] c[p,o]
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    if (x < nq) {
+      const int j = lane + 32 * x;
+      const float v = __bfloat162float(Wb[row + j]);
+      wb[j] = v;
+      dv[x] = D[row + j];
+      wv[x] = W[row + j];
+      t += static_cast<double>(v) * static_cast<double>(dv[x]);
+    }
+  }
+  // column sum of dz: T partial rows, 8 independent loads in flight per lane
+  float sd[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) sd[x] = 0.f;
+  for (int r0 = lane; r0 < T; r0 += 256) {
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+      const int r = r0 + 32 * x;
+      if (r < T) sd[x] += __ldg(dz_partial + (static_cast<long long>(r) * 2) * N + o);
+    }
+  }
+  double sdz = 0.0;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) sdz += static_cast<double>(sd[x]);
+  t = warp_sum_d(t);
+  sdz = warp_sum_d(sdz);
+  __syncwarp();
+  const double mu = mean[o], is = invstd[o], g = gamma ? gamma[o] : 1.0f;
+  const double dg = is * (t - mu * sdz);   // sum dz * xhat
+  const double a = g * is;
+  const double b = -a * is * (dg / count);
+  const double k = -a * (sdz / count) - b * mu;
+  if (lane == 0) {
+    dgamma[o] = accumulate ? dgamma[o] + static_cast<float>(dg) : static_cast<float>(dg);
+    dbeta[o] = accumulate ? dbeta[o] + static_cast<float>(sdz) : static_cast<float>(sdz);
+    coef[o] = make_float2(static_cast<float>(b), static_cast<float>(k));
+  }
+  // q_j = sum_i Wb[o][i] G[i][j]   (lane owns j = lane + 32 x; 8 rows of G in flight)
+  float q[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) q[x] = 0.f;
+  for (int i0 = 0; i0 < K; i0 += 8) {
+    float gv[8][8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int x = 0; x < 8; ++x)
+        if (x < nq) gv[r][x] = __ldg(G + static_cast<long long>(i0 + r) * K + lane + 32 * x);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const float wi = wb[i0 + r];
+#pragma unroll
+      for (int x = 0; x < 8; ++x)
+        if (x < nq) q[x] = fmaf(wi, gv[r][x], q[x]);
+    }
+  }
+  const float af = static_cast<float>(a), bf = static_cast<float>(b), kf = static_cast<float>(k);
+  const int ld = N + K;
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    if (x < nq) {
+      const int j = lane + 32 * x;
+      const float v = af * dv[x] + bf * q[x] + kf * s[j];
+      dW[row + j] = accumulate ? dW[row + j] + v : v;
+      wcat[static_cast<long long>(j) * ld + o] = __float2bfloat16(af * wv[x]);
+    }
+  }
+}
+
+// M[j][i] = sum_o b_o Wb[o][j] W[o][i]  ->  wcat[i][N + j];   bias[i] = sum_o k_o W[o][i].
+// grid (K/32, K/32): a block computes a 32 x 32 tile of M; the reduction over o runs in chunks of 32 rows staged through
+// shared memory (coalesced loads, 32 rows in flight); thread = (i, 4 values of j).  Blocks with blockIdx.y == 0 also produce
+// their 32 entries of the bias.
+__global__ void __launch_bounds__(256) bn_conv1x1_bwd_m_kernel(const float2* __restrict__ coef, const __nv_bfloat16* __restrict__ Wb,
+                                                               const float* __restrict__ W, int N, int K,
+                                                               __nv_bfloat16* __restrict__ wcat, float* __restrict__ bias) {
+  __shared__ float sa[32][33];   // b_o * Wb[o][j0 + .]
+  __shared__ float sw[32][33];   // W[o][i0 + .]
+  __shared__ float sk[32];       // k_o
+  const int ti = threadIdx.x & 31, tq = threadIdx.x >> 5;   // i = i0 + ti; j = j0 + tq * 4 + {0..3}
+  const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
+  for (int o0 = 0; o0 < N; o0 += 32) {
+    // 256 threads load 32 x 32 of each operand: thread (ti, tq) loads rows tq*4 .. tq*4+3, column ti
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int o = o0 + tq * 4 + r;
+      float av = 0.f, wv = 0.f;
+      if (o < N) {
+        const long long base = static_cast<long long>(o) * K;
+        const float2 c = coef[o];
+        av = c.x * __bfloat162float(Wb[base + j0 + ti]);
+        wv = W[base + i0 + ti];
+        if (ti == 0) sk[tq * 4 + r] = c.y;
+      } else if (ti == 0) {
+        sk[tq * 4 + r] = 0.f;
+      }
+      sa[tq * 4 + r][ti] = av;
+      sw[tq * 4 + r][ti] = wv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 0; o < 32; ++o) {
+      const float wv = sw[o][ti];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) acc[x] = fmaf(sa[o][tq * 4 + x], wv, acc[x]);
+      if (tq == 0) accb = fmaf(sk[o], wv, accb);
+    }
+    __syncthreads();
+  }
+  const long long ld = N + K;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) wcat[static_cast<long long>(i0 + ti) * ld + N + j0 + tq * 4 + x] = __float2bfloat16(acc[x]);
+  if (blockIdx.y == 0 && tq == 0) bias[i0 + ti] = accb;
+}
+
+}  // namespace b200

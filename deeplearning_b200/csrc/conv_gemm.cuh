@@ -61,6 +61,17 @@ struct alignas(64) ConvGemmParams {
   // residual add: sample = flat output pixel / rows_per_sample  (drop_path of the reference: convNext/models/networks.py:11-26)
   const float* rowscale;
   int rows_per_sample;
+  // --- K made of several sources of different widths (dual-source dgrad of the BN-algebra path, [dz | y2] x [aW | M]^T):
+  // with var_taps != 0 tap t spans tap_kb[t] k-blocks of activation view tap_map[t] (channel offset cb * 64) and multiplies
+  // the weight columns starting at tap_k0[t]; kb_total = sum of tap_kb.
+  int var_taps;
+  int kb_total;
+  int16_t tap_kb[kMaxTaps];
+  int32_t tap_k0[kMaxTaps];
+  // --- kEpiMask: tensor whose sign decides which outputs survive (ReLU mask of the block output), pixel strides ms1..ms3
+  const __nv_bfloat16* mask_in;
+  long long ms1, ms2, ms3;
+  int affine;               // host-side: kEpiAffine (colscale = BN scale, bias = BN shift)
 };
 
 template <int BLOCK_N, bool kPair = false>
@@ -158,7 +169,12 @@ __device__ __forceinline__ void gelu_erf_grad_mul2(float a0, float a1, float& f0
 constexpr int kEpiGeneric = -1;
 constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEpiResBf16 = 16, kEpiResF32 = 32,
               kEpiAux = 64, kEpiOutF32 = 128, kEpiDirect = 256, kEpiStats = 512,
-              kEpiRowscale = 1024 /* never specialised: selects the generic kernel */;
+              kEpiRowscale = 1024 /* never specialised: selects the generic kernel */,
+              // BatchNorm folded into a 1x1 convolution (specialised kernels only):
+              //   kEpiAffine: f = f * colscale[n] + bias[n]  (scale / shift of the batch statistics) BEFORE the residual add,
+              //               and the ReLU (act == 1) moves AFTER the residual add:  y = relu(bn(conv) + identity)
+              //   kEpiMask:   after the residual add, f = mask_in > 0 ? f : 0      (dz = relu'(y) * (dgrad + identity gradient))
+              kEpiAffine = 2048, kEpiMask = 4096;
 
 // kPair (validated on B200, default for the 256-wide linear layers, see abi_conv.cu gemm_pair_enabled()): the two CTAs of a cluster
 // compute one 256-pixel x 256-channel tile with tcgen05.mma.cta_group::2. Each CTA stages its own 128 pixels of A and HALF
@@ -191,7 +207,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
   //  instantiations compile to exactly the code they had before the pair mode existed - checked by diffing the SASS)
 #define B200_TILE_FIRST (kPair ? (blockIdx.x >> 1) : blockIdx.x)
 #define B200_TILE_STEP (kPair ? (gridDim.x >> 1) : gridDim.x)
-  const int num_kb = p.num_taps * p.k_blocks_per_tap;
+  const int num_kb = p.var_taps ? p.kb_total : p.num_taps * p.k_blocks_per_tap;
   // Epilogue work units: 64 bf16 (or 32 fp32) channels x one warp's 32 rows. Two warps share a TMEM lane quadrant and
   // take alternate units; with a single unit per tile the second warp of each pair has nothing to do.
   const int unit_cols = ((EPI < 0) ? (p.out_f32 != 0) : ((EPI & kEpiOutF32) != 0)) ? 32 : 64;
@@ -242,11 +258,14 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
         const int t3 = m_tile / (p.tiles1 * p.tiles2);   // (an odd tile count leaves the last peer tile past the tensor: zero fill)
         const int c1 = t1 * p.box1, c2 = t2 * p.box2, c3 = t3 * p.box3;
         int tap = 0, cb = 0;   // running (tap, channel block) of k-block kb: no division in the single-thread issue loop
+        int kb_in_tap = p.var_taps ? p.tap_kb[0] : p.k_blocks_per_tap;
         for (int kb = 0; kb < num_kb; ++kb, ++cb) {
-          if (cb == p.k_blocks_per_tap) {
+          if (cb == kb_in_tap) {
             cb = 0;
             ++tap;
+            if (p.var_taps) kb_in_tap = p.tap_kb[tap];
           }
+          const int wk = p.var_taps ? p.tap_k0[tap] + cb * 64 : p.tap_w[tap] * p.k_per_tap + cb * 64;
           CPROF_TICK(1)
           mbar_wait_backoff(&empty_bar[stage], phase ^ 1);
           CPROF_TICK(0)
@@ -257,13 +276,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             const uint32_t full_leader = mapa_leader(smem_u32(&full_bar[stage]));
             if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
             tma_load_4d_2cta(a_dst, &p.a_maps[p.tap_map[tap]], full_leader, cb * 64, c1 + p.tap_o1[tap], c2 + p.tap_o2[tap], c3);
-            tma_load_2d_2cta(b_dst, &p.b_map_half, full_leader, p.tap_w[tap] * p.k_per_tap + cb * 64,
+            tma_load_2d_2cta(b_dst, &p.b_map_half, full_leader, wk,
                              n_tile * BLOCK_N + static_cast<int>(cta_rank) * (BLOCK_N / 2));
           } else {
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           tma_load_4d(a_dst, &p.a_maps[p.tap_map[tap]], &full_bar[stage], cb * 64, c1 + p.tap_o1[tap],
                       c2 + p.tap_o2[tap], c3);
-          tma_load_2d(b_dst, &p.b_map, &full_bar[stage], p.tap_w[tap] * p.k_per_tap + cb * 64, n_tile * BLOCK_N);
+          tma_load_2d(b_dst, &p.b_map, &full_bar[stage], wk, n_tile * BLOCK_N);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -352,10 +371,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     for (int m = 0; m < 8; ++m) stat_off[m] = m * 128 + ((((lane >> 2) ^ m) << 4) | ((lane & 3) << 2));
     // kernel parameters used in the inner loops, hoisted into registers
     constexpr bool G = EPI < 0;
+    constexpr bool kAffine = !G && (EPI & kEpiAffine) != 0;   // BatchNorm scale / shift, ReLU after the residual add
+    constexpr bool kMask = !G && (EPI & kEpiMask) != 0;       // ReLU-derivative mask from a second tensor
     const int N = p.N;
-    const float* const bias = (G || (EPI & kEpiBias)) ? p.bias : nullptr;
-    const float* const colscale = (G || (EPI & kEpiColscale)) ? p.colscale : nullptr;
-    const int act = G ? p.act : ((EPI >> kEpiActShift) & 3);
+    const float* const bias = (!kAffine && (G || (EPI & kEpiBias))) ? p.bias : nullptr;
+    const float* const colscale = (!kAffine && (G || (EPI & kEpiColscale))) ? p.colscale : nullptr;
+    const int act_bits = G ? p.act : ((EPI >> kEpiActShift) & 3);
+    const int act = kAffine ? 0 : act_bits;                   // (kAffine: the activation is applied after the residual)
     const bool has_res = G ? (p.residual != nullptr) : ((EPI & (kEpiResBf16 | kEpiResF32)) != 0);
     const bool res_f32 = G ? (p.res_f32 != 0) : ((EPI & kEpiResF32) != 0);
     const bool has_aux = G ? (p.has_aux_out != 0) : ((EPI & kEpiAux) != 0);
@@ -364,7 +386,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     float* const stats = (G || (EPI & kEpiStats)) ? p.stats : nullptr;
     const float* const rowscale = G ? p.rowscale : nullptr;
     // (pair mode with an odd number of pixel tiles: the last peer tile lies past the tensor and must not touch memory)
-    const bool need_rowmap = has_res || act == 3 || out_direct != nullptr || rowscale != nullptr || p.dim1 % p.box1 != 0 ||
+    const bool need_rowmap = has_res || act == 3 || kMask || out_direct != nullptr || rowscale != nullptr || p.dim1 % p.box1 != 0 ||
                              p.dim2 % p.box2 != 0 || p.dim3 % p.box3 != 0 || (kPair && (m_tiles & 1) != 0);
     const bool full_cols = (N % BLOCK_N) == 0;  // no partially valid 32-column group anywhere
     uint32_t store_counter = 0;
@@ -408,6 +430,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
       // complete), so every epilogue warp always has 64-128 B per lane in flight towards HBM.
       uint4 nx_b[4];   // bf16 residual or aux_in: 32 x bf16
       float4 nx_f[8];  // fp32 residual: 32 x fp32
+      uint4 nx_m[4];   // kMask: 32 x bf16 of the mask tensor
       auto issue_pre = [&](int u, int h) {
         const int ncp = n_tile * BLOCK_N + u * unit_cols + h * 32;
         if (n_tile * BLOCK_N + u * unit_cols >= N || !row_ok) return;
@@ -431,8 +454,14 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           for (int j = 0; j < 4; ++j)
             if (full_cols || ncp + j * 8 < N) nx_b[j] = __ldg(ap + j);
         }
+        if constexpr (kMask) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask_in + p3 * p.ms3 + p2 * p.ms2 + p1 * p.ms1 + ncp);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (full_cols || ncp + j * 8 < N) nx_m[j] = __ldg(mp + j);
+        }
       };
-      if (has_res || act == 3) issue_pre(u_first, 0);
+      if (has_res || act == 3 || kMask) issue_pre(u_first, 0);
 
       CPROF_TICK(1)
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -459,11 +488,16 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           tmem_ld_32x32(tmem_acc + u * unit_cols + h * 32, v);
           uint4 pre_b[4];
           float4 pre_f[8];
-          if (has_res || act == 3) {
+          uint4 pre_m[4];
+          if (has_res || act == 3 || kMask) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) pre_b[j] = nx_b[j];
 #pragma unroll
             for (int j = 0; j < 8; ++j) pre_f[j] = nx_f[j];
+            if constexpr (kMask) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pre_m[j] = nx_m[j];
+            }
             if (h + 1 < nsub)
               issue_pre(u, h + 1);
             else if (u + 2 < units)
@@ -486,6 +520,16 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           float f[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if constexpr (kAffine) {
+            // train / eval BatchNorm of the convolution output: f * scale[n] + shift[n]  (channel counts are multiples of 32)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.colscale + nc) + j);
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nc) + j);
+              f2_unpack(f2_fma(f2_pack(f[j * 4 + 0], f[j * 4 + 1]), f2_pack(s4.x, s4.y), f2_pack(b4.x, b4.y)), f[j * 4 + 0], f[j * 4 + 1]);
+              f2_unpack(f2_fma(f2_pack(f[j * 4 + 2], f[j * 4 + 3]), f2_pack(s4.z, s4.w), f2_pack(b4.z, b4.w)), f[j * 4 + 2], f[j * 4 + 3]);
+            }
+          }
           if (bias != nullptr) {
             if (full_cols) {
 #pragma unroll
@@ -555,6 +599,26 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
                   for (int i = 0; i < 8; i += 2)
                     f2_unpack(f2_add(f2_pack(f[j * 8 + i], f[j * 8 + i + 1]), f2_pack(r[i], r[i + 1])), f[j * 8 + i],
                               f[j * 8 + i + 1]);
+                }
+              }
+            }
+          }
+          if constexpr (kAffine) {
+            if (act_bits == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
+            }
+          }
+          if constexpr (kMask) {
+            // the mask tensor is a ReLU output (>= 0): an element is alive iff its bf16 bits are non-zero
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t w[4] = {pre_m[j].x, pre_m[j].y, pre_m[j].z, pre_m[j].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  if ((w[i] & 0x7fffu) == 0u) f[j * 8 + 2 * i] = 0.f;
+                  if ((w[i] & 0x7fff0000u) == 0u) f[j * 8 + 2 * i + 1] = 0.f;
                 }
               }
             }

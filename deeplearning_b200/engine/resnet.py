@@ -7,7 +7,20 @@ gradient is added in the epilogue of the first conv's dgrad GEMM.
 
 Mirrors ``ResNet._forward_impl`` / ``Bottleneck.forward`` / ``BasicBlock.forward`` of the reference
 (classification/resnet/models/networks.py:204-220, :104-124, :59-75); activations are NHWC bf16, parameters fp32.
+
+Bottleneck tail (conv3 1x1 -> bn3 -> + identity -> ReLU, :116-124) runs on the "algebra" path whenever conv3's input is
+narrow (<= 256 channels; csrc/bn_algebra.cuh): train-mode BatchNorm is folded THROUGH the 1x1 convolution, so the 4x wider
+conv3 output is never written, normalised or re-read -
+
+    forward   G = y2^T y2, s = colsum(y2)  ->  batch statistics of conv3(y2)  ->  ONE GEMM: y = relu(acc*scale + shift + identity)
+    backward  dz = relu'(y) * gradient comes out of the NEXT block's conv1 dgrad epilogue (mask + column sums);
+              D = dz^T y2  ->  dgamma, dbeta, dW3, packed [a W3 | M] operand  ->  ONE GEMM over [dz | y2] gives dL/dy2
+
+which removes the bn3 apply pass of the forward and both bn3 passes (reduce, apply) of the backward: 8 of the 17 passes a
+bottleneck makes over its block-width tensors.  ``B200_RESNET_ALGEBRA=0`` selects the plain conv -> BN pass schedule.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -59,8 +72,46 @@ _pack_spec = _PackSpec()
 
 
 class _Unit:
-    """Saved state of one conv -> BN (-> ReLU) (-> + residual) application."""
-    __slots__ = ("conv", "bn", "x", "c", "co", "y", "relu", "has_res")
+    """Saved state of one conv -> BN (-> ReLU) (-> + residual) application.  ``algebra`` units (bottleneck conv3 with the
+    BatchNorm folded through the convolution) have no raw conv output ``c``; they keep the Gram matrix ``G`` and the column
+    sums ``s`` of their input instead."""
+    __slots__ = ("conv", "bn", "x", "c", "co", "y", "relu", "has_res", "algebra", "G", "s")
+
+
+def _algebra_enabled():
+    return os.environ.get("B200_RESNET_ALGEBRA", "1") != "0"
+
+
+def _algebra_ok(block, train, want_tape):
+    """Bottleneck whose tail can run with bn3 folded through conv3 (train mode, or a forward that records no tape)."""
+    if not _algebra_enabled() or not hasattr(block, "conv3") or not (train or not want_tape):
+        return False
+    c3, c1 = block.conv3, block.conv1
+    return (c3.kernel_size == (1, 1) and c3.stride == (1, 1) and c3.groups == 1 and c3.bias is None and c3.dilation == (1, 1)
+            and c3.in_channels % 64 == 0 and c3.in_channels <= 256 and c3.out_channels % 64 == 0
+            and c1.kernel_size == (1, 1) and c1.stride == (1, 1) and c1.in_channels % 64 == 0 and c1.out_channels % 64 == 0)
+
+
+def _conv3_bn_res_relu(pack, tape, y2, conv, bn, train, identity, name=""):
+    """Algebra path of ``out = relu(bn3(conv3(y2)) + identity)``: statistics from the Gram matrix of y2, BN + add + ReLU in
+    the GEMM epilogue."""
+    _check_bn(bn, name)
+    wp = pack.get(conv.weight, 0)
+    G = s = None
+    if train:
+        G, s = ops.gram_colsum(y2)
+        rows = y2.numel() // y2.shape[-1]
+        co = ops.bn_gram_stats(G, s, wp, rows, bn.weight, bn.bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                               bn.num_batches_tracked)
+    else:
+        co = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+    y = ops.conv1x1_bn_act(y2, wp, co, identity)
+    if tape is not None:
+        u = _Unit()
+        u.conv, u.bn, u.x, u.c, u.co, u.y, u.relu, u.has_res = conv, bn, y2, None, co, y, True, True
+        u.algebra, u.G, u.s = True, G, s
+        tape.append(u)
+    return y
 
 
 def _conv_bn(pack, tape, x, conv, bn, train, relu, residual=None, name=""):
@@ -79,8 +130,14 @@ def _conv_bn(pack, tape, x, conv, bn, train, relu, residual=None, name=""):
     if tape is not None:
         u = _Unit()
         u.conv, u.bn, u.x, u.c, u.co, u.y, u.relu, u.has_res = conv, bn, x, c, co, y, relu, residual is not None
+        u.algebra, u.G, u.s = False, None, None
         tape.append(u)
     return y
+
+
+def _algebra_ok_dgrad(conv1):
+    return (conv1.kernel_size == (1, 1) and conv1.stride == (1, 1) and conv1.in_channels % 64 == 0
+            and conv1.out_channels % 64 == 0)
 
 
 def _block_units(block):
@@ -135,7 +192,11 @@ def forward(model, x, train, want_tape):
             else:
                 identity = x_in
             conv, bn = pairs[-1]
-            h = _conv_bn(pack, units, h, conv, bn, train, relu=True, residual=identity, name=f"{name}.conv{len(pairs)}")
+            if _algebra_ok(block, train, want_tape):
+                _check_conv(conv, f"{name}.conv3")
+                h = _conv3_bn_res_relu(pack, units, h, conv, bn, train, identity, name=f"{name}.conv3")
+            else:
+                h = _conv_bn(pack, units, h, conv, bn, train, relu=True, residual=identity, name=f"{name}.conv{len(pairs)}")
             if want_tape:
                 tape["blocks"].append((units, ds_units[0] if ds_units else None, x_in))
     # ---- head: global average pool + fc (fp32 logits)
@@ -211,12 +272,39 @@ def backward(model, tape, dlogits, sink=None):
     dpooled = ops.conv2d_dgrad(dl16, wfc_d, (1, 1))
     g = ops.avgpool_bwd(dpooled.view(B, -1), hw)
 
-    for units, ds, x_in in reversed(tape["blocks"]):
+    # The gradient of a block output travels either as the raw gradient ``g`` (then the block masks it itself) or, when the
+    # consumer's conv1 dgrad epilogue already applied this block's ReLU mask, as ``dz`` with its partial column sums.
+    blocks = tape["blocks"]
+    dz = dz_stats = None
+    for bi in range(len(blocks) - 1, -1, -1):
+        units, ds, x_in = blocks[bi]
         last = units[-1]
         has_ds = ds is not None
-        # out = relu(bn_last(c) + identity): dz is the gradient of the pre-ReLU sum, shared by both branches
-        dc, dz = _unit_backward(last, g, grads, want_dz=True)
-        for j in range(len(units) - 1, -1, -1):
+        if last.algebra:
+            # out = relu(conv3(y2) * scale + shift + identity): BatchNorm backward folded through the 1x1 convolution
+            if dz is None:
+                dz, dz_stats = ops.relu_mask_sum(g, last.y)
+            y2 = last.x
+            N, K = last.conv.out_channels, last.conv.in_channels
+            D = ops.conv2d_wgrad(dz, y2, 1, 1)                       # raw dz^T y2 [N, K, 1, 1]
+            count = dz.numel() // N
+            dgamma, dbeta, dW, wcat, wbias = ops.bn_conv1x1_bwd(
+                dz_stats, D, last.G, last.s, pack.get(last.conv.weight, 0), last.conv.weight, count, last.bn.weight, last.co,
+                dgamma=grads.dest(last.bn.weight), dbeta=grads.dest(last.bn.bias), dW=grads.dest(last.conv.weight))
+            grads.put(last.bn.weight, dgamma)
+            grads.put(last.bn.bias, dbeta)
+            grads.put(last.conv.weight, dW)
+            g_prev = ops.gemm_dual(dz, y2, wcat, wbias)              # dL/dy2 = [dz | y2] [a W3 | M]^T + k W3
+            dc, _ = _unit_backward(units[-2], g_prev, grads)
+            first = len(units) - 2
+        else:
+            # out = relu(bn_last(c) + identity): dz is the gradient of the pre-ReLU sum, shared by both branches
+            dc, dz = _unit_backward(last, g, grads, want_dz=True)
+            first = len(units) - 1
+        # does the producer of x_in (the previous block) take its gradient pre-masked from this block's conv1 dgrad?
+        prev_masked = (bi > 0 and not has_ds and blocks[bi - 1][0][-1].algebra and _algebra_ok_dgrad(units[0].conv))
+        dz_prev = dz_prev_stats = None
+        for j in range(first, -1, -1):
             u = units[j]
             k, s = u.conv.kernel_size[0], u.conv.stride[0]
             grads.put(u.conv.weight, ops.conv2d_wgrad(dc, u.x, k, s, out=grads.dest(u.conv.weight)))
@@ -228,6 +316,10 @@ def backward(model, tape, dlogits, sink=None):
             else:
                 if has_ds:
                     gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
+                elif prev_masked:
+                    # + identity-branch gradient, x_in's ReLU mask and the column sums the previous block needs, in the epilogue
+                    dz_prev, dz_prev_stats = ops.conv1x1_dgrad_masked(dc, wd, residual=dz, mask_src=x_in)
+                    gx = None
                 else:
                     gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s, residual=dz)  # + identity-branch gradient
         if has_ds:
@@ -236,7 +328,7 @@ def backward(model, tape, dlogits, sink=None):
             grads.put(ds.conv.weight, ops.conv2d_wgrad(dcd, x_in, kd, sd, out=grads.dest(ds.conv.weight)))
             wdd = pack.get(ds.conv.weight, 1)
             gx = ops.conv2d_dgrad(dcd, wdd, tuple(x_in.shape[1:3]), kd, sd, residual=gx, out=gx)
-        g = gx
+        g, dz, dz_stats = gx, dz_prev, dz_prev_stats
 
     a, c1, co1, idx, (Ho, Wo) = tape["stem"]
     g_act = ops.maxpool_bwd(g, idx, (Ho, Wo))

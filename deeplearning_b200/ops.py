@@ -318,6 +318,122 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     return dx, dgamma, dbeta, dz
 
 
+# ------------------------------------------------------------------------------ BatchNorm folded through a 1x1 convolution
+def gram_colsum(y2):
+    """y2 bf16 [..., K] -> (G = y2^T y2 fp32 [K, K], s = column sums fp32 [K]): everything train-mode BatchNorm needs to know
+    about the output of a 1x1 convolution of y2 (csrc/bn_algebra.cuh)."""
+    K = y2.shape[-1]
+    flat = y2.view(-1, 1, 1, K)
+    G = conv2d_wgrad(flat, flat).view(K, K)
+    s = colsum_tall(y2.view(-1, K))
+    return G, s
+
+
+def bn_gram_stats(G, s, w_packed, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked):
+    """Batch statistics of conv1x1(y2, w) from (G, s); returns BnCoeffs and updates the running statistics."""
+    lib = _lib.load()
+    N, K = w_packed.shape
+    co = BnCoeffs(N, G.device)
+    rc = lib.b200_bn_gram_stats(_p(G), _p(s), _p(w_packed), N, K, float(count), _p(gamma), _p(beta), eps, momentum,
+                                _p(running_mean), _p(running_var), _p(num_batches_tracked), _p(co.mean), _p(co.invstd),
+                                _p(co.scale), _p(co.shift), _stream())
+    _lib.check(rc, "b200_bn_gram_stats")
+    return co
+
+
+def conv1x1_bn_act(x, w_packed, co, residual):
+    """y = relu(conv1x1(x, w) * co.scale + co.shift + residual): conv + BatchNorm + identity + ReLU in one GEMM."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    _chk_act(residual, "residual")
+    Cin = x.shape[-1]
+    Cout = w_packed.shape[0]
+    y = torch.empty(*x.shape[:-1], Cout, dtype=BF16, device=x.device)
+    pixels = x.numel() // Cin
+    sp = _span("conv_gemm_fwd", 2.0 * pixels * Cin * Cout, _nb(x, w_packed, residual, y))
+    rc = lib.b200_conv1x1_bn_act_fwd(_p(x), _p(w_packed), _p(co.scale), _p(co.shift), _p(residual), _p(y), pixels, Cin, Cout, 1,
+                                     _stream())
+    _lib.check(rc, "b200_conv1x1_bn_act_fwd")
+    if sp:
+        sp.end()
+    return y
+
+
+def conv1x1_dgrad_masked(dy, wd_packed, residual, mask_src):
+    """dz = (mask_src > 0) * (dy @ wd^T + residual); returns (dz bf16, stats fp32 [T,2,Cin] with plane 0 = partial sums of dz)."""
+    lib = _lib.load()
+    _chk_act(dy, "dy")
+    Cout = dy.shape[-1]
+    Cin = wd_packed.shape[0]
+    pixels = dy.numel() // Cout
+    dz = torch.empty(*dy.shape[:-1], Cin, dtype=BF16, device=dy.device)
+    T = lib.b200_conv1x1_dgrad_masked_stats_rows(pixels, Cin)
+    stats = torch.empty(T, 2, Cin, dtype=F32, device=dy.device)
+    sp = _span("conv_gemm_dgrad", 2.0 * pixels * Cin * Cout, _nb(dy, wd_packed, residual, mask_src, dz))
+    rc = lib.b200_conv1x1_dgrad_masked(_p(dy), _p(wd_packed), _p(dz), pixels, Cin, Cout, _p(residual), _p(mask_src), _p(stats),
+                                       _stream())
+    _lib.check(rc, "b200_conv1x1_dgrad_masked")
+    if sp:
+        sp.end()
+    return dz, stats
+
+
+def relu_mask_sum(g, y):
+    """dz = (y > 0) * g with per-block partial column sums [T,2,C] (plane 0), for block outputs whose gradient does not come
+    out of a masked dgrad epilogue (the BatchNorm-backward reduce pass with x = y; its second plane is unused)."""
+    lib = _lib.load()
+    C = y.shape[-1]
+    rows = y.numel() // C
+    nblk = lib.b200_bn_bwd_blocks(rows, C)
+    partial = torch.empty(nblk, 2, C, dtype=F32, device=y.device)
+    dz = torch.empty_like(y)
+    sp = _span("bn_bwd_reduce", 0.0, _nb(g, y, dz))
+    rc = lib.b200_bn_bwd_reduce(_p(g), _p(y), _p(y), _p(dz), None, None, 1, rows, C, _p(partial), _stream())
+    _lib.check(rc, "b200_bn_bwd_reduce")
+    if sp:
+        sp.end()
+    return dz, partial
+
+
+def bn_conv1x1_bwd(dz_partial, D, G, s, w_packed, w_f32, count, gamma, co, dgamma=None, dbeta=None, dW=None):
+    """BatchNorm + 1x1-conv backward algebra (csrc/bn_algebra.cuh). Returns (dgamma, dbeta, dW [N,K,1,1], wcat bf16 [K, N+K],
+    bias fp32 [K]); wcat / bias are the operands of gemm_dual([dz | y2])."""
+    lib = _lib.load()
+    N, K = w_packed.shape
+    dev = D.device
+    if dgamma is None:
+        dgamma = torch.empty(N, dtype=F32, device=dev)
+        dbeta = torch.empty(N, dtype=F32, device=dev)
+    if dW is None:
+        dW = torch.empty(N, K, 1, 1, dtype=F32, device=dev)
+    wcat = torch.empty(K, N + K, dtype=BF16, device=dev)
+    bias = torch.empty(K, dtype=F32, device=dev)
+    coef = torch.empty(N, 2, dtype=F32, device=dev)
+    w32 = w_f32.detach()
+    rc = lib.b200_bn_conv1x1_bwd(_p(dz_partial), dz_partial.shape[0], _p(D), _p(G), _p(s), _p(w_packed), _p(w32), N, K, float(count),
+                                 _p(gamma), _p(co.mean), _p(co.invstd), _p(dgamma), _p(dbeta), _p(dW), 0, _p(wcat), _p(bias),
+                                 _p(coef), _stream())
+    _lib.check(rc, "b200_bn_conv1x1_bwd")
+    return dgamma, dbeta, dW, wcat, bias
+
+
+def gemm_dual(a0, a1, wcat, bias):
+    """out bf16 [..., N] = [a0 | a1] @ wcat^T + bias (a0 [..., K0], a1 [..., K1] bf16, wcat bf16 [N, K0 + K1])."""
+    lib = _lib.load()
+    _chk_act(a0, "a0")
+    _chk_act(a1, "a1")
+    K0, K1 = a0.shape[-1], a1.shape[-1]
+    N = wcat.shape[0]
+    pixels = a0.numel() // K0
+    out = torch.empty(*a0.shape[:-1], N, dtype=BF16, device=a0.device)
+    sp = _span("conv_gemm_dgrad", 2.0 * pixels * N * (K0 + K1), _nb(a0, a1, wcat, out))
+    rc = lib.b200_gemm_dual(_p(a0), K0, _p(a1), K1, _p(wcat), _p(bias), _p(out), pixels, N, _stream())
+    _lib.check(rc, "b200_gemm_dual")
+    if sp:
+        sp.end()
+    return out
+
+
 # --------------------------------------------------------------------------------------------------------- pooling
 def bn_relu_maxpool_fwd(x, co):
     lib = _lib.load()

@@ -280,6 +280,32 @@ int b200_stem_wgrad_relayout(const float* src, float* dst, int Cout, int Cin, in
 int b200_sgd_momentum(float* p, const float* g, float* buf, long long n, float lr, const float* lr_dev, float momentum,
                       float weight_decay, float gscale, int first_step, const float* clip_coef, void* stream);
 
+/* ---- train-mode BatchNorm folded through a 1x1 convolution (ResNet bottleneck conv3 -> bn3 -> +identity -> ReLU,
+ * classification/resnet/models/networks.py:116-124): the wide conv output is never written; see csrc/bn_algebra.cuh.
+ * forward: G = y2^T y2 (b200_conv2d_wgrad(y2, y2)), s = colsum(y2) -> b200_bn_gram_stats -> scale / shift ->
+ *          b200_conv1x1_bn_act_fwd: y = relu(conv1x1(y2, w) * scale + shift + residual)       (w bf16 [Cout][Cin])
+ * backward: dz = relu-mask * gradient (b200_conv1x1_dgrad_masked of the NEXT block, with its per-CTA column sums),
+ *          D = dz^T y2 (b200_conv2d_wgrad) -> b200_bn_conv1x1_bwd -> dgamma, dbeta, dW, wcat [Cin][Cout + Cin] bf16, bias [Cin]
+ *          -> b200_gemm_dual: g2 = [dz | y2] wcat^T + bias                                     */
+int b200_bn_gram_stats(const float* G, const float* s, const void* w_bf16, int N, int K, double count, const float* gamma,
+                       const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                       long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift, void* stream);
+int b200_conv1x1_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
+                            void* y, long long pixels, int Cin, int Cout, int relu, void* stream);
+/* dx[pixels][Cin] = (mask_src > 0) ? (dy[pixels][Cout] * wd^T + residual) : 0  (wd bf16 [Cin][Cout], b200_pack_weight mode 1);
+ * stats fp32 [b200_conv1x1_dgrad_masked_stats_rows()][2][Cin]: per-CTA column sums (plane 0) of dx as stored */
+int b200_conv1x1_dgrad_masked_stats_rows(long long pixels, int Cin);
+int b200_conv1x1_dgrad_masked(const void* dy, const void* wd, void* dx, long long pixels, int Cin, int Cout,
+                              const void* residual, const void* mask_src, float* stats, void* stream);
+/* dz_partial fp32 [T][2][N] (plane 0 = partial column sums of dz); coef_scratch: 2 * N floats */
+int b200_bn_conv1x1_bwd(const float* dz_partial, int T, const float* D, const float* G, const float* s, const void* w_bf16,
+                        const float* w_f32, int N, int K, double count, const float* gamma, const float* mean,
+                        const float* invstd, float* dgamma, float* dbeta, float* dW, int accumulate, void* wcat, float* bias,
+                        void* coef_scratch, void* stream);
+/* out[pixels][N] (bf16) = [a0[pixels][K0] | a1[pixels][K1]] * wcat[N][K0 + K1]^T + bias[N] */
+int b200_gemm_dual(const void* a0, int K0, const void* a1, int K1, const void* wcat, const float* bias, void* out,
+                   long long pixels, int N, void* stream);
+
 /* ---- stochastic depth / pre_logits helpers -------------------------------------------------------------------------------
  * y[b, :] = x[b, :] * scale[b] over bf16 samples of elems_per_sample elements: the gradient entering a residual branch whose
  * forward was scaled per sample by drop_path (convNext/models/networks.py:11-26, vit_model.py:12-40, swin_transformer.py:282,285;
