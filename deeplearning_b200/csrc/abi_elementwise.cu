@@ -291,27 +291,48 @@ int b200_bn_gram_stats(const float* G, const float* s, const void* w_bf16, int N
                        const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                        long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift, void* stream) {
   B200_REQUIRE(N > 0 && K >= 32 && K <= 256 && K % 32 == 0 && count > 0, "bn_gram_stats: N=%d K=%d (K must be 32..256, multiple of 32)", N, K);
-  const size_t smem = static_cast<size_t>(5) * K * sizeof(float);
-  bn_gram_stats_kernel<<<(N + 3) / 4, 128, smem, static_cast<cudaStream_t>(stream)>>>(
+  const size_t smem = static_cast<size_t>(32 + 8 + 1) * K * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(bn_gram_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 41 * 256 * 4));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(bn_conv1x1_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 256 * 4));
+    configured = true;
+  }
+  bn_gram_stats_kernel<<<(N + 7) / 8, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       G, s, static_cast<const __nv_bfloat16*>(w_bf16), N, K, count, gamma, beta, eps, momentum, running_mean, running_var,
       num_batches_tracked, mean, invstd, scale, shift);
   B200_LAUNCHED();
   return OK;
 }
 
+size_t b200_bn_conv1x1_bwd_scratch_bytes(int N, int K) {
+  const size_t tiles = static_cast<size_t>(K / 32) * (K / 32);
+  return static_cast<size_t>(2) * N * sizeof(float) + static_cast<size_t>(kAlgebraSlices) * tiles * 33 * 32 * sizeof(float);
+}
+
 int b200_bn_conv1x1_bwd(const float* dz_partial, int T, const float* D, const float* G, const float* s, const void* w_bf16,
                         const float* w_f32, int N, int K, double count, const float* gamma, const float* mean,
                         const float* invstd, float* dgamma, float* dbeta, float* dW, int accumulate, void* wcat, float* bias,
-                        void* coef_scratch, void* stream) {
+                        void* scratch, size_t scratch_bytes, void* tickets, void* stream) {
   B200_REQUIRE(N > 0 && T > 0 && K >= 32 && K <= 256 && K % 32 == 0 && count > 0, "bn_conv1x1_bwd: N=%d K=%d T=%d unsupported", N, K, T);
+  B200_REQUIRE(scratch != nullptr && scratch_bytes >= b200_bn_conv1x1_bwd_scratch_bytes(N, K) && tickets != nullptr,
+               "bn_conv1x1_bwd: scratch too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  bn_conv1x1_bwd_rows_kernel<<<(N + 3) / 4, 128, static_cast<size_t>(4) * K * sizeof(float), st>>>(
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(bn_gram_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 41 * 256 * 4));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(bn_conv1x1_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 40 * 256 * 4));
+    configured = true;
+  }
+  float2* coef = static_cast<float2*>(scratch);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + static_cast<size_t>(2) * N * sizeof(float));
+  bn_conv1x1_bwd_rows_kernel<<<(N + 7) / 8, 256, static_cast<size_t>(32 + 8) * K * sizeof(float), st>>>(
       dz_partial, T, D, G, s, static_cast<const __nv_bfloat16*>(w_bf16), w_f32, N, K, count, gamma, mean, invstd, dgamma, dbeta,
-      dW, accumulate, static_cast<__nv_bfloat16*>(wcat), static_cast<float2*>(coef_scratch));
+      dW, accumulate, static_cast<__nv_bfloat16*>(wcat), coef);
   B200_LAUNCHED();
-  bn_conv1x1_bwd_m_kernel<<<dim3(K / 32, K / 32), 256, 0, st>>>(
-      static_cast<const float2*>(coef_scratch), static_cast<const __nv_bfloat16*>(w_bf16), w_f32, N, K,
-      static_cast<__nv_bfloat16*>(wcat), bias);
+  bn_conv1x1_bwd_m_kernel<<<dim3(K / 32, K / 32, kAlgebraSlices), 256, 0, st>>>(
+      coef, static_cast<const __nv_bfloat16*>(w_bf16), w_f32, N, K, static_cast<__nv_bfloat16*>(wcat), bias,
+      static_cast<unsigned int*>(tickets), partial);
   B200_LAUNCHED();
   return OK;
 }

@@ -30,58 +30,72 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// One warp per output channel o (4 per block).  G fp32 [K][K] (symmetric), s fp32 [K], Wb bf16 [N][K] (the forward operand).
+// ---- q = w G for 8 channels per block (one per warp), G staged through shared memory in chunks of 32 rows --------------------
+// All 256 threads load a 32 x K chunk of G with coalesced 16-byte loads (one round of latency per chunk instead of one per
+// row), then every warp accumulates its channel:  acc[x] = sum_i w_i * (G[i][j] * inv_n - m_i * m_j),  j = lane + 32 x.
+// kCov = false drops the mean correction (plain q = w G).  w: this warp's K weights in shared memory, m: K means (kCov).
+template <bool kCov>
+__device__ __forceinline__ void warp_wG(const float* __restrict__ G, int K, float* Gs /* [32][K] */, const float* w,
+                                        const float* m, float inv_n, float (&acc)[8]) {
+  const int lane = threadIdx.x & 31;
+  const int nq = K / 32;
+  __syncthreads();   // w / m were just written by other threads of the block
+  float mj[8];
+#pragma unroll
+  for (int x = 0; x < 8; ++x) {
+    acc[x] = 0.f;
+    mj[x] = (kCov && x < nq) ? m[lane + 32 * x] : 0.f;
+  }
+  const int vec_per_chunk = 32 * K / 4;   // float4 per chunk
+  for (int r0 = 0; r0 < K; r0 += 32) {
+    __syncthreads();   // previous chunk consumed
+    const float4* src = reinterpret_cast<const float4*>(G + static_cast<long long>(r0) * K);
+    for (int v = threadIdx.x; v < vec_per_chunk; v += blockDim.x) reinterpret_cast<float4*>(Gs)[v] = __ldg(src + v);
+    __syncthreads();
+#pragma unroll 4
+    for (int r = 0; r < 32; ++r) {
+      const float wi = w[r0 + r];
+      const float mi = kCov ? m[r0 + r] : 0.f;
+      const float* grow = Gs + r * K + lane;
+#pragma unroll
+      for (int x = 0; x < 8; ++x) {
+        if (x < nq) {
+          const float g = grow[32 * x];
+          acc[x] = fmaf(wi, kCov ? fmaf(g, inv_n, -mi * mj[x]) : g, acc[x]);
+        }
+      }
+    }
+  }
+}
+
+// One warp per output channel o (8 per block).  G fp32 [K][K] (symmetric), s fp32 [K], Wb bf16 [N][K] (the forward operand).
 // Writes mean / invstd / scale / shift and updates the running statistics like nn.BatchNorm2d (momentum, unbiased var).
-// The row loop is unrolled by 8 so that 8 x K/32 independent loads are in flight per lane (the loop is latency-bound).
-__global__ void __launch_bounds__(128) bn_gram_stats_kernel(const float* __restrict__ G, const float* __restrict__ s,
+__global__ void __launch_bounds__(256) bn_gram_stats_kernel(const float* __restrict__ G, const float* __restrict__ s,
                                                             const __nv_bfloat16* __restrict__ Wb, int N, int K, double count,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps, float momentum, float* running_mean,
                                                             float* running_var, long long* num_batches, float* mean_out,
                                                             float* invstd_out, float* scale_out, float* shift_out) {
-  extern __shared__ float sm_gs[];   // [4 warps][K] weights of the warp's channel, then [K] column means
+  extern __shared__ float sm_gs[];   // [32][K] chunk of G | [8 warps][K] weights | [K] column means
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 4 + warp;
-  float* w = sm_gs + warp * K;
-  float* m = sm_gs + 4 * K;
+  const int o = blockIdx.x * 8 + warp;
+  float* Gs = sm_gs;
+  float* w = sm_gs + 32 * K + warp * K;
+  float* m = sm_gs + 32 * K + 8 * K;
   const double inv_n = 1.0 / count;
-  const float inv_nf = static_cast<float>(inv_n);
   for (int j = threadIdx.x; j < K; j += blockDim.x) m[j] = static_cast<float>(static_cast<double>(s[j]) * inv_n);
-  if (o < N)
-    for (int j = lane; j < K; j += 32) w[j] = __bfloat162float(Wb[static_cast<long long>(o) * K + j]);
-  __syncthreads();
+  for (int j = lane; j < K; j += 32) w[j] = o < N ? __bfloat162float(Wb[static_cast<long long>(o) * K + j]) : 0.f;
+  // (warp_wG starts with a block barrier: m and w are visible to everyone)
+  float acc[8];
+  warp_wG<true>(G, K, Gs, w, m, static_cast<float>(inv_n), acc);
   if (o >= N) return;
-  // acc_j = sum_i w_i Cov[i][j],  Cov = G / count - m m^T   (lane owns columns j = lane + 32 q; fp32 products, fp64 sums)
-  double acc[8];   // K <= 256
-  float mj[8];
   const int nq = K / 32;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    acc[q] = 0.0;
-    mj[q] = q < nq ? m[lane + 32 * q] : 0.f;
-  }
-  for (int i0 = 0; i0 < K; i0 += 8) {
-    float gv[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < nq) gv[r][q] = __ldg(G + static_cast<long long>(i0 + r) * K + lane + 32 * q);
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float wi = w[i0 + r], mi = m[i0 + r];
-#pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (q < nq) acc[q] += static_cast<double>(wi * fmaf(gv[r][q], inv_nf, -mi * mj[q]));
-    }
-  }
   double var = 0.0, mean = 0.0;
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    if (q < nq) {
-      const int j = lane + 32 * q;
-      var += acc[q] * static_cast<double>(w[j]);
+  for (int x = 0; x < 8; ++x) {
+    if (x < nq) {
+      const int j = lane + 32 * x;
+      var += static_cast<double>(acc[x]) * static_cast<double>(w[j]);
       mean += static_cast<double>(w[j]) * static_cast<double>(m[j]);
     }
   }
@@ -104,22 +118,23 @@ __global__ void __launch_bounds__(128) bn_gram_stats_kernel(const float* __restr
   }
 }
 
-// Backward, per output channel o (one warp each, 4 per block):
+// Backward, per output channel o (one warp each, 8 per block):
 //   sum_dz from the partial rows dz_partial[T][2][N] (plane 0), D fp32 [N][K] (raw dz^T y2), G, s, Wb as above, W fp32 [N][K]
 //   (the master weights, for the data-gradient operand), mean / invstd / gamma of the BatchNorm.
 // Writes dgamma[o], dbeta[o] (optionally accumulating), dW[o][:] = a D + b (Wb G) + k s (optionally accumulating),
 // the bf16 column o of the dgrad operand wcat[i][o] = a_o W[o][i] (ld = N + K) and coef[o] = {b_o, k_o} for the M kernel.
-__global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
+__global__ void __launch_bounds__(256) bn_conv1x1_bwd_rows_kernel(
     const float* __restrict__ dz_partial, int T, const float* __restrict__ D, const float* __restrict__ G,
     const float* __restrict__ s, const __nv_bfloat16* __restrict__ Wb, const float* __restrict__ W, int N, int K, double count,
     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma,
     float* dbeta, float* dW, int accumulate, __nv_bfloat16* __restrict__ wcat, float2* __restrict__ coef) {
-  extern __shared__ float sm_f[];   // [4 warps][K] bf16 weights (as float) of the warp's channel
+  extern __shared__ float sm_f[];   // [32][K] chunk of G | [8 warps][K] bf16 weights (as float) of the warp's channel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o = blockIdx.x * 4 + warp;
-  if (o >= N) return;
-  float* wb = sm_f + warp * K;
-  const long long row = static_cast<long long>(o) * K;
+  const int o = blockIdx.x * 8 + warp;
+  const bool live = o < N;
+  float* Gs = sm_f;
+  float* wb = sm_f + 32 * K + warp * K;
+  const long long row = static_cast<long long>(live ? o : 0) * K;
   const int nq = K / 32;
   float dv[8], wv[8];
   double t = 0.0;   // sum_j Wb[o][j] D[o][j] = sum_p dz[p,o] c[p,o]
@@ -127,7 +142,7 @@ __global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
   for (int x = 0; x < 8; ++x) {
     if (x < nq) {
       const int j = lane + 32 * x;
-      const float v = __bfloat162float(Wb[row + j]);
+      const float v = live ? __bfloat162float(Wb[row + j]) : 0.f;
       wb[j] = v;
       dv[x] = D[row + j];
       wv[x] = W[row + j];
@@ -138,11 +153,13 @@ __global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
   float sd[8];
 #pragma unroll
   for (int x = 0; x < 8; ++x) sd[x] = 0.f;
-  for (int r0 = lane; r0 < T; r0 += 256) {
+  if (live) {
+    for (int r0 = lane; r0 < T; r0 += 256) {
 #pragma unroll
-    for (int x = 0; x < 8; ++x) {
-      const int r = r0 + 32 * x;
-      if (r < T) sd[x] += __ldg(dz_partial + (static_cast<long long>(r) * 2) * N + o);
+      for (int x = 0; x < 8; ++x) {
+        const int r = r0 + 32 * x;
+        if (r < T) sd[x] += __ldg(dz_partial + (static_cast<long long>(r) * 2) * N + o);
+      }
     }
   }
   double sdz = 0.0;
@@ -150,7 +167,10 @@ __global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
   for (int x = 0; x < 8; ++x) sdz += static_cast<double>(sd[x]);
   t = warp_sum_d(t);
   sdz = warp_sum_d(sdz);
-  __syncwarp();
+  // q_j = sum_i Wb[o][i] G[i][j]   (starts with a block barrier: wb is visible)
+  float q[8];
+  warp_wG<false>(G, K, Gs, wb, nullptr, 0.f, q);
+  if (!live) return;
   const double mu = mean[o], is = invstd[o], g = gamma ? gamma[o] : 1.0f;
   const double dg = is * (t - mu * sdz);   // sum dz * xhat
   const double a = g * is;
@@ -160,26 +180,6 @@ __global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
     dgamma[o] = accumulate ? dgamma[o] + static_cast<float>(dg) : static_cast<float>(dg);
     dbeta[o] = accumulate ? dbeta[o] + static_cast<float>(sdz) : static_cast<float>(sdz);
     coef[o] = make_float2(static_cast<float>(b), static_cast<float>(k));
-  }
-  // q_j = sum_i Wb[o][i] G[i][j]   (lane owns j = lane + 32 x; 8 rows of G in flight)
-  float q[8];
-#pragma unroll
-  for (int x = 0; x < 8; ++x) q[x] = 0.f;
-  for (int i0 = 0; i0 < K; i0 += 8) {
-    float gv[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-#pragma unroll
-      for (int x = 0; x < 8; ++x)
-        if (x < nq) gv[r][x] = __ldg(G + static_cast<long long>(i0 + r) * K + lane + 32 * x);
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const float wi = wb[i0 + r];
-#pragma unroll
-      for (int x = 0; x < 8; ++x)
-        if (x < nq) q[x] = fmaf(wi, gv[r][x], q[x]);
-    }
   }
   const float af = static_cast<float>(a), bf = static_cast<float>(b), kf = static_cast<float>(k);
   const int ld = N + K;
@@ -195,35 +195,42 @@ __global__ void __launch_bounds__(128) bn_conv1x1_bwd_rows_kernel(
 }
 
 // M[j][i] = sum_o b_o Wb[o][j] W[o][i]  ->  wcat[i][N + j];   bias[i] = sum_o k_o W[o][i].
-// grid (K/32, K/32): a block computes a 32 x 32 tile of M; the reduction over o runs in chunks of 32 rows staged through
-// shared memory (coalesced loads, 32 rows in flight); thread = (i, 4 values of j).  Blocks with blockIdx.y == 0 also produce
-// their 32 entries of the bias.
+// grid (K/32, K/32, S): a block computes a 32 x 32 tile of M over ITS slice of the channels o (N / S of them, staged through
+// shared memory 32 rows at a time) and publishes the partial tile; the last block of a tile to finish (ticket counter, reset
+// for the next launch) adds the S partials in a fixed order - deterministic - and writes the bf16 operand.  Thread = (i, 4 j's).
+// Tiles with blockIdx.y == 0 also carry the 32 bias entries of their i range.
+// scratch: [K/32 * K/32] uint32 tickets (zero before the first launch) | partial [S][K/32*K/32][33][32] floats.
+constexpr int kAlgebraSlices = 8;
 __global__ void __launch_bounds__(256) bn_conv1x1_bwd_m_kernel(const float2* __restrict__ coef, const __nv_bfloat16* __restrict__ Wb,
                                                                const float* __restrict__ W, int N, int K,
-                                                               __nv_bfloat16* __restrict__ wcat, float* __restrict__ bias) {
+                                                               __nv_bfloat16* __restrict__ wcat, float* __restrict__ bias,
+                                                               unsigned int* __restrict__ tickets, float* __restrict__ partial) {
   __shared__ float sa[32][33];   // b_o * Wb[o][j0 + .]
   __shared__ float sw[32][33];   // W[o][i0 + .]
   __shared__ float sk[32];       // k_o
+  __shared__ int is_last;
   const int ti = threadIdx.x & 31, tq = threadIdx.x >> 5;   // i = i0 + ti; j = j0 + tq * 4 + {0..3}
   const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
+  const int S = gridDim.z, z = blockIdx.z;
+  const int per = (N + S - 1) / S;
+  const int o_begin = z * per, o_end = min(N, o_begin + per);
+  const int tile = blockIdx.y * gridDim.x + blockIdx.x, n_tile = gridDim.x * gridDim.y;
   float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
-  for (int o0 = 0; o0 < N; o0 += 32) {
-    // 256 threads load 32 x 32 of each operand: thread (ti, tq) loads rows tq*4 .. tq*4+3, column ti
+  for (int o0 = o_begin; o0 < o_end; o0 += 32) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int o = o0 + tq * 4 + r;
-      float av = 0.f, wv = 0.f;
-      if (o < N) {
+      float av = 0.f, wv = 0.f, kv = 0.f;
+      if (o < o_end) {
         const long long base = static_cast<long long>(o) * K;
         const float2 c = coef[o];
         av = c.x * __bfloat162float(Wb[base + j0 + ti]);
         wv = W[base + i0 + ti];
-        if (ti == 0) sk[tq * 4 + r] = c.y;
-      } else if (ti == 0) {
-        sk[tq * 4 + r] = 0.f;
+        kv = c.y;
       }
       sa[tq * 4 + r][ti] = av;
       sw[tq * 4 + r][ti] = wv;
+      if (ti == 0) sk[tq * 4 + r] = kv;
     }
     __syncthreads();
 #pragma unroll
@@ -235,10 +242,32 @@ __global__ void __launch_bounds__(256) bn_conv1x1_bwd_m_kernel(const float2* __r
     }
     __syncthreads();
   }
+  // publish this slice's partial tile: [z][tile][row 0..31 = j, row 32 = bias][i]
+  float* mine = partial + (static_cast<long long>(z) * n_tile + tile) * 33 * 32;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) mine[(tq * 4 + x) * 32 + ti] = acc[x];
+  if (tq == 0) mine[32 * 32 + ti] = accb;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[tile], 1u);
+    is_last = (t == static_cast<unsigned int>(S - 1));
+    if (is_last) tickets[tile] = 0;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float fin[4] = {0.f, 0.f, 0.f, 0.f}, finb = 0.f;
+  for (int zz = 0; zz < S; ++zz) {
+    const float* src = partial + (static_cast<long long>(zz) * n_tile + tile) * 33 * 32;
+#pragma unroll
+    for (int x = 0; x < 4; ++x) fin[x] += __ldcg(src + (tq * 4 + x) * 32 + ti);
+    if (tq == 0) finb += __ldcg(src + 32 * 32 + ti);
+  }
   const long long ld = N + K;
 #pragma unroll
-  for (int x = 0; x < 4; ++x) wcat[static_cast<long long>(i0 + ti) * ld + N + j0 + tq * 4 + x] = __float2bfloat16(acc[x]);
-  if (blockIdx.y == 0 && tq == 0) bias[i0 + ti] = accb;
+  for (int x = 0; x < 4; ++x) wcat[static_cast<long long>(i0 + ti) * ld + N + j0 + tq * 4 + x] = __float2bfloat16(fin[x]);
+  if (blockIdx.y == 0 && tq == 0) bias[i0 + ti] = finb;
 }
 
 }  // namespace b200

@@ -395,6 +395,19 @@ def relu_mask_sum(g, y):
     return dz, partial
 
 
+_ticket_cache = {}
+
+
+def _algebra_tickets(device):
+    """Persistent zero-initialised ticket counters of the M-tile reduction (per stream; the kernel leaves them zero)."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    t = _ticket_cache.get(key)
+    if t is None:
+        t = torch.zeros(64, dtype=torch.int32, device=device)
+        _ticket_cache[key] = t
+    return t
+
+
 def bn_conv1x1_bwd(dz_partial, D, G, s, w_packed, w_f32, count, gamma, co, dgamma=None, dbeta=None, dW=None):
     """BatchNorm + 1x1-conv backward algebra (csrc/bn_algebra.cuh). Returns (dgamma, dbeta, dW [N,K,1,1], wcat bf16 [K, N+K],
     bias fp32 [K]); wcat / bias are the operands of gemm_dual([dz | y2])."""
@@ -408,11 +421,13 @@ def bn_conv1x1_bwd(dz_partial, D, G, s, w_packed, w_f32, count, gamma, co, dgamm
         dW = torch.empty(N, K, 1, 1, dtype=F32, device=dev)
     wcat = torch.empty(K, N + K, dtype=BF16, device=dev)
     bias = torch.empty(K, dtype=F32, device=dev)
-    coef = torch.empty(N, 2, dtype=F32, device=dev)
+    nbytes = lib.b200_bn_conv1x1_bwd_scratch_bytes(N, K)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    tickets = _algebra_tickets(dev)
     w32 = w_f32.detach()
     rc = lib.b200_bn_conv1x1_bwd(_p(dz_partial), dz_partial.shape[0], _p(D), _p(G), _p(s), _p(w_packed), _p(w32), N, K, float(count),
                                  _p(gamma), _p(co.mean), _p(co.invstd), _p(dgamma), _p(dbeta), _p(dW), 0, _p(wcat), _p(bias),
-                                 _p(coef), _stream())
+                                 _p(scratch), nbytes, _p(tickets), _stream())
     _lib.check(rc, "b200_bn_conv1x1_bwd")
     return dgamma, dbeta, dW, wcat, bias
 

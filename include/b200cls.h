@@ -297,11 +297,13 @@ int b200_conv1x1_bn_act_fwd(const void* x, const void* w, const float* scale, co
 int b200_conv1x1_dgrad_masked_stats_rows(long long pixels, int Cin);
 int b200_conv1x1_dgrad_masked(const void* dy, const void* wd, void* dx, long long pixels, int Cin, int Cout,
                               const void* residual, const void* mask_src, float* stats, void* stream);
-/* dz_partial fp32 [T][2][N] (plane 0 = partial column sums of dz); coef_scratch: 2 * N floats */
+/* dz_partial fp32 [T][2][N] (plane 0 = partial column sums of dz); scratch: b200_bn_conv1x1_bwd_scratch_bytes(N, K) bytes;
+ * tickets: 64 uint32 counters, zero before the first call (the kernel leaves them zero) */
+size_t b200_bn_conv1x1_bwd_scratch_bytes(int N, int K);
 int b200_bn_conv1x1_bwd(const float* dz_partial, int T, const float* D, const float* G, const float* s, const void* w_bf16,
                         const float* w_f32, int N, int K, double count, const float* gamma, const float* mean,
                         const float* invstd, float* dgamma, float* dbeta, float* dW, int accumulate, void* wcat, float* bias,
-                        void* coef_scratch, void* stream);
+                        void* scratch, size_t scratch_bytes, void* tickets, void* stream);
 /* out[pixels][N] (bf16) = [a0[pixels][K0] | a1[pixels][K1]] * wcat[N][K0 + K1]^T + bias[N] */
 int b200_gemm_dual(const void* a0, int K0, const void* a1, int K1, const void* wcat, const float* bias, void* out,
                    long long pixels, int N, void* stream);
