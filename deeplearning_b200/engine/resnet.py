@@ -229,7 +229,12 @@ class _Grads(dict):
         return self.sink(param) if self.sink is not None else None
 
     def put(self, param, value):
+        """Record the (final) gradient of ``param``; a sink with a ``notify`` method is told so that the data-parallel
+        trainer can start all-reducing completed stretches of the gradient arena while the backward pass continues."""
         self[param.data_ptr()] = value
+        notify = getattr(self.sink, "notify", None)
+        if notify is not None:
+            notify(param)
 
 
 def _unit_backward(u, g, grads, want_dz=False):

@@ -3,8 +3,11 @@
 B200-native counterpart of the reference's DDP recipe (others/train_with_DDP/train.py:106-111,188-201,245-253 and
 classification/swin_transformer/main.py:101-103): one process per GPU, identical replicas, per-GPU BatchNorm statistics
 (DDP *without* SyncBN, as the north-star asks), gradients averaged across ranks after backward, identical update on every
-rank.  Instead of DDP's bucketed reducer the backward kernels write straight into one contiguous fp32 arena which is
-all-reduced with a single NCCL call over NVLink/NVSwitch; the 1/world scale is folded into the fused SGD kernel.
+rank.  The backward kernels write straight into one contiguous fp32 arena; like DDP's bucketed reducer the all-reduce is
+overlapped with the backward pass: gradients are produced from the end of the arena towards its start, and every time a
+stretch of ``bucket_mb`` of completed gradients has accumulated it is all-reduced (NCCL over NVLink/NVSwitch) on a side
+stream while the remaining layers are still computing.  The 1/world scale is folded into the fused optimizer kernel, and
+the whole step (collectives included) is captured in ONE CUDA graph.
 
 ``model.parameters()`` keep their identity: each ``p.data`` becomes a view into the parameter arena and ``p.grad`` a
 view into the gradient arena, so ``state_dict()`` / checkpoints / user code reading ``.grad`` behave as in the reference.
@@ -56,8 +59,10 @@ class FlatArena:
     Every ``p.data`` becomes a view into ``flat_p`` and every ``p.grad`` a view into ``flat_g``; ``all_reduce_grads`` is the
     single collective of the data-parallel step and ``broadcast`` makes the replicas identical at start-up."""
 
-    def __init__(self, params, process_group=None, world_size=None):
+    def __init__(self, params, process_group=None, world_size=None, bucket_mb=25.0):
         self.params = [p for p in params if p.requires_grad]
+        self.bucket_elems = max(1, int(bucket_mb * 1e6 / 4))
+        self._comm = None
         if not self.params:
             raise ValueError("no trainable parameters")
         self.group = process_group
@@ -86,6 +91,59 @@ class FlatArena:
 
     def grad_view(self, param):
         return self._gviews.get(param.data_ptr())
+
+    # ---- overlapped all-reduce: the engines produce gradients roughly in reverse parameter order ------------------------
+    def begin_backward(self):
+        """Start tracking which gradients are final (``notify``) so that completed stretches [lo, hi) at the END of the
+        arena can be all-reduced while the backward pass is still running."""
+        self._index = {p.data_ptr(): i for i, p in enumerate(self.params)}
+        self._done = [False] * len(self.params)
+        self._next = len(self.params) - 1          # highest-offset parameter whose gradient is still outstanding
+        self._hi = self.flat_g.numel()             # everything in [_hi, end) has been handed to NCCL already
+        self.buckets_launched = 0
+        if self._comm is None and self.flat_g.is_cuda:
+            self._comm = torch.cuda.Stream()
+
+    def notify(self, param):
+        if self.world <= 1 or getattr(self, "_done", None) is None:
+            return
+        i = self._index.get(param.data_ptr())
+        if i is None or self._done[i]:
+            return
+        self._done[i] = True
+        while self._next >= 0 and self._done[self._next]:
+            self._next -= 1
+        lo = self.offsets[self._next + 1] if self._next + 1 < len(self.offsets) else self.flat_g.numel()
+        if self._next < 0:
+            lo = 0
+        if self._hi - lo >= self.bucket_elems or (lo == 0 and self._hi > 0):
+            self._reduce_range(lo, self._hi)
+            self._hi = lo
+
+    def _reduce_range(self, lo, hi):
+        if hi <= lo:
+            return
+        chunk = self.flat_g[lo:hi]
+        if self._comm is not None:
+            ev = torch.cuda.Event()
+            ev.record()
+            with torch.cuda.stream(self._comm):
+                self._comm.wait_event(ev)
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+        self.buckets_launched += 1
+
+    def finish_backward(self):
+        """Reduce whatever has not been handed to NCCL yet and make the compute stream wait for the collectives."""
+        if self.world <= 1 or getattr(self, "_done", None) is None:
+            self._done = None
+            return
+        self._reduce_range(0, self._hi)
+        self._hi = 0
+        self._done = None
+        if self._comm is not None:
+            torch.cuda.current_stream().wait_stream(self._comm)
 
     def broadcast(self, buffers=()):
         if self.world > 1:
@@ -122,9 +180,23 @@ def model_no_decay_rule(model):
     return rule
 
 
+class _GradSink:
+    """Gradient destination handed to the engines: views of the arena, plus completion notices for the overlapped reduce."""
+
+    def __init__(self, arena):
+        self.arena = arena
+
+    def __call__(self, param):
+        return self.arena.grad_view(param)
+
+    def notify(self, param):
+        self.arena.notify(param)
+
+
 class TrainStep:
     def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
-                 broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None, clip_grad=None):
+                 broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None, clip_grad=None,
+                 overlap=True, bucket_mb=25.0):
         """optimizer="sgd": torch.optim.SGD(momentum, weight_decay on every parameter) - resnet/vit train.py:96,94.
         optimizer="adamw": torch.optim.AdamW(betas, eps, weight_decay) with the reference's decay / no-decay groups
         (``no_decay(name, param) -> bool``, default ``no_decay_rule``) - convNext/train.py:96,102.
@@ -136,7 +208,8 @@ class TrainStep:
         self.optimizer, self.betas, self.eps = optimizer, betas, eps
         if optimizer not in ("sgd", "adamw"):
             raise ValueError(f"unknown optimizer {optimizer!r}")
-        self.arena = FlatArena(model.parameters(), process_group, world_size)
+        self.arena = FlatArena(model.parameters(), process_group, world_size, bucket_mb=bucket_mb)
+        self.overlap = overlap   # bucketed all-reduce on a side stream during the backward pass (False: one call after it)
         if self.arena.flat_p.device.type != "cuda":
             raise RuntimeError("TrainStep needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
         self.world = self.arena.world
@@ -163,11 +236,18 @@ class TrainStep:
 
     # ------------------------------------------------------------------------------------------------ eager step
     def _fwd_bwd(self, images, labels):
+        """Forward, loss, backward AND the gradient all-reduce (overlapped with the backward pass when ``overlap``)."""
         model, arena = self.model, self.arena
         logits, tape = self.engine.forward(model, images, True, True)
         n_pad = (logits.shape[1] + 7) // 8 * 8
         loss, dlogits, correct = ops.softmax_xent(logits, labels, want_grad=True, ld_d=n_pad)
-        self.engine.backward(model, tape, dlogits, sink=arena.grad_view)
+        if self.world > 1 and self.overlap:
+            arena.begin_backward()
+            self.engine.backward(model, tape, dlogits, sink=_GradSink(arena))
+            arena.finish_backward()
+        else:
+            self.engine.backward(model, tape, dlogits, sink=arena.grad_view)
+            arena.all_reduce_grads()
         return loss, correct
 
     @property
@@ -199,15 +279,14 @@ class TrainStep:
         if not self.model.training:
             self.model.train()
         loss, correct = self._fwd_bwd(images, labels)
-        self.arena.all_reduce_grads()
         self._update(self.lr if lr is None else lr)
         self.steps += 1
         return loss, correct
 
     # ------------------------------------------------------------------------------------------------ CUDA-graph step
     def capture(self, images, labels):
-        """Capture fwd+loss+bwd(+update) into CUDA graphs with static input buffers of the given shapes.
-        world == 1: one graph for the whole step.  world > 1: graph(fwd+bwd) -> NCCL all-reduce -> graph(update)."""
+        """Capture fwd + loss + bwd + gradient all-reduce + update into ONE CUDA graph with static input buffers of the given
+        shapes (world > 1: the NCCL collectives of the gradient buckets are graph nodes on a side stream)."""
         if not self.model.training:
             self.model.train()
         dev = self.arena.flat_p.device
@@ -230,7 +309,6 @@ class TrainStep:
         with torch.cuda.stream(side):
             for _ in range(2):
                 self._fwd_bwd(self._g_images, self._g_labels)
-                self.arena.all_reduce_grads()
                 self._update(self.lr, self._lr_dev)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -245,18 +323,13 @@ class TrainStep:
                 b.copy_(sb)
         self.steps = saved_steps
         weight_cache.bump()
+        # ONE graph for the whole step; with world > 1 it contains the NCCL all-reduces of the gradient buckets on their side
+        # stream ("thread_local": the NCCL watchdog thread's CUDA calls must not invalidate the capture)
         self._graph_fb = torch.cuda.CUDAGraph()
         self._graph_up = None
-        if self.world == 1:
-            with torch.cuda.graph(self._graph_fb):
-                self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels)
-                self._update(self.lr, self._lr_dev)
-        else:
-            with torch.cuda.graph(self._graph_fb):
-                self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels)
-            self._graph_up = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self._graph_up, pool=self._graph_fb.pool()):
-                self._update(self.lr, self._lr_dev)
+        with torch.cuda.graph(self._graph_fb, capture_error_mode="thread_local"):
+            self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels)
+            self._update(self.lr, self._lr_dev)
         self._captured_shape = (tuple(images.shape), tuple(labels.shape))
         return self
 
@@ -276,9 +349,6 @@ class TrainStep:
                 self._hyper[0:1].fill_(float(lr))
                 self._hyper_lr_value = float(lr)
         self._graph_fb.replay()
-        if self._graph_up is not None:
-            self.arena.all_reduce_grads()
-            self._graph_up.replay()
         self.steps += 1
         # the replay updated the parameters behind autograd's back (and repacked the bf16 operands from the PRE-update
         # values at its start): any forward outside the graph must repack first

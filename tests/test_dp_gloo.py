@@ -72,3 +72,45 @@ def test_two_rank_gloo_equals_single_process_full_batch():
         opt.step()
     flat = torch.cat([torch.nn.functional.pad(p.detach().reshape(-1), (0, (-p.numel()) % 4)) for p in model.parameters()])
     assert torch.allclose(flat, p0, rtol=1e-5, atol=1e-6)
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from deeplearning_b200.classification.mnist.models.network import mnist_fcn
+        from deeplearning_b200.engine.trainer import FlatArena
+
+        torch.manual_seed(5)
+        model = mnist_fcn(10)
+        arena = FlatArena(model.parameters(), bucket_mb=0.02)     # ~5000-element buckets: several per backward
+        g = torch.Generator().manual_seed(40 + rank)
+        local = torch.randn(arena.flat_g.numel(), generator=g)
+        # (a) gradients become final in reverse parameter order (what the engines do), (b) in a scrambled order
+        for order in (list(reversed(arena.params)), [arena.params[i] for i in torch.randperm(len(arena.params), generator=torch.Generator().manual_seed(3)).tolist()]):
+            arena.flat_g.copy_(local)
+            arena.begin_backward()
+            for p in order:
+                arena.notify(p)
+            launched = arena.buckets_launched
+            arena.finish_backward()
+            out[(rank, len(out))] = (arena.flat_g.clone(), launched, arena.buckets_launched)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_bucket_allreduce_equals_one_allreduce():
+    """FlatArena.begin_backward / notify / finish_backward (the bucketed reduce the GPU step overlaps with its backward pass)
+    sums exactly what a single all-reduce of the arena sums, whatever order the gradients complete in."""
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, port, out), nprocs=world, join=True)
+    vals = list(out.values())
+    n = vals[0][0].numel()
+    expect = torch.randn(n, generator=torch.Generator().manual_seed(40)) + torch.randn(n, generator=torch.Generator().manual_seed(41))
+    for flat, launched_mid, launched_all in vals:
+        assert torch.allclose(flat, expect, rtol=0, atol=1e-6)
+        assert launched_all >= launched_mid >= 1
+    # in reverse parameter order the buckets go out while "the backward" is still running, not all at the end
+    assert max(v[1] for v in vals) >= 2
