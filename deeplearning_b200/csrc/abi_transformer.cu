@@ -415,7 +415,9 @@ int b200_window_partition(const void* in, void* out, int B, int H, int W, int C,
   B200_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_partition: %dx%d not divisible by window %d", H, W, ws);
   B200_REQUIRE((static_cast<long long>(C) * elem_bytes) % 16 == 0, "window_partition: C*elem_bytes must be a multiple of 16");
   const int cvec = C * elem_bytes / 16;
-  window_partition_kernel<<<grid_for(static_cast<long long>(B) * H * W * cvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const long long nvec = static_cast<long long>(B) * H * W * cvec;
+  B200_REQUIRE(nvec < (1LL << 31), "window_partition: tensor too large (%lld 16-byte vectors)", nvec);
+  window_permute_kernel<false><<<grid_for((nvec + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, cvec, shift, ws);
   B200_LAUNCHED();
   return OK;
@@ -425,7 +427,9 @@ int b200_window_merge(const void* in, void* out, int B, int H, int W, int C, int
   B200_REQUIRE(ws > 0 && H % ws == 0 && W % ws == 0, "window_merge: %dx%d not divisible by window %d", H, W, ws);
   B200_REQUIRE((static_cast<long long>(C) * elem_bytes) % 16 == 0, "window_merge: C*elem_bytes must be a multiple of 16");
   const int cvec = C * elem_bytes / 16;
-  window_merge_kernel<<<grid_for(static_cast<long long>(B) * H * W * cvec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const long long nvec = static_cast<long long>(B) * H * W * cvec;
+  B200_REQUIRE(nvec < (1LL << 31), "window_merge: tensor too large (%lld 16-byte vectors)", nvec);
+  window_permute_kernel<true><<<grid_for((nvec + 3) / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(in), static_cast<uint4*>(out), B, H, W, cvec, shift, ws);
   B200_LAUNCHED();
   return OK;

@@ -677,45 +677,56 @@ __global__ void wattn_bias_scatter_kernel(const float* __restrict__ dbias, const
 // Stand-alone permutations of kernels/window_process (the reference's only first-party CUDA; B2 seam), 16-byte vectors:
 //   partition: out[b*nW + win][wy][wx][:] = in[b][(wh*ws + wy - shift) mod H][(ww*ws + wx - shift) mod W][:]
 //   merge:     out[b][h][w][:] = in[b*nW + win(h', w')][h' % ws][w' % ws][:],  (h', w') = ((h - shift) mod H, (w - shift) mod W)
-__global__ void window_partition_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W,
-                                        int cvec, int shift, int ws) {
-  const int nWx = W / ws, nWy = H / ws;
-  const long long total = static_cast<long long>(B) * H * W * cvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cvec);
-    long long t = i / cvec;
-    const int wx = static_cast<int>(t % ws);
-    t /= ws;
-    const int wy = static_cast<int>(t % ws);
-    t /= ws;
-    const int ww = static_cast<int>(t % nWx);
-    t /= nWx;
-    const int wh = static_cast<int>(t % nWy);
-    const long long b = t / nWy;
-    int y = (wh * ws + wy - shift) % H, x = (ww * ws + wx - shift) % W;
-    if (y < 0) y += H;
-    if (x < 0) x += W;
-    out[i] = __ldg(in + ((b * H + y) * W + x) * cvec + c);
-  }
-}
-__global__ void window_merge_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H, int W, int cvec,
-                                    int shift, int ws) {
-  const int nWx = W / ws, nWy = H / ws;
-  const long long total = static_cast<long long>(B) * H * W * cvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int c = static_cast<int>(i % cvec);
-    long long t = i / cvec;
-    const int w = static_cast<int>(t % W);
-    t /= W;
-    const int h = static_cast<int>(t % H);
-    const long long b = t / H;
-    int y = (h - shift) % H, x = (w - shift) % W;
-    if (y < 0) y += H;
-    if (x < 0) x += W;
-    const long long win = (b * nWy + y / ws) * nWx + x / ws;
-    out[i] = __ldg(in + ((win * ws + y % ws) * ws + x % ws) * cvec + c);
+// Each thread moves four independent 16-byte vectors per iteration (index arithmetic in 32 bits: the tensors of this path hold
+// far fewer than 2^32 vectors), so ~64 B per thread are in flight - a permutation kernel is pure HBM latency hiding.
+template <bool kMerge>
+__global__ void __launch_bounds__(256) window_permute_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H,
+                                                             int W, int cvec, int shift, int ws) {
+  const unsigned nWx = W / ws, nWy = H / ws;
+  const unsigned total = static_cast<unsigned>(B) * H * W * cvec;
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    uint4 v[4];
+    unsigned src[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned i = i0 + u * stride;
+      if (i >= total) break;
+      const unsigned c = i % cvec;
+      unsigned t = i / cvec;
+      if (kMerge) {
+        // out[b][h][w] = in[b*nW + win(h', w')][h' % ws][w' % ws],  (h', w') = ((h - shift) mod H, (w - shift) mod W)
+        const unsigned w = t % W;
+        t /= W;
+        const unsigned h = t % H;
+        const unsigned b = t / H;
+        int y = (static_cast<int>(h) - shift) % H, x = (static_cast<int>(w) - shift) % W;
+        if (y < 0) y += H;
+        if (x < 0) x += W;
+        const unsigned win = (b * nWy + y / ws) * nWx + x / ws;
+        src[u] = ((win * ws + y % ws) * ws + x % ws) * cvec + c;
+      } else {
+        // out[b*nW + win][wy][wx] = in[b][(wh*ws + wy - shift) mod H][(ww*ws + wx - shift) mod W]
+        const unsigned wx = t % ws;
+        t /= ws;
+        const unsigned wy = t % ws;
+        t /= ws;
+        const unsigned ww = t % nWx;
+        t /= nWx;
+        const unsigned wh = t % nWy;
+        const unsigned b = t / nWy;
+        int y = (static_cast<int>(wh * ws + wy) - shift) % H, x = (static_cast<int>(ww * ws + wx) - shift) % W;
+        if (y < 0) y += H;
+        if (x < 0) x += W;
+        src[u] = ((b * H + y) * W + x) * cvec + c;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < total) v[u] = __ldg(in + src[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * stride < total) out[i0 + u * stride] = v[u];
   }
 }
 
