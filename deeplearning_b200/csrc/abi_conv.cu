@@ -17,6 +17,7 @@ uint32_t g_fwd_lbo = 16, g_fwd_sbo = 1024;
 uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024, g_wg_kstep = 2048;
 // one-shot per-output-channel multiplier for the next b200_conv2d_wgrad call (see b200_conv2d_wgrad_set_rowscale)
 thread_local const float* g_wgrad_rowscale = nullptr;
+thread_local float* g_wgrad_bias_partial = nullptr;
 
 struct Box3 {
   int b1, b2, b3;
@@ -237,6 +238,7 @@ int launch_conv_gemm_pair(const ConvGemmParams& q, cudaStream_t st) {
   const int items = (q.tiles1 * q.tiles2 * q.tiles3 + 1) / 2 * q.n_tiles;   // pairs of pixel tiles x channel blocks
   int pairs = device_sm_count() / 2;
   if (items < pairs) pairs = items;
+  if (q.stats != nullptr) pairs = pairs / q.n_tiles * q.n_tiles;   // a pair must keep seeing the same channel block
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * pairs);
@@ -263,6 +265,7 @@ int launch_conv_gemm_pair(const ConvGemmParams& q, cudaStream_t st) {
   X(kEpiBias | kEpiColscale | kEpiResF32 | kEpiOutF32)   \
   X(kEpiBias | (2 << kEpiActShift) | kEpiAux)            \
   X(3 << kEpiActShift)                                   \
+  X((3 << kEpiActShift) | kEpiStats)                     \
   X(kEpiOutF32)                                          \
   X(kEpiBias | kEpiOutF32)
 
@@ -379,7 +382,9 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   using Cfg = WgradCfg<BLOCK_NG>;
   static bool configured = false;
   if (!configured) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_NG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_NG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::SMEM_BYTES));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(wgrad_gemm_kernel<BLOCK_NG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::SMEM_BYTES));
     configured = true;
   }
@@ -389,7 +394,10 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   q.desc_lbo = g_wg_lbo;
   q.desc_sbo = g_wg_sbo;
   q.desc_kstep = g_wg_kstep;
-  wgrad_gemm_kernel<BLOCK_NG><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
+  if (q.bias_partial != nullptr)   // + four warps that sum the dY tiles' columns (the layer's bias gradient)
+    wgrad_gemm_kernel<BLOCK_NG, true><<<grid, 320, Cfg::SMEM_BYTES, st>>>(q);
+  else
+    wgrad_gemm_kernel<BLOCK_NG, false><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
   B200_LAUNCHED();
   return OK;
 }
@@ -727,7 +735,21 @@ int b200_gemm_ex(const b200_view_t* a, const b200_view_t* out, const b200_gemm_a
     uint64_t strides[2] = {1, static_cast<uint64_t>(g->K)};
     uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
     if ((rc = encode_tmap_bf16(&p.b_map, g->w, 2, dims, strides, box))) return rc;
-    if (BN == 256 && g->stats == nullptr && gemm_pair_enabled()) {   // bring-up switch, see launch_conv_gemm_pair
+    bool pair_ok = BN == 256 && gemm_pair_enabled();
+    if (pair_ok && g->stats != nullptr) {
+      // the pair kernel writes (2 * pairs / n_tiles) * 4 partial rows; use it only when that is exactly what the caller
+      // allocated from b200_conv2d_fwd_stats_rows (the single-CTA grid), e.g. the fc2 dgrad of ViT-B/16 (N = 3072: 48 rows)
+      const int n_tiles = (g->N + 255) / 256;
+      const long long m_tiles = static_cast<long long>(p.tiles1) * p.tiles2 * p.tiles3;
+      const long long items = (m_tiles + 1) / 2 * n_tiles;
+      long long pairs = device_sm_count() / 2;
+      if (items < pairs) pairs = items;
+      pairs = pairs / n_tiles * n_tiles;
+      const long long tiles = m_tiles * n_tiles;
+      const int single = conv_grid(tiles > (1 << 30) ? (1 << 30) : static_cast<int>(tiles), n_tiles, true);
+      pair_ok = pairs > 0 && 2 * pairs == single && g->act == B200_ACT_GELU_GRAD;
+    }
+    if (pair_ok) {
       uint32_t half[2] = {64, 128};
       if ((rc = encode_tmap_bf16(&p.b_map_half, g->w, 2, dims, strides, half))) return rc;
       p.pair = 1;
@@ -761,6 +783,15 @@ int b200_conv2d_wgrad_set_rowscale(const float* rowscale) {
   return OK;
 }
 
+int b200_conv2d_wgrad_set_bias_partial(float* bias_partial) {
+  g_wgrad_bias_partial = bias_partial;
+  return OK;
+}
+
+int b200_conv2d_wgrad_splits(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
+  return plan_wgrad(B, H, W, Cin, Cout, ksize, stride).splits;
+}
+
 size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
   const WgradPlan pl = plan_wgrad(B, H, W, Cin, Cout, ksize, stride);
   return static_cast<size_t>(pl.splits) * Cout * pl.taps * Cin * sizeof(float);
@@ -788,6 +819,8 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   p.splits = pl.splits, p.kb_per_split = pl.kb_per_split, p.kb_total = pl.kb_total;
   p.ld_partial = static_cast<long long>(pl.taps) * Cin;
   p.partial = static_cast<float*>(workspace);
+  p.bias_partial = g_wgrad_bias_partial;   // one-shot (b200_conv2d_wgrad_set_bias_partial)
+  g_wgrad_bias_partial = nullptr;
   const bool flat = (ksize == 1 && stride == 1);
   int rc;
   View dyv = flat ? make_flat_view(dy, static_cast<long long>(B) * H * W, Cout)

@@ -182,7 +182,7 @@ constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEp
 // both and commits to the barriers of both; every CTA drains its own 128 accumulator rows with the unchanged epilogue.
 template <int BLOCK_N, int EPI = kEpiGeneric, bool kPair = false>
 __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  static_assert(!kPair || (BLOCK_N == 256 && EPI >= 0 && !(EPI & kEpiStats) && !(EPI & kEpiDirect)),
+  static_assert(!kPair || (BLOCK_N == 256 && EPI >= 0 && !(EPI & kEpiDirect)),
                 "pair mode: 256-wide tiles of the linear layers only");
   using Cfg = ConvGemmCfg<BLOCK_N, kPair>;
   constexpr int STAGES = Cfg::STAGES;
@@ -701,7 +701,11 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     }
 #endif
     if (stats != nullptr) {
-      const int n_tile = blockIdx.x % p.n_tiles, grp = blockIdx.x / p.n_tiles;
+      // (pair mode: the host keeps (gridDim.x / 2) % n_tiles == 0, so a CTA pair always works on channel block
+      //  (blockIdx.x >> 1) % n_tiles; each CTA of the pair owns its own 128 accumulator rows and writes its own partial rows)
+      const int cta = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+      const int n_tile = cta % p.n_tiles;
+      const int grp = kPair ? (cta / p.n_tiles) * 2 + static_cast<int>(cta_rank) : cta / p.n_tiles;
       const int srow = split_tiles ? (grp * 4 + q) * 2 + pair : grp * 4 + q;
 #pragma unroll
       for (int k = 0; k < UN; ++k) {

@@ -726,14 +726,59 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const long long
   }
 
   if (mode == 0 && taps == 1) {
-    // dst[o][i] = src[o][i]: contiguous rows
+    // dst[o][i] = src[o][i]: contiguous rows; 8 floats -> one 16-byte store per thread when the row allows it
+    const bool vec = (I % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
     for (int o = blk; o < O; o += nblk) {
       const float sc = oscale ? oscale[o] : 1.f;
       const float* s0 = src + static_cast<long long>(o) * I;
       __nv_bfloat16* d0 = dst + o * ld;
-      for (int i = tid; i < I; i += 256) d0[i] = __float2bfloat16_rn(s0[i] * sc);
+      if (vec) {
+        for (int i = tid * 8; i < I; i += 256 * 8) {
+          float f[8];
+          load8f(s0 + i, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] *= sc;
+          *reinterpret_cast<uint4*>(d0 + i) = pack8(f);
+        }
+      } else {
+        for (int i = tid; i < I; i += 256) d0[i] = __float2bfloat16_rn(s0[i] * sc);
+      }
     }
     pack_zero_pad(dst, O, rows_out, I, ld, blk, nblk);
+    return;
+  }
+
+  if (mode == 1 && taps == 1 && O % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    // plain transpose [O][I] -> [I][O] (every linear layer's dgrad operand): 32 (i) x 64 (o) tiles, reads run along i
+    // (128-byte rows), every thread writes 8 consecutive o of one i as ONE 16-byte store
+    constexpr int TP = 33;                       // pitch of sm[o][i]
+    const int tiles_o = (O + 63) / 64, tiles_i = (I + 31) / 32;
+    for (int w = blk; w < tiles_o * tiles_i; w += nblk) {
+      const int o0 = (w % tiles_o) * 64, i0 = (w / tiles_o) * 32;
+      const int no = min(64, O - o0), ni = min(32, I - i0);
+      __syncthreads();
+      for (int e = tid; e < 64 * 32; e += 256) {
+        const int oo = e >> 5, ii = e & 31;
+        float v = 0.f;
+        if (oo < no && ii < ni) {
+          v = src[static_cast<long long>(o0 + oo) * I + i0 + ii];
+          if (oscale) v *= oscale[o0 + oo];
+        }
+        sm[oo * TP + ii] = v;
+      }
+      __syncthreads();
+      {
+        const int ii = tid >> 3, og = (tid & 7) * 8;     // 32 i x 8 groups of 8 o
+        if (ii < ni && og < no) {                        // (O % 8 == 0: a group is all-valid or all-invalid)
+          float f[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = sm[(og + k) * TP + ii];
+          *reinterpret_cast<uint4*>(dst + static_cast<long long>(i0 + ii) * ld + o0 + og) = pack8(f);
+        }
+      }
+    }
+    pack_zero_pad(dst, I, rows_out, static_cast<long long>(O), ld, blk, nblk);
     return;
   }
 

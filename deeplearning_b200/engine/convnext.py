@@ -150,13 +150,19 @@ def _lin_wgrad(grads, lin, dy2d, x2d, dy_stats=None):
     M, N = dy2d.shape
     K = x2d.shape[1]
     dst = grads.dest(lin.weight)
-    gw = ops.conv2d_wgrad(dy2d.view(M, 1, 1, N), x2d.view(M, 1, 1, K), out=dst.view(N, K, 1, 1) if dst is not None else None)
+    gb = None
+    if lin.bias is not None and dy_stats is None:
+        gb = grads.dest(lin.bias)      # bias gradient summed inside the wgrad kernel (no pass over dy)
+        if gb is None:
+            gb = torch.empty(N, dtype=F32, device=dy2d.device)
+    gw = ops.conv2d_wgrad(dy2d.view(M, 1, 1, N), x2d.view(M, 1, 1, K), out=dst.view(N, K, 1, 1) if dst is not None else None,
+                          bias_out=gb)
     grads.put(lin.weight, gw)
     if lin.bias is not None:
         if dy_stats is not None:   # column sums already produced by the epilogue of the GEMM that wrote dy
             grads.put(lin.bias, ops.stats_colsum(dy_stats, out=grads.dest(lin.bias)))
         else:
-            grads.put(lin.bias, ops.colsum_tall(dy2d, out=grads.dest(lin.bias)))
+            grads.put(lin.bias, gb)
 
 
 def backward(model, tape, dlogits, sink=None):
@@ -196,8 +202,8 @@ def backward(model, tape, dlogits, sink=None):
             # the gradient entering the residual branch carries the sample's stochastic-depth multiplier; the identity path keeps g
             g2 = (g if dps is None else ops.rowscale(g, dps)).view(M, C)
             # x' = x + gamma * (post W2^T + b2)
-            gsum = ops.colsum_tall(g2)
-            G = ops.conv2d_wgrad(g2.view(M, 1, 1, C), post.view(M, 1, 1, 4 * C)).view(C, 4 * C)   # unscaled g^T post
+            gsum = torch.empty(C, dtype=F32, device=g2.device)   # column sums of g2, from the wgrad kernel's dy tiles
+            G = ops.conv2d_wgrad(g2.view(M, 1, 1, C), post.view(M, 1, 1, 4 * C), bias_out=gsum).view(C, 4 * C)   # unscaled g^T post
             dW2, db2, dgam = ops.layerscale_grads(G, blk.pwconv2.weight.detach(), blk.pwconv2.bias, gsum, blk.gamma,
                                                   dW2=grads.dest(blk.pwconv2.weight), db2=grads.dest(blk.pwconv2.bias),
                                                   dgamma=grads.dest(blk.gamma) if blk.gamma is not None else None)
@@ -220,9 +226,12 @@ def backward(model, tape, dlogits, sink=None):
         if rec["down"] is not None:
             h_prev, y, m, r = rec["down"]
             ln, conv = model.downsample_layers[i][0], model.downsample_layers[i][1]
-            grads.put(conv.weight, ops.conv2d_wgrad(g, y, 2, 2, out=grads.dest(conv.weight)))
             Bb, Ho, Wo, Co = g.shape
-            grads.put(conv.bias, ops.colsum_tall(g.view(-1, Co), out=grads.dest(conv.bias)))
+            gb = grads.dest(conv.bias)
+            if gb is None:
+                gb = torch.empty(Co, dtype=F32, device=g.device)
+            grads.put(conv.weight, ops.conv2d_wgrad(g, y, 2, 2, out=grads.dest(conv.weight), bias_out=gb))
+            grads.put(conv.bias, gb)
             d_y = ops.conv2d_dgrad(g, pack.get(conv.weight, 1), tuple(h_prev.shape[1:3]), 2, 2)
             Cp = h_prev.shape[3]
             g2, dgl, dbl = ops.layernorm_bwd(d_y.view(-1, Cp), h_prev.view(-1, Cp), m, r, ln.weight, dx_dtype=BF16,
@@ -241,9 +250,13 @@ def backward(model, tape, dlogits, sink=None):
     K0 = a.shape[-1]
     Mp = du0.shape[0]
     dst = grads.dest(stem_conv.weight)
-    gw = ops.conv2d_wgrad(du0.view(Mp, 1, 1, C0), a.view(Mp, 1, 1, K0), out=dst.view(C0, K0, 1, 1) if dst is not None else None)
+    gb = grads.dest(stem_conv.bias)
+    if gb is None:
+        gb = torch.empty(C0, dtype=F32, device=du0.device)
+    gw = ops.conv2d_wgrad(du0.view(Mp, 1, 1, C0), a.view(Mp, 1, 1, K0), out=dst.view(C0, K0, 1, 1) if dst is not None else None,
+                          bias_out=gb)
     grads.put(stem_conv.weight, gw)
-    grads.put(stem_conv.bias, ops.colsum_tall(du0, out=grads.dest(stem_conv.bias)))
+    grads.put(stem_conv.bias, gb)
     return grads
 
 

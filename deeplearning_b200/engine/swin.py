@@ -227,10 +227,16 @@ def backward(model, tape, dlogits, sink=None):
     D, K0 = u0.shape[-1], a.shape[-1]
     rows = u0.numel() // D
     dst = grads.dest(pe.proj.weight)
-    gw = ops.conv2d_wgrad(du0.view(rows, 1, 1, D), a.view(rows, 1, 1, K0), out=dst.view(D, K0, 1, 1) if dst is not None else None)
+    gb = None
+    if pe.proj.bias is not None:
+        gb = grads.dest(pe.proj.bias)
+        if gb is None:
+            gb = torch.empty(D, dtype=F32, device=du0.device)
+    gw = ops.conv2d_wgrad(du0.view(rows, 1, 1, D), a.view(rows, 1, 1, K0), out=dst.view(D, K0, 1, 1) if dst is not None else None,
+                          bias_out=gb)
     grads.put(pe.proj.weight, gw)
     if pe.proj.bias is not None:
-        grads.put(pe.proj.bias, ops.colsum_tall(du0.view(rows, D), out=grads.dest(pe.proj.bias)))
+        grads.put(pe.proj.bias, gb)
     return grads
 
 

@@ -147,13 +147,20 @@ def _lin_grads(grads, lin, dy2d, x2d, dy_stats=None):
     M, N = dy2d.shape
     K = x2d.shape[1]
     dst = grads.dest(lin.weight)
-    gw = ops.conv2d_wgrad(dy2d.view(M, 1, 1, N), x2d.view(M, 1, 1, K), out=dst.view(N, K, 1, 1) if dst is not None else None)
+    gb = None
+    if lin.bias is not None and dy_stats is None:
+        # bias gradient = column sums of dy: summed inside the wgrad kernel from the dy tiles it already holds
+        gb = grads.dest(lin.bias)
+        if gb is None:
+            gb = torch.empty(N, dtype=F32, device=dy2d.device)
+    gw = ops.conv2d_wgrad(dy2d.view(M, 1, 1, N), x2d.view(M, 1, 1, K), out=dst.view(N, K, 1, 1) if dst is not None else None,
+                          bias_out=gb)
     grads.put(lin.weight, gw)
     if lin.bias is not None:
         if dy_stats is not None:
             grads.put(lin.bias, ops.stats_colsum(dy_stats, out=grads.dest(lin.bias)))
         else:
-            grads.put(lin.bias, ops.colsum_tall(dy2d, out=grads.dest(lin.bias)))
+            grads.put(lin.bias, gb)
 
 
 def backward(model, tape, dlogits, sink=None):
@@ -229,10 +236,16 @@ def backward(model, tape, dlogits, sink=None):
     pe = model.patch_embed.proj
     K0 = a.shape[-1]
     dst = grads.dest(pe.weight)
-    gw = ops.conv2d_wgrad(gp.view(B * P, 1, 1, D), a.view(B * P, 1, 1, K0), out=dst.view(D, K0, 1, 1) if dst is not None else None)
+    gb = None
+    if pe.bias is not None:
+        gb = grads.dest(pe.bias)
+        if gb is None:
+            gb = torch.empty(D, dtype=F32, device=gp.device)
+    gw = ops.conv2d_wgrad(gp.view(B * P, 1, 1, D), a.view(B * P, 1, 1, K0), out=dst.view(D, K0, 1, 1) if dst is not None else None,
+                          bias_out=gb)
     grads.put(pe.weight, gw)
     if pe.bias is not None:
-        grads.put(pe.bias, ops.colsum_tall(gp.view(B * P, D), out=grads.dest(pe.bias)))
+        grads.put(pe.bias, gb)
     return grads
 
 

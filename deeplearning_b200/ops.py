@@ -199,8 +199,10 @@ def _workspace(nbytes, device):
     return ws
 
 
-def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False, rowscale=None):
-    """dw fp32 OIHW [Cout, Cin, k, k] = sum over pixels of dy (x) x  (row `cout` optionally scaled by rowscale[cout])."""
+def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False, rowscale=None, bias_out=None):
+    """dw fp32 OIHW [Cout, Cin, k, k] = sum over pixels of dy (x) x  (row `cout` optionally scaled by rowscale[cout]).
+    bias_out (fp32 [Cout]): also write the bias gradient (column sums of dy), summed from the dy tiles the kernel already
+    holds in shared memory - no extra pass over dy."""
     lib = _lib.load()
     _chk_act(dy, "dy")
     _chk_act(x, "x")
@@ -214,9 +216,16 @@ def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False, rowscale=
     sp = _span("wgrad_gemm", 2.0 * dy.numel() * Cin * ksize * ksize, _nb(dy, x, out))
     if rowscale is not None:
         lib.b200_conv2d_wgrad_set_rowscale(_p(rowscale))
+    bias_partial = None
+    if bias_out is not None:
+        splits = lib.b200_conv2d_wgrad_splits(B, H, W, Cin, Cout, ksize, stride)
+        bias_partial = torch.empty(splits, 2, Cout, dtype=F32, device=x.device)
+        lib.b200_conv2d_wgrad_set_bias_partial(_p(bias_partial))
     rc = lib.b200_conv2d_wgrad(_p(dy), _p(x), _p(out), _p(ws), ws.numel(), B, H, W, Cin, Cout, ksize, stride,
                                1 if accumulate else 0, _stream())
     _lib.check(rc, "b200_conv2d_wgrad")
+    if bias_partial is not None:
+        stats_colsum(bias_partial, out=bias_out)
     if sp:
         sp.end()
     return out

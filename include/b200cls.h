@@ -72,6 +72,12 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
 size_t b200_conv2d_wgrad_workspace_bytes(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
 /* one-shot (this thread, next b200_conv2d_wgrad call): multiply gradient row `cout` by rowscale[cout] (layer scale) */
 int b200_conv2d_wgrad_set_rowscale(const float* rowscale);
+/* one-shot (this thread, next b200_conv2d_wgrad call): also produce the BIAS gradient = column sums of dy, as per-split
+ * partial sums bias_partial fp32 [b200_conv2d_wgrad_splits()][2][Cout] (plane 0; fold with b200_bn_bwd_finalize).  The dy tiles
+ * are summed from shared memory by four extra warps of the wgrad kernel: no separate pass over dy
+ * (replaces the bias part of loss.backward() for nn.Linear / nn.Conv2d(bias=True): vit_model.py:95,109,127-133). */
+int b200_conv2d_wgrad_set_bias_partial(float* bias_partial);
+int b200_conv2d_wgrad_splits(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
 
 /* ---- general GEMM with strided pixel views (transformer layers, patch embedding) ----------------------------------------
  * out[pixel, n] = epilogue( sum_k a[pixel, k] * w[n, k] ), pixels = dim[0] x dim[1] x dim[2] (w fastest), channel stride 1.

@@ -289,3 +289,22 @@ def test_pack_weights_multi_matches_single(O, I, kh, mode, ld_pad, rows_pad, sca
         assert torch.equal(dst[:nrow, :ncol], ref)
         assert float(dst[nrow:].float().abs().max() if dst.shape[0] > nrow else 0.0) == 0.0
         assert float(dst[:, ncol:].float().abs().max() if dst.shape[1] > ncol else 0.0) == 0.0
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", [(3, 9, 7, 64, 200, 1, 1), (4, 14, 14, 96, 384, 1, 1), (2, 16, 16, 64, 64, 3, 1),
+                                                  (2, 14, 14, 96, 192, 2, 2), (37, 1, 1, 768, 2304, 1, 1)])
+def test_wgrad_bias_sums_from_the_dy_tiles(B, H, W, Cin, Cout, k, s):
+    """conv2d_wgrad(bias_out=...) = column sums of dy (the layer's bias gradient), added up by the extra warps of the wgrad
+    kernel from the dy tiles it already stages in shared memory; the weight gradient itself is unchanged."""
+    from deeplearning_b200 import ops
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(B, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    Ho, Wo = ops.out_hw(H, k, s), ops.out_hw(W, k, s)
+    dy = torch.randn(B, Ho, Wo, Cout, device="cuda", generator=g).to(torch.bfloat16)
+    ref_w = ops.conv2d_wgrad(dy, x, k, s)
+    bias = torch.full((Cout,), float("nan"), device="cuda")
+    got_w = ops.conv2d_wgrad(dy, x, k, s, bias_out=bias)
+    assert torch.equal(ref_w, got_w)
+    ref_b = dy.float().sum((0, 1, 2))
+    assert torch.allclose(bias, ref_b, rtol=1e-4, atol=1e-3 * float(dy.float().abs().sum((0, 1, 2)).max())), float((bias - ref_b).abs().max())
