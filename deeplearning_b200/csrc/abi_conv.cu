@@ -303,7 +303,7 @@ int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Streaming kernel for the narrow-K -> wide-N 1x1 layers (conv1x1_stream.cuh): K in {64, 128}, N % 256 == 0, pixels % 128 == 0.
+// Streaming kernel for the narrow-K -> wide-N 1x1 layers (conv1x1_stream.cuh): K in {64, 128, 256}, N % 256 == 0, pixels % 128 == 0.
 bool stream_enabled() {
   static const bool on = [] {
     const char* e = getenv("B200_STREAM");
@@ -312,7 +312,7 @@ bool stream_enabled() {
   return on;
 }
 bool stream_ok(long long pixels, int K, int N) {
-  return stream_enabled() && (K == 64 || K == 128) && N % 256 == 0 && pixels % 128 == 0 && pixels / 128 < (1LL << 30);
+  return stream_enabled() && (K == 64 || K == 128 || K == 256) && N % 256 == 0 && pixels % 128 == 0 && pixels / 128 < (1LL << 30);
 }
 int stream_grid(long long pixels, int N) {
   const int n_tiles = N / 256;
@@ -366,8 +366,11 @@ int run_stream(int mode, const void* a, const void* w, void* out, const void* re
   q.N = N;
   q.scale = scale, q.shift = shift, q.stats = stats;
   const int grid = stream_grid(pixels, N);
-  if (mode == kStreamBnRelu) return K == 64 ? launch_stream<1, kStreamBnRelu>(q, grid, st) : launch_stream<2, kStreamBnRelu>(q, grid, st);
-  return K == 64 ? launch_stream<1, kStreamMask>(q, grid, st) : launch_stream<2, kStreamMask>(q, grid, st);
+  if (mode == kStreamBnRelu)
+    return K == 64 ? launch_stream<1, kStreamBnRelu>(q, grid, st)
+                   : (K == 128 ? launch_stream<2, kStreamBnRelu>(q, grid, st) : launch_stream<4, kStreamBnRelu>(q, grid, st));
+  return K == 64 ? launch_stream<1, kStreamMask>(q, grid, st)
+                 : (K == 128 ? launch_stream<2, kStreamMask>(q, grid, st) : launch_stream<4, kStreamMask>(q, grid, st));
 }
 
 int dispatch_conv_gemm(ConvGemmParams& p, int N, cudaStream_t st) {

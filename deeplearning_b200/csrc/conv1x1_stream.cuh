@@ -1,6 +1,6 @@
 // Streaming 1x1-convolution GEMM for the HBM-bound "narrow K -> wide N" layers of a ResNet bottleneck (sm_100a):
 //
-//   out[P][N] = epilogue( A[P][K] * W[N][K]^T ),   K = 64 or 128 (KB = 1, 2 k-blocks), N a multiple of 256, P a multiple of 128
+//   out[P][N] = epilogue( A[P][K] * W[N][K]^T ),   K = 64, 128 or 256 (KB = 1, 2, 4 k-blocks), N a multiple of 256, P a multiple of 128
 //
 //   kStreamBnRelu : out = relu(acc * scale[n] + shift[n] + residual)         conv3 -> bn3 -> + identity -> ReLU
 //                   (classification/resnet/models/networks.py:116-124, BatchNorm folded through the conv: bn_algebra.cuh)
@@ -11,8 +11,9 @@
 // ~7000.  The generic implicit-GEMM kernel (conv_gemm.cuh) runs them at ~3 TB/s because its epilogue fetches the residual
 // with per-lane LDG.128 (32 scattered rows per instruction, two column groups in flight) and spends ~10 instructions per
 // output value on predicates and register shuffling.  Here everything that touches HBM is a bulk tensor copy:
-//   * W (32 / 64 KB) is loaded ONCE per CTA and stays in shared memory (a CTA always works on the same 256-channel block);
-//   * A tiles (16 / 32 KB) stream through a 4- / 2-deep TMA ring;
+//   * K <= 128: W (32 / 64 KB) is loaded ONCE per CTA and stays in shared memory (a CTA always works on the same 256-channel
+//     block) and the A tiles (16 / 32 KB) stream through a 4- / 2-deep TMA ring;  K = 256 (layer3): W no longer fits beside
+//     the slab rings, so (A, W) k-blocks of 16 + 32 KB stream through a 3-deep ring as in the generic kernel;
 //   * every epilogue warp (one per TMEM lane quadrant) prefetches its own 32-row x 64-channel residual / mask slabs by TMA
 //     into a private ring (no cross-warp synchronisation), two or three slabs ahead, reads them back with conflict-free
 //     128-bit shared loads, and stores its output slab by TMA;
@@ -39,14 +40,16 @@ struct alignas(64) StreamParams {
 
 template <int KB, int MODE>
 struct StreamCfg {
-  static constexpr int A_STAGE = KB * 16384;
-  static constexpr int STAGES = KB == 1 ? 4 : 2;
-  static constexpr int B_BYTES = KB * 32768;
-  static constexpr int NBUF = (MODE == kStreamMask && KB == 2) ? 2 : 3;   // slabs in flight per warp and source
+  static constexpr bool STREAM_B = KB > 2;                                 // W streamed with A instead of resident
+  static constexpr int A_STAGE = STREAM_B ? 16384 + 32768 : KB * 16384;    // STREAM_B: one k-block of A and of W
+  static constexpr int STAGES = STREAM_B ? 3 : (KB == 1 ? 4 : 2);
+  static constexpr int B_BYTES = STREAM_B ? 0 : KB * 32768;
+  static constexpr int NBUF = (KB >= 2 && (MODE == kStreamMask || STREAM_B)) ? 2 : 3;   // slabs in flight per warp and source
   static constexpr int SLAB = 4096;                                        // 32 rows x 128 B
   static constexpr int RES_BYTES = 4 * NBUF * SLAB;
   static constexpr int MASK_BYTES = MODE == kStreamMask ? RES_BYTES : 0;
-  static constexpr int OUT_BYTES = 4 * 2 * SLAB;
+  static constexpr int OUT_SLABS = (STREAM_B && MODE == kStreamMask) ? 1 : 2;   // output slabs per warp (shared memory is full)
+  static constexpr int OUT_BYTES = 4 * OUT_SLABS * SLAB;
   static constexpr int COEF_BYTES = MODE == kStreamBnRelu ? 2 * 256 * 4 : 0;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = B_BYTES + STAGES * A_STAGE + RES_BYTES + MASK_BYTES + OUT_BYTES + COEF_BYTES + BAR_BYTES + 1024;
@@ -125,19 +128,35 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
   if (warp_idx == 0) {
     // ===================== TMA producer: W once, then the A tiles =====================
     if (lane == 0) {
-      mbar_expect_tx(b_full, Cfg::B_BYTES);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * 32768, &p.b_map, b_full, kb * 64, n_tile * 256);
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = 0; t < my_tiles; ++t) {
-        const int m_tile = m_first + t * m_step;
-        mbar_wait_backoff(&a_empty[stage], phase ^ 1);
-        mbar_expect_tx(&a_full[stage], Cfg::A_STAGE);
-        for (int kb = 0; kb < KB; ++kb)
-          tma_load_2d(sA + stage * Cfg::A_STAGE + kb * 16384, &p.a_map, &a_full[stage], kb * 64, m_tile * 128);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
+      if constexpr (Cfg::STREAM_B) {
+        for (int t = 0; t < my_tiles; ++t) {
+          const int m_tile = m_first + t * m_step;
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait_backoff(&a_empty[stage], phase ^ 1);
+            mbar_expect_tx(&a_full[stage], Cfg::A_STAGE);
+            tma_load_2d(sA + stage * Cfg::A_STAGE, &p.a_map, &a_full[stage], kb * 64, m_tile * 128);
+            tma_load_2d(sA + stage * Cfg::A_STAGE + 16384, &p.b_map, &a_full[stage], kb * 64, n_tile * 256);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      } else {
+        mbar_expect_tx(b_full, Cfg::B_BYTES);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sB + kb * 32768, &p.b_map, b_full, kb * 64, n_tile * 256);
+        for (int t = 0; t < my_tiles; ++t) {
+          const int m_tile = m_first + t * m_step;
+          mbar_wait_backoff(&a_empty[stage], phase ^ 1);
+          mbar_expect_tx(&a_full[stage], Cfg::A_STAGE);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(sA + stage * Cfg::A_STAGE + kb * 16384, &p.a_map, &a_full[stage], kb * 64, m_tile * 128);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -147,27 +166,43 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
       constexpr uint32_t idesc = make_idesc_bf16(128, 256, 0, 0);
       const uint64_t desc_b0 = make_smem_desc_sw128(smem_u32(sB), 16, 1024);
       const uint64_t desc_a0 = make_smem_desc_sw128(smem_u32(sA), 16, 1024);
-      mbar_wait_backoff(b_full, 0);
+      if constexpr (!Cfg::STREAM_B) mbar_wait_backoff(b_full, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int t = 0; t < my_tiles; ++t) {
         mbar_wait_backoff(&tmem_empty[acc], acc_phase ^ 1);
-        mbar_wait_backoff(&a_full[stage], phase);
-        tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * 256;
+        if constexpr (Cfg::STREAM_B) {
+          for (int kb = 0; kb < KB; ++kb) {
+            mbar_wait_backoff(&a_full[stage], phase);
+            tc_fence_after();
+            const uint64_t da = desc_a0 + static_cast<uint64_t>((stage * Cfg::A_STAGE) >> 4);
+            const uint64_t db = da + static_cast<uint64_t>(16384 >> 4);
 #pragma unroll
-        for (int kb = 0; kb < KB; ++kb) {
-          const uint64_t da = desc_a0 + static_cast<uint64_t>((stage * Cfg::A_STAGE + kb * 16384) >> 4);
-          const uint64_t db = desc_b0 + static_cast<uint64_t>((kb * 32768) >> 4);
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&a_empty[stage]);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        } else {
+          mbar_wait_backoff(&a_full[stage], phase);
+          tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t da = desc_a0 + static_cast<uint64_t>((stage * Cfg::A_STAGE + kb * 16384) >> 4);
+            const uint64_t db = desc_b0 + static_cast<uint64_t>((kb * 32768) >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16(tmem_d, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&a_empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
         }
-        umma_commit(&a_empty[stage]);
         umma_commit(&tmem_full[acc]);
-        if (++stage == STAGES) {
-          stage = 0;
-          phase ^= 1;
-        }
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -180,7 +215,7 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
     const int ew = warp_idx - 2;
     const uint32_t res_s = smem_u32(sRes + ew * NBUF * Cfg::SLAB);
     const uint32_t mask_s = smem_u32(sMask + ew * NBUF * Cfg::SLAB);
-    const uint32_t out_s = smem_u32(sOut + ew * 2 * Cfg::SLAB);
+    const uint32_t out_s = smem_u32(sOut + ew * Cfg::OUT_SLABS * Cfg::SLAB);
     uint64_t* my_full = slab_full + ew * NBUF;
     const uint32_t row_s = lane * 128;
     const uint32_t sw = (lane & 7) << 4;
@@ -218,9 +253,11 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
       for (int u = 0; u < 4; ++u, ++g) {
         const int slot = g % NBUF;
         const uint32_t rs = res_s + slot * Cfg::SLAB, ms = mask_s + slot * Cfg::SLAB;
-        const uint32_t os = out_s + (g & 1) * Cfg::SLAB;
-        // the TMA store that used this output slab two units ago has finished reading it
-        if (lane == 0) tma_store_wait_read<1>();
+        const uint32_t os = out_s + (Cfg::OUT_SLABS == 2 ? (g & 1) : 0) * Cfg::SLAB;
+        // the TMA store that last used this output slab (two units ago; one with a single slab) has finished reading it
+        if (lane == 0) {
+          if constexpr (Cfg::OUT_SLABS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
+        }
         mbar_wait(&my_full[slot], (g / NBUF) & 1);
         __syncwarp();
 #pragma unroll

@@ -25,9 +25,9 @@ def _close(a, b, rtol, atol, what):
     assert not bad.any(), f"{what}: {int(bad.sum())}/{bad.numel()} bad, max abs err {float(err.max()):.4g} (ref max {float(b.abs().max()):.4g})"
 
 
-# (pixels % 128 == 0 with K in {64, 128}, N % 256 == 0 run on the streaming kernel conv1x1_stream.cuh, the rest on the generic one)
+# (pixels % 128 == 0 with K in {64, 128, 256}, N % 256 == 0 run on the streaming kernel conv1x1_stream.cuh, the rest on the generic one)
 SHAPES = [(4, 14, 14, 64, 256), (3, 10, 6, 128, 512), (2, 7, 7, 256, 1024), (8, 28, 28, 64, 256), (8, 16, 16, 128, 512),
-          (37, 32, 32, 64, 256), (19, 16, 24, 128, 512), (2, 8, 8, 64, 512)]
+          (37, 32, 32, 64, 256), (19, 16, 24, 128, 512), (2, 8, 8, 64, 512), (8, 16, 16, 256, 1024), (5, 16, 24, 256, 512)]
 
 
 @pytest.mark.parametrize("B,H,W,K,N", SHAPES)

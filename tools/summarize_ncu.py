@@ -77,9 +77,9 @@ _SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us
 # bench.py span name -> ncu kernel names whose bytes belong to it (a span covers the kernels one C-ABI entry point launches)
 _SPANS = {"wgrad_gemm": ("wgrad_gemm_kernel", "wgrad_reduce_rows_kernel", "wgrad_reduce_flat_kernel"),
           "bn_bwd_reduce": ("bn_bwd_reduce_kernel",), "bn_bwd_apply": ("bn_bwd_apply_kernel",),
-          "bn_apply": ("bn_apply_kernel",), "attention_fwd": ("attention_fwd_kernel",),
-          "attention_bwd": ("attention_bwd_kernel", "attn_delta_kernel"),
-          "window_attention_fwd": ("window_attention_fwd_kernel",), "window_attention_bwd": ("window_attention_bwd_kernel",),
+          "bn_apply": ("bn_apply_kernel",), "attention_fwd": ("attn_fwd_kernel",),
+          "attention_bwd": ("attn_bwd_kernel", "attn_delta_kernel"),
+          "window_attention_fwd": ("wattn_fwd_kernel",), "window_attention_bwd": ("wattn_bwd_kernel",),
           "layernorm_fwd": ("layernorm_fwd_kernel",), "layernorm_bwd": ("layernorm_bwd_kernel",),
           "dwconv7": ("dwconv7_tile_kernel", "dwconv7_kernel"), "dwconv7_wgrad": ("dwconv7_wgrad_tile_kernel",)}
 
@@ -105,6 +105,8 @@ def traffic(inp, out, model):
         n = L["name"]
         if n == "softmax_xent_kernel":
             seen_loss = True
+        if n == "conv1x1_stream_kernel":   # the streaming 1x1 kernel serves the same C-ABI spans as the implicit-GEMM kernel
+            n = "conv_gemm_kernel"
         if n == "conv_gemm_kernel" and model == "resnet50":
             n = "conv_gemm_kernel (backward: dgrad)" if seen_loss else "conv_gemm_kernel (forward)"
         a = agg.setdefault(n, [0, 0.0, 0.0, 0.0])
@@ -140,7 +142,7 @@ def traffic(inp, out, model):
     allm[model] = per
     allm["_note"] = {"what": "DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, averaged over the launches of "
                              "one training step) for every bench.py kernel span, per model; wgrad_gemm includes its reduce pass",
-                     "source": "tools/summarize_ncu.py traffic on the launch lists under profiles/ (r01_*_launches_final.md)"}
+                     "source": "tools/summarize_ncu.py traffic on the launch lists under profiles/ (r02_*_launches.md; r01_*_launches_final.md for models not re-profiled)"}
     json.dump(allm, open(tpath, "w"), indent=1)
 
 
