@@ -127,6 +127,7 @@ int b200_bn_relu_maxpool_fwd(const void* x, void* y, void* idx, const float* sca
   B200_REQUIRE(C % 8 == 0, "maxpool: C=%d must be a multiple of 8", C);
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long long nvec = static_cast<long long>(B) * Ho * Wo * (C / 8);
+  B200_REQUIRE(static_cast<long long>(B) * H * W * (C / 8) < (1LL << 32), "maxpool: tensor too large");
   bn_relu_maxpool_fwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(y), static_cast<unsigned long long*>(idx), scale, shift, B, H, W,
       C / 8);
@@ -136,7 +137,8 @@ int b200_bn_relu_maxpool_fwd(const void* x, void* y, void* idx, const float* sca
 
 int b200_maxpool_bwd(const void* g_out, const void* idx, void* g_in, int B, int H, int W, int C, void* stream) {
   B200_REQUIRE(C % 8 == 0, "maxpool_bwd: C=%d must be a multiple of 8", C);
-  const long long nvec = static_cast<long long>(B) * H * W * (C / 8);
+  B200_REQUIRE(static_cast<long long>(B) * H * W * (C / 8) < (1LL << 32), "maxpool_bwd: tensor too large");
+  const long long nvec = static_cast<long long>(B) * ((H - 1) / 2 + 1) * ((W - 1) / 2 + 1) * (C / 8);   // 2x2 input blocks
   maxpool_bwd_kernel<<<ew_grid(nvec), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(g_out), static_cast<const unsigned long long*>(idx), static_cast<uint4*>(g_in), B, H, W,
       C / 8);

@@ -344,19 +344,35 @@ __global__ void bn_bwd_apply_kernel(const uint4* __restrict__ g, const uint4* __
 
 // ------------------------------------------------------------------------------------------------------------------
 // Stem: y = maxpool3x3s2p1(relu(x*scale+shift)); also records the arg-max tap (0..8) for the backward pass.
-__global__ void bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
-                                           unsigned long long* __restrict__ idx, const float* __restrict__ scale,
-                                           const float* __restrict__ shift, int B, int H, int W, int cvec) {
+// All nine taps are loaded before any arithmetic (nine independent 16-byte loads in flight per thread); the arg-max is taken
+// over the fp32 activations - rounding to bf16 is monotonic, so the pooled VALUE equals the max of the rounded activations a
+// stand-alone BN+ReLU pass would have stored, and ties between activations that only coincide after rounding go to the
+// larger fp32 value, which is what the fp32 reference does.  Index arithmetic in 32 bits.
+__global__ void __launch_bounds__(256) bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y,
+                                                                  unsigned long long* __restrict__ idx,
+                                                                  const float* __restrict__ scale,
+                                                                  const float* __restrict__ shift, int B, int H, int W, int cvec) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long nvec = static_cast<long long>(B) * Ho * Wo * cvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % cvec);
-    long long t = i / cvec;
+  const unsigned nvec = static_cast<unsigned>(B) * Ho * Wo * cvec;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % cvec;
+    unsigned t = i / cvec;
     const int ow = static_cast<int>(t % Wo);
     t /= Wo;
     const int oh = static_cast<int>(t % Ho);
-    const int b = static_cast<int>(t / Ho);
+    const unsigned b = t / Ho;
+    uint4 v[9];
+    bool ok[9];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = oh * 2 - 1 + kh, iw = ow * 2 - 1 + kw;
+        ok[kh * 3 + kw] = ih >= 0 && ih < H && iw >= 0 && iw < W;
+        v[kh * 3 + kw] = ok[kh * 3 + kw] ? __ldg(x + ((b * H + ih) * W + iw) * cvec + cg) : zero;
+      }
+    }
     float sc[8], sh[8], best[8];
     int bi[8];
     load8f(scale + cg * 8, sc);
@@ -367,23 +383,16 @@ __global__ void bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* _
       bi[j] = 0;
     }
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int ih = oh * 2 - 1 + kh;
-      if (ih < 0 || ih >= H) continue;
+    for (int tap = 0; tap < 9; ++tap) {
+      if (!ok[tap]) continue;
+      float f[8];
+      unpack8(v[tap], f);
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int iw = ow * 2 - 1 + kw;
-        if (iw < 0 || iw >= W) continue;
-        float v[8];
-        unpack8(__ldg(x + ((static_cast<long long>(b) * H + ih) * W + iw) * cvec + cg), v);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // round through bf16 so that the comparison sees exactly the activation a stand-alone pass would store
-          const float a = __bfloat162float(__float2bfloat16_rn(fmaxf(fmaf(v[j], sc[j], sh[j]), 0.f)));
-          if (a > best[j]) {
-            best[j] = a;
-            bi[j] = kh * 3 + kw;
-          }
+      for (int j = 0; j < 8; ++j) {
+        const float a = fmaxf(fmaf(f[j], sc[j], sh[j]), 0.f);
+        if (a > best[j]) {
+          best[j] = a;
+          bi[j] = tap;
         }
       }
     }
@@ -396,43 +405,54 @@ __global__ void bn_relu_maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* _
 }
 
 // Max-pool backward: g_in[b,h,w,c] = sum over the (<=4) windows covering (h,w) whose arg-max is this pixel.
-__global__ void maxpool_bwd_kernel(const uint4* __restrict__ g_out, const unsigned long long* __restrict__ idx,
-                                   uint4* __restrict__ g_in, int B, int H, int W, int cvec) {
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const long long nvec = static_cast<long long>(B) * H * W * cvec;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int cg = static_cast<int>(i % cvec);
-    long long t = i / cvec;
-    const int w = static_cast<int>(t % W);
-    t /= W;
-    const int h = static_cast<int>(t % H);
-    const int b = static_cast<int>(t / H);
-    float acc[8];
+// One thread produces the 2x2 input block (2a..2a+1, 2b..2b+1) of one 8-channel group: exactly the four windows
+// (a,b), (a,b+1), (a+1,b), (a+1,b+1) touch it - (even,even) belongs to tap (1,1) of window (a,b) only, the odd row / column
+// pixels to two, the (odd,odd) pixel to all four - so four (arg-max, gradient) loads feed four outputs (the per-pixel
+// version loaded nine and spent ~3x the instructions).
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const uint4* __restrict__ g_out,
+                                                          const unsigned long long* __restrict__ idx, uint4* __restrict__ g_in,
+                                                          int B, int H, int W, int cvec) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;   // = H / 2, W / 2
+  const unsigned nblk = static_cast<unsigned>(B) * Ho * Wo * cvec;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < nblk; i += gridDim.x * blockDim.x) {
+    const unsigned cg = i % cvec;
+    unsigned t = i / cvec;
+    const int bw = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int ah = static_cast<int>(t % Ho);
+    const unsigned b = t / Ho;
+    // windows (ah + dy, bw + dx), dy, dx in {0, 1}
+    uint4 gq[4];
+    unsigned long long pk[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
-    // windows oh with 2*oh-1+kh == h  ->  oh = (h+1-kh)/2 for kh with matching parity
-    for (int kh = 0; kh < 3; ++kh) {
-      const int th = h + 1 - kh;
-      if (th < 0 || (th & 1)) continue;
-      const int oh = th >> 1;
-      if (oh >= Ho) continue;
-      for (int kw = 0; kw < 3; ++kw) {
-        const int tw = w + 1 - kw;
-        if (tw < 0 || (tw & 1)) continue;
-        const int ow = tw >> 1;
-        if (ow >= Wo) continue;
-        const long long o = ((static_cast<long long>(b) * Ho + oh) * Wo + ow) * cvec + cg;
-        const unsigned long long pk = __ldg(idx + o);
-        float gv[8];
-        unpack8(__ldg(g_out + o), gv);
-        const int tap = kh * 3 + kw;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (static_cast<int>((pk >> (8 * j)) & 0xFF) == tap) acc[j] += gv[j];
-      }
+    for (int d = 0; d < 4; ++d) {
+      const int oh = ah + (d >> 1), ow = bw + (d & 1);
+      const bool ok = oh < Ho && ow < Wo;
+      const unsigned o = ((b * Ho + (ok ? oh : ah)) * Wo + (ok ? ow : bw)) * cvec + cg;
+      gq[d] = ok ? __ldg(g_out + o) : make_uint4(0u, 0u, 0u, 0u);
+      pk[d] = ok ? __ldg(idx + o) : 0xFFFFFFFFFFFFFFFFull;   // tap 255: never matches
     }
-    g_in[i] = pack8(acc);
+    float g[4][8];
+#pragma unroll
+    for (int d = 0; d < 4; ++d) unpack8(gq[d], g[d]);
+    float o00[8], o01[8], o10[8], o11[8];   // input pixels (2a, 2b), (2a, 2b+1), (2a+1, 2b), (2a+1, 2b+1)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t0 = static_cast<int>((pk[0] >> (8 * j)) & 0xFF), t1 = static_cast<int>((pk[1] >> (8 * j)) & 0xFF);
+      const int t2 = static_cast<int>((pk[2] >> (8 * j)) & 0xFF), t3 = static_cast<int>((pk[3] >> (8 * j)) & 0xFF);
+      // window (a,b): taps (kh,kw) -> input (2a-1+kh, 2b-1+kw): (1,1)->(2a,2b) (1,2)->(2a,2b+1) (2,1)->(2a+1,2b) (2,2)->(2a+1,2b+1)
+      o00[j] = (t0 == 4) ? g[0][j] : 0.f;
+      o01[j] = ((t0 == 5) ? g[0][j] : 0.f) + ((t1 == 3) ? g[1][j] : 0.f);                 // window (a,b+1): tap (1,0)
+      o10[j] = ((t0 == 7) ? g[0][j] : 0.f) + ((t2 == 1) ? g[2][j] : 0.f);                 // window (a+1,b): tap (0,1)
+      o11[j] = ((t0 == 8) ? g[0][j] : 0.f) + ((t1 == 6) ? g[1][j] : 0.f) +               // (a,b+1): tap (2,0)
+               ((t2 == 2) ? g[2][j] : 0.f) + ((t3 == 0) ? g[3][j] : 0.f);                 // (a+1,b): (0,2); (a+1,b+1): (0,0)
+    }
+    const unsigned base = ((b * H + 2 * ah) * W + 2 * bw) * cvec + cg;
+    const bool w1 = 2 * bw + 1 < W, h1 = 2 * ah + 1 < H;   // (odd H / W: the last block is half outside)
+    g_in[base] = pack8(o00);
+    if (w1) g_in[base + cvec] = pack8(o01);
+    if (h1) g_in[base + W * cvec] = pack8(o10);
+    if (h1 && w1) g_in[base + W * cvec + cvec] = pack8(o11);
   }
 }
 

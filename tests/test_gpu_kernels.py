@@ -159,9 +159,9 @@ def test_batchnorm_train_fwd_bwd(rows, C):
         _close(dbet, gbet, 2e-2, 2e-2 * float(gbet.abs().max()), "dbeta")
 
 
-def test_stem_pool_and_avgpool():
+@pytest.mark.parametrize("B,H,W,C", [(2, 16, 16, 64), (3, 14, 10, 64), (2, 7, 9, 64), (5, 56, 56, 64)])
+def test_stem_pool_and_avgpool(B, H, W, C):
     ops = _ops()
-    B, H, W, C = 2, 16, 16, 64
     x = _rand(B, H, W, C, seed=31)
     co = ops.BnCoeffs(C, "cuda")
     co.scale.copy_(torch.rand(C, device="cuda") + 0.5)
@@ -170,11 +170,12 @@ def test_stem_pool_and_avgpool():
     a = F.relu(x.float() * co.scale + co.shift).to(torch.bfloat16).float().permute(0, 3, 1, 2).requires_grad_(True)
     ref = F.max_pool2d(a, 3, 2, 1)
     assert torch.equal(y.float(), ref.permute(0, 2, 3, 1))
-    g = _rand(B, H // 2, W // 2, C, seed=32)
+    g = _rand(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, seed=32)
     (ga,) = torch.autograd.grad(ref, a, g.float().permute(0, 3, 1, 2))
     gin = ops.maxpool_bwd(g, idx, (H, W))
     # ties between equal bf16 activations may route to a different (equal-valued) element: compare window sums
-    _close(gin.float().sum((1, 2)), ga.permute(0, 2, 3, 1).sum((1, 2)), 1e-2, 5e-2, "maxpool bwd mass")
+    # (every input gradient is rounded to bf16 once: the noise of a sum over H*W entries grows with sqrt(H*W))
+    _close(gin.float().sum((1, 2)), ga.permute(0, 2, 3, 1).sum((1, 2)), 1e-2, 5e-2 + 4e-3 * (H * W) ** 0.5, "maxpool bwd mass")
     nz = (a.permute(0, 2, 3, 1) > 0)
     match = ((gin.float() - ga.permute(0, 2, 3, 1)).abs() < 1e-2) | ~nz
     assert match.float().mean() > 0.98
