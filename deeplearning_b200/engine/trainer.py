@@ -12,6 +12,8 @@ the whole step (collectives included) is captured in ONE CUDA graph.
 ``model.parameters()`` keep their identity: each ``p.data`` becomes a view into the parameter arena and ``p.grad`` a
 view into the gradient arena, so ``state_dict()`` / checkpoints / user code reading ``.grad`` behave as in the reference.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -208,6 +210,7 @@ class TrainStep:
         self.optimizer, self.betas, self.eps = optimizer, betas, eps
         if optimizer not in ("sgd", "adamw"):
             raise ValueError(f"unknown optimizer {optimizer!r}")
+        bucket_mb = float(os.environ.get("B200_BUCKET_MB", bucket_mb))   # tuning knob
         self.arena = FlatArena(model.parameters(), process_group, world_size, bucket_mb=bucket_mb)
         self.overlap = overlap   # bucketed all-reduce on a side stream during the backward pass (False: one call after it)
         if self.arena.flat_p.device.type != "cuda":

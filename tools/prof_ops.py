@@ -170,6 +170,56 @@ def res_l2_dgrad_res():   # ResNet layer2 conv1 dgrad (1x1 512 <- 128) + identit
     return lambda: ops.conv2d_dgrad(dy, wd, (28, 28), residual=res)
 
 
+def _res_tail(H, K, N):
+    y2 = rnd(256, H, H, K).relu_()
+    wp = ops.pack_weight(torch.randn(N, K, 1, 1, device=dev) * K ** -0.5)
+    ident = rnd(256, H, H, N)
+    co = ops.BnCoeffs(N, dev)
+    co.scale.fill_(1.0), co.shift.fill_(0.1)
+    return y2, wp, ident, co
+
+
+def res_l1_conv3_bn_add_relu():   # round 2: ResNet layer1 conv3 + BN + identity + ReLU in ONE streaming GEMM (K=64 -> N=256, 56x56)
+    y2, wp, ident, co = _res_tail(56, 64, 256)
+    return lambda: ops.conv1x1_bn_act(y2, wp, co, ident)
+
+
+def res_l2_conv3_bn_add_relu():
+    y2, wp, ident, co = _res_tail(28, 128, 512)
+    return lambda: ops.conv1x1_bn_act(y2, wp, co, ident)
+
+
+def res_l3_conv3_bn_add_relu():
+    y2, wp, ident, co = _res_tail(14, 256, 1024)
+    return lambda: ops.conv1x1_bn_act(y2, wp, co, ident)
+
+
+def res_l1_dgrad_masked():        # round 2: conv1 dgrad + identity gradient + ReLU mask + column sums (K=64 -> N=256)
+    dc = rnd(256, 56, 56, 64, scale=0.1)
+    wd = ops.pack_weight(torch.randn(64, 256, 1, 1, device=dev) * 0.05, mode=1)
+    res, y = rnd(256, 56, 56, 256, scale=0.1), rnd(256, 56, 56, 256).relu_()
+    return lambda: ops.conv1x1_dgrad_masked(dc, wd, residual=res, mask_src=y)
+
+
+def res_l1_gemm_dual():           # round 2: dL/dy2 = [dz | y2] [aW | M]^T + kW  (K = 256 + 64 -> N = 64)
+    dz, y2 = rnd(256, 56, 56, 256, scale=0.1), rnd(256, 56, 56, 64).relu_()
+    wcat = rnd(64, 320, scale=0.05)
+    b = torch.zeros(64, device=dev)
+    return lambda: ops.gemm_dual(dz, y2, wcat, b)
+
+
+def res_l1_gram():                # round 2: G = y2^T y2 (wgrad kernel on the narrow tensor) + column sums
+    y2 = rnd(256, 56, 56, 64).relu_()
+    return lambda: ops.gram_colsum(y2)
+
+
+def vit_qkv_wgrad_bias():         # round 2: qkv weight gradient with the bias gradient summed from the dY tiles
+    dy = rnd(256 * 197, 1, 1, 2304, scale=0.1)
+    x = rnd(256 * 197, 1, 1, 768)
+    b = torch.empty(2304, device=dev)
+    return lambda: ops.conv2d_wgrad(dy, x, bias_out=b)
+
+
 if __name__ == "__main__":
     fns = [(n, globals()[n]()) for n in sys.argv[1:]]
     for _, f in fns:
