@@ -39,6 +39,7 @@ SIGNATURES = {
     "b200_launch_count": (ctypes.c_ulonglong, []),
     "b200_conv2d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     "b200_conv2d_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
+    "b200_conv2d_fwd_set_bn": (_I, [_P, _P]),
     "b200_conv2d_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200_conv2d_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),

@@ -18,6 +18,8 @@ uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024, g_wg_kstep = 2048;
 // one-shot per-output-channel multiplier for the next b200_conv2d_wgrad call (see b200_conv2d_wgrad_set_rowscale)
 thread_local const float* g_wgrad_rowscale = nullptr;
 thread_local float* g_wgrad_bias_partial = nullptr;
+thread_local const float* g_fwd_bn_scale = nullptr;   // one-shot: fold y = conv * scale + shift (eval-mode BN) into the epilogue
+thread_local const float* g_fwd_bn_shift = nullptr;
 
 struct Box3 {
   int b1, b2, b3;
@@ -212,6 +214,8 @@ int epilogue_flags(const ConvGemmParams& p) {
   X(kEpiOutF32)                                           /* Swin patch-merging reduction            */  \
   X(kEpiBias | kEpiOutF32)                                /* ConvNeXt downsample conv                */  \
   X(kEpiAffine | kEpiResBf16 | (1 << kEpiActShift))       /* bottleneck conv3: relu(bn(conv) + identity) */ \
+  X(kEpiAffine | (1 << kEpiActShift))                     /* eval mode: relu(bn(conv))                   */ \
+  X(kEpiAffine)                                           /* eval mode: bn(conv) (downsample branch)     */ \
   X(kEpiMask | kEpiResBf16 | kEpiStats)                   /* dgrad + identity gradient, ReLU mask, sum dz */
 
 // ---- CTA-pair GEMM (tcgen05 cta_group::2): the 256-wide linear layers of the transformer / ConvNeXt paths run as pairs
@@ -616,7 +620,25 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
   p.rs3 = static_cast<long long>(d1) * d2 * Cout;
   p.out_direct = out_f32;
   p.ld_out = ld_out;
+  if (g_fwd_bn_scale != nullptr) {
+    // b200_conv2d_fwd_set_bn: y = act(conv * scale[c] + shift[c] (+ residual)) - BatchNorm with fixed (running) statistics
+    // folded into the epilogue; the activation moves AFTER the residual add (conv_gemm.cuh kEpiAffine)
+    const float* sc = g_fwd_bn_scale;
+    const float* sh = g_fwd_bn_shift;
+    g_fwd_bn_scale = g_fwd_bn_shift = nullptr;
+    B200_REQUIRE(Cout % 64 == 0 && bias == nullptr && stats == nullptr && out_f32 == nullptr && act <= 1 && !g_conv_out_f32_tma,
+                 "conv2d_fwd + folded BN: Cout=%d must be a multiple of 64, no bias / statistics / fp32 output", Cout);
+    p.affine = 1;
+    p.colscale = sc;
+    p.bias = sh;
+  }
   return dispatch_conv_gemm(p, Cout, st);
+}
+
+int b200_conv2d_fwd_set_bn(const float* scale, const float* shift) {
+  g_fwd_bn_scale = scale;
+  g_fwd_bn_shift = shift;
+  return OK;
 }
 
 int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, int W, int Cin, int Cout, int ksize,

@@ -119,6 +119,10 @@ def _conv_bn(pack, tape, x, conv, bn, train, relu, residual=None, name=""):
     _check_bn(bn, name)
     k, s = conv.kernel_size[0], conv.stride[0]
     wp = pack.get(conv.weight, 0)
+    if not train and tape is None and conv.out_channels % 64 == 0 and _algebra_enabled():
+        # eval forward (no tape): running statistics are constants, BatchNorm (+ identity) (+ ReLU) live in the conv epilogue
+        co = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        return ops.conv2d_bn_act(x, wp, co, k, s, relu=relu, residual=residual)
     c, st = ops.conv2d_fwd(x, wp, k, s, want_stats=train)
     if train:
         rows = c.numel() // c.shape[-1]

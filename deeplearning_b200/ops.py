@@ -164,6 +164,25 @@ def conv2d_fwd(x, w_packed, ksize=1, stride=1, want_stats=False, bias=None, act=
     return y, stats
 
 
+def conv2d_bn_act(x, w_packed, co, ksize=1, stride=1, relu=True, residual=None):
+    """Eval-mode conv -> BatchNorm(fixed statistics) (-> + residual) (-> ReLU) as ONE implicit-GEMM launch: the BN scale / shift
+    live in the epilogue, no BatchNorm pass at all."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = w_packed.shape[0]
+    Ho, Wo = out_hw(H, ksize, stride), out_hw(W, ksize, stride)
+    y = torch.empty(B, Ho, Wo, Cout, dtype=BF16, device=x.device)
+    sp = _span("conv_gemm_fwd", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize, _nb(x, w_packed, y, residual))
+    lib.b200_conv2d_fwd_set_bn(_p(co.scale), _p(co.shift))
+    rc = lib.b200_conv2d_fwd(_p(x), _p(w_packed), _p(y), B, H, W, Cin, Cout, ksize, stride, None, None, 1 if relu else 0,
+                             _p(residual), None, 0, _stream())
+    _lib.check(rc, "b200_conv2d_fwd")
+    if sp:
+        sp.end()
+    return y
+
+
 def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=None):
     """dx[B,H,W,Cin] from dy[B,Ho,Wo,Cout]; wd_packed = pack_weight(w, mode=1). `out` lets 1x1/s2 accumulate in place."""
     lib = _lib.load()

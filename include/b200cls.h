@@ -53,6 +53,11 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
                     float* stats, const float* bias, int act, const void* residual, float* out_f32, long long ld_out,
                     void* stream);
 int b200_conv2d_fwd_stats_rows(int B, int H, int W, int Cout, int ksize, int stride);
+/* one-shot (this thread, next b200_conv2d_fwd call): fold BatchNorm with FIXED statistics into the epilogue,
+ * y = act(conv(x) * scale[c] + shift[c] (+ residual)) with act (0 / B200_ACT_RELU) applied after the residual add - the
+ * eval-mode forward of conv -> bn -> (+identity) -> relu (classification/resnet/models/networks.py:104-124, utils.py:61-83
+ * `evaluate`) without any BatchNorm pass.  scale / shift from b200_bn_eval_coeffs; Cout % 64 == 0. */
+int b200_conv2d_fwd_set_bn(const float* scale, const float* shift);
 /* same convolution writing an fp32 NHWC output (+bias) through TMA - ConvNeXt downsample conv feeding the fp32 stream */
 int b200_conv2d_fwd_f32(const void* x, const void* w, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                         int stride, const float* bias, void* stream);

@@ -135,3 +135,30 @@ def test_cpu_tensor_raises():
     m, _ = _models()
     with pytest.raises(RuntimeError):
         m(torch.randn(1, 3, 32, 32))
+
+
+def test_reference_evaluate_and_train_loops_run_on_the_dropin():
+    """the reference's OWN `evaluate` and `train_one_epoch` (classification/resnet/utils.py:61-83,28-57,
+    staged unmodified under oracle/_ref by oracle/build_ref.py) drive the drop-in module; the eval pass runs with BatchNorm
+    folded into the conv epilogues and agrees with the fp32 oracle on the same weights."""
+    from oracle import build_ref
+    from oracle.resnet import resnet_forward
+
+    if not build_ref.available():
+        pytest.skip("oracle/_ref not staged (python oracle/build_ref.py in the build container)")
+    utils = build_ref.load("resnet", "utils")
+    m, state = _models()
+    xc = torch.randn(32, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    with torch.no_grad():
+        resnet_forward(state, xc, train=True, momentum=1.0)       # calibrate the running statistics
+    m.load_state_dict(state)
+    g = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(8, 3, 224, 224, generator=g), torch.randint(0, 1000, (8,), generator=g)) for _ in range(2)]
+    loss_fn = torch.nn.CrossEntropyLoss()
+    loss, acc = utils.evaluate(m, batches, torch.device("cuda"), loss_fn, 0)
+    with torch.no_grad():
+        ref = sum(float(F.cross_entropy(resnet_forward(state, x, train=False), y)) for x, y in batches) / len(batches)
+    assert abs(loss - ref) < 2e-2, (loss, ref)
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-5)
+    tl, ta = utils.train_one_epoch(m, batches, torch.device("cuda"), opt, loss_fn, 0)
+    assert tl == tl and 0.0 <= ta <= 1.0   # finite loss, loop ran to the end
