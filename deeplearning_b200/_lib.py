@@ -102,6 +102,8 @@ SIGNATURES = {
     "b200_debug_set_desc": (_I, [_I, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
     "b200_stem_wgrad_relayout": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "b200_stem_s2d": (_I, [_P, _P, _I, _I, _I, _P]),
+    "b200_stem_s2d_u8": (_I, [_P, _P, _I, _I, _I, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P]),
+    "b200_normalize_u8_nhwc": (_I, [_P, _P, _I, _I, _I, ctypes.POINTER(c_float), ctypes.POINTER(c_float), _P]),
     "b200_stem_s2d_conv_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "b200_stem_s2d_conv_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I]),
     "b200_stem_s2d_conv_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _P]),

@@ -339,4 +339,33 @@ int b200_bn_conv1x1_bwd(const float* dz_partial, int T, const float* D, const fl
   return OK;
 }
 
+int b200_stem_s2d_u8(const void* x_u8_nhwc, void* z, int B, int H, int W, const float* mean3, const float* std3, void* stream) {
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, "stem_s2d_u8: H=%d W=%d must be even", H, W);
+  B200_REQUIRE(mean3 != nullptr && std3 != nullptr, "stem_s2d_u8: host mean / std (3 floats each) required");
+  float a[3], b[3];
+  for (int c = 0; c < 3; ++c) {
+    a[c] = 1.0f / (255.0f * std3[c]);
+    b[c] = -mean3[c] / std3[c];
+  }
+  const long long total = static_cast<long long>(B) * (H / 2 + 3) * (W / 2 + 3);
+  stem_s2d_u8_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned char*>(x_u8_nhwc), static_cast<uint4*>(z), B, H, W, a[0], a[1], a[2], b[0], b[1], b[2]);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_normalize_u8_nhwc(const void* x_u8_nhwc, float* y_nchw, int B, int H, int W, const float* mean3, const float* std3,
+                           void* stream) {
+  B200_REQUIRE(B > 0 && H > 0 && W > 0 && mean3 != nullptr && std3 != nullptr, "normalize_u8_nhwc: bad arguments");
+  float a[3], b[3];
+  for (int c = 0; c < 3; ++c) {
+    a[c] = 1.0f / (255.0f * std3[c]);
+    b[c] = -mean3[c] / std3[c];
+  }
+  u8_nhwc_to_f32_nchw_kernel<<<ew_grid(static_cast<long long>(B) * H * W), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const unsigned char*>(x_u8_nhwc), y_nchw, B, H, W, a[0], a[1], a[2], b[0], b[1], b[2]);
+  B200_LAUNCHED();
+  return OK;
+}
+
 }  // extern "C"

@@ -943,6 +943,61 @@ __global__ void stem_s2d_kernel(const float* __restrict__ x, uint4* __restrict__
   }
 }
 
+// GPU input pipeline: the same space-to-depth operand straight from the DECODED image batch,
+// x uint8 NHWC [B][H][W][3] (what a JPEG decoder / PIL produces), with the reference's ToTensor + Normalize
+// (classification/resnet/train.py:46-71: x / 255, then (x - mean[c]) / std[c]) fused in: z = bf16((u8 * a[c]) + b[c]),
+// a = 1 / (255 std), b = -mean / std.  The host->device copy shrinks 4x (1 byte instead of 4 per value) and the
+// fp32 NCHW batch never exists.
+__global__ void stem_s2d_u8_kernel(const unsigned char* __restrict__ x, uint4* __restrict__ z, int B, int H, int W, float a0,
+                                   float a1, float a2, float b0, float b1, float b2) {
+  const int Hz = H / 2 + 3, Wz = W / 2 + 3;
+  const long long total = static_cast<long long>(B) * Hz * Wz;
+  const float a[3] = {a0, a1, a2}, bb[3] = {b0, b1, b2};
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int X = static_cast<int>(i % Wz);
+    const int Y = static_cast<int>((i / Wz) % Hz);
+    const long long b = i / (static_cast<long long>(Wz) * Hz);
+    float v[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v[q] = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int h = 2 * Y + dy - 3;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int w = 2 * X + dx - 3;
+        if (w < 0 || w >= W) continue;
+        const unsigned char* px = x + ((b * H + h) * W + w) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(dy * 2 + dx) * 3 + c] = fmaf(static_cast<float>(px[c]), a[c], bb[c]);
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lo[q] = v[q], hi[q] = v[8 + q];
+    z[2 * i] = pack8(lo);
+    z[2 * i + 1] = pack8(hi);
+  }
+}
+
+// The same ToTensor + Normalize for the other families: uint8 NHWC -> fp32 NCHW (the layout their patch-embedding kernels read).
+__global__ void u8_nhwc_to_f32_nchw_kernel(const unsigned char* __restrict__ x, float* __restrict__ y, int B, int H, int W,
+                                           float a0, float a1, float a2, float b0, float b1, float b2) {
+  const long long total = static_cast<long long>(B) * H * W;
+  const long long plane = static_cast<long long>(H) * W;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / plane, p = i - b * plane;
+    const unsigned char* px = x + i * 3;
+    float* o = y + b * 3 * plane + p;
+    o[0] = fmaf(static_cast<float>(px[0]), a0, b0);
+    o[plane] = fmaf(static_cast<float>(px[1]), a1, b1);
+    o[2 * plane] = fmaf(static_cast<float>(px[2]), a2, b2);
+  }
+}
+
 // Weight gradient of the space-to-depth stem: g[64][k64 = kx4*16 + (dy*2+dx)*3 + c][ky4] -> dW [64][3][7][7] (OIHW).
 __global__ void stem_s2d_wgrad_relayout_kernel(const float* __restrict__ g, float* __restrict__ dw, int accumulate) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

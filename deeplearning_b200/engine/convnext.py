@@ -91,6 +91,8 @@ _dw_cache = _DwCache()
 
 def forward(model, x, train, want_tape):
     _check(model)
+    if x.dtype == torch.uint8:      # GPU input pipeline: decoded uint8 NHWC batch -> ToTensor + Normalize on the device
+        x = ops.normalize_u8_nhwc(x, *getattr(model, "input_norm", (ops.IMAGENET_MEAN, ops.IMAGENET_STD)))
     x = x.contiguous().float()
     B = x.shape[0]
     pack = weight_cache.model_pack(model, _pack_spec)

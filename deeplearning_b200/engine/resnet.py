@@ -153,9 +153,17 @@ def _block_units(block):
 
 def forward(model, x, train, want_tape):
     """x: fp32 NCHW CUDA batch. Returns (logits fp32 [B, num_classes], tape or None)."""
-    if x.dim() != 4 or x.shape[1] != 3:
-        raise ValueError(f"expected an [B,3,H,W] image batch, got {tuple(x.shape)}")
-    x = x.contiguous().float()
+    u8 = x.dtype == torch.uint8     # GPU input pipeline: decoded uint8 NHWC batch, ToTensor + Normalize fused into the stem operand
+    if u8:
+        if x.dim() != 4 or x.shape[3] != 3:
+            raise ValueError(f"uint8 input must be a decoded NHWC batch [B,H,W,3], got {tuple(x.shape)}")
+        x = x.contiguous()
+        x_hw = (x.shape[1], x.shape[2])
+    else:
+        if x.dim() != 4 or x.shape[1] != 3:
+            raise ValueError(f"expected an [B,3,H,W] image batch, got {tuple(x.shape)}")
+        x = x.contiguous().float()
+        x_hw = (x.shape[2], x.shape[3])
     B = x.shape[0]
     if not isinstance(model.fc, nn.Linear):
         raise NotImplementedError("model.fc must be an nn.Linear")
@@ -166,10 +174,10 @@ def forward(model, x, train, want_tape):
     _check_bn(bn1, "bn1")
     if conv1.kernel_size != (7, 7) or conv1.stride != (2, 2) or conv1.padding != (3, 3) or conv1.bias is not None:
         raise NotImplementedError("stem must be the 7x7/2 pad-3 bias-free convolution of the reference")
-    if conv1.out_channels != 64 or x.shape[2] % 2 or x.shape[3] % 2:
+    if conv1.out_channels != 64 or x_hw[0] % 2 or x_hw[1] % 2:
         raise NotImplementedError("stem: 64 output channels and an even input size are required")
     # space-to-depth operand (108 MB at bs 256 instead of a 1 GB patch matrix); the conv reads it through overlapping TMA rows
-    a = ops.stem_s2d(x)
+    a = ops.stem_s2d_u8(x, *getattr(model, "input_norm", (ops.IMAGENET_MEAN, ops.IMAGENET_STD))) if u8 else ops.stem_s2d(x)
     Ho, Wo = a.shape[1] - 3, a.shape[2] - 3
     c1, st = ops.stem_s2d_conv_fwd(a, pack.get(conv1.weight, 2), want_stats=train)
     if train:

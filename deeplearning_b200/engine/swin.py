@@ -79,6 +79,8 @@ def _check(model):
 
 def forward(model, x, train, want_tape):
     _check(model)
+    if x.dtype == torch.uint8:      # GPU input pipeline: decoded uint8 NHWC batch -> ToTensor + Normalize on the device
+        x = ops.normalize_u8_nhwc(x, *getattr(model, "input_norm", (ops.IMAGENET_MEAN, ops.IMAGENET_STD)))
     x = x.contiguous().float()
     B, Cin, Hi, Wi = x.shape
     pe = model.patch_embed

@@ -293,7 +293,8 @@ class TrainStep:
         if not self.model.training:
             self.model.train()
         dev = self.arena.flat_p.device
-        self._g_images = torch.empty_like(images, dtype=torch.float32, device=dev)
+        # (a decoded uint8 NHWC batch stays uint8: ToTensor + Normalize run inside the step, see ops.stem_s2d_u8)
+        self._g_images = torch.empty_like(images, dtype=torch.uint8 if images.dtype == torch.uint8 else torch.float32, device=dev)
         self._g_labels = torch.empty_like(labels, device=dev)
         self._g_images.copy_(images)
         self._g_labels.copy_(labels)

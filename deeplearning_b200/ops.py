@@ -572,6 +572,39 @@ def stem_s2d(x):
     return z
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)   # classification/resnet/train.py:51
+
+
+def _f3(v):
+    import ctypes
+
+    return (ctypes.c_float * 3)(*[float(t) for t in v])
+
+
+def stem_s2d_u8(x_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """Decoded uint8 NHWC [B,H,W,3] -> the stem's space-to-depth operand, with ToTensor + Normalize fused in (GPU input pipeline)."""
+    lib = _lib.load()
+    if x_u8.dtype != torch.uint8 or x_u8.dim() != 4 or x_u8.shape[-1] != 3 or not x_u8.is_cuda or not x_u8.is_contiguous():
+        raise ValueError("stem_s2d_u8 expects a contiguous CUDA uint8 [B,H,W,3] batch")
+    B, H, W, _ = x_u8.shape
+    z = torch.empty(B, H // 2 + 3, W // 2 + 3, 16, dtype=BF16, device=x_u8.device)
+    sp = _span("stem_s2d", 0.0, _nb(x_u8, z))
+    _lib.check(lib.b200_stem_s2d_u8(_p(x_u8), _p(z), B, H, W, _f3(mean), _f3(std), _stream()), "b200_stem_s2d_u8")
+    if sp:
+        sp.end()
+    return z
+
+
+def normalize_u8_nhwc(x_u8, mean=IMAGENET_MEAN, std=IMAGENET_STD):
+    """Decoded uint8 NHWC [B,H,W,3] -> normalised fp32 NCHW [B,3,H,W] (ToTensor + Normalize on the GPU)."""
+    lib = _lib.load()
+    B, H, W, _ = x_u8.shape
+    y = torch.empty(B, 3, H, W, dtype=F32, device=x_u8.device)
+    _lib.check(lib.b200_normalize_u8_nhwc(_p(x_u8.contiguous()), _p(y), B, H, W, _f3(mean), _f3(std), _stream()),
+               "b200_normalize_u8_nhwc")
+    return y
+
+
 def stem_s2d_conv_fwd(z, w_packed, want_stats=False):
     """conv 7x7/2/pad 3 from the space-to-depth operand: returns (y bf16 [B,Ho,Wo,64], BN statistics partials or None)."""
     lib = _lib.load()

@@ -276,6 +276,12 @@ int b200_im2col_nchw(const float* x, void* a, int B, int Cin, int H, int W, int 
  * y bf16 [B][Ho][Wo][64] (Ho = H/2), stats as for b200_conv2d_fwd (rows: b200_conv2d_fwd_stats_rows(B, Ho, Wo, 64, 3, 1)).
  * wgrad: g fp32 [64][64][4] scratch gradient in the operand layout -> b200_stem_s2d_wgrad_relayout -> dW [64][3][7][7]. */
 int b200_stem_s2d(const float* x, void* z, int B, int H, int W, void* stream);
+/* GPU input pipeline (replaces the CPU ToTensor + Normalize of classification/resnet/train.py:46-71):
+ * decoded uint8 NHWC [B][H][W][3] -> the same space-to-depth operand (ResNet), or -> normalised fp32 NCHW (other families).
+ * mean3 / std3 are HOST pointers to 3 floats each (the reference's [0.485, 0.456, 0.406] / [0.229, 0.224, 0.225]). */
+int b200_stem_s2d_u8(const void* x_u8_nhwc, void* z, int B, int H, int W, const float* mean3, const float* std3, void* stream);
+int b200_normalize_u8_nhwc(const void* x_u8_nhwc, float* y_nchw, int B, int H, int W, const float* mean3, const float* std3,
+                           void* stream);
 int b200_stem_s2d_conv_fwd(const void* z, const void* w, void* y, float* stats, int B, int Ho, int Wo, void* stream);
 size_t b200_stem_s2d_conv_wgrad_workspace_bytes(int B, int Ho, int Wo);
 int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* workspace, size_t workspace_bytes, int B, int Ho,

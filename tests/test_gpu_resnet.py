@@ -162,3 +162,26 @@ def test_reference_evaluate_and_train_loops_run_on_the_dropin():
     opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-5)
     tl, ta = utils.train_one_epoch(m, batches, torch.device("cuda"), opt, loss_fn, 0)
     assert tl == tl and 0.0 <= ta <= 1.0   # finite loss, loop ran to the end
+
+
+def test_gpu_input_pipeline_uint8_nhwc_equals_cpu_totensor_normalize():
+    """a decoded uint8 NHWC batch fed straight to the drop-in (ToTensor + Normalize fused into the stem's
+    space-to-depth operand; 4x less host->device traffic) gives the logits of the reference's CPU preprocessing
+    (classification/resnet/train.py:46-71: ToTensor, Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])) + float input."""
+    from deeplearning_b200 import ops
+
+    m, _ = _models()
+    m.eval()
+    g = torch.Generator().manual_seed(9)
+    u8 = torch.randint(0, 256, (4, 64, 64, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(ops.IMAGENET_MEAN), torch.tensor(ops.IMAGENET_STD)
+    xf = ((u8.float() / 255.0 - mean) / std).permute(0, 3, 1, 2).contiguous()
+    with torch.no_grad():
+        a = m(u8.cuda()).float().cpu()
+        b = m(xf.cuda()).float().cpu()
+    assert float((a - b).abs().max()) <= 2e-2 * max(1.0, float(b.abs().max())), float((a - b).abs().max())
+    z1 = ops.stem_s2d_u8(u8.cuda())
+    z2 = ops.stem_s2d(xf.cuda())
+    assert float((z1.float() - z2.float()).abs().max()) <= 2e-2        # same operand up to one bf16 rounding of (u8*a + b)
+    y = ops.normalize_u8_nhwc(u8.cuda())
+    assert torch.allclose(y.cpu(), xf, rtol=1e-5, atol=1e-5)
