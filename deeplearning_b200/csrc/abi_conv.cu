@@ -362,7 +362,7 @@ int run_stream(int mode, const void* a, const void* w, void* out, const void* re
     uint64_t strides[2] = {1, static_cast<uint64_t>(N)};
     uint32_t box[2] = {64, 32};
     if ((rc = encode_tmap_bf16(&q.out_map, out, 2, dims, strides, box))) return rc;
-    if ((rc = encode_tmap_bf16(&q.res_map, res, 2, dims, strides, box))) return rc;
+    if (res != nullptr && (rc = encode_tmap_bf16(&q.res_map, res, 2, dims, strides, box))) return rc;
     if (mask != nullptr && (rc = encode_tmap_bf16(&q.mask_map, mask, 2, dims, strides, box))) return rc;
   }
   q.m_tiles = static_cast<int>(pixels / 128);
@@ -370,6 +370,9 @@ int run_stream(int mode, const void* a, const void* w, void* out, const void* re
   q.N = N;
   q.scale = scale, q.shift = shift, q.stats = stats;
   const int grid = stream_grid(pixels, N);
+  if (mode == kStreamAffine)
+    return K == 64 ? launch_stream<1, kStreamAffine>(q, grid, st)
+                   : (K == 128 ? launch_stream<2, kStreamAffine>(q, grid, st) : launch_stream<4, kStreamAffine>(q, grid, st));
   if (mode == kStreamBnRelu)
     return K == 64 ? launch_stream<1, kStreamBnRelu>(q, grid, st)
                    : (K == 128 ? launch_stream<2, kStreamBnRelu>(q, grid, st) : launch_stream<4, kStreamBnRelu>(q, grid, st));
@@ -995,6 +998,17 @@ int b200_conv1x1_bn_act_fwd(const void* x, const void* w, const float* scale, co
   p.rs2 = static_cast<long long>(dv.strides[2]);
   p.rs3 = static_cast<long long>(dv.strides[3]);
   return dispatch_conv_gemm(p, Cout, static_cast<cudaStream_t>(stream));
+}
+
+int b200_conv1x1_bn_fwd(const void* x, const void* w, const float* scale, const float* shift, void* y, long long pixels,
+                        int Cin, int Cout, void* stream) {
+  B200_REQUIRE(pixels > 0 && Cin % 64 == 0 && Cout % 64 == 0, "conv1x1_bn_fwd: Cin=%d / Cout=%d must be multiples of 64", Cin, Cout);
+  B200_REQUIRE(scale != nullptr && shift != nullptr, "conv1x1_bn_fwd: scale / shift required");
+  if (stream_ok(pixels, Cin, Cout))
+    return run_stream(kStreamAffine, x, w, y, nullptr, nullptr, scale, shift, nullptr, pixels, Cin, Cout,
+                      static_cast<cudaStream_t>(stream));
+  b200_conv2d_fwd_set_bn(scale, shift);
+  return b200_conv2d_fwd(x, w, y, 1, 1, static_cast<int>(pixels), Cin, Cout, 1, 1, nullptr, nullptr, 0, nullptr, nullptr, 0, stream);
 }
 
 int b200_conv1x1_dgrad_masked_stats_rows(long long pixels, int Cin) {

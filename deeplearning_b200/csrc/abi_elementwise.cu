@@ -368,4 +368,24 @@ int b200_normalize_u8_nhwc(const void* x_u8_nhwc, float* y_nchw, int B, int H, i
   return OK;
 }
 
+int b200_subsample2(const void* x, void* xs, int B, int H, int W, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && B > 0 && H > 0 && W > 0, "subsample2: C=%d must be a multiple of 8", C);
+  B200_REQUIRE(static_cast<long long>(B) * H * W * (C / 8) < (1LL << 32), "subsample2: tensor too large");
+  const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  subsample2_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), static_cast<uint4*>(xs), B, H, W, C / 8);
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_add_even_pixels(void* gx, const void* gs, int B, int H, int W, int C, void* stream) {
+  B200_REQUIRE(C % 8 == 0 && B > 0 && H > 0 && W > 0, "add_even_pixels: C=%d must be a multiple of 8", C);
+  B200_REQUIRE(static_cast<long long>(B) * H * W * (C / 8) < (1LL << 32), "add_even_pixels: tensor too large");
+  const long long total = static_cast<long long>(B) * ((H + 1) / 2) * ((W + 1) / 2) * (C / 8);
+  add_even_pixels_kernel<<<ew_grid(total), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<uint4*>(gx), static_cast<const uint4*>(gs), B, H, W, C / 8);
+  B200_LAUNCHED();
+  return OK;
+}
+
 }  // extern "C"

@@ -6,6 +6,7 @@
 //                   (classification/resnet/models/networks.py:116-124, BatchNorm folded through the conv: bn_algebra.cuh)
 //   kStreamMask   : out = mask > 0 ? acc + residual : 0,  + per-CTA column sums  dgrad of conv1 + identity gradient, masked by
 //                   the ReLU of the block input; the sums are sum(dz) of the previous block's BatchNorm backward
+//   kStreamAffine : out = acc * scale[n] + shift[n]                            downsample conv -> BatchNorm (no residual, no ReLU)
 //
 // These layers move 9 bytes of activations per byte of operand: per 128-pixel tile the tensor core needs ~512 clocks, HBM
 // ~7000.  The generic implicit-GEMM kernel (conv_gemm.cuh) runs them at ~3 TB/s because its epilogue fetches the residual
@@ -23,7 +24,7 @@
 
 namespace b200 {
 
-enum : int { kStreamBnRelu = 0, kStreamMask = 1 };
+enum : int { kStreamBnRelu = 0, kStreamMask = 1, kStreamAffine = 2 };
 
 struct alignas(64) StreamParams {
   CUtensorMap a_map;     // A   [P][K] bf16, box {64, 128}
@@ -46,11 +47,11 @@ struct StreamCfg {
   static constexpr int B_BYTES = STREAM_B ? 0 : KB * 32768;
   static constexpr int NBUF = (KB >= 2 && (MODE == kStreamMask || STREAM_B)) ? 2 : 3;   // slabs in flight per warp and source
   static constexpr int SLAB = 4096;                                        // 32 rows x 128 B
-  static constexpr int RES_BYTES = 4 * NBUF * SLAB;
+  static constexpr int RES_BYTES = MODE == kStreamAffine ? 0 : 4 * NBUF * SLAB;
   static constexpr int MASK_BYTES = MODE == kStreamMask ? RES_BYTES : 0;
   static constexpr int OUT_SLABS = (STREAM_B && MODE == kStreamMask) ? 1 : 2;   // output slabs per warp (shared memory is full)
   static constexpr int OUT_BYTES = 4 * OUT_SLABS * SLAB;
-  static constexpr int COEF_BYTES = MODE == kStreamBnRelu ? 2 * 256 * 4 : 0;
+  static constexpr int COEF_BYTES = MODE != kStreamMask ? 2 * 256 * 4 : 0;
   static constexpr int BAR_BYTES = 512;
   static constexpr int SMEM_BYTES = B_BYTES + STAGES * A_STAGE + RES_BYTES + MASK_BYTES + OUT_BYTES + COEF_BYTES + BAR_BYTES + 1024;
   static constexpr int THREADS = 192;   // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (one per TMEM quadrant)
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
     tma_prefetch_desc(&p.a_map);
     tma_prefetch_desc(&p.b_map);
     tma_prefetch_desc(&p.out_map);
-    tma_prefetch_desc(&p.res_map);
+    if constexpr (MODE != kStreamAffine) tma_prefetch_desc(&p.res_map);
     if constexpr (MODE == kStreamMask) tma_prefetch_desc(&p.mask_map);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&a_full[i], 1);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
-  if constexpr (MODE == kStreamBnRelu) {
+  if constexpr (MODE != kStreamMask) {
     // this CTA's 256 scale / shift values (its channel block never changes)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
       sCoef[i] = __ldg(p.scale + n_tile * 256 + i);
@@ -232,8 +233,10 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
       if constexpr (MODE == kStreamMask)
         tma_load_2d(reinterpret_cast<void*>(sMask + (ew * NBUF + slot) * Cfg::SLAB), &p.mask_map, &my_full[slot], col, row);
     };
-    if (lane == 0)
-      for (int g = 0; g < NBUF && g < total_units; ++g) issue_unit(g);
+    if constexpr (MODE != kStreamAffine) {
+      if (lane == 0)
+        for (int g = 0; g < NBUF && g < total_units; ++g) issue_unit(g);
+    }
 
     // column sums (kStreamMask): lane owns columns 2*lane, 2*lane + 1 of each of the four 64-column units
     uint32_t stat_off[8];
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
         if (lane == 0) {
           if constexpr (Cfg::OUT_SLABS == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>();
         }
-        mbar_wait(&my_full[slot], (g / NBUF) & 1);
+        if constexpr (MODE != kStreamAffine) mbar_wait(&my_full[slot], (g / NBUF) & 1);
         __syncwarp();
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -267,7 +270,8 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
           uint4 r4[4], m4[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            r4[j] = lds128(rs + row_s + (((h * 4 + j) << 4) ^ sw));
+            if constexpr (MODE != kStreamAffine) r4[j] = lds128(rs + row_s + (((h * 4 + j) << 4) ^ sw));
+            else r4[j] = make_uint4(0u, 0u, 0u, 0u);
             if constexpr (MODE == kStreamMask) m4[j] = lds128(ms + row_s + (((h * 4 + j) << 4) ^ sw));
           }
           tmem_ld_wait();
@@ -290,6 +294,12 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
                 const float2 sh = *reinterpret_cast<const float2*>(sCoef + 256 + c);
                 f0 = fmaxf(fmaf(f0, sc.x, sh.x) + bf16_lo(rw[i]), 0.0f);
                 f1 = fmaxf(fmaf(f1, sc.y, sh.y) + bf16_hi(rw[i]), 0.0f);
+              } else if constexpr (MODE == kStreamAffine) {
+                const int c = u * 64 + h * 32 + j * 8 + 2 * i;
+                const float2 sc = *reinterpret_cast<const float2*>(sCoef + c);
+                const float2 sh = *reinterpret_cast<const float2*>(sCoef + 256 + c);
+                f0 = fmaf(f0, sc.x, sh.x);
+                f1 = fmaf(f1, sc.y, sh.y);
               } else {
                 const uint32_t mw = i == 0 ? m4[j].x : (i == 1 ? m4[j].y : (i == 2 ? m4[j].z : m4[j].w));
                 f0 = (mw & 0x7fffu) ? f0 + bf16_lo(rw[i]) : 0.0f;
@@ -315,7 +325,9 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
         if (lane == 0) {
           tma_store_2d(&p.out_map, os, col0 + u * 64, row0);
           tma_store_commit();
-          if (g + NBUF < total_units) issue_unit(g + NBUF);   // all lanes have consumed ring slot `slot` (__syncwarp above)
+          if constexpr (MODE != kStreamAffine) {
+            if (g + NBUF < total_units) issue_unit(g + NBUF);   // all lanes have consumed ring slot `slot` (__syncwarp above)
+          }
         }
       }
     }

@@ -943,6 +943,44 @@ __global__ void stem_s2d_kernel(const float* __restrict__ x, uint4* __restrict__
   }
 }
 
+// Stride-2 helpers of the downsample branch on the BatchNorm-algebra path (engine/resnet.py): the 1x1 / stride-2 convolution
+// only ever sees the even pixels of its input, so the branch runs on a COMPACT copy xs[b][i][j][:] = x[b][2i][2j][:] (a quarter
+// of x) as a flat GEMM, and its data gradient is added back onto the even pixels: gx[b][2i][2j][:] += gs[b][i][j][:].
+__global__ void __launch_bounds__(256) subsample2_kernel(const uint4* __restrict__ x, uint4* __restrict__ xs, int B, int H, int W,
+                                                         int cvec) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const unsigned total = static_cast<unsigned>(B) * Ho * Wo * cvec;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % cvec;
+    unsigned t = i / cvec;
+    const unsigned ow = t % Wo;
+    t /= Wo;
+    const unsigned oh = t % Ho;
+    const unsigned b = t / Ho;
+    xs[i] = __ldg(x + ((b * H + 2 * oh) * W + 2 * ow) * cvec + c);
+  }
+}
+__global__ void __launch_bounds__(256) add_even_pixels_kernel(uint4* __restrict__ gx, const uint4* __restrict__ gs, int B, int H,
+                                                              int W, int cvec) {
+  const int Ho = (H + 1) / 2, Wo = (W + 1) / 2;
+  const unsigned total = static_cast<unsigned>(B) * Ho * Wo * cvec;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned c = i % cvec;
+    unsigned t = i / cvec;
+    const unsigned ow = t % Wo;
+    t /= Wo;
+    const unsigned oh = t % Ho;
+    const unsigned b = t / Ho;
+    uint4* dst = gx + ((b * H + 2 * oh) * W + 2 * ow) * cvec + c;
+    float a[8], d[8];
+    unpack8(*dst, a);
+    unpack8(__ldg(gs + i), d);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] += d[k];
+    *dst = pack8(a);
+  }
+}
+
 // GPU input pipeline: the same space-to-depth operand straight from the DECODED image batch,
 // x uint8 NHWC [B][H][W][3] (what a JPEG decoder / PIL produces), with the reference's ToTensor + Normalize
 // (classification/resnet/train.py:46-71: x / 255, then (x - mean[c]) / std[c]) fused in: z = bf16((u8 * a[c]) + b[c]),

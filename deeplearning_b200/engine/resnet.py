@@ -114,6 +114,38 @@ def _conv3_bn_res_relu(pack, tape, y2, conv, bn, train, identity, name=""):
     return y
 
 
+def _ds_algebra_ok(block, train, want_tape):
+    """Downsample branch (1x1 conv, stride 1 or 2 -> BatchNorm) of an algebra bottleneck that can run with its BatchNorm folded
+    through the convolution too (train mode; input width <= 256)."""
+    if not train or block.downsample is None or not _algebra_ok(block, train, want_tape):
+        return False
+    ds = block.downsample
+    if len(ds) != 2 or not isinstance(ds[0], nn.Conv2d) or not isinstance(ds[1], nn.BatchNorm2d):
+        return False
+    c = ds[0]
+    return (c.kernel_size == (1, 1) and c.stride in ((1, 1), (2, 2)) and c.groups == 1 and c.bias is None and c.padding == (0, 0)
+            and c.in_channels % 64 == 0 and c.in_channels <= 256 and c.out_channels % 64 == 0)
+
+
+def _ds_conv_bn_algebra(pack, tape, x_in, conv, bn, name=""):
+    """identity = bn_ds(conv_ds(x_in)) with the batch statistics from the Gram matrix of the (compact) input: the raw conv output
+    is never written.  A stride-2 branch runs on the compact copy of the even pixels it reads."""
+    _check_bn(bn, name)
+    xs = x_in if conv.stride == (1, 1) else ops.subsample2(x_in)
+    wp = pack.get(conv.weight, 0)
+    G, s = ops.gram_colsum(xs)
+    rows = xs.numel() // xs.shape[-1]
+    co = ops.bn_gram_stats(G, s, wp, rows, bn.weight, bn.bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
+                           bn.num_batches_tracked)
+    ident = ops.conv1x1_bn(xs, wp, co)
+    if tape is not None:
+        u = _Unit()
+        u.conv, u.bn, u.x, u.c, u.co, u.y, u.relu, u.has_res = conv, bn, xs, None, co, ident, False, False
+        u.algebra, u.G, u.s = True, G, s
+        tape.append(u)
+    return ident
+
+
 def _conv_bn(pack, tape, x, conv, bn, train, relu, residual=None, name=""):
     _check_conv(conv, name)
     _check_bn(bn, name)
@@ -198,7 +230,10 @@ def forward(model, x, train, want_tape):
             for j, (conv, bn) in enumerate(pairs[:-1]):
                 h = _conv_bn(pack, units, h, conv, bn, train, relu=True, name=f"{name}.conv{j + 1}")
             ds_units = [] if want_tape else None
-            if block.downsample is not None:
+            if block.downsample is not None and _ds_algebra_ok(block, train, want_tape):
+                identity = _ds_conv_bn_algebra(pack, ds_units, x_in, block.downsample[0], block.downsample[1],
+                                               name=f"{name}.downsample")
+            elif block.downsample is not None:
                 identity = _conv_bn(pack, ds_units, x_in, block.downsample[0], block.downsample[1], train, relu=False,
                                     name=f"{name}.downsample")
             else:
@@ -318,6 +353,19 @@ def backward(model, tape, dlogits, sink=None):
             # out = relu(bn_last(c) + identity): dz is the gradient of the pre-ReLU sum, shared by both branches
             dc, dz = _unit_backward(last, g, grads, want_dz=True)
             first = len(units) - 1
+        # downsample branch on the algebra path: its data gradient gxs (on the compact even-pixel grid for stride 2) and all its
+        # parameter gradients come from dz directly (no pass over a raw conv output, which does not exist)
+        gxs = None
+        if has_ds and ds.algebra:
+            Nd, Kd = ds.conv.out_channels, ds.conv.in_channels
+            Dd = ops.conv2d_wgrad(dz, ds.x, 1, 1)
+            dgd, dbd, dWd, wcat_d, wbias_d = ops.bn_conv1x1_bwd(
+                dz_stats, Dd, ds.G, ds.s, pack.get(ds.conv.weight, 0), ds.conv.weight, dz.numel() // Nd, ds.bn.weight, ds.co,
+                dgamma=grads.dest(ds.bn.weight), dbeta=grads.dest(ds.bn.bias), dW=grads.dest(ds.conv.weight))
+            grads.put(ds.bn.weight, dgd)
+            grads.put(ds.bn.bias, dbd)
+            grads.put(ds.conv.weight, dWd)
+            gxs = ops.gemm_dual(dz, ds.x, wcat_d, wbias_d)
         # does the producer of x_in (the previous block) take its gradient pre-masked from this block's conv1 dgrad?
         prev_masked = (bi > 0 and not has_ds and blocks[bi - 1][0][-1].algebra and _algebra_ok_dgrad(units[0].conv))
         dz_prev = dz_prev_stats = None
@@ -331,15 +379,19 @@ def backward(model, tape, dlogits, sink=None):
                 g_prev = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
                 dc, _ = _unit_backward(units[j - 1], g_prev, grads)
             else:
-                if has_ds:
+                if has_ds and gxs is not None and ds.conv.stride == (1, 1):
+                    gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s, residual=gxs)   # + downsample-branch gradient (same grid)
+                elif has_ds:
                     gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
+                    if gxs is not None:
+                        ops.add_even_pixels_(gx, gxs)                            # stride-2 branch: onto the even pixels
                 elif prev_masked:
                     # + identity-branch gradient, x_in's ReLU mask and the column sums the previous block needs, in the epilogue
                     dz_prev, dz_prev_stats = ops.conv1x1_dgrad_masked(dc, wd, residual=dz, mask_src=x_in)
                     gx = None
                 else:
                     gx = ops.conv2d_dgrad(dc, wd, in_hw, k, s, residual=dz)  # + identity-branch gradient
-        if has_ds:
+        if has_ds and not ds.algebra:
             dcd, _ = _unit_backward(ds, dz, grads)
             kd, sd = ds.conv.kernel_size[0], ds.conv.stride[0]
             grads.put(ds.conv.weight, ops.conv2d_wgrad(dcd, x_in, kd, sd, out=grads.dest(ds.conv.weight)))

@@ -387,6 +387,40 @@ def conv1x1_bn_act(x, w_packed, co, residual):
     return y
 
 
+def conv1x1_bn(x, w_packed, co):
+    """y = conv1x1(x, w) * co.scale + co.shift (downsample conv + BatchNorm in one GEMM; no residual, no ReLU)."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    Cin = x.shape[-1]
+    Cout = w_packed.shape[0]
+    y = torch.empty(*x.shape[:-1], Cout, dtype=BF16, device=x.device)
+    pixels = x.numel() // Cin
+    sp = _span("conv_gemm_fwd", 2.0 * pixels * Cin * Cout, _nb(x, w_packed, y))
+    rc = lib.b200_conv1x1_bn_fwd(_p(x), _p(w_packed), _p(co.scale), _p(co.shift), _p(y), pixels, Cin, Cout, _stream())
+    _lib.check(rc, "b200_conv1x1_bn_fwd")
+    if sp:
+        sp.end()
+    return y
+
+
+def subsample2(x):
+    """xs[b, i, j] = x[b, 2i, 2j]: the pixels a 1x1 / stride-2 convolution reads, as a compact NHWC tensor."""
+    lib = _lib.load()
+    _chk_act(x, "x")
+    B, H, W, C = x.shape
+    xs = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, dtype=BF16, device=x.device)
+    _lib.check(lib.b200_subsample2(_p(x), _p(xs), B, H, W, C, _stream()), "b200_subsample2")
+    return xs
+
+
+def add_even_pixels_(gx, gs):
+    """gx[b, 2i, 2j] += gs[b, i, j] in place."""
+    lib = _lib.load()
+    B, H, W, C = gx.shape
+    _lib.check(lib.b200_add_even_pixels(_p(gx), _p(gs), B, H, W, C, _stream()), "b200_add_even_pixels")
+    return gx
+
+
 def conv1x1_dgrad_masked(dy, wd_packed, residual, mask_src):
     """dz = (mask_src > 0) * (dy @ wd^T + residual); returns (dz bf16, stats fp32 [T,2,Cin] with plane 0 = partial sums of dz)."""
     lib = _lib.load()

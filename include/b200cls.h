@@ -309,6 +309,13 @@ int b200_bn_gram_stats(const float* G, const float* s, const void* w_bf16, int N
                        long long* num_batches_tracked, float* mean, float* invstd, float* scale, float* shift, void* stream);
 int b200_conv1x1_bn_act_fwd(const void* x, const void* w, const float* scale, const float* shift, const void* residual,
                             void* y, long long pixels, int Cin, int Cout, int relu, void* stream);
+/* y[pixels][Cout] = conv1x1(x, w) * scale + shift: the downsample branch conv -> BatchNorm (networks.py:118-119, 196-199) with the
+ * batch statistics from b200_bn_gram_stats of its (compact, see b200_subsample2) input; no residual, no ReLU */
+int b200_conv1x1_bn_fwd(const void* x, const void* w, const float* scale, const float* shift, void* y, long long pixels,
+                        int Cin, int Cout, void* stream);
+/* xs[b][i][j][:] = x[b][2i][2j][:] (the pixels a 1x1 / stride-2 convolution reads);  gx[b][2i][2j][:] += gs[b][i][j][:] */
+int b200_subsample2(const void* x, void* xs, int B, int H, int W, int C, void* stream);
+int b200_add_even_pixels(void* gx, const void* gs, int B, int H, int W, int C, void* stream);
 /* dx[pixels][Cin] = (mask_src > 0) ? (dy[pixels][Cout] * wd^T + residual) : 0  (wd bf16 [Cin][Cout], b200_pack_weight mode 1);
  * stats fp32 [b200_conv1x1_dgrad_masked_stats_rows()][2][Cin]: per-CTA column sums (plane 0) of dx as stored */
 int b200_conv1x1_dgrad_masked_stats_rows(long long pixels, int Cin);
