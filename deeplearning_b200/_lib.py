@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200cls.so")
+# (B200_LIB: an alternate build of the same ABI, for A/B experiments)
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "lib", "libb200cls.so")
 
 _lib = None
 
@@ -40,6 +41,7 @@ SIGNATURES = {
     "b200_conv2d_fwd": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _L, _P]),
     "b200_conv2d_fwd_stats_rows": (_I, [_I, _I, _I, _I, _I, _I]),
     "b200_conv2d_fwd_set_bn": (_I, [_P, _P]),
+    "b200_dgrad_set_bn_mask": (_I, [_P, _P, _P, _P]),
     "b200_conv2d_dgrad": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "b200_conv2d_wgrad": (_I, [_P, _P, _P, _P, c_size_t, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "b200_conv2d_wgrad_workspace_bytes": (c_size_t, [_I, _I, _I, _I, _I, _I, _I]),

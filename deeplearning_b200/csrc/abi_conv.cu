@@ -5,6 +5,7 @@
 #include "../../include/b200cls.h"
 #include "conv_gemm.cuh"
 #include "conv1x1_stream.cuh"
+#include "conv_tap64.cuh"
 #include "host_utils.h"
 #include "wgrad_gemm.cuh"
 
@@ -20,6 +21,12 @@ thread_local const float* g_wgrad_rowscale = nullptr;
 thread_local float* g_wgrad_bias_partial = nullptr;
 thread_local const float* g_fwd_bn_scale = nullptr;   // one-shot: fold y = conv * scale + shift (eval-mode BN) into the epilogue
 thread_local const float* g_fwd_bn_shift = nullptr;
+// one-shot (b200_dgrad_set_bn_mask): the next stride-1 dgrad / dual GEMM masks its output with relu'(bn(x_raw)) and writes the
+// sum(dz), sum(dz * x_raw) partial rows of that BatchNorm's backward
+thread_local const void* g_bnmask_x = nullptr;
+thread_local const float* g_bnmask_scale = nullptr;
+thread_local const float* g_bnmask_shift = nullptr;
+thread_local float* g_bnmask_stats = nullptr;
 
 struct Box3 {
   int b1, b2, b3;
@@ -178,7 +185,7 @@ int launch_conv_gemm_epi(const ConvGemmParams& q, int grid, cudaStream_t st) {
                                          Cfg::SMEM_BYTES));
     configured = true;
   }
-  conv_gemm_kernel<BLOCK_N, EPI><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
+  B200_CHECK_CUDA(launch_pdl(conv_gemm_kernel<BLOCK_N, EPI>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, q));
   B200_LAUNCHED();
   return OK;
 }
@@ -196,7 +203,8 @@ int epilogue_flags(const ConvGemmParams& p) {
   if (p.stats) f |= kEpiStats;
   if (p.rowscale) f |= kEpiRowscale;
   if (p.affine) f = (f & ~(kEpiBias | kEpiColscale)) | kEpiAffine;   // colscale / bias carry the BatchNorm scale / shift
-  if (p.mask_in) f |= kEpiMask;
+  if (p.mask_in) f |= p.bn_scale ? kEpiBnMask : kEpiMask;
+  if (p.bn_scale) f &= ~kEpiStats;   // (kEpiBnMask always writes its two statistics rows)
   return f;
 }
 
@@ -216,7 +224,9 @@ int epilogue_flags(const ConvGemmParams& p) {
   X(kEpiAffine | kEpiResBf16 | (1 << kEpiActShift))       /* bottleneck conv3: relu(bn(conv) + identity) */ \
   X(kEpiAffine | (1 << kEpiActShift))                     /* eval mode: relu(bn(conv))                   */ \
   X(kEpiAffine)                                           /* eval mode: bn(conv) (downsample branch)     */ \
-  X(kEpiMask | kEpiResBf16 | kEpiStats)                   /* dgrad + identity gradient, ReLU mask, sum dz */
+  X(kEpiMask | kEpiResBf16 | kEpiStats)                   /* dgrad + identity gradient, ReLU mask, sum dz */ \
+  X(kEpiBnMask)                                           /* 3x3 dgrad + reduce half of the producer's BN backward */ \
+  X(kEpiBnMask | kEpiBias)                                /* the same behind the BN-algebra dual GEMM (bias = k W) */
 
 // ---- CTA-pair GEMM (tcgen05 cta_group::2): the 256-wide linear layers of the transformer / ConvNeXt paths run as pairs
 // of CTAs on one 256-pixel x 256-channel tile (each CTA stages half of the B tile).  Validated on B200 in round 2 (bit-exact
@@ -249,13 +259,15 @@ int launch_conv_gemm_pair(const ConvGemmParams& q, cudaStream_t st) {
   cfg.blockDim = dim3(Cfg::THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<256, EPI, true>, q));
   B200_LAUNCHED();
   return OK;
@@ -273,6 +285,33 @@ int launch_conv_gemm_pair(const ConvGemmParams& q, cudaStream_t st) {
   X(kEpiOutF32)                                          \
   X(kEpiBias | kEpiOutF32)
 
+// ---- 64 -> 64 channel convolutions with the weights resident in shared memory (conv_tap64.cuh): ResNet layer1's 3x3
+// forward / dgrad and the space-to-depth stem.  B200_TAP64=0 in the environment switches back to the generic kernel.
+bool tap64_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_TAP64");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+bool tap64_ok(const ConvGemmParams& p) {
+  const int f = epilogue_flags(p);
+  return tap64_enabled() && p.N == 64 && p.n_tiles == 1 && p.k_per_tap == 64 && p.k_blocks_per_tap == 1 && !p.var_taps &&
+         p.num_taps >= 2 && p.num_taps <= 9 && (f == 0 || f == kEpiStats) && p.dim1 % p.box1 == 0 && p.dim2 % p.box2 == 0 &&
+         p.dim3 % p.box3 == 0;
+}
+template <bool kStats>
+int launch_tap64(const ConvGemmParams& q, int grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    B200_CHECK_CUDA(cudaFuncSetAttribute(conv_tap64_kernel<kStats>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTap64SmemBytes));
+    configured = true;
+  }
+  B200_CHECK_CUDA(launch_pdl(conv_tap64_kernel<kStats>, dim3(grid), dim3(192), kTap64SmemBytes, st, q));
+  B200_LAUNCHED();
+  return OK;
+}
+
 template <int BLOCK_N>
 int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   const int tiles = p.tiles1 * p.tiles2 * p.tiles3 * p.n_tiles;
@@ -281,6 +320,9 @@ int launch_conv_gemm(const ConvGemmParams& p, cudaStream_t st) {
   ConvGemmParams q = p;
   q.desc_lbo = g_fwd_lbo;
   q.desc_sbo = g_fwd_sbo;
+  if constexpr (BLOCK_N == 64) {
+    if (tap64_ok(p)) return p.stats != nullptr ? launch_tap64<true>(q, grid, st) : launch_tap64<false>(q, grid, st);
+  }
   if constexpr (BLOCK_N == 256) {
     if (p.pair) {
       switch (epilogue_flags(p)) {
@@ -334,7 +376,7 @@ int launch_stream(const StreamParams& q, int grid, cudaStream_t st) {
                                          Cfg::SMEM_BYTES));
     configured = true;
   }
-  conv1x1_stream_kernel<KB, MODE><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(q);
+  B200_CHECK_CUDA(launch_pdl(conv1x1_stream_kernel<KB, MODE>, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, st, q));
   B200_LAUNCHED();
   return OK;
 }
@@ -405,15 +447,15 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
   q.desc_sbo = g_wg_sbo;
   q.desc_kstep = g_wg_kstep;
   if (q.bias_partial != nullptr)   // + four warps that sum the dY tiles' columns (the layer's bias gradient)
-    wgrad_gemm_kernel<BLOCK_NG, true><<<grid, 320, Cfg::SMEM_BYTES, st>>>(q);
+    B200_CHECK_CUDA(launch_pdl(wgrad_gemm_kernel<BLOCK_NG, true>, dim3(grid), dim3(320), Cfg::SMEM_BYTES, st, q));
   else
-    wgrad_gemm_kernel<BLOCK_NG, false><<<grid, 192, Cfg::SMEM_BYTES, st>>>(q);
+    B200_CHECK_CUDA(launch_pdl(wgrad_gemm_kernel<BLOCK_NG, false>, dim3(grid), dim3(192), Cfg::SMEM_BYTES, st, q));
   B200_LAUNCHED();
   return OK;
 }
 
 // partial[splits][Cout][taps*Cin] -> grad[Cout][Cin][taps] (+)=, see wgrad_gemm.cuh
-void launch_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, int Cin, int taps, int accumulate,
+int launch_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, int Cin, int taps, int accumulate,
                          const float* rowscale, cudaStream_t st) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   if (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
@@ -424,13 +466,14 @@ void launch_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, 
     const size_t smem = static_cast<size_t>(SL) * taps * chunk * sizeof(float);
     if (smem <= 48 * 1024 && Cout <= 65535 * 32) {
       dim3 grid(Cout, (Cin + chunk - 1) / chunk);
-      wgrad_reduce_rows_kernel<<<grid, 256, smem, st>>>(partial, dw, splits, Cout, Cin, taps, chunk, SL, accumulate, rowscale);
-      return;
+      B200_CHECK_CUDA(launch_pdl(wgrad_reduce_rows_kernel, dim3(grid), dim3(256), smem, st, partial, dw, splits, Cout, Cin, taps, chunk, SL, accumulate, rowscale));
+      return OK;
     }
   }
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
-  wgrad_reduce_flat_kernel<<<blocks, 256, 0, st>>>(partial, dw, splits, Cout, Cin, taps, accumulate, rowscale);
+  B200_CHECK_CUDA(launch_pdl(wgrad_reduce_flat_kernel, dim3(blocks), dim3(256), 0, st, partial, dw, splits, Cout, Cin, taps, accumulate, rowscale));
+  return OK;
 }
 
 struct WgradPlan {
@@ -638,6 +681,11 @@ int b200_conv2d_fwd(const void* x, const void* w, void* y, int B, int H, int W, 
   return dispatch_conv_gemm(p, Cout, st);
 }
 
+int b200_dgrad_set_bn_mask(const void* x_raw, const float* scale, const float* shift, float* stats) {
+  g_bnmask_x = x_raw, g_bnmask_scale = scale, g_bnmask_shift = shift, g_bnmask_stats = stats;
+  return OK;
+}
+
 int b200_conv2d_fwd_set_bn(const float* scale, const float* shift) {
   g_fwd_bn_scale = scale;
   g_fwd_bn_shift = shift;
@@ -662,6 +710,13 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
     if ((rc = encode_tmap_bf16(&b_map, wd, 2, dims, strides, box))) return rc;
   }
   const int nphase = (stride == 2 && ksize >= 2) ? 2 : 1;  // phases per spatial dim that need their own launch
+  const void* const bnmask_x = g_bnmask_x;
+  const float* const bnmask_scale = g_bnmask_scale;
+  const float* const bnmask_shift = g_bnmask_shift;
+  float* const bnmask_stats = g_bnmask_stats;
+  g_bnmask_x = nullptr;
+  B200_REQUIRE(bnmask_x == nullptr || (stride == 1 && Cin % 64 == 0 && bnmask_scale && bnmask_shift && bnmask_stats),
+               "conv2d_dgrad: the fused BatchNorm-backward reduce needs stride 1 and Cin %% 64 == 0 (Cin=%d, stride=%d)", Cin, stride);
   for (int ph = 0; ph < nphase; ++ph) {
     for (int pw = 0; pw < nphase; ++pw) {
       ConvGemmParams p;
@@ -718,6 +773,13 @@ int b200_conv2d_dgrad(const void* dy, const void* wd, void* dx, int B, int H, in
         p.rs1 = static_cast<long long>(dv.strides[1]);
         p.rs2 = static_cast<long long>(dv.strides[2]);
         p.rs3 = static_cast<long long>(dv.strides[3]);
+      }
+      if (bnmask_x != nullptr) {
+        p.mask_in = static_cast<const __nv_bfloat16*>(bnmask_x);
+        p.ms1 = static_cast<long long>(dv.strides[1]);
+        p.ms2 = static_cast<long long>(dv.strides[2]);
+        p.ms3 = static_cast<long long>(dv.strides[3]);
+        p.bn_scale = bnmask_scale, p.bn_shift = bnmask_shift, p.stats = bnmask_stats;
       }
       if ((rc = dispatch_conv_gemm(p, Cin, st))) return rc;
     }
@@ -891,7 +953,7 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   else
     rc = launch_wgrad<256>(p, st);
   if (rc) return rc;
-  launch_wgrad_reduce(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale, st);
+  if ((rc = launch_wgrad_reduce(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale, st))) return rc;
   g_wgrad_rowscale = nullptr;
   B200_LAUNCHED();
   return OK;
@@ -956,7 +1018,7 @@ int b200_stem_s2d_conv_wgrad(const void* dy, const void* z, float* g, void* work
   for (int ky = 0; ky < 4; ++ky) p.tap_map[ky] = 0, p.tap_o1[ky] = 0, p.tap_o2[ky] = static_cast<int8_t>(ky);
   if ((rc = launch_wgrad<256>(p, st))) return rc;  // merged-tap mode: the four y-taps are the four 64-column atoms
   // g[cout][k64][ky] (the generic "OIHW" layout of a 64-channel, 4-tap conv); b200_stem_s2d_wgrad_relayout maps it to [64,3,7,7]
-  launch_wgrad_reduce(p.partial, g, pl.splits, Cout, Cin, taps, 0, nullptr, st);
+  if ((rc = launch_wgrad_reduce(p.partial, g, pl.splits, Cout, Cin, taps, 0, nullptr, st))) return rc;
   B200_LAUNCHED();
   return OK;
 }
@@ -1077,6 +1139,15 @@ int b200_gemm_dual(const void* a0, int K0, const void* a1, int K1, const void* w
     if ((rc = encode_tmap_bf16(&p.b_map, wcat, 2, dims, strides, box))) return rc;
   }
   p.bias = bias;
+  if (g_bnmask_x != nullptr) {
+    B200_REQUIRE(N % 64 == 0 && g_bnmask_scale && g_bnmask_shift && g_bnmask_stats, "gemm_dual: fused BN-backward reduce needs N %% 64 == 0 (N=%d)", N);
+    p.mask_in = static_cast<const __nv_bfloat16*>(g_bnmask_x);
+    p.ms1 = static_cast<long long>(dv.strides[1]);
+    p.ms2 = static_cast<long long>(dv.strides[2]);
+    p.ms3 = static_cast<long long>(dv.strides[3]);
+    p.bn_scale = g_bnmask_scale, p.bn_shift = g_bnmask_shift, p.stats = g_bnmask_stats;
+    g_bnmask_x = nullptr;
+  }
   return dispatch_conv_gemm(p, N, static_cast<cudaStream_t>(stream));
 }
 

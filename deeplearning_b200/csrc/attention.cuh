@@ -36,6 +36,8 @@ constexpr int kAttnSmemBytes = 16384 /*Q*/ + 32768 /*K*/ + 16384 /*pad so that P
                                256 + 1024;
 
 __global__ void __launch_bounds__(160, 2) attn_fwd_kernel(const __grid_constant__ AttnFwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;                 // [128][128B]
@@ -232,6 +234,8 @@ namespace b200 {
 // per lane and ran at a quarter of the HBM rate)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                                                          float* __restrict__ delta, int B, int T, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * T * H;
   for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < total;
        row += static_cast<long long>(gridDim.x) * blockDim.x) {

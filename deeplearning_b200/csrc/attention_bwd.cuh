@@ -40,6 +40,8 @@ struct alignas(64) AttnBwdParams {
 constexpr int kAttnBwdSmemBytes = 4 * 16384 + 32768 + 256 + 1024;
 
 __global__ void __launch_bounds__(288, 2) attn_bwd_kernel(const __grid_constant__ AttnBwdParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem;

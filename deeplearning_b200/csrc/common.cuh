@@ -10,6 +10,31 @@ namespace b200 {
 
 constexpr int kNumSMs = 148;
 
+// ---- Programmatic dependent launch.  Every kernel of the library is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization (host_utils.h launch_pdl): the next kernel of the stream is scheduled
+// when the CTAs of its predecessor have finished, without waiting for the grid's completion / memory flush to be processed
+// by the launch path; its CTAs run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in
+// pdl_wait() until the PREVIOUS kernel has completed and its memory is visible.  Every kernel executes the wait before it
+// touches global memory (and before it can exit), so completion stays transitive along the stream: the data dependencies
+// are exactly those of plain stream order, only launch latency and prologues overlap the predecessor's end.
+// Measured on B200, ResNet-50 step (same box, ms): plain launches 16.92; attribute + implicit trigger at grid completion
+// 16.70 (default); explicit griddepcontrol.launch_dependents right after the wait 17.14; at kernel entry 17.70 - dependents
+// scheduled early pile onto the SMs that drain first and unbalance the next grid, so no kernel triggers explicitly.
+#ifndef B200_PDL_TRIGGER
+#define B200_PDL_TRIGGER 0   // 0: never (implicit at grid completion), 1: at kernel entry, 2: right after the wait
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {
+#if B200_PDL_TRIGGER == 1
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#if B200_PDL_TRIGGER == 2
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -71,6 +71,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_
 
 template <int KB, int MODE>
 __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_constant__ StreamParams p) {
+  pdl_launch_dependents();
   using Cfg = StreamCfg<KB, MODE>;
   constexpr int STAGES = Cfg::STAGES, NBUF = Cfg::NBUF;
   extern __shared__ uint8_t smem_raw[];
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(192, 1) conv1x1_stream_kernel(const __grid_con
     fence_mbar_init();
   }
   if (warp_idx == 1) tmem_alloc<512>(tmem_ptr_smem);
+  pdl_wait();   // everything above touched only this CTA's shared memory / TMEM and the kernel parameters
   if constexpr (MODE != kStreamMask) {
     // this CTA's 256 scale / shift values (its channel block never changes)
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {

@@ -72,6 +72,10 @@ struct alignas(64) ConvGemmParams {
   const __nv_bfloat16* mask_in;
   long long ms1, ms2, ms3;
   int affine;               // host-side: kEpiAffine (colscale = BN scale, bias = BN shift)
+  // --- kEpiBnMask: the output is the gradient of relu(bn(x)); mask_in holds the RAW convolution output x of that BatchNorm,
+  // alive = x * bn_scale + bn_shift > 0; the statistics rows carry sum(dz) and sum(dz * x) (what bn_bwd_reduce produces)
+  const float* bn_scale;
+  const float* bn_shift;
 };
 
 template <int BLOCK_N, bool kPair = false>
@@ -174,7 +178,10 @@ constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEp
               //   kEpiAffine: f = f * colscale[n] + bias[n]  (scale / shift of the batch statistics) BEFORE the residual add,
               //               and the ReLU (act == 1) moves AFTER the residual add:  y = relu(bn(conv) + identity)
               //   kEpiMask:   after the residual add, f = mask_in > 0 ? f : 0      (dz = relu'(y) * (dgrad + identity gradient))
-              kEpiAffine = 2048, kEpiMask = 4096;
+              //   kEpiBnMask: after everything else, f = (mask_in * bn_scale + bn_shift > 0) ? f : 0 and the statistics rows
+              //               hold sum(f), sum(f * mask_in): the reduce half of the BatchNorm(+ReLU) backward of the PRODUCER of
+              //               this gradient, which therefore needs no pass of its own (bn_bwd_reduce in elementwise.cuh)
+              kEpiAffine = 2048, kEpiMask = 4096, kEpiBnMask = 8192;
 
 // kPair (validated on B200, default for the 256-wide linear layers, see abi_conv.cu gemm_pair_enabled()): the two CTAs of a cluster
 // compute one 256-pixel x 256-channel tile with tcgen05.mma.cta_group::2. Each CTA stages its own 128 pixels of A and HALF
@@ -182,6 +189,7 @@ constexpr int kEpiBias = 1, kEpiColscale = 2, kEpiActShift = 2 /* 2 bits */, kEp
 // both and commits to the barriers of both; every CTA drains its own 128 accumulator rows with the unchanged epilogue.
 template <int BLOCK_N, int EPI = kEpiGeneric, bool kPair = false>
 __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  pdl_launch_dependents();
   static_assert(!kPair || (BLOCK_N == 256 && EPI >= 0 && !(EPI & kEpiDirect)),
                 "pair mode: 256-wide tiles of the linear layers only");
   using Cfg = ConvGemmCfg<BLOCK_N, kPair>;
@@ -243,6 +251,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // everything above touched only this CTA's shared memory / TMEM and the kernel parameters
 
   if (warp_idx == 0) {
     // ===================== TMA producer =====================
@@ -372,7 +381,8 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     // kernel parameters used in the inner loops, hoisted into registers
     constexpr bool G = EPI < 0;
     constexpr bool kAffine = !G && (EPI & kEpiAffine) != 0;   // BatchNorm scale / shift, ReLU after the residual add
-    constexpr bool kMask = !G && (EPI & kEpiMask) != 0;       // ReLU-derivative mask from a second tensor
+    constexpr bool kBnMask = !G && (EPI & kEpiBnMask) != 0;   // ReLU mask recomputed from the raw BN input + sum(dz * x)
+    constexpr bool kMask = !G && (EPI & (kEpiMask | kEpiBnMask)) != 0;   // a second tensor decides which outputs survive
     const int N = p.N;
     const float* const bias = (!kAffine && (G || (EPI & kEpiBias))) ? p.bias : nullptr;
     const float* const colscale = (!kAffine && (G || (EPI & kEpiColscale))) ? p.colscale : nullptr;
@@ -383,7 +393,7 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     const bool has_aux = G ? (p.has_aux_out != 0) : ((EPI & kEpiAux) != 0);
     const bool out_f32 = G ? (p.out_f32 != 0) : ((EPI & kEpiOutF32) != 0);
     float* const out_direct = (G || (EPI & kEpiDirect)) ? p.out_direct : nullptr;
-    float* const stats = (G || (EPI & kEpiStats)) ? p.stats : nullptr;
+    float* const stats = (G || (EPI & (kEpiStats | kEpiBnMask))) ? p.stats : nullptr;
     const float* const rowscale = G ? p.rowscale : nullptr;
     // (pair mode with an odd number of pixel tiles: the last peer tile lies past the tensor and must not touch memory)
     const bool need_rowmap = has_res || act == 3 || kMask || out_direct != nullptr || rowscale != nullptr || p.dim1 % p.box1 != 0 ||
@@ -400,8 +410,9 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
     // writes ONE partial row at the end of the kernel - ~150 x 4 rows per conv instead of one per 32 pixels.
     constexpr int UN = BLOCK_N >= 128 ? BLOCK_N / 128 : 1;
     uint64_t run_s[UN], run_q[UN];
+    float run_x[UN][2];   // kBnMask: sum(dz * x) of column (unit k, half h, lane)
 #pragma unroll
-    for (int k = 0; k < UN; ++k) run_s[k] = 0, run_q[k] = 0;
+    for (int k = 0; k < UN; ++k) run_s[k] = 0, run_q[k] = 0, run_x[k][0] = run_x[k][1] = 0.f;
     int it = 0;
     CPROF_DECL(2)
     for (int tile = B200_TILE_FIRST; tile < num_tiles; tile += B200_TILE_STEP, ++it) {
@@ -609,7 +620,55 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
               for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
             }
           }
-          if constexpr (kMask) {
+          if constexpr (kBnMask) {
+            // BatchNorm(+ReLU) backward of the layer that produced this gradient's argument: alive iff x * scale + shift > 0
+            // (exactly the forward's ReLU input), and the column sums of dz * x by a 5-step butterfly over the warp's 32 rows
+            float px[32];
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float x8[8];
+                unpack8(pre_m[j], x8);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) px[j * 8 + i] = x8[i];
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 s4 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + nc) + j);
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + nc) + j);
+                const float sc4[4] = {s4.x, s4.y, s4.z, s4.w}, sh4[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  // (rounded to the stored bf16 value first: both sums are sums over dz exactly as bn_bwd_apply will read it)
+                  const float fm =
+                      fmaf(px[j * 4 + i], sc4[i], sh4[i]) > 0.f ? __bfloat162float(__float2bfloat16_rn(f[j * 4 + i])) : 0.f;
+                  f[j * 4 + i] = fm;
+                  px[j * 4 + i] *= fm;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) px[j] = 0.f;
+            }
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+              const bool up = (lane & s) != 0;
+#pragma unroll
+              for (int i = 0; i < s; ++i) {
+                const float send = up ? px[i] : px[i + s];
+                const float keep = up ? px[i + s] : px[i];
+                px[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+              }
+            }
+            const int ui = u >> 1;
+#pragma unroll
+            for (int k = 0; k < UN; ++k) {
+              if (k == ui) {
+                run_x[k][0] += h == 0 ? px[0] : 0.f;
+                run_x[k][1] += h == 0 ? 0.f : px[0];
+              }
+            }
+          } else if constexpr (kMask) {
             // the mask tensor is a ReLU output (>= 0): an element is alive iff its bf16 bits are non-zero
             if (row_ok) {
 #pragma unroll
@@ -717,7 +776,13 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
           f2_unpack(run_q[k], q_lo, q_hi);
           float* sp = stats + static_cast<long long>(srow) * 2 * N + col;
           *reinterpret_cast<float2*>(sp) = make_float2(s_lo, s_hi);
-          *reinterpret_cast<float2*>(sp + N) = make_float2(q_lo, q_hi);
+          if constexpr (kBnMask) {
+            sp += N - lane;   // second row: this lane owns column `lane` of each 32-column half
+            sp[0] = run_x[k][0];
+            sp[32] = run_x[k][1];
+          } else {
+            *reinterpret_cast<float2*>(sp + N) = make_float2(q_lo, q_hi);
+          }
         }
       }
     }

@@ -1,4 +1,5 @@
 #include "host_utils.h"
+#include <stdlib.h>
 
 #include <stdarg.h>
 #include <string.h>
@@ -86,6 +87,14 @@ static int encode_tmap_any(CUtensorMap* out, const void* base, int rank, const u
     return ECUDA_;
   }
   return OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("B200_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 int device_sm_count() {

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 namespace b200 {
 
@@ -49,5 +50,25 @@ extern unsigned long long g_launch_count;
     ++::b200::g_launch_count;                             \
     B200_CHECK_CUDA(cudaPeekAtLastError());               \
   } while (0)
+
+// Launch with programmatic stream serialization (see common.cuh pdl_wait): the kernel may be scheduled while its
+// predecessor in the stream drains; every kernel of the library waits for that predecessor (griddepcontrol.wait) before it
+// touches global memory.  B200_PDL=0 in the environment launches plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace b200

@@ -50,6 +50,8 @@ __global__ void layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __r
                                      const float* __restrict__ beta, TY* __restrict__ y,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long rows, int C,
                                      float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, sub = lane % LPR, grp = lane / LPR;
   const int nvec = C >> 3;
@@ -112,6 +114,8 @@ __global__ void __launch_bounds__(256, 3)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
                      const float* __restrict__ rstd, const float* __restrict__ gamma, const TOut* __restrict__ add,
                      TOut* __restrict__ dx, float* __restrict__ partial, long long rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [warps][rows per warp][2][C]
   constexpr int RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -190,6 +194,8 @@ __global__ void patch_merge_ln_fwd_kernel(const float* __restrict__ x, const flo
                                           const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                           float* __restrict__ mean_out, float* __restrict__ rstd_out, int B, int H, int W,
                                           int C, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int C4 = 4 * C, nvec = C4 >> 3, cvec = C >> 3;
   const int Ho = H / 2, Wo = W / 2;
@@ -255,6 +261,8 @@ __global__ void __launch_bounds__(256, 2)
 patch_merge_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                           const float* __restrict__ rstd, const float* __restrict__ gamma, __nv_bfloat16* __restrict__ dx,
                           float* __restrict__ partial, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float red[];  // [warps][2][4C]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int C4 = 4 * C, nvec = C4 >> 3, cvec = C >> 3;
@@ -326,6 +334,8 @@ patch_merge_ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const float* __r
 // (the flattening order of an OIHW conv weight, so the weight matrix is weight.view(D, -1) unchanged). ps % 8 == 0... or 4.
 __global__ void patchify_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ a, int B, int Cin, int H,
                                      int W, int ps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int ph = H / ps, pw = W / ps;
   const int K = Cin * ps * ps;
   const int kv = K / 4;  // 4 consecutive kw per thread (ps is a multiple of 4)
@@ -352,6 +362,8 @@ __global__ void patchify_nchw_kernel(const float* __restrict__ x, __nv_bfloat16*
 // ViT class-token row: tokens[b][0][:] = cls[:] + pos[0][:]   (tokens fp32 [B][T][D])
 __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __restrict__ pos, float* __restrict__ tokens,
                                int B, int T, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(B) * D;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -364,6 +376,8 @@ __global__ void cls_row_kernel(const float* __restrict__ cls, const float* __res
 // Strided 2-D copy of 16-byte vectors: dst[r][0:cols] = src[r][0:cols] with independent row pitches (in bytes).
 __global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long long src_pitch, uint8_t* __restrict__ dst,
                                  long long dst_pitch, long long rows, long long row_bytes) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long vecs = row_bytes >> 4;
   const long long total = rows * vecs;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -379,6 +393,8 @@ __global__ void copy_rows_kernel(const uint8_t* __restrict__ src, long long src_
 // through shared memory. (The first version read one bf16 per thread from ~128 blocks: 1 TB/s; this one is HBM bound.)
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16* __restrict__ m, long long rows, long long ld,
                                                              int cols, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sh[256 * 8];
   const int nvec = cols >> 3;                        // cols is a multiple of 8
   const int vpr = min(nvec - static_cast<int>(blockIdx.x) * 256, 256);   // vectors of this column block
@@ -437,6 +453,8 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const __nv_bfloat16
 template <typename T>
 __global__ void batch_rowsum_kernel(const T* __restrict__ g, long long stride_b, int B, int D, float* __restrict__ out,
                                     int accumulate) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
   float s = 0.f;

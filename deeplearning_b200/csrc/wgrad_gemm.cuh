@@ -56,6 +56,7 @@ struct WgradCfg {
 
 template <int BLOCK_NG, bool kBias = false>
 __global__ void __launch_bounds__(kBias ? 320 : 192, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams p) {
+  pdl_launch_dependents();
   using Cfg = WgradCfg<BLOCK_NG>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(kBias ? 320 : 192, 1) wgrad_gemm_kernel(const 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // everything above touched only this CTA's shared memory / TMEM and the kernel parameters
 
   if (warp_idx == 0) {
     if (lane == 0) {
@@ -332,6 +334,8 @@ __global__ void __launch_bounds__(kBias ? 320 : 192, 1) wgrad_gemm_kernel(const 
 __global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ grad,
                                                                 int splits, int Cout, int Cin, int taps, int chunk, int SL,
                                                                 int accumulate, const float* __restrict__ rowscale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float4 rows_sm4[];
   const int cout = blockIdx.x;
   const int c0 = blockIdx.y * chunk;
@@ -378,6 +382,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __r
 // Same reduction, one thread per element walking the splits: fallback for shapes the row kernel does not take.
 __global__ void wgrad_reduce_flat_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
                                     int Cin, int taps, int accumulate, const float* __restrict__ rowscale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   const long long slice = total;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;

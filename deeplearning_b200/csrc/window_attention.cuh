@@ -100,6 +100,8 @@ __device__ __forceinline__ void wattn_item(const WAttnParams& p, int item, int n
 //   soft-max group g (warps 4g..4g+3) owns the steps with n&1 == g: S -> P (bf16, block diagonal) -> wait O -> write out
 // so the gathers of step n+1, the soft-max of step n and the P V product / output of step n-1 overlap.
 __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_fwd_kernel(const WAttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // stage s: two tiles [128][128B] (rows 0..48: window A, 64..112: window B). A head row is only 64 B, so Q and K share
@@ -313,6 +315,8 @@ constexpr int kWAttnBwdSmem = kWAttnStages * 2 * 16384 + 2 * 32768 + 256 + 1024;
 // columns and P/dS tile). Per step m the MMA warp issues   A(m): S = Q K^T   B(m): dP = dO V^T, dV = P^T dO   C(m): dQ = dS K,
 // dK = dS^T Q   in the order  B(n-1), A(n), C(n-1)  so that one group computes P while the other computes dS / stores.
 __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WAttnParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int kStage = 2 * 16384;   // tile 0: Q (chunks 0..3 of a row) | K (chunks 4..7); tile 1: V | dO
@@ -646,6 +650,8 @@ __global__ void __launch_bounds__(kWAttnFwdThreads, 1) wattn_bwd_kernel(const WA
 // rows (one per query) that the soft-max threads read with 13 vector loads.
 __global__ void wattn_bias_gather_kernel(const float* __restrict__ table, const long long* __restrict__ index,
                                          const float* __restrict__ mask, int nWm, float* __restrict__ tab, int nH) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long n = static_cast<long long>(nH) * nWm * kWT * 64;
   for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n;
        e += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -667,6 +673,8 @@ __global__ void wattn_bias_gather_kernel(const float* __restrict__ table, const 
 // dtable[index[i][j]][h] (+)= dbias[h][i][j]   (dtable zeroed / holding the running gradient)
 __global__ void wattn_bias_scatter_kernel(const float* __restrict__ dbias, const long long* __restrict__ index,
                                           float* __restrict__ dtable, int nH) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nH * kWT * kWT) return;
   const int h = i / (kWT * kWT), ij = i - h * kWT * kWT;
@@ -682,6 +690,8 @@ __global__ void wattn_bias_scatter_kernel(const float* __restrict__ dbias, const
 template <bool kMerge>
 __global__ void __launch_bounds__(256) window_permute_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, int B, int H,
                                                              int W, int cvec, int shift, int ws) {
+  pdl_launch_dependents();
+  pdl_wait();
   const unsigned nWx = W / ws, nWy = H / ws;
   const unsigned total = static_cast<unsigned>(B) * H * W * cvec;
   const unsigned stride = gridDim.x * blockDim.x;

@@ -82,6 +82,9 @@ def _algebra_enabled():
     return os.environ.get("B200_RESNET_ALGEBRA", "1") != "0"
 
 
+_FUSED_REDUCE = os.environ.get("B200_RESNET_FUSED_BN_REDUCE", "1") != "0"
+
+
 def _algebra_ok(block, train, want_tape):
     """Bottleneck whose tail can run with bn3 folded through conv3 (train mode, or a forward that records no tape)."""
     if not _algebra_enabled() or not hasattr(block, "conv3") or not (train or not want_tape):
@@ -293,6 +296,19 @@ def _unit_backward(u, g, grads, want_dz=False):
     return dc, dz
 
 
+def _fused_reduce_ok(u):
+    """Can the dgrad GEMM that produces the gradient of unit u's output also do the reduce half of u's BN backward?
+    (relu(bn(c)) without a residual, 64-channel multiples; B200_RESNET_FUSED_BN_REDUCE=0 switches it off)"""
+    return _FUSED_REDUCE and u.relu and not u.has_res and u.c.shape[-1] % 64 == 0
+
+
+def _unit_backward_from_sums(u, dz, sums, grads):
+    dc, dgamma, dbeta = ops.bn_backward_from_sums(dz, sums, u.c, u.co, dgamma=grads.dest(u.bn.weight), dbeta=grads.dest(u.bn.bias))
+    grads.put(u.bn.weight, dgamma)
+    grads.put(u.bn.bias, dbeta)
+    return dc
+
+
 def backward(model, tape, dlogits, sink=None):
     """dlogits: fp32 [B, num_classes] (or the bf16 [B, n_pad] product of ops.softmax_xent).
     Returns {parameter.data_ptr(): fp32 gradient}; with ``sink`` the gradients are written into caller-owned buffers."""
@@ -346,8 +362,14 @@ def backward(model, tape, dlogits, sink=None):
             grads.put(last.bn.weight, dgamma)
             grads.put(last.bn.bias, dbeta)
             grads.put(last.conv.weight, dW)
-            g_prev = ops.gemm_dual(dz, y2, wcat, wbias)              # dL/dy2 = [dz | y2] [a W3 | M]^T + k W3
-            dc, _ = _unit_backward(units[-2], g_prev, grads)
+            # dL/dy2 = [dz | y2] [a W3 | M]^T + k W3; its epilogue also masks with bn2's ReLU and sums for bn2's backward
+            u2 = units[-2]
+            if _fused_reduce_ok(u2):
+                dz2, sums2 = ops.gemm_dual(dz, y2, wcat, wbias, bn_mask=(u2.c, u2.co))
+                dc = _unit_backward_from_sums(u2, dz2, sums2, grads)
+            else:
+                g_prev = ops.gemm_dual(dz, y2, wcat, wbias)
+                dc, _ = _unit_backward(u2, g_prev, grads)
             first = len(units) - 2
         else:
             # out = relu(bn_last(c) + identity): dz is the gradient of the pre-ReLU sum, shared by both branches
@@ -375,7 +397,10 @@ def backward(model, tape, dlogits, sink=None):
             grads.put(u.conv.weight, ops.conv2d_wgrad(dc, u.x, k, s, out=grads.dest(u.conv.weight)))
             wd = pack.get(u.conv.weight, 1)
             in_hw = tuple(u.x.shape[1:3])
-            if j > 0:
+            if j > 0 and s == 1 and _fused_reduce_ok(units[j - 1]):
+                dzj, sumsj = ops.conv2d_dgrad(dc, wd, in_hw, k, s, bn_mask=(units[j - 1].c, units[j - 1].co))
+                dc = _unit_backward_from_sums(units[j - 1], dzj, sumsj, grads)
+            elif j > 0:
                 g_prev = ops.conv2d_dgrad(dc, wd, in_hw, k, s)
                 dc, _ = _unit_backward(units[j - 1], g_prev, grads)
             else:

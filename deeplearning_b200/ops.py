@@ -183,8 +183,20 @@ def conv2d_bn_act(x, w_packed, co, ksize=1, stride=1, relu=True, residual=None):
     return y
 
 
-def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=None):
-    """dx[B,H,W,Cin] from dy[B,Ho,Wo,Cout]; wd_packed = pack_weight(w, mode=1). `out` lets 1x1/s2 accumulate in place."""
+def _arm_bn_mask(lib, bn_mask, B, H, W, C, ksize):
+    """One-shot: the next dgrad / dual GEMM masks its output with relu'(bn(x_raw)) and writes the BN-backward partial sums."""
+    x_raw, co = bn_mask
+    assert x_raw.dtype == BF16 and x_raw.is_contiguous() and x_raw.shape[-1] == C and C % 64 == 0
+    rows = lib.b200_conv2d_fwd_stats_rows(B, H, W, C, ksize, 1)
+    stats = torch.empty(rows, 2, C, dtype=F32, device=x_raw.device)
+    _lib.check(lib.b200_dgrad_set_bn_mask(_p(x_raw), _p(co.scale), _p(co.shift), _p(stats)), "b200_dgrad_set_bn_mask")
+    return stats
+
+
+def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=None, bn_mask=None):
+    """dx[B,H,W,Cin] from dy[B,Ho,Wo,Cout]; wd_packed = pack_weight(w, mode=1). `out` lets 1x1/s2 accumulate in place.
+    bn_mask = (x_raw, BnCoeffs) (stride 1): dx is the gradient of relu(bn(x_raw)); returns (dz, partial sums) for
+    bn_backward_from_sums instead of dx."""
     lib = _lib.load()
     _chk_act(dy, "dy")
     B, Ho, Wo, Cout = dy.shape
@@ -198,12 +210,17 @@ def conv2d_dgrad(dy, wd_packed, in_hw, ksize=1, stride=1, residual=None, out=Non
         dx = torch.zeros(B, H, W, Cin, dtype=BF16, device=dy.device)
     else:
         dx = torch.empty(B, H, W, Cin, dtype=BF16, device=dy.device)
-    sp = _span("conv_gemm_dgrad", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize, _nb(dy, wd_packed, dx, residual))
+    stats = None
+    if bn_mask is not None:
+        assert stride == 1, "bn_mask needs a stride-1 convolution"
+        stats = _arm_bn_mask(lib, bn_mask, B, H, W, Cin, ksize)
+    sp = _span("conv_gemm_dgrad", 2.0 * B * Ho * Wo * Cout * Cin * ksize * ksize,
+               _nb(dy, wd_packed, dx, residual, bn_mask[0] if bn_mask else None))
     rc = lib.b200_conv2d_dgrad(_p(dy), _p(wd_packed), _p(dx), B, H, W, Cin, Cout, ksize, stride, _p(residual), _stream())
     _lib.check(rc, "b200_conv2d_dgrad")
     if sp:
         sp.end()
-    return dx
+    return dx if bn_mask is None else (dx, stats)
 
 
 _ws_cache = {}
@@ -344,6 +361,30 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     if sp:
         sp.end()
     return dx, dgamma, dbeta, dz
+
+
+def bn_backward_from_sums(dz, partial, x, co, dgamma=None, dbeta=None):
+    """Second half of bn_backward(relu=True) when the producer of the gradient already masked it (dz) and summed
+    partial[rows][2][C] = sum(dz), sum(dz * x) in its epilogue (conv2d_dgrad / gemm_dual with bn_mask=)."""
+    lib = _lib.load()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if dgamma is None:
+        dgamma = torch.empty(C, dtype=F32, device=x.device)
+        dbeta = torch.empty(C, dtype=F32, device=x.device)
+    m = torch.empty(2, C, dtype=F32, device=x.device)
+    sc = _reduce_scratch(x.device)
+    rc = lib.b200_bn_bwd_finalize(_p(partial), partial.shape[0], C, float(rows), _p(dgamma), _p(dbeta), 0, _p(m[0]), _p(m[1]),
+                                  _p(co.mean), _p(co.invstd), _p(sc), sc.numel(), _stream())
+    _lib.check(rc, "b200_bn_bwd_finalize")
+    dx = torch.empty_like(x)
+    sp = _span("bn_bwd_apply", 0.0, _nb(dz, x, dx))
+    rc = lib.b200_bn_bwd_apply(_p(dz), _p(x), None, 1, _p(dx), _p(co.scale), _p(co.shift), _p(co.mean), _p(co.invstd),
+                               _p(m[0]), _p(m[1]), 1, rows, C, _stream())
+    _lib.check(rc, "b200_bn_bwd_apply")
+    if sp:
+        sp.end()
+    return dx, dgamma, dbeta
 
 
 # ------------------------------------------------------------------------------ BatchNorm folded through a 1x1 convolution
@@ -494,8 +535,9 @@ def bn_conv1x1_bwd(dz_partial, D, G, s, w_packed, w_f32, count, gamma, co, dgamm
     return dgamma, dbeta, dW, wcat, bias
 
 
-def gemm_dual(a0, a1, wcat, bias):
-    """out bf16 [..., N] = [a0 | a1] @ wcat^T + bias (a0 [..., K0], a1 [..., K1] bf16, wcat bf16 [N, K0 + K1])."""
+def gemm_dual(a0, a1, wcat, bias, bn_mask=None):
+    """out bf16 [..., N] = [a0 | a1] @ wcat^T + bias (a0 [..., K0], a1 [..., K1] bf16, wcat bf16 [N, K0 + K1]).
+    bn_mask: as in conv2d_dgrad - returns (dz, partial sums)."""
     lib = _lib.load()
     _chk_act(a0, "a0")
     _chk_act(a1, "a1")
@@ -503,12 +545,13 @@ def gemm_dual(a0, a1, wcat, bias):
     N = wcat.shape[0]
     pixels = a0.numel() // K0
     out = torch.empty(*a0.shape[:-1], N, dtype=BF16, device=a0.device)
-    sp = _span("conv_gemm_dgrad", 2.0 * pixels * N * (K0 + K1), _nb(a0, a1, wcat, out))
+    stats = _arm_bn_mask(lib, bn_mask, 1, 1, pixels, N, 1) if bn_mask is not None else None
+    sp = _span("conv_gemm_dgrad", 2.0 * pixels * N * (K0 + K1), _nb(a0, a1, wcat, out, bn_mask[0] if bn_mask else None))
     rc = lib.b200_gemm_dual(_p(a0), K0, _p(a1), K1, _p(wcat), _p(bias), _p(out), pixels, N, _stream())
     _lib.check(rc, "b200_gemm_dual")
     if sp:
         sp.end()
-    return out
+    return out if bn_mask is None else (out, stats)
 
 
 # --------------------------------------------------------------------------------------------------------- pooling

@@ -58,6 +58,12 @@ int b200_conv2d_fwd_stats_rows(int B, int H, int W, int Cout, int ksize, int str
  * eval-mode forward of conv -> bn -> (+identity) -> relu (classification/resnet/models/networks.py:104-124, utils.py:61-83
  * `evaluate`) without any BatchNorm pass.  scale / shift from b200_bn_eval_coeffs; Cout % 64 == 0. */
 int b200_conv2d_fwd_set_bn(const float* scale, const float* shift);
+/* one-shot (this thread, next b200_conv2d_dgrad with stride 1 or b200_gemm_dual): the output is the gradient of
+ * relu(bn(x_raw)) - the kernel zeroes it where x_raw * scale + shift <= 0 (dz) and writes the per-CTA partial rows
+ * stats[rows][2][C] = sum(dz), sum(dz * x_raw), rows = b200_conv2d_fwd_stats_rows(B, H, W, C, ksize, 1) of the dx geometry:
+ * the reduce half of F.batch_norm's backward (classification/resnet/models/networks.py:108,112 bn1 / bn2 under loss.backward(),
+ * utils.py:33) without a pass over the gradient.  Feed the rows to b200_bn_bwd_finalize, then b200_bn_bwd_apply(src_is_dz=1). */
+int b200_dgrad_set_bn_mask(const void* x_raw, const float* scale, const float* shift, float* stats);
 /* same convolution writing an fp32 NHWC output (+bias) through TMA - ConvNeXt downsample conv feeding the fp32 stream */
 int b200_conv2d_fwd_f32(const void* x, const void* w, float* y, int B, int H, int W, int Cin, int Cout, int ksize,
                         int stride, const float* bias, void* stream);

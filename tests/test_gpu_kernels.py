@@ -42,6 +42,7 @@ CONV_CASES = [
     (2, 14, 14, 256, 1000, 1, 1),
     (4, 1, 1, 72, 40, 1, 1),
     (2, 56, 56, 64, 64, 3, 1),
+    (24, 56, 56, 64, 64, 3, 1),   # 588 pixel tiles: several per CTA of the resident-weight kernel (conv_tap64.cuh)
     (2, 14, 14, 128, 128, 3, 1),
     (3, 7, 7, 64, 192, 3, 1),
     (2, 28, 28, 128, 128, 3, 2),
@@ -309,3 +310,60 @@ def test_wgrad_bias_sums_from_the_dy_tiles(B, H, W, Cin, Cout, k, s):
     assert torch.equal(ref_w, got_w)
     ref_b = dy.float().sum((0, 1, 2))
     assert torch.allclose(bias, ref_b, rtol=1e-4, atol=1e-3 * float(dy.float().abs().sum((0, 1, 2)).max())), float((bias - ref_b).abs().max())
+
+
+def _bn_coeffs(ops, c, gamma, beta):
+    """BnCoeffs of train-mode BatchNorm over the raw conv output c (bf16 NHWC)."""
+    C = c.shape[-1]
+    cf = c.float().reshape(-1, C)
+    co = ops.BnCoeffs(C, c.device)
+    co.mean.copy_(cf.mean(0))
+    co.invstd.copy_((cf.var(0, unbiased=False) + 1e-5).rsqrt())
+    co.scale.copy_(gamma * co.invstd)
+    co.shift.copy_(beta - co.mean * co.scale)
+    return co
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k", [(4, 56, 56, 64, 64, 3), (3, 14, 14, 256, 256, 3), (2, 9, 11, 128, 128, 3),
+                                               (2, 28, 28, 128, 512, 1)])
+def test_dgrad_with_fused_bn_backward_reduce(B, H, W, Cin, Cout, k):
+    """conv2d_dgrad(bn_mask=(c, co)): the dgrad epilogue masks its output with relu'(bn(c)) and sums dz, dz * c per channel -
+    bn_backward_from_sums then gives the same dx / dgamma / dbeta as the two-pass bn_backward on the unmasked gradient."""
+    from deeplearning_b200 import ops
+
+    dy = _rand(B, H, W, Cout, seed=3)
+    w = _rand(Cout, Cin, k, k, scale=(Cout * k * k) ** -0.5, seed=4)
+    wd = ops.pack_weight(w.float(), mode=1)
+    c = _rand(B, H, W, Cin, seed=5) + 0.25
+    g = torch.Generator(device="cuda").manual_seed(6)
+    gamma = torch.rand(Cin, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cin, device="cuda", generator=g) * 0.3
+    co = _bn_coeffs(ops, c, gamma, beta)
+    g_ref = ops.conv2d_dgrad(dy, wd, (H, W), k, 1)
+    dx_ref, dgamma_ref, dbeta_ref, dz_ref = ops.bn_backward(g_ref, c, co, relu=True, want_dz=True)
+    dz, sums = ops.conv2d_dgrad(dy, wd, (H, W), k, 1, bn_mask=(c, co))
+    assert torch.equal(dz, dz_ref)
+    dx, dgamma, dbeta = ops.bn_backward_from_sums(dz, sums, c, co)
+    scale = float(dgamma_ref.abs().max())
+    assert torch.allclose(dbeta, dbeta_ref, rtol=1e-3, atol=1e-3 * float(dbeta_ref.abs().max()))
+    assert torch.allclose(dgamma, dgamma_ref, rtol=2e-3, atol=2e-3 * scale), float((dgamma - dgamma_ref).abs().max())
+    _close(dx, dx_ref, 2e-2, 2e-2 * float(dx_ref.float().abs().max()), "dx")
+
+
+def test_dual_gemm_with_fused_bn_backward_reduce():
+    from deeplearning_b200 import ops
+
+    px, K0, K1, N = 2 * 28 * 28, 512, 128, 128
+    a0, a1 = _rand(2, 28, 28, K0, seed=1), _rand(2, 28, 28, K1, seed=2)
+    wcat = _rand(N, K0 + K1, scale=(K0 + K1) ** -0.5, seed=3)
+    bias = _rand(N, seed=4).float()
+    c = _rand(2, 28, 28, N, seed=5)
+    co = _bn_coeffs(ops, c, torch.ones(N, device="cuda"), torch.zeros(N, device="cuda"))
+    g_ref = ops.gemm_dual(a0, a1, wcat, bias)
+    dx_ref, dgamma_ref, dbeta_ref, dz_ref = ops.bn_backward(g_ref, c, co, relu=True, want_dz=True)
+    dz, sums = ops.gemm_dual(a0, a1, wcat, bias, bn_mask=(c, co))
+    assert torch.equal(dz, dz_ref)
+    dx, dgamma, dbeta = ops.bn_backward_from_sums(dz, sums, c, co)
+    assert torch.allclose(dbeta, dbeta_ref, rtol=1e-3, atol=1e-3 * float(dbeta_ref.abs().max()))
+    assert torch.allclose(dgamma, dgamma_ref, rtol=2e-3, atol=2e-3 * float(dgamma_ref.abs().max()))
+    _close(dx, dx_ref, 2e-2, 2e-2 * float(dx_ref.float().abs().max()), "dx")
