@@ -94,6 +94,7 @@ SIGNATURES = {
     "b200_avgpool_fwd": (_I, [_P, _P, _I, _I, _I, _P]),
     "b200_avgpool_bwd": (_I, [_P, _P, _I, _I, _I, _P]),
     "b200_softmax_xent": (_I, [_P, _L, _P, _I, _I, _F, _P, _P, _L, _P, _P]),
+    "b200_softmax_xent_soft": (_I, [_P, _L, _P, _P, _L, _F, _I, _I, _F, _P, _P, _L, _P, _P]),
     "b200_mean": (_I, [_P, _I, _P, _P]),
     "b200_colsum_bf16": (_I, [_P, _L, _L, _I, _P, _I, _P]),
     "b200_pack_weight": (_I, [_P, _P, _I, _I, _I, _I, _L, _P]),

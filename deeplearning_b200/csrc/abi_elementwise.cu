@@ -167,7 +167,21 @@ int b200_softmax_xent(const float* logits, long long ld, const long long* labels
                       float* loss_rows, void* dlogits, long long ld_d, int* correct, void* stream) {
   B200_REQUIRE(B > 0 && N > 0, "softmax_xent: empty input");
   B200_CHECK_CUDA(launch_pdl(softmax_xent_kernel, dim3(B), dim3(256), 0, static_cast<cudaStream_t>(stream), 
-      logits, ld, labels, N, gscale, loss_rows, static_cast<__nv_bfloat16*>(dlogits), ld_d, correct));
+      logits, ld, labels, N, gscale, loss_rows, static_cast<__nv_bfloat16*>(dlogits), ld_d, correct,
+      static_cast<const float*>(nullptr), 0ll, 0.f));
+  B200_LAUNCHED();
+  return OK;
+}
+
+int b200_softmax_xent_soft(const float* logits, long long ld, const long long* labels, const float* soft_targets,
+                           long long ld_soft, float smoothing, int B, int N, float gscale, float* loss_rows, void* dlogits,
+                           long long ld_d, int* correct, void* stream) {
+  B200_REQUIRE(B > 0 && N > 0, "softmax_xent_soft: empty input");
+  B200_REQUIRE(soft_targets != nullptr || labels != nullptr, "softmax_xent_soft: soft targets or labels are required");
+  B200_REQUIRE(smoothing >= 0.f && smoothing < 1.f, "softmax_xent_soft: smoothing %f outside [0, 1)", smoothing);
+  B200_CHECK_CUDA(launch_pdl(softmax_xent_kernel, dim3(B), dim3(256), 0, static_cast<cudaStream_t>(stream),
+      logits, ld, labels, N, gscale, loss_rows, static_cast<__nv_bfloat16*>(dlogits), ld_d, correct, soft_targets, ld_soft,
+      smoothing));
   B200_LAUNCHED();
   return OK;
 }

@@ -29,7 +29,22 @@ __device__ __forceinline__ bool reduce_partials_last_block(const float* __restri
   const int t0 = blockIdx.y * chunk, t1 = min(T, t0 + chunk);
   double s = 0.0, ss = 0.0;
   if (c < C) {
-    for (int t = t0 + ry; t < t1; t += 8) {
+    // four rows (eight loads) in flight per thread: the kernel is a chain of L2 round trips, not bandwidth
+    int t = t0 + ry;
+    for (; t + 24 < t1; t += 32) {
+      float v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[u][0] = __ldg(partial + (static_cast<long long>(t + 8 * u) * 2 + 0) * C + c);
+        v[u][1] = __ldg(partial + (static_cast<long long>(t + 8 * u) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s += static_cast<double>(v[u][0]);
+        ss += static_cast<double>(v[u][1]);
+      }
+    }
+    for (; t < t1; t += 8) {
       s += static_cast<double>(__ldg(partial + (static_cast<long long>(t) * 2 + 0) * C + c));
       ss += static_cast<double>(__ldg(partial + (static_cast<long long>(t) * 2 + 1) * C + c));
     }
@@ -517,9 +532,15 @@ __global__ void avgpool_bwd_kernel(const uint4* __restrict__ gy, uint4* __restri
 // ------------------------------------------------------------------------------------------------------------------
 // Soft-max cross-entropy (mean reduction) forward + backward in one pass. One block per row.
 //   logits fp32 [B][ld], labels int64 -> loss_rows[B] (fp32, un-normalised), dlogits bf16 [B][ld_d] = (p - onehot)*gscale
+// Soft targets (timm SoftTargetCrossEntropy behind Mixup / CutMix, swin_transformer/main.py:111-113) and label smoothing
+// (LabelSmoothingCrossEntropy, main.py:114-115) are the same kernel with target distribution t instead of a one-hot:
+//   t_c = soft[b][c]                      (soft != null), or
+//   t_c = (1 - eps) [c == label] + eps/N  (smoothing eps),
+//   loss_b = sum_c t_c (lse - x_c),  dlogits = (p_c * sum_c t_c - t_c) * gscale.
 __global__ void softmax_xent_kernel(const float* __restrict__ logits, long long ld, const long long* __restrict__ labels,
                                     int N, float gscale, float* __restrict__ loss_rows,
-                                    __nv_bfloat16* __restrict__ dlogits, long long ld_d, int* __restrict__ correct) {
+                                    __nv_bfloat16* __restrict__ dlogits, long long ld_d, int* __restrict__ correct,
+                                    const float* __restrict__ soft, long long ld_soft, float smoothing) {
   pdl_launch_dependents();
   pdl_wait();
   __shared__ float sh[32];
@@ -564,8 +585,59 @@ __global__ void softmax_xent_kernel(const float* __restrict__ logits, long long 
   __syncthreads();
   s = 0.f;
   for (int i = 0; i < nw; ++i) s += sh[i];
-  const int label = static_cast<int>(labels[b]);
   const float lse = mx + logf(s);
+  if (soft != nullptr || smoothing > 0.f) {
+    // general target distribution: sum_c t_c and sum_c t_c x_c by a block reduction, arg-max of t as the "label"
+    const float* trow = soft ? soft + b * ld_soft : nullptr;
+    const int hard = labels ? static_cast<int>(labels[b]) : -1;
+    const float off = smoothing / static_cast<float>(N), on = 1.f - smoothing;
+    auto target = [&](int j) { return trow ? trow[j] : (off + (j == hard ? on : 0.f)); };
+    float st = 0.f, stx = 0.f, tmx = -INFINITY;
+    int tam = 0;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float t = target(j);
+      st += t;
+      stx = fmaf(t, row[j], stx);
+      if (t > tmx) tmx = t, tam = j;
+    }
+    st = warp_sum(st);
+    stx = warp_sum(stx);
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, tmx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, tam, o);
+      if (om > tmx || (om == tmx && oa < tam)) tmx = om, tam = oa;
+    }
+    __shared__ float sh2[2][32];
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      sh2[0][threadIdx.x >> 5] = st;
+      sh2[1][threadIdx.x >> 5] = stx;
+      sh[threadIdx.x >> 5] = tmx;
+      shi[threadIdx.x >> 5] = tam;
+    }
+    __syncthreads();
+    st = stx = 0.f;
+    tmx = sh[0], tam = shi[0];
+    for (int i = 0; i < nw; ++i) {
+      st += sh2[0][i];
+      stx += sh2[1][i];
+      if (sh[i] > tmx || (sh[i] == tmx && shi[i] < tam)) tmx = sh[i], tam = shi[i];
+    }
+    if (threadIdx.x == 0) {
+      loss_rows[b] = lse * st - stx;
+      if (correct) correct[b] = (amax == (hard >= 0 ? hard : tam)) ? 1 : 0;
+    }
+    if (dlogits) {
+      const float inv = st / s;
+      for (int j = threadIdx.x; j < ld_d; j += blockDim.x) {
+        float d = 0.f;
+        if (j < N) d = (__expf(row[j] - mx) * inv - target(j)) * gscale;
+        dlogits[b * ld_d + j] = __float2bfloat16_rn(d);
+      }
+    }
+    return;
+  }
+  const int label = static_cast<int>(labels[b]);
   if (threadIdx.x == 0) {
     loss_rows[b] = lse - row[label];
     if (correct) correct[b] = (amax == label) ? 1 : 0;

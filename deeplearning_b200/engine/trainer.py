@@ -198,12 +198,17 @@ class _GradSink:
 class TrainStep:
     def __init__(self, model, lr=0.01, momentum=0.9, weight_decay=5e-5, process_group=None, world_size=None,
                  broadcast=True, optimizer="sgd", betas=(0.9, 0.999), eps=1e-8, no_decay=None, clip_grad=None,
-                 overlap=True, bucket_mb=25.0):
+                 overlap=True, bucket_mb=25.0, label_smoothing=0.0, accum_steps=1):
         """optimizer="sgd": torch.optim.SGD(momentum, weight_decay on every parameter) - resnet/vit train.py:96,94.
         optimizer="adamw": torch.optim.AdamW(betas, eps, weight_decay) with the reference's decay / no-decay groups
         (``no_decay(name, param) -> bool``, default ``no_decay_rule``) - convNext/train.py:96,102.
         clip_grad: max global L2 norm of the (all-reduced, averaged) gradient, ``clip_grad_norm_`` of the Swin recipe
-        (swin_transformer/main.py:197, config TRAIN.CLIP_GRAD = 5.0); the norm of the last step is ``self.grad_norm``."""
+        (swin_transformer/main.py:197, config TRAIN.CLIP_GRAD = 5.0); the norm of the last step is ``self.grad_norm``.
+        label_smoothing: LabelSmoothingCrossEntropy of the Swin recipe (main.py:114-115); floating-point ``labels`` of
+        shape [B, num_classes] (Mixup / CutMix targets, engine/mixup.py) select SoftTargetCrossEntropy (main.py:111-113).
+        accum_steps: gradient accumulation (main.py:190-199, TRAIN.ACCUMULATION_STEPS): every call runs forward + backward of
+        one micro-batch with the loss gradient scaled by 1/accum_steps; the all-reduce, clipping and the optimizer update
+        happen on every accum_steps-th call."""
         self.model = model
         self.engine = _engine_for(model)
         self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
@@ -217,6 +222,12 @@ class TrainStep:
             raise RuntimeError("TrainStep needs the model on a CUDA (sm_100a) device; there is no CPU fallback")
         self.world = self.arena.world
         self.steps = 0
+        self.label_smoothing = float(label_smoothing)
+        self.accum_steps = int(accum_steps)
+        if self.accum_steps < 1:
+            raise ValueError("accum_steps must be >= 1")
+        self._micro = 0   # micro-batches accumulated since the last update
+        self._acc = torch.zeros_like(self.arena.flat_g) if self.accum_steps > 1 else None
         self.clip_grad = clip_grad
         self._clip = None
         if clip_grad is not None:
@@ -238,12 +249,23 @@ class TrainStep:
         weight_cache.bump()
 
     # ------------------------------------------------------------------------------------------------ eager step
-    def _fwd_bwd(self, images, labels):
-        """Forward, loss, backward AND the gradient all-reduce (overlapped with the backward pass when ``overlap``)."""
+    def _fwd_bwd(self, images, labels, last=True):
+        """Forward, loss, backward AND the gradient all-reduce (overlapped with the backward pass when ``overlap``).
+        With gradient accumulation only the ``last`` micro-batch of a group reduces (the sum of the group's gradients)."""
         model, arena = self.model, self.arena
         logits, tape = self.engine.forward(model, images, True, True)
         n_pad = (logits.shape[1] + 7) // 8 * 8
-        loss, dlogits, correct = ops.softmax_xent(logits, labels, want_grad=True, ld_d=n_pad)
+        loss, dlogits, correct = ops.softmax_xent(logits, labels, want_grad=True, ld_d=n_pad,
+                                                  label_smoothing=self.label_smoothing, loss_scale=1.0 / self.accum_steps)
+        if self.accum_steps > 1:
+            self.engine.backward(model, tape, dlogits, sink=arena.grad_view)
+            if last:
+                arena.flat_g.add_(self._acc)
+                self._acc.zero_()
+                arena.all_reduce_grads()
+            else:
+                self._acc.add_(arena.flat_g)
+            return loss, correct
         if self.world > 1 and self.overlap:
             arena.begin_backward()
             self.engine.backward(model, tape, dlogits, sink=_GradSink(arena))
@@ -281,9 +303,12 @@ class TrainStep:
     def step_eager(self, images, labels, lr=None):
         if not self.model.training:
             self.model.train()
-        loss, correct = self._fwd_bwd(images, labels)
-        self._update(self.lr if lr is None else lr)
-        self.steps += 1
+        last = self._micro + 1 == self.accum_steps
+        loss, correct = self._fwd_bwd(images, labels, last)
+        self._micro = 0 if last else self._micro + 1
+        if last:
+            self._update(self.lr if lr is None else lr)
+            self.steps += 1
         return loss, correct
 
     # ------------------------------------------------------------------------------------------------ CUDA-graph step
@@ -308,11 +333,14 @@ class TrainStep:
         saved_hyper = self._hyper.clone() if hasattr(self, "_hyper") else None
         saved_bufs = [b.clone() for b in self.model.buffers()]
         saved_steps = self.steps
+        if self._micro != 0:
+            raise RuntimeError("capture() in the middle of a gradient-accumulation group")
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self._fwd_bwd(self._g_images, self._g_labels)
+                for m in range(self.accum_steps):
+                    self._fwd_bwd(self._g_images, self._g_labels, m + 1 == self.accum_steps)
                 self._update(self.lr, self._lr_dev)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
@@ -331,8 +359,15 @@ class TrainStep:
         # stream ("thread_local": the NCCL watchdog thread's CUDA calls must not invalidate the capture)
         self._graph_fb = torch.cuda.CUDAGraph()
         self._graph_up = None
+        self._graph_acc = None
+        if self.accum_steps > 1:
+            # the micro-batches before the last of a group: forward + backward + accumulate, no collective, no update
+            self._graph_acc = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_acc, capture_error_mode="thread_local"):
+                self._g_loss_acc, self._g_correct_acc = self._fwd_bwd(self._g_images, self._g_labels, False)
+            self._acc.zero_()
         with torch.cuda.graph(self._graph_fb, capture_error_mode="thread_local"):
-            self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels)
+            self._g_loss, self._g_correct = self._fwd_bwd(self._g_images, self._g_labels, True)
             self._update(self.lr, self._lr_dev)
         self._captured_shape = (tuple(images.shape), tuple(labels.shape))
         return self
@@ -352,6 +387,11 @@ class TrainStep:
             if self.optimizer == "adamw":
                 self._hyper[0:1].fill_(float(lr))
                 self._hyper_lr_value = float(lr)
+        if self._micro + 1 < self.accum_steps:
+            self._micro += 1
+            self._graph_acc.replay()
+            return self._g_loss_acc, self._g_correct_acc
+        self._micro = 0
         self._graph_fb.replay()
         self.steps += 1
         # the replay updated the parameters behind autograd's back (and repacked the bf16 operands from the PRE-update

@@ -609,17 +609,32 @@ def avgpool_bwd(gy, hw):
 
 
 # --------------------------------------------------------------------------------------------------------- loss / optimiser
-def softmax_xent(logits, labels, want_grad=True, ld_d=None):
-    """Mean cross-entropy. Returns (loss scalar tensor, dlogits bf16 [B, ld_d] or None, correct int32 [B])."""
+def softmax_xent(logits, labels, want_grad=True, ld_d=None, label_smoothing=0.0, loss_scale=1.0):
+    """Mean cross-entropy. Returns (loss scalar tensor, dlogits bf16 [B, ld_d] or None, correct int32 [B]).
+    labels: int64 [B] class indices (optionally smoothed: LabelSmoothingCrossEntropy) or a floating [B, N] target
+    distribution (SoftTargetCrossEntropy behind Mixup / CutMix).  loss_scale multiplies the GRADIENT only (1 / accumulation
+    steps: swin_transformer/main.py:190)."""
     lib = _lib.load()
     B, N = logits.shape
     ld_d = ld_d or ((N + 7) // 8) * 8
     rows = torch.empty(B, dtype=F32, device=logits.device)
     correct = torch.empty(B, dtype=torch.int32, device=logits.device)
     d = torch.empty(B, ld_d, dtype=BF16, device=logits.device) if want_grad else None
-    rc = lib.b200_softmax_xent(_p(logits), logits.stride(0), _p(labels), B, N, 1.0 / B, _p(rows), _p(d), ld_d,
-                               _p(correct), _stream())
-    _lib.check(rc, "b200_softmax_xent")
+    gscale = float(loss_scale) / B
+    if labels.is_floating_point():
+        soft = labels if labels.dtype == F32 and labels.stride(1) == 1 else labels.float().contiguous()
+        assert soft.shape == (B, N), f"soft targets must be [B, num_classes], got {tuple(soft.shape)}"
+        rc = lib.b200_softmax_xent_soft(_p(logits), logits.stride(0), None, _p(soft), soft.stride(0), 0.0, B, N, gscale, _p(rows),
+                                        _p(d), ld_d, _p(correct), _stream())
+        _lib.check(rc, "b200_softmax_xent_soft")
+    elif label_smoothing > 0.0:
+        rc = lib.b200_softmax_xent_soft(_p(logits), logits.stride(0), _p(labels), None, 0, float(label_smoothing), B, N, gscale,
+                                        _p(rows), _p(d), ld_d, _p(correct), _stream())
+        _lib.check(rc, "b200_softmax_xent_soft")
+    else:
+        rc = lib.b200_softmax_xent(_p(logits), logits.stride(0), _p(labels), B, N, gscale, _p(rows), _p(d), ld_d,
+                                   _p(correct), _stream())
+        _lib.check(rc, "b200_softmax_xent")
     loss = torch.empty(1, dtype=F32, device=logits.device)
     _lib.check(lib.b200_mean(_p(rows), B, _p(loss), _stream()), "b200_mean")
     return loss, d, correct

@@ -260,6 +260,13 @@ int b200_avgpool_bwd(const void* gy, void* gx, int B, int HW, int C, void* strea
  *   loss_rows[B] per-sample loss; dlogits (optional) bf16 [B][ld_d] = (softmax - onehot)*gscale; correct (optional) int[B] */
 int b200_softmax_xent(const float* logits, long long ld, const long long* labels, int B, int N, float gscale,
                       float* loss_rows, void* dlogits, long long ld_d, int* correct, void* stream);
+/* the same with a target DISTRIBUTION per sample: soft_targets fp32 [B][ld_soft] (timm SoftTargetCrossEntropy behind
+ * Mixup / CutMix, classification/swin_transformer/main.py:111-113) or, with soft_targets == NULL, hard labels smoothed by
+ * `smoothing` (LabelSmoothingCrossEntropy, main.py:114-115):  loss_b = sum_c t_c (lse - x_c),
+ * dlogits = (softmax * sum_c t_c - t) * gscale; correct[b] compares the arg-max with the label (or the arg-max of t). */
+int b200_softmax_xent_soft(const float* logits, long long ld, const long long* labels, const float* soft_targets,
+                           long long ld_soft, float smoothing, int B, int N, float gscale, float* loss_rows, void* dlogits,
+                           long long ld_d, int* correct, void* stream);
 int b200_mean(const float* v, int n, float* out, void* stream);
 int b200_colsum_bf16(const void* m, long long rows, long long ld, int cols, float* out, int accumulate, void* stream);
 

@@ -140,3 +140,66 @@ def test_forward_after_graph_replay_sees_updated_weights():
     with torch.no_grad():
         ob2 = b(x)
     assert float((ob2 - ob).abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,N", [(16, 10), (64, 1000), (7, 37)])
+def test_soft_target_and_label_smoothing_cross_entropy(B, N):
+    """The fused loss kernel with a target distribution == timm SoftTargetCrossEntropy (sum(-t log_softmax(x)).mean(),
+    swin_transformer/main.py:111-113) and with smoothed hard labels == LabelSmoothingCrossEntropy (main.py:114-115, the same
+    value as F.cross_entropy(label_smoothing=eps)); gradients against autograd."""
+    from deeplearning_b200 import ops
+    from deeplearning_b200.engine.mixup import mixup_target
+
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + N)
+    x = torch.randn(B, N, device="cuda", generator=g) * 3
+    y = torch.randint(0, N, (B,), device="cuda", generator=g)
+    n_pad = (N + 7) // 8 * 8
+    # soft targets (mixup of two smoothed one-hots)
+    t = mixup_target(y, N, lam=0.3, smoothing=0.1)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.sum(-t * torch.log_softmax(xr, dim=-1), dim=-1).mean()
+    ref.backward()
+    loss, d, _ = ops.softmax_xent(x, t, ld_d=n_pad)
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    assert torch.allclose(d[:, :N].float(), xr.grad, rtol=1e-2, atol=1e-4), float((d[:, :N].float() - xr.grad).abs().max())
+    assert float(d[:, N:].float().abs().max() if n_pad > N else 0.0) == 0.0
+    # label smoothing on hard labels, gradient scaled for 4 accumulation steps
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(xr, y, label_smoothing=0.1)
+    (ref / 4).backward()
+    loss, d, correct = ops.softmax_xent(x, y, ld_d=n_pad, label_smoothing=0.1, loss_scale=0.25)
+    assert abs(float(loss) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    assert torch.allclose(d[:, :N].float(), xr.grad, rtol=1e-2, atol=1e-4)
+    assert torch.equal(correct.bool(), x.argmax(1) == y)
+
+
+def _small_vit(seed=0):
+    from deeplearning_b200.classification.vision_transformer.vit_model import VisionTransformer
+
+    torch.manual_seed(seed)
+    return VisionTransformer(img_size=224, patch_size=16, embed_dim=768, depth=2, num_heads=12, num_classes=16).cuda().train()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_gradient_accumulation_equals_one_large_batch(graph):
+    """accum_steps=2 over two half batches == one step on the whole batch (BatchNorm-free model, mean loss): the Swin loop's
+    ``loss / ACCUMULATION_STEPS`` with an update every second micro-batch (swin_transformer/main.py:190-199)."""
+    from deeplearning_b200.engine.trainer import TrainStep
+
+    m1, m2 = _small_vit(5), _small_vit(5)
+    t1 = TrainStep(m1, lr=0.05, momentum=0.9, weight_decay=1e-2, label_smoothing=0.1)
+    t2 = TrainStep(m2, lr=0.05, momentum=0.9, weight_decay=1e-2, label_smoothing=0.1, accum_steps=2)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(16, 3, 224, 224, device="cuda", generator=g)
+    y = torch.randint(0, 16, (16,), device="cuda", generator=g)
+    if graph:
+        t2.capture(x[:8], y[:8])
+    for _ in range(2):
+        t1.step_eager(x, y)
+        before = [p.detach().clone() for p in m2.parameters()]
+        t2.step(x[:8], y[:8])
+        assert all(torch.equal(a, p.detach()) for a, p in zip(before, m2.parameters())), "no update inside a group"
+        t2.step(x[8:], y[8:])
+    assert t1.steps == t2.steps == 2
+    for (n, p), q in zip(m1.named_parameters(), m2.parameters()):
+        assert torch.allclose(p.detach(), q.detach(), rtol=2e-2, atol=2e-4), (n, float((p - q).abs().max()))
