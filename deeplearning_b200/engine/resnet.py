@@ -39,8 +39,25 @@ def _check_conv(conv, name):
 
 
 def _check_bn(bn, name):
-    if not isinstance(bn, nn.BatchNorm2d) or not bn.affine or not bn.track_running_stats or bn.momentum is None:
-        raise NotImplementedError(f"{name}: the B200 engine implements affine nn.BatchNorm2d with running statistics (got {bn})")
+    if (not isinstance(bn, (nn.BatchNorm2d, nn.SyncBatchNorm)) or not bn.affine or not bn.track_running_stats
+            or bn.momentum is None):
+        raise NotImplementedError(f"{name}: the B200 engine implements affine nn.BatchNorm2d / nn.SyncBatchNorm with running "
+                                  f"statistics (got {bn})")
+
+
+def _bn_sync(bn):
+    """(process_group, world_size) when ``bn`` is a SyncBatchNorm in a multi-rank job (the recipe converts every BatchNorm
+    with ``nn.SyncBatchNorm.convert_sync_batchnorm``: others/train_with_DDP/train.py:190), else None.  Statistics and the
+    two backward sums are then all-reduced per layer (ops._sync_sums); such layers stay on the plain conv -> BN schedule."""
+    if not isinstance(bn, nn.SyncBatchNorm) or not bn.training:
+        return None
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return None
+    group = bn.process_group if bn.process_group is not None else dist.group.WORLD
+    world = dist.get_world_size(group)
+    return (group, world) if world > 1 else None
 
 
 class _PackSpec:
@@ -88,6 +105,8 @@ _FUSED_REDUCE = os.environ.get("B200_RESNET_FUSED_BN_REDUCE", "1") != "0"
 def _algebra_ok(block, train, want_tape):
     """Bottleneck whose tail can run with bn3 folded through conv3 (train mode, or a forward that records no tape)."""
     if not _algebra_enabled() or not hasattr(block, "conv3") or not (train or not want_tape):
+        return False
+    if isinstance(block.bn3, nn.SyncBatchNorm) and train:
         return False
     c3, c1 = block.conv3, block.conv1
     return (c3.kernel_size == (1, 1) and c3.stride == (1, 1) and c3.groups == 1 and c3.bias is None and c3.dilation == (1, 1)
@@ -162,7 +181,7 @@ def _conv_bn(pack, tape, x, conv, bn, train, relu, residual=None, name=""):
     if train:
         rows = c.numel() // c.shape[-1]
         co = ops.bn_finalize(st, rows, bn.weight, bn.bias, bn.eps, bn.momentum, bn.running_mean, bn.running_var,
-                             bn.num_batches_tracked)
+                             bn.num_batches_tracked, sync=_bn_sync(bn))
     else:
         co = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
     y = ops.bn_apply(c, co, relu=relu, residual=residual)
@@ -217,7 +236,7 @@ def forward(model, x, train, want_tape):
     c1, st = ops.stem_s2d_conv_fwd(a, pack.get(conv1.weight, 2), want_stats=train)
     if train:
         co1 = ops.bn_finalize(st, B * Ho * Wo, bn1.weight, bn1.bias, bn1.eps, bn1.momentum, bn1.running_mean,
-                              bn1.running_var, bn1.num_batches_tracked)
+                              bn1.running_var, bn1.num_batches_tracked, sync=_bn_sync(bn1))
     else:
         co1 = ops.bn_eval_coeffs(bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var, bn1.eps)
     h, idx = ops.bn_relu_maxpool_fwd(c1, co1)
@@ -290,7 +309,8 @@ class _Grads(dict):
 def _unit_backward(u, g, grads, want_dz=False):
     """Backward of BN(+ReLU) of unit u for upstream gradient g; returns (dc, dz) and records BN param grads."""
     dc, dgamma, dbeta, dz = ops.bn_backward(g, u.c, u.co, relu=u.relu, y_out=u.y if (u.relu and u.has_res) else None,
-                                            want_dz=want_dz, dgamma=grads.dest(u.bn.weight), dbeta=grads.dest(u.bn.bias))
+                                            want_dz=want_dz, dgamma=grads.dest(u.bn.weight), dbeta=grads.dest(u.bn.bias),
+                                            sync=_bn_sync(u.bn))
     grads.put(u.bn.weight, dgamma)
     grads.put(u.bn.bias, dbeta)
     return dc, dz
@@ -303,7 +323,8 @@ def _fused_reduce_ok(u):
 
 
 def _unit_backward_from_sums(u, dz, sums, grads):
-    dc, dgamma, dbeta = ops.bn_backward_from_sums(dz, sums, u.c, u.co, dgamma=grads.dest(u.bn.weight), dbeta=grads.dest(u.bn.bias))
+    dc, dgamma, dbeta = ops.bn_backward_from_sums(dz, sums, u.c, u.co, dgamma=grads.dest(u.bn.weight), dbeta=grads.dest(u.bn.bias),
+                                                  sync=_bn_sync(u.bn))
     grads.put(u.bn.weight, dgamma)
     grads.put(u.bn.bias, dbeta)
     return dc
@@ -426,7 +447,7 @@ def backward(model, tape, dlogits, sink=None):
 
     a, c1, co1, idx, (Ho, Wo) = tape["stem"]
     g_act = ops.maxpool_bwd(g, idx, (Ho, Wo))
-    dc, dgamma, dbeta, _ = ops.bn_backward(g_act, c1, co1, relu=True, dgamma=grads.dest(model.bn1.weight),
+    dc, dgamma, dbeta, _ = ops.bn_backward(g_act, c1, co1, relu=True, sync=_bn_sync(model.bn1), dgamma=grads.dest(model.bn1.weight),
                                            dbeta=grads.dest(model.bn1.bias))
     grads.put(model.bn1.weight, dgamma)
     grads.put(model.bn1.bias, dbeta)

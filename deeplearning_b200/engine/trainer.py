@@ -399,6 +399,67 @@ class TrainStep:
         weight_cache.bump()
         return self._g_loss, self._g_correct
 
+    # ------------------------------------------------------------------------------------------- checkpoint / resume
+    def optimizer_state_dict(self):
+        """The fused optimizer's state in ``torch.optim`` format: what ``optimizer.state_dict()`` of the reference's
+        ``torch.optim.SGD(model.parameters(), ...)`` (resnet/train.py:96) or grouped ``AdamW`` (convNext/train.py:102,
+        swin utils/optimizer.py) would hold after the same steps - parameters indexed in ``model.parameters()`` order - so it
+        drops into the reference's checkpoint dict (swin_transformer/utils/torch_utils.py ``save_checkpoint``:
+        {'model', 'optimizer', 'lr_scheduler', 'max_accuracy', 'scaler', 'epoch', 'config'}) and into a real torch optimizer."""
+        arena = self.arena
+        state = {}
+        decay, nodecay = [], []
+        for i, (prm, o) in enumerate(zip(arena.params, arena.offsets)):
+            n = prm.numel()
+            if self.optimizer == "sgd":
+                if self.steps > 0:
+                    state[i] = {"momentum_buffer": arena.flat_m[o:o + n].view_as(prm).clone()}
+            else:
+                if self.steps > 0:
+                    state[i] = {"step": torch.tensor(float(self.steps)), "exp_avg": arena.flat_m[o:o + n].view_as(prm).clone(),
+                                "exp_avg_sq": arena.flat_v[o:o + n].view_as(prm).clone()}
+                (decay if float(arena.flat_wd[o]) != 0.0 else nodecay).append(i)
+        if self.optimizer == "sgd":
+            groups = [{"lr": self.lr, "momentum": self.momentum, "dampening": 0, "weight_decay": self.weight_decay,
+                       "nesterov": False, "params": list(range(len(arena.params)))}]
+        else:
+            base = {"lr": self._hyper_lr(), "betas": tuple(self.betas), "eps": self.eps, "amsgrad": False}
+            groups = [dict(base, weight_decay=self.weight_decay, params=decay), dict(base, weight_decay=0.0, params=nodecay)]
+        return {"state": state, "param_groups": groups}
+
+    def load_optimizer_state_dict(self, sd):
+        """Inverse of ``optimizer_state_dict`` (also accepts the state dict of a torch optimizer built over
+        ``model.parameters()`` in order): resume of the reference's ``load_checkpoint``."""
+        arena = self.arena
+        steps = 0
+        with torch.no_grad():
+            arena.flat_m.zero_()
+            if hasattr(arena, "flat_v"):
+                arena.flat_v.zero_()
+            for i, st in sd["state"].items():
+                o, prm = arena.offsets[int(i)], arena.params[int(i)]
+                n = prm.numel()
+                if self.optimizer == "sgd":
+                    if st.get("momentum_buffer") is not None:
+                        arena.flat_m[o:o + n].copy_(st["momentum_buffer"].reshape(-1))
+                        steps = max(steps, 1)
+                else:
+                    arena.flat_m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    arena.flat_v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps = max(steps, int(float(st["step"])))
+        lr = sd["param_groups"][0]["lr"]
+        self.lr = float(lr)
+        if self.optimizer == "adamw":
+            b1, b2 = self.betas
+            self._hyper.copy_(torch.tensor([self.lr, 1.0 - b1 ** steps, 1.0 - b2 ** steps, b1 ** steps, b2 ** steps],
+                                           dtype=torch.float32))
+            self._hyper_lr_value = self.lr
+            self.steps = steps
+        elif steps and self.steps == 0:
+            self.steps = steps   # (SGD keeps no step counter; only "has stepped" matters)
+        if getattr(self, "_lr_dev", None) is not None:
+            self._lr_dev.fill_(self.lr)
+
     @property
     def static_inputs(self):
         """(images, labels) buffers the captured graph reads; fill them directly to avoid the device-to-device copy."""

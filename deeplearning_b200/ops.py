@@ -292,8 +292,27 @@ class BnCoeffs:
         self.mean, self.invstd, self.scale, self.shift = buf[0], buf[1], buf[2], buf[3]
 
 
-def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked):
+def _sync_sums(partial, sync, average=False):
+    """SyncBatchNorm (torch.nn.SyncBatchNorm of the DDP recipe, others/train_with_DDP/train.py:190): the rank's partial rows
+    [T, 2, C] collapse to one row that is summed over the ranks of ``sync = (process_group, world_size)`` - one 2*C-float
+    all-reduce per BatchNorm pass.  ``average`` divides by the world size: the backward pass then yields m1 / m2 of the GLOBAL
+    batch from the local row count, and dgamma / dbeta equal to (global sum) / world on every rank, which the gradient
+    all-reduce (SUM, scaled by 1 / world) turns into exactly the reference's averaged gradient."""
+    import torch.distributed as dist
+
+    group, world = sync
+    row = partial.sum(0, keepdim=True)
+    dist.all_reduce(row, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        row.mul_(1.0 / world)
+    return row
+
+
+def bn_finalize(stats, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches_tracked, sync=None):
     lib = _lib.load()
+    if sync is not None:
+        stats = _sync_sums(stats, sync)
+        count = count * sync[1]
     T, _, C = stats.shape
     co = BnCoeffs(C, stats.device)
     sc = _reduce_scratch(stats.device)
@@ -328,7 +347,7 @@ def bn_apply(x, co, relu=True, residual=None):
     return y
 
 
-def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbeta=None, accumulate=False):
+def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbeta=None, accumulate=False, sync=None):
     """Train-mode BN (+ReLU) backward. g: grad wrt the post-activation output; x: raw conv output.
     Returns (dx, dgamma, dbeta, dz) with dz only when want_dz (masked upstream gradient, bf16)."""
     lib = _lib.load()
@@ -345,6 +364,9 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     _lib.check(rc, "b200_bn_bwd_reduce")
     if sp:
         sp.end()
+    if sync is not None:
+        partial = _sync_sums(partial, sync, average=True)
+        nblk = 1
     acc = 1 if (accumulate and dgamma is not None) else 0
     if dgamma is None:
         dgamma = torch.empty(C, dtype=F32, device=x.device)
@@ -365,12 +387,14 @@ def bn_backward(g, x, co, relu=True, y_out=None, want_dz=False, dgamma=None, dbe
     return dx, dgamma, dbeta, dz
 
 
-def bn_backward_from_sums(dz, partial, x, co, dgamma=None, dbeta=None):
+def bn_backward_from_sums(dz, partial, x, co, dgamma=None, dbeta=None, sync=None):
     """Second half of bn_backward(relu=True) when the producer of the gradient already masked it (dz) and summed
     partial[rows][2][C] = sum(dz), sum(dz * x) in its epilogue (conv2d_dgrad / gemm_dual with bn_mask=)."""
     lib = _lib.load()
     C = x.shape[-1]
     rows = x.numel() // C
+    if sync is not None:
+        partial = _sync_sums(partial, sync, average=True)
     if dgamma is None:
         dgamma = torch.empty(C, dtype=F32, device=x.device)
         dbeta = torch.empty(C, dtype=F32, device=x.device)

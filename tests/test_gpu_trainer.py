@@ -203,3 +203,44 @@ def test_gradient_accumulation_equals_one_large_batch(graph):
     assert t1.steps == t2.steps == 2
     for (n, p), q in zip(m1.named_parameters(), m2.parameters()):
         assert torch.allclose(p.detach(), q.detach(), rtol=2e-2, atol=2e-4), (n, float((p - q).abs().max()))
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adamw"])
+def test_optimizer_state_dict_round_trips_through_torch_optim(opt):
+    """TrainStep.optimizer_state_dict() loads into the reference's torch optimizer (and back): after two fused steps a torch
+    optimizer resumed from the exported state takes the same third step; a fresh TrainStep resumed from it does too."""
+    from deeplearning_b200.engine.trainer import TrainStep, no_decay_rule
+
+    m = _small_resnet(7)
+    tr = TrainStep(m, lr=0.03, momentum=0.9, weight_decay=5e-2, optimizer=opt)
+    x = torch.randn(8, 3, 64, 64, device="cuda")
+    y = torch.randint(0, 16, (8,), device="cuda")
+    for _ in range(2):
+        tr.step_eager(x, y)
+    sd = tr.optimizer_state_dict()
+    ref = copy.deepcopy(m)
+    named = dict(ref.named_parameters())
+    if opt == "sgd":
+        ropt = torch.optim.SGD(ref.parameters(), lr=0.03, momentum=0.9, weight_decay=5e-2)
+    else:
+        plist = list(ref.parameters())
+        ropt = torch.optim.AdamW([{"params": [plist[i] for i in g["params"]], "weight_decay": g["weight_decay"]}
+                                  for g in sd["param_groups"]], lr=0.03)
+        # (torch numbers the parameters group by group: re-key the exported state accordingly)
+        order = [i for g in sd["param_groups"] for i in g["params"]]
+        sd_t = {"state": {k: sd["state"][i] for k, i in enumerate(order)},
+                "param_groups": [dict(g, params=list(range(s0, s0 + len(g["params"]))))
+                                 for g, s0 in zip(sd["param_groups"], [0, len(sd["param_groups"][0]["params"])])]}
+    ropt.load_state_dict(sd if opt == "sgd" else {**ropt.state_dict(), "state": sd_t["state"]})
+    resumed = copy.deepcopy(m)
+    tr2 = TrainStep(resumed, lr=0.5, momentum=0.9, weight_decay=5e-2, optimizer=opt)
+    tr2.load_optimizer_state_dict(sd)
+    # third step: fused, torch (on the fused step's gradients), resumed-fused
+    tr.step_eager(x, y)
+    for (n, p) in m.named_parameters():
+        named[n].grad = p.grad.detach().clone()
+    ropt.step()
+    tr2.step_eager(x, y)
+    for (n, p), q in zip(m.named_parameters(), resumed.parameters()):
+        assert torch.allclose(p.detach(), named[n].detach(), rtol=2e-4, atol=2e-6), (opt, "torch", n)
+        assert torch.allclose(p.detach(), q.detach(), rtol=1e-5, atol=1e-7), (opt, "resumed", n)
