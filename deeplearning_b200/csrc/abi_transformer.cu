@@ -494,7 +494,7 @@ int b200_attention_bwd(const void* qkv, const void* out, const void* dout, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   {
     const long long rows = static_cast<long long>(B) * T * H;
-    B200_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(grid_for(rows, 256)), dim3(256), 0, st, 
+    B200_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(grid_for(rows, 128)), dim3(256), 0, st, 
         static_cast<const __nv_bfloat16*>(dout), static_cast<const __nv_bfloat16*>(out), delta, B, T, H));
     B200_LAUNCHED();
   }

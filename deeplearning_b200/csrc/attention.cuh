@@ -229,32 +229,51 @@ namespace b200 {
 // Backward: attention_bwd.cuh (attn_bwd_kernel, two CTAs per SM); the row term delta_i = sum_d dO[i,d] O[i,d] it needs is
 // produced by attn_delta_kernel below.
 
-// delta[b][h][t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one THREAD per (b,t,h) row: 2 x 128 contiguous bytes, 8 x 16-byte loads;
-// consecutive threads walk consecutive head rows, so a warp streams 2 x 4 KB - the one-warp-per-row version moved 4 bytes
-// per lane and ran at a quarter of the HBM rate)
+// delta[b][h][t] = sum_d dO[b,t,h,d] * O[b,t,h,d].  Eight lanes per (b,t,h) row (one 16-byte vector of dO and of O each, the
+// row sum by three shuffles), four rows in flight per lane: every load instruction of a warp covers 512 contiguous bytes.
+// (The one-thread-per-row version this replaces touched 32 different 128-byte lines per instruction: 2.9 TB/s.)
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ dO, const __nv_bfloat16* __restrict__ O,
                                                          float* __restrict__ delta, int B, int T, int H) {
   pdl_launch_dependents();
   pdl_wait();
   const long long total = static_cast<long long>(B) * T * H;
-  for (long long row = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; row < total;
-       row += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int h = static_cast<int>(row % H);
-    const long long bt = row / H;
-    const int t = static_cast<int>(bt % T);
-    const long long b = bt / T;
-    const uint4* a = reinterpret_cast<const uint4*>(dO + row * 64);
-    const uint4* o = reinterpret_cast<const uint4*>(O + row * 64);
-    float s = 0.f;
+  const int sub = threadIdx.x & 7;
+  const long long rows_per_pass = static_cast<long long>(gridDim.x) * (blockDim.x >> 3);
+  // (the loop bound is warp-uniform: the shuffles below run with the full mask)
+  for (long long rw = blockIdx.x * static_cast<long long>(blockDim.x >> 3) + ((threadIdx.x >> 5) << 2); rw < total;
+       rw += 4 * rows_per_pass) {
+    const long long r0 = rw + ((threadIdx.x & 31) >> 3);
+    uint4 a[4], o[4];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float x[8], y[8];
-      unpack8(__ldg(a + c), x);
-      unpack8(__ldg(o + c), y);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s = fmaf(x[j], y[j], s);
+    for (int u = 0; u < 4; ++u) {
+      const long long row = r0 + u * rows_per_pass;
+      if (row < total) {
+        a[u] = __ldg(reinterpret_cast<const uint4*>(dO + row * 64) + sub);
+        o[u] = __ldg(reinterpret_cast<const uint4*>(O + row * 64) + sub);
+      }
     }
-    delta[(b * H + h) * T + t] = s;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long row = r0 + u * rows_per_pass;
+      float s = 0.f;
+      if (row < total) {
+        float x[8], y[8];
+        unpack8(a[u], x);
+        unpack8(o[u], y);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s = fmaf(x[j], y[j], s);
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (sub == 0 && row < total) {
+        const int h = static_cast<int>(row % H);
+        const long long bt = row / H;
+        const int t = static_cast<int>(bt % T);
+        const long long b = bt / T;
+        delta[(b * H + h) * T + t] = s;
+      }
+    }
   }
 }
 

@@ -27,6 +27,17 @@ if "conv" in fam:
     w1 = torch.randn(64, 128, 1, 1, device=dev) * 0.05
     z = ops.gemm_dual(y, x, torch.randn(64, 192, device=dev).to(BF), torch.zeros(64, device=dev))
     print("conv ok", float(y.float().abs().mean()), float(dx.float().abs().mean()), float(z.float().abs().mean()))
+    # round 2, late: resident-weight 64 -> 64 kernel (conv_tap64.cuh: forward with statistics, plain dgrad) and the dgrad /
+    # dual-GEMM epilogue that masks with relu'(bn(x)) and sums dz, dz * x (kEpiBnMask)
+    x64 = r(4, 16, 16, 64)
+    w64 = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+    y64, st64 = ops.conv2d_fwd(x64, ops.pack_weight(w64), 3, 1, want_stats=True)
+    d64 = ops.conv2d_dgrad(y64, ops.pack_weight(w64, 1), (16, 16), 3, 1)
+    co = ops.bn_finalize(st64, 1024, torch.ones(64, device=dev), torch.zeros(64, device=dev), 1e-5, 0.1, None, None, None)
+    dzm, sums = ops.conv2d_dgrad(y64, ops.pack_weight(w64, 1), (16, 16), 3, 1, bn_mask=(y64, co))
+    dxm, dgm, dbm = ops.bn_backward_from_sums(dzm, sums, y64, co)
+    zm, sums2 = ops.gemm_dual(y, x, torch.randn(64, 192, device=dev).to(BF), torch.zeros(64, device=dev), bn_mask=(x, co))
+    print("tap64 / bn-mask ok", float(d64.float().abs().mean()), float(dxm.float().abs().mean()), float(zm.float().abs().mean()))
 if "stream" in fam or "algebra" in fam:
     y2 = r(4, 16, 16, 64).relu_()
     w3 = torch.randn(256, 64, 1, 1, device=dev) * 0.1
