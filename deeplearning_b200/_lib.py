@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200_attention_bwd": (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _P]),
     "b200_conv2d_wgrad_set_rowscale": (_I, [_P]),
     "b200_conv2d_wgrad_set_bias_partial": (_I, [_P]),
+    "b200_conv2d_wgrad_set_bias_out": (_I, [_P]),
     "b200_conv2d_wgrad_splits": (_I, [_I, _I, _I, _I, _I, _I, _I]),
     "b200_dwconv7_pack": (_I, [_P, _P, _I, _P]),
     "b200_dwconv7": (_I, [_P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),

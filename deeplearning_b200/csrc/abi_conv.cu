@@ -19,6 +19,7 @@ uint32_t g_wg_lbo = 8192, g_wg_sbo = 1024, g_wg_kstep = 2048;
 // one-shot per-output-channel multiplier for the next b200_conv2d_wgrad call (see b200_conv2d_wgrad_set_rowscale)
 thread_local const float* g_wgrad_rowscale = nullptr;
 thread_local float* g_wgrad_bias_partial = nullptr;
+thread_local float* g_wgrad_bias_out = nullptr;   // one-shot with bias_partial: the reduce kernel writes the finished bias gradient
 thread_local const float* g_fwd_bn_scale = nullptr;   // one-shot: fold y = conv * scale + shift (eval-mode BN) into the epilogue
 thread_local const float* g_fwd_bn_shift = nullptr;
 // one-shot (b200_dgrad_set_bn_mask): the next stride-1 dgrad / dual GEMM masks its output with relu'(bn(x_raw)) and writes the
@@ -456,7 +457,7 @@ int launch_wgrad(const WgradParams& p, cudaStream_t st) {
 
 // partial[splits][Cout][taps*Cin] -> grad[Cout][Cin][taps] (+)=, see wgrad_gemm.cuh
 int launch_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, int Cin, int taps, int accumulate,
-                         const float* rowscale, cudaStream_t st) {
+                         const float* rowscale, cudaStream_t st, const float* bias_partial = nullptr, float* bias_out = nullptr) {
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   if (Cin % 8 == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
     int chunk = taps == 1 ? 256 : 64;
@@ -466,13 +467,13 @@ int launch_wgrad_reduce(const float* partial, float* dw, int splits, int Cout, i
     const size_t smem = static_cast<size_t>(SL) * taps * chunk * sizeof(float);
     if (smem <= 48 * 1024 && Cout <= 65535 * 32) {
       dim3 grid(Cout, (Cin + chunk - 1) / chunk);
-      B200_CHECK_CUDA(launch_pdl(wgrad_reduce_rows_kernel, dim3(grid), dim3(256), smem, st, partial, dw, splits, Cout, Cin, taps, chunk, SL, accumulate, rowscale));
+      B200_CHECK_CUDA(launch_pdl(wgrad_reduce_rows_kernel, dim3(grid), dim3(256), smem, st, partial, dw, splits, Cout, Cin, taps, chunk, SL, accumulate, rowscale, bias_partial, bias_out));
       return OK;
     }
   }
   int blocks = static_cast<int>((total + 255) / 256);
   if (blocks > device_sm_count() * 8) blocks = device_sm_count() * 8;
-  B200_CHECK_CUDA(launch_pdl(wgrad_reduce_flat_kernel, dim3(blocks), dim3(256), 0, st, partial, dw, splits, Cout, Cin, taps, accumulate, rowscale));
+  B200_CHECK_CUDA(launch_pdl(wgrad_reduce_flat_kernel, dim3(blocks), dim3(256), 0, st, partial, dw, splits, Cout, Cin, taps, accumulate, rowscale, bias_partial, bias_out));
   return OK;
 }
 
@@ -878,6 +879,11 @@ int b200_conv2d_wgrad_set_bias_partial(float* bias_partial) {
   return OK;
 }
 
+int b200_conv2d_wgrad_set_bias_out(float* bias_out) {
+  g_wgrad_bias_out = bias_out;
+  return OK;
+}
+
 int b200_conv2d_wgrad_splits(int B, int H, int W, int Cin, int Cout, int ksize, int stride) {
   return plan_wgrad(B, H, W, Cin, Cout, ksize, stride).splits;
 }
@@ -911,6 +917,8 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   p.partial = static_cast<float*>(workspace);
   p.bias_partial = g_wgrad_bias_partial;   // one-shot (b200_conv2d_wgrad_set_bias_partial)
   g_wgrad_bias_partial = nullptr;
+  float* const bias_out = p.bias_partial != nullptr ? g_wgrad_bias_out : nullptr;
+  g_wgrad_bias_out = nullptr;
   const bool flat = (ksize == 1 && stride == 1);
   int rc;
   View dyv = flat ? make_flat_view(dy, static_cast<long long>(B) * H * W, Cout)
@@ -953,7 +961,9 @@ int b200_conv2d_wgrad(const void* dy, const void* x, float* dw, void* workspace,
   else
     rc = launch_wgrad<256>(p, st);
   if (rc) return rc;
-  if ((rc = launch_wgrad_reduce(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale, st))) return rc;
+  if ((rc = launch_wgrad_reduce(p.partial, dw, pl.splits, Cout, Cin, pl.taps, accumulate, g_wgrad_rowscale, st, p.bias_partial,
+                                bias_out)))
+    return rc;
   g_wgrad_rowscale = nullptr;
   B200_LAUNCHED();
   return OK;

@@ -333,11 +333,20 @@ __global__ void __launch_bounds__(kBias ? 320 : 192, 1) wgrad_gemm_kernel(const 
 // out tap-innermost, so that both the partial reads and the OIHW gradient writes are fully coalesced. Fixed summation order.
 __global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __restrict__ partial, float* __restrict__ grad,
                                                                 int splits, int Cout, int Cin, int taps, int chunk, int SL,
-                                                                int accumulate, const float* __restrict__ rowscale) {
+                                                                int accumulate, const float* __restrict__ rowscale,
+                                                                const float* __restrict__ bias_partial,
+                                                                float* __restrict__ bias_out) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float4 rows_sm4[];
   const int cout = blockIdx.x;
+  // the layer's bias gradient: the per-split column sums of dY the kBias wgrad kernel left in bias_partial[splits][2][Cout],
+  // folded in split order by the first block of each output channel (it used to be a launch of its own per layer)
+  if (bias_out != nullptr && blockIdx.y == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += bias_partial[static_cast<long long>(k) * 2 * Cout + cout];
+    bias_out[cout] = s;
+  }
   const int c0 = blockIdx.y * chunk;
   const int cw = min(chunk, Cin - c0);
   const int vpt = cw >> 2;          // float4 vectors per tap
@@ -381,11 +390,19 @@ __global__ void __launch_bounds__(256) wgrad_reduce_rows_kernel(const float* __r
 
 // Same reduction, one thread per element walking the splits: fallback for shapes the row kernel does not take.
 __global__ void wgrad_reduce_flat_kernel(const float* __restrict__ partial, float* __restrict__ grad, int splits, int Cout,
-                                    int Cin, int taps, int accumulate, const float* __restrict__ rowscale) {
+                                    int Cin, int taps, int accumulate, const float* __restrict__ rowscale,
+                                    const float* __restrict__ bias_partial, float* __restrict__ bias_out) {
   pdl_launch_dependents();
   pdl_wait();
   const long long total = static_cast<long long>(Cout) * Cin * taps;
   const long long slice = total;
+  if (bias_out != nullptr) {
+    for (int cout = blockIdx.x * blockDim.x + threadIdx.x; cout < Cout; cout += gridDim.x * blockDim.x) {
+      float s = 0.f;
+      for (int k = 0; k < splits; ++k) s += bias_partial[static_cast<long long>(k) * 2 * Cout + cout];
+      bias_out[cout] = s;
+    }
+  }
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     // i indexes the partial layout (coalesced reads): [cout][tap][cin]

@@ -259,11 +259,10 @@ def conv2d_wgrad(dy, x, ksize=1, stride=1, out=None, accumulate=False, rowscale=
         splits = lib.b200_conv2d_wgrad_splits(B, H, W, Cin, Cout, ksize, stride)
         bias_partial = torch.empty(splits, 2, Cout, dtype=F32, device=x.device)
         lib.b200_conv2d_wgrad_set_bias_partial(_p(bias_partial))
+        lib.b200_conv2d_wgrad_set_bias_out(_p(bias_out))   # finished by the split-reduction kernel of the same call
     rc = lib.b200_conv2d_wgrad(_p(dy), _p(x), _p(out), _p(ws), ws.numel(), B, H, W, Cin, Cout, ksize, stride,
                                1 if accumulate else 0, _stream())
     _lib.check(rc, "b200_conv2d_wgrad")
-    if bias_partial is not None:
-        stats_colsum(bias_partial, out=bias_out)
     if sp:
         sp.end()
     return out

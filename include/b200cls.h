@@ -88,6 +88,9 @@ int b200_conv2d_wgrad_set_rowscale(const float* rowscale);
  * are summed from shared memory by four extra warps of the wgrad kernel: no separate pass over dy
  * (replaces the bias part of loss.backward() for nn.Linear / nn.Conv2d(bias=True): vit_model.py:95,109,127-133). */
 int b200_conv2d_wgrad_set_bias_partial(float* bias_partial);
+/* one-shot, together with set_bias_partial: the split reduction that follows the wgrad GEMM also folds bias_partial into the
+ * finished bias gradient bias_out[Cout] (nn.Linear / nn.Conv2d bias under loss.backward()) - no launch of its own */
+int b200_conv2d_wgrad_set_bias_out(float* bias_out);
 int b200_conv2d_wgrad_splits(int B, int H, int W, int Cin, int Cout, int ksize, int stride);
 
 /* ---- general GEMM with strided pixel views (transformer layers, patch embedding) ----------------------------------------
