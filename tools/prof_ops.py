@@ -220,6 +220,71 @@ def vit_qkv_wgrad_bias():         # round 2: qkv weight gradient with the bias g
     return lambda: ops.conv2d_wgrad(dy, x, bias_out=b)
 
 
+def _bn_co(c):
+    C = c.shape[-1]
+    co = ops.BnCoeffs(C, c.device)
+    cf = c.float().reshape(-1, C)
+    co.mean.copy_(cf.mean(0))
+    co.invstd.copy_((cf.var(0, unbiased=False) + 1e-5).rsqrt())
+    co.scale.copy_(co.invstd)
+    co.shift.copy_(-co.mean * co.invstd)
+    return co
+
+
+def res_l1_dgrad3x3_bn_reduce():  # round 2 (late): layer1 conv2 dgrad (3x3 64 <- 64) + ReLU mask of bn1 + sum dz, sum dz*x
+    dc = rnd(256, 56, 56, 64, scale=0.1)
+    wd = ops.pack_weight(torch.randn(64, 64, 3, 3, device=dev) * 0.05, mode=1)
+    c = rnd(256, 56, 56, 64)
+    co = _bn_co(c)
+    return lambda: ops.conv2d_dgrad(dc, wd, (56, 56), 3, 1, bn_mask=(c, co))
+
+
+def res_l2_dgrad3x3_bn_reduce():  # layer2 conv2 dgrad (3x3 128 <- 128 at 28x28) with the fused BN-backward reduce
+    dc = rnd(256, 28, 28, 128, scale=0.1)
+    wd = ops.pack_weight(torch.randn(128, 128, 3, 3, device=dev) * 0.05, mode=1)
+    c = rnd(256, 28, 28, 128)
+    co = _bn_co(c)
+    return lambda: ops.conv2d_dgrad(dc, wd, (28, 28), 3, 1, bn_mask=(c, co))
+
+
+def res_l1_gemm_dual_bn_reduce():  # dL/dy2 dual GEMM (K = 256 + 64 -> N = 64) + bn2's mask and backward sums in the epilogue
+    dz, y2 = rnd(256, 56, 56, 256, scale=0.1), rnd(256, 56, 56, 64).relu_()
+    wcat = rnd(64, 320, scale=0.05)
+    b = torch.zeros(64, device=dev)
+    c = rnd(256, 56, 56, 64)
+    co = _bn_co(c)
+    return lambda: ops.gemm_dual(dz, y2, wcat, b, bn_mask=(c, co))
+
+
+def res_l1_conv2_tap64():         # layer1 conv2 forward 3x3 64 -> 64 with resident weights (conv_tap64.cuh) + BN statistics
+    return res_l1_conv2()
+
+
+def res_stem_conv():              # space-to-depth stem conv (4 taps x 64 -> 64 at 112x112, conv_tap64.cuh) + BN statistics
+    x = torch.randn(256, 3, 224, 224, device=dev)
+    a = ops.stem_s2d(x)
+    wp = rnd(64, 256, scale=0.05)   # [Cout][4 y-taps x 64] (values are irrelevant for the profile)
+    return lambda: ops.stem_s2d_conv_fwd(a, wp, want_stats=True)
+
+
+def res_l3_algebra_small():       # layer3 BN-algebra kernels: statistics from the Gram matrix and the backward rows / M kernels
+    y2 = rnd(256, 14, 14, 256).relu_()
+    w3 = torch.randn(1024, 256, 1, 1, device=dev) * 0.05
+    wp = ops.pack_weight(w3)
+    G, s = ops.gram_colsum(y2)
+    gamma, beta = torch.ones(1024, device=dev), torch.zeros(1024, device=dev)
+    rows = 256 * 14 * 14
+    co = ops.bn_gram_stats(G, s, wp, rows, gamma, beta, 1e-5, 0.1, None, None, None)
+    dz = rnd(256, 14, 14, 1024, scale=0.1)
+    D = ops.conv2d_wgrad(dz, y2, 1, 1)
+    st = torch.zeros(4, 2, 1024, device=dev)
+
+    def run():
+        ops.bn_gram_stats(G, s, wp, rows, gamma, beta, 1e-5, 0.1, None, None, None)
+        ops.bn_conv1x1_bwd(st, D, G, s, wp, w3, rows, gamma, co)
+    return run
+
+
 if __name__ == "__main__":
     fns = [(n, globals()[n]()) for n in sys.argv[1:]]
     for _, f in fns:
