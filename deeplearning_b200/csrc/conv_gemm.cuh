@@ -43,13 +43,13 @@ struct alignas(64) ConvGemmParams {
   float* stats;             // [stats_rows][2][N] per-CTA partial sums (see conv_stats_rows), or null; needs grid % n_tiles == 0
   const float* bias;        // [N] or null
   const float* colscale;    // [N] per-channel multiplier applied after bias/activation (layer scale), or null
-  int act;                  // 0 none, 1 relu, 2 gelu(erf), 3 multiply by gelu'(aux_in) (backward of 2)
+  int act;                  // 0 none, 1 relu, 2 gelu(erf), 3 multiply by aux_in = GELU'(pre) saved by the forward (backward of 2)
   int out_f32;              // 1: d_map is fp32 (32-channel slabs)
   int res_f32;              // 1: residual tensor is fp32
-  int has_aux_out;          // 1: also store the pre-activation through aux_map
+  int has_aux_out;          // 1: second output through aux_map: the pre-activation (act 0/1) or GELU'(pre) (act 2)
   const void* residual;     // tensor added in the epilogue (pixel strides rs1..rs3, in elements) or null
   long long rs1, rs2, rs3;
-  const __nv_bfloat16* aux_in;  // act == 3: pre-activation tensor (pixel strides as1..as3)
+  const __nv_bfloat16* aux_in;  // act == 3: GELU'(pre) tensor written by the forward GEMM (pixel strides as1..as3)
   long long as1, as2, as3;
   uint32_t desc_lbo, desc_sbo;  // K-major smem descriptor strides (bytes): 16 / 1024
   float* out_direct;        // direct fp32 output ([pixels][ld_out]) for tiny N (logits) or null
@@ -151,12 +151,16 @@ __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   gelu_parts2(x0, x1, cdf, e);
   f2_unpack(f2_mul(f2_pack(x0, x1), cdf), x0, x1);
 }
-// f0 *= GELU'(a0), f1 *= GELU'(a1)
-__device__ __forceinline__ void gelu_erf_grad_mul2(float a0, float a1, float& f0, float& f1) {
+// x <- GELU(x), g <- GELU'(x) = Phi(x) + x phi(x) for two values: the derivative shares the cdf / exp work of the value (two
+// more packed instructions), which is why the FORWARD GEMM of an MLP saves GELU'(pre) for the backward pass instead of the
+// pre-activation itself - the dgrad epilogue of the following layer then only multiplies (it used to re-evaluate the whole
+// erf polynomial per element and was instruction-issue bound: ViT-B/16 fc2 dgrad 282 us against 161 us for the same-size fc1 dgrad).
+__device__ __forceinline__ void gelu_erf_val_grad2(float& x0, float& x1, float& g0, float& g1) {
   uint64_t cdf, e;
-  gelu_parts2(a0, a1, cdf, e);
-  const uint64_t g = f2_fma(f2_mul(f2_pack(a0, a1), f2_bcast(0.3989422804014327f)), e, cdf);
-  f2_unpack(f2_mul(f2_pack(f0, f1), g), f0, f1);
+  gelu_parts2(x0, x1, cdf, e);
+  const uint64_t x = f2_pack(x0, x1);
+  f2_unpack(f2_fma(f2_mul(x, f2_bcast(0.3989422804014327f)), e, cdf), g0, g1);
+  f2_unpack(f2_mul(x, cdf), x0, x1);
 }
 
 // Optional phase timers (-DCONV_PROFILE): CTA 0 prints average cycles per tile of every wait / work phase of each role.
@@ -555,28 +559,45 @@ __global__ void __launch_bounds__(320, 1) conv_gemm_kernel(const __grid_constant
             }
           }
           if (has_aux) {
-            // pre-activation copy (bf16) for the backward pass
+            // second output (bf16) for the backward pass: the pre-activation, or - when the activation is GELU - its
+            // derivative GELU'(pre), computed together with the value (what act == 3 of the next layer's dgrad multiplies by)
             const uint32_t z = row_ok ? 0xffffffffu : 0u;
+            if (act == 2) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts128(aux_s + row_s + ((((h * 4 + j) << 4)) ^ sw), pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]) & z,
-                     pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]) & z, pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]) & z,
-                     pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]) & z);
+              for (int j = 0; j < 4; ++j) {
+                float g[8];
+#pragma unroll
+                for (int i = 0; i < 8; i += 2) gelu_erf_val_grad2(f[j * 8 + i], f[j * 8 + i + 1], g[i], g[i + 1]);
+                sts128(aux_s + row_s + ((((h * 4 + j) << 4)) ^ sw), pack_bf16x2(g[0], g[1]) & z, pack_bf16x2(g[2], g[3]) & z,
+                       pack_bf16x2(g[4], g[5]) & z, pack_bf16x2(g[6], g[7]) & z);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                sts128(aux_s + row_s + ((((h * 4 + j) << 4)) ^ sw), pack_bf16x2(f[j * 8 + 0], f[j * 8 + 1]) & z,
+                       pack_bf16x2(f[j * 8 + 2], f[j * 8 + 3]) & z, pack_bf16x2(f[j * 8 + 4], f[j * 8 + 5]) & z,
+                       pack_bf16x2(f[j * 8 + 6], f[j * 8 + 7]) & z);
+            }
           }
           if (act == 1) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
           } else if (act == 2) {
+            if (!has_aux) {   // (with a second output the value was computed together with the derivative above)
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
+              for (int j = 0; j < 32; j += 2) gelu_erf2(f[j], f[j + 1]);
+            }
           } else if (act == 3 && row_ok) {
+            // backward of GELU: aux_in holds GELU'(pre) as saved by the forward GEMM
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (full_cols || nc + j * 8 < N) {
                 float a[8];
                 unpack8(pre_b[j], a);
 #pragma unroll
-                for (int i = 0; i < 8; i += 2) gelu_erf_grad_mul2(a[i], a[i + 1], f[j * 8 + i], f[j * 8 + i + 1]);
+                for (int i = 0; i < 8; i += 2)
+                  f2_unpack(f2_mul(f2_pack(f[j * 8 + i], f[j * 8 + i + 1]), f2_pack(a[i], a[i + 1])), f[j * 8 + i],
+                            f[j * 8 + i + 1]);
               }
             }
           }

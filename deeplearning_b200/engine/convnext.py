@@ -4,7 +4,7 @@ Mirrors ``ConvNeXt.forward_features`` / ``Block.forward`` of the reference (clas
 :92-105).  The residual stream ``x`` is fp32 NHWC; everything feeding a tensor core is bf16:
 
     stem      patch matrix (4x4) GEMM + bias -> LayerNorm -> x
-    Block     u = dwconv7x7(x)+b (CUDA cores) -> y = LN(u) -> GELU(y W1^T + b1) (pre-activation kept) ->
+    Block     u = dwconv7x7(x)+b (CUDA cores) -> y = LN(u) -> GELU(y W1^T + b1) (its derivative kept) ->
               x' = x + gamma * (. W2^T + b2)        (bias, layer scale and the residual add live in the GEMM epilogue)
     downsample  LN(x) -> 2x2/s2 conv as a 4-tap implicit GEMM writing the fp32 stream
     head      mean over H,W -> LayerNorm -> Linear (fp32 logits)
@@ -120,12 +120,12 @@ def forward(model, x, train, want_tape):
             Bb, H, W, C = h.shape
             u = ops.dwconv7(h, _dw_cache.get(blk.dwconv.weight), blk.dwconv.bias)       # bf16 NHWC
             y, m, r = ops.layernorm_fwd(u, blk.norm.weight, blk.norm.bias, blk.norm.eps)
-            post, pre = ops.gemm(y.view(-1, C), pack.get(blk.pwconv1.weight, 0), bias=blk.pwconv1.bias, act=2, aux_out=want_tape)
+            post, dact = ops.gemm(y.view(-1, C), pack.get(blk.pwconv1.weight, 0), bias=blk.pwconv1.bias, act=2, aux_out=want_tape)
             dps = droppath.sample_scale(droppath.drop_prob_of(blk, train), Bb, 4, h.device)   # x = shortcut + drop_path(x)
             h_new, _ = ops.gemm(post, pack.get(blk.pwconv2.weight, 0), bias=blk.pwconv2.bias, colscale=blk.gamma,
                                 residual=h, out_f32=True, rowscale=None if dps is None else (dps, H * W))
             if want_tape:
-                rec["blocks"].append((blk, h, u, m, r, y, pre, post, dps))
+                rec["blocks"].append((blk, h, u, m, r, y, dact, post, dps))
             h = h_new.view(Bb, H, W, C)
         if want_tape:
             tape["stages"].append(rec)
@@ -198,7 +198,7 @@ def backward(model, tape, dlogits, sink=None):
     g = ops.avgpool_bwd(d_pool, (Hf, Wf))                          # bf16 [B, Hf, Wf, Cf]: gradient of the stream
     for i in range(3, -1, -1):
         rec = tape["stages"][i]
-        for (blk, h, u, m, r, y, pre, post, dps) in reversed(rec["blocks"]):
+        for (blk, h, u, m, r, y, dact, post, dps) in reversed(rec["blocks"]):
             Bb, H, W, C = h.shape
             M = Bb * H * W
             # the gradient entering the residual branch carries the sample's stochastic-depth multiplier; the identity path keeps g
@@ -214,7 +214,7 @@ def backward(model, tape, dlogits, sink=None):
             if blk.gamma is not None:
                 grads.put(blk.gamma, dgam)
             # (g*gamma) W2, times GELU'(pre); the epilogue also sums the columns of d_pre (= pwconv1 bias gradient)
-            d_pre, _, st_pre = ops.gemm(g2, pack.get(blk.pwconv2.weight, 1), act=3, aux_in=pre, want_stats=True)
+            d_pre, _, st_pre = ops.gemm(g2, pack.get(blk.pwconv2.weight, 1), act=3, aux_in=dact, want_stats=True)
             _lin_wgrad(grads, blk.pwconv1, d_pre, y.view(M, C), dy_stats=st_pre)
             d_y, _ = ops.gemm(d_pre, pack.get(blk.pwconv1.weight, 1))
             du, dgl, dbl = ops.layernorm_bwd(d_y, u.view(M, C), m, r, blk.norm.weight, dx_dtype=BF16,

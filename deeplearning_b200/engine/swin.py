@@ -7,7 +7,7 @@ Mirrors ``SwinTransformer.forward_features`` / ``BasicLayer.forward`` / ``SwinTr
 Data flow per block (residual stream ``h`` fp32 [B, H*W, C] in natural pixel order; tensor-core operands bf16):
     LN1(h) -> qkv GEMM(+bias) -> shifted-window attention (roll, partition, bias, mask, softmax, reverse, un-roll all inside
     one tcgen05 kernel that gathers its 49-token windows straight from the pixel-ordered qkv tensor)
-    -> proj GEMM(+bias, +h, fp32 out) = h2 -> LN2 -> fc1 GEMM(+bias, GELU, keeps pre-activation) -> fc2 GEMM(+bias, +h2) = h3
+    -> proj GEMM(+bias, +h, fp32 out) = h2 -> LN2 -> fc1 GEMM(+bias, GELU, keeps GELU'(pre)) -> fc2 GEMM(+bias, +h2) = h3
 PatchMerging = one gather+LayerNorm kernel (the 2x2 concat never exists in HBM) + the bias-free reduction GEMM (fp32 out).
 """
 import torch
@@ -111,12 +111,12 @@ def forward(model, x, train, want_tape):
             h2, _ = ops.gemm(att.view(B, H * W, C), pack.get(att_m.proj.weight, 0), bias=att_m.proj.bias, residual=h,
                              out_f32=True, rowscale=None if dp1 is None else (dp1, H * W))
             y2, m2, r2 = ops.layernorm_fwd(h2, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-            post, pre = ops.gemm(y2, pack.get(mlp.fc1.weight, 0), bias=mlp.fc1.bias, act=2, aux_out=want_tape)
+            post, dact = ops.gemm(y2, pack.get(mlp.fc1.weight, 0), bias=mlp.fc1.bias, act=2, aux_out=want_tape)
             dp2 = droppath.sample_scale(dp, B, 3, x.device)   # x = x + drop_path(mlp(norm2(x)))    (swin_transformer.py:285)
             h3, _ = ops.gemm(post, pack.get(mlp.fc2.weight, 0), bias=mlp.fc2.bias, residual=h2, out_f32=True,
                              rowscale=None if dp2 is None else (dp2, H * W))
             if want_tape:
-                recs.append((blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2))
+                recs.append((blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, dact, post, dp1, dp2))
             h = h3
         merge = None
         if layer.downsample is not None:
@@ -190,13 +190,13 @@ def backward(model, tape, dlogits, sink=None):
             grads.put(ds.norm.bias, dbm)
         M = B * H * W
         g = g.view(B, H * W, C)
-        for (blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2) in reversed(recs):
+        for (blk, h, y1, m1, r1, qkv, bias, att, lse, h2, y2, m2, r2, dact, post, dp1, dp2) in reversed(recs):
             att_m, mlp = blk.attn, blk.mlp
             nH = att_m.num_heads
             # (stochastic depth: the branch sees the per-sample scaled gradient, the identity path - `add=g` - the full one)
             g2 = (g if dp2 is None else ops.rowscale(g, dp2)).view(M, C)
             _lin_grads(grads, mlp.fc2, g2, post.view(M, -1))
-            d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1), want_stats=True)
+            d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=dact.view(M, -1), want_stats=True)
             _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, C), dy_stats=st_pre)
             d_y2, _ = ops.gemm(d_pre, pack.get(mlp.fc1.weight, 1))
             g, dg2, db2 = ops.layernorm_bwd(d_y2, h2, m2, r2, blk.norm2.weight, add=g, dx_dtype=BF16,

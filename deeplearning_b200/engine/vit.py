@@ -5,7 +5,7 @@ reference (classification/vision_transformer/vit_model.py:240-268, :158-161, :88
 
 Data flow per block (residual stream ``h`` fp32 [B,T,D], everything feeding a tensor core bf16):
     LN1(h) -> qkv GEMM(+bias) -> tcgen05 attention -> proj GEMM(+bias, +h, fp32 out) = h2
-    LN2(h2) -> fc1 GEMM(+bias, GELU, keeps the pre-activation) -> fc2 GEMM(+bias, +h2, fp32 out) = h3
+    LN2(h2) -> fc1 GEMM(+bias, GELU; also writes GELU'(pre) for the backward) -> fc2 GEMM(+bias, +h2, fp32 out) = h3
 Residual adds, biases, GELU, GELU' (backward) and the pos-embed add of the patch embedding all live in GEMM epilogues; the
 attention scores never touch HBM.  The gradient of the residual stream is carried in bf16 and accumulated inside the
 LayerNorm-backward kernel.
@@ -111,12 +111,12 @@ def forward(model, x, train, want_tape):
         h2, _ = ops.gemm(att, pack.get(att_m.proj.weight, 0), bias=att_m.proj.bias, residual=h, out_f32=True,
                          rowscale=None if dp1 is None else (dp1, T))
         y2, m2, r2 = ops.layernorm_fwd(h2, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
-        post, pre = ops.gemm(y2, pack.get(mlp.fc1.weight, 0), bias=mlp.fc1.bias, act=2, aux_out=want_tape)
+        post, dact = ops.gemm(y2, pack.get(mlp.fc1.weight, 0), bias=mlp.fc1.bias, act=2, aux_out=want_tape)
         dp2 = droppath.sample_scale(dp, B, 3, x.device)     # x = x + drop_path(mlp(norm2(x)))    (vit_model.py:160)
         h3, _ = ops.gemm(post, pack.get(mlp.fc2.weight, 0), bias=mlp.fc2.bias, residual=h2, out_f32=True,
                          rowscale=None if dp2 is None else (dp2, T))
         if want_tape:
-            tape["blocks"].append((blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2))
+            tape["blocks"].append((blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, dact, post, dp1, dp2))
         h = h3
     # ---- head: final LayerNorm on the class-token rows only, then the classifier (fp32 logits)
     cls_rows = torch.empty(B, D, dtype=F32, device=x.device)
@@ -202,7 +202,7 @@ def backward(model, tape, dlogits, sink=None):
     g = torch.zeros(B, T, D, dtype=BF16, device=d_cls.device)   # gradient of the residual stream
     ops.copy_rows(d_cls, 0, D, g, 0, T * D, B, D)
     M = B * T
-    for (blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, pre, post, dp1, dp2) in reversed(tape["blocks"]):
+    for (blk, h, y1, m1, r1, qkv, att, lse, h2, y2, m2, r2, dact, post, dp1, dp2) in reversed(tape["blocks"]):
         att_m, mlp = blk.attn, blk.mlp
         H = att_m.num_heads
         # (stochastic depth: the branch sees the per-sample scaled gradient, the identity path - `add=g` below - the full one)
@@ -210,7 +210,7 @@ def backward(model, tape, dlogits, sink=None):
         # h3 = h2 + fc2(gelu(fc1(LN2(h2))))
         _lin_grads(grads, mlp.fc2, g2, post.view(M, -1))
         # dgrad + GELU' in the epilogue, which also sums the columns of d_pre (= fc1 bias gradient) on the way out
-        d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=pre.view(M, -1), want_stats=True)
+        d_pre, _, st_pre = ops.gemm(g2, pack.get(mlp.fc2.weight, 1), act=3, aux_in=dact.view(M, -1), want_stats=True)
         _lin_grads(grads, mlp.fc1, d_pre, y2.view(M, D), dy_stats=st_pre)
         d_y2, _ = ops.gemm(d_pre, pack.get(mlp.fc1.weight, 1))
         g, dg2, db2 = ops.layernorm_bwd(d_y2, h2, m2, r2, blk.norm2.weight, add=g, dx_dtype=BF16,

@@ -801,7 +801,8 @@ def gemm(a, w_packed, bias=None, act=0, out=None, out_f32=False, residual=None, 
          a_view=None, out_view=None, residual_view=None, out_offset=0, want_stats=False, colscale=None, rowscale=None):
     """out[rows, N] = epilogue(a[rows, K] @ w_packed[N, K]^T). `*_view` = (pix_dims, pix_strides) for strided layouts.
     rowscale = (fp32 [n_samples] tensor, rows_per_sample): stochastic-depth multiplier of every sample's rows, applied
-    before the residual add.  Returns (out, aux) where aux is the bf16 pre-activation copy when aux_out=True."""
+    before the residual add.  Returns (out, aux); with aux_out=True aux is the bf16 tensor the backward pass needs: GELU'(pre) for
+    act=2 (the dgrad GEMM of the next layer multiplies by it: act=3, aux_in=aux), the pre-activation otherwise."""
     import ctypes
 
     lib = _lib.load()

@@ -31,7 +31,8 @@ extern "C" {
 #define B200_ACT_NONE 0
 #define B200_ACT_RELU 1
 #define B200_ACT_GELU 2
-#define B200_ACT_GELU_GRAD 3 /* multiply the accumulator by gelu'(aux_in) - backward of B200_ACT_GELU */
+#define B200_ACT_GELU_GRAD 3 /* multiply the accumulator by aux_in, which holds GELU'(pre-activation) as written through aux_out
+                                by the forward GEMM with B200_ACT_GELU - backward of B200_ACT_GELU */
 
 const char* b200_last_error(void);
 int b200_abi_version(void);
@@ -114,8 +115,9 @@ typedef struct {
   int out_f32;                 /* 1: `out` is an fp32 tensor (residual stream) */
   const b200_view_t* residual; /* added after bias/act, or NULL */
   int residual_f32;
-  const b200_view_t* aux_out;  /* bf16 copy of the pre-activation (act == GELU), or NULL */
-  const b200_view_t* aux_in;   /* act == B200_ACT_GELU_GRAD: pre-activation tensor */
+  const b200_view_t* aux_out;  /* second bf16 output kept for the backward pass, or NULL: with act == GELU it receives the derivative
+                                  GELU'(pre-activation) (evaluated together with the value), otherwise the pre-activation itself */
+  const b200_view_t* aux_in;   /* act == B200_ACT_GELU_GRAD: the GELU'(pre-activation) tensor a forward call wrote through aux_out */
   float* stats;                /* optional per-32-row-slab column sum / sum of squares, or NULL */
   const float* rowscale;       /* stochastic depth: per-SAMPLE multiplier [n_samples] applied after bias/act/colscale and
                                   before the residual (drop_path: convNext/models/networks.py:11-26, vit_model.py:12-40,

@@ -62,16 +62,20 @@ def test_gemm_views_fp32_residual_aux_and_gelu_grad():
     out, _ = ops.gemm(a, wp, bias=bias, residual=res32, out_f32=True)
     assert out.dtype == torch.float32
     _close(out, ref + res32, 1e-4, 2e-4, "fp32 out + fp32 residual")
-    post, pre = ops.gemm(a, wp, bias=bias, act=2, aux_out=True)
-    _close(pre, ref, 1e-2, 1e-2, "aux pre-activation")
+    # GELU forward: the second output is GELU'(pre) (evaluated together with the value), which is all the backward needs
+    post, dact = ops.gemm(a, wp, bias=bias, act=2, aux_out=True)
+    prer = ref.clone().requires_grad_(True)
+    (gelu_grad,) = torch.autograd.grad(F.gelu(prer).sum(), prer)
+    _close(dact, gelu_grad, 1e-2, 1e-2, "aux GELU'(pre)")
     _close(post, F.gelu(ref), 1e-2, 1e-2, "gelu")
-    # backward through GELU fused into the dgrad GEMM of the following layer
+    post_only, _ = ops.gemm(a, wp, bias=bias, act=2)
+    assert torch.equal(post_only, post), "GELU value must not depend on whether the derivative is saved"
+    # backward through GELU fused into the dgrad GEMM of the following layer (multiplies by the saved derivative)
     dy = _rand(M, 96, seed=4)
     w2 = _rand(96, N, seed=5, scale=0.1)
     w2d = ops.pack_weight(w2.float(), mode=1)  # [N][96]
-    d_pre, _ = ops.gemm(dy, w2d, act=3, aux_in=pre)
-    prer = pre.float().requires_grad_(True)
-    (gref,) = torch.autograd.grad(F.gelu(prer), prer, dy.float() @ w2.float())
+    d_pre, _ = ops.gemm(dy, w2d, act=3, aux_in=dact)
+    gref = gelu_grad * (dy.float() @ w2.float())
     _close(d_pre, gref, 2e-2, 2e-2, "gelu grad epilogue")
 
 
