@@ -4,6 +4,7 @@
 #include "../../include/b200cls.h"
 #include "attention.cuh"
 #include "attention_bwd.cuh"
+#include "attention_fwd2.cuh"
 #include "host_utils.h"
 #include "convnext.cuh"
 #include "transformer.cuh"
@@ -479,11 +480,23 @@ int b200_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int
   if ((rc = encode3(&p.kv_map, qkv, 3 * HD, T, B, p.Tpad))) return rc;
   if ((rc = encode3(&p.o_map, out, HD, T, B, 128))) return rc;
   static bool cfg = false;
+  static int version = 0;
   if (!cfg) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes));
+    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes));
+    // default: the persistent kernel (attention_fwd2.cuh; ViT-B/16 layer at bs 256: 101 us);  B200_ATTN_FWD=1 selects the
+    // one-CTA-per-(batch, head, query block) kernel it replaced (attention.cuh; 148 us), kept as the A/B reference
+    const char* e = getenv("B200_ATTN_FWD");
+    version = (e != nullptr && e[0] == '1') ? 1 : 2;
     cfg = true;
   }
-  B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel, dim3(B * H * p.mblocks), dim3(160), kAttnSmemBytes, st, p));
+  if (version == 2) {
+    const int items = B * H;
+    const int grid = items < device_sm_count() ? items : device_sm_count();
+    B200_CHECK_CUDA(launch_pdl(attn_fwd2_kernel, dim3(grid), dim3(kAttn2Threads), kAttn2SmemBytes, st, p));
+  } else {
+    B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel, dim3(B * H * p.mblocks), dim3(160), kAttnSmemBytes, st, p));
+  }
   B200_LAUNCHED();
   return OK;
 }

@@ -138,6 +138,10 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
     uint8_t* sPg = sP + g * 65536;
     const int nfull = p.Tpad / 32;           // 32-column chunks
     const bool tail16 = (p.Tpad & 31) != 0;  // one extra 16-column chunk
+    // a warp whose 32 query rows all lie beyond T (ViT: rows 224-255 of the 197 tokens) only keeps the barrier protocol
+    // alive: its S / P / O rows are never stored (TMA clips them) and cannot leak into other rows of P V
+    const bool warp_live = g * 128 + wq * 32 < p.T;
+    const bool pingpong = mblocks == 2;
     int it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
       const uint32_t ph = it & 1;
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
       mbar_wait(bar_s + g, ph);
       tc_fence_after();
       float mx = -INFINITY;
-      for (int c = 0; c < nfull; ++c) {
+      for (int c = 0; warp_live && c < nfull; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
@@ -158,13 +162,22 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
             if (c * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
         }
       }
-      if (tail16) {
+      if (warp_live && tail16) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + nfull * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
           if (nfull * 32 + j < p.T) mx = fmaxf(mx, __uint_as_float(v[j]));
+      }
+      // The exponential pass is bound by the SM's MUFU rate: the two groups take turns at it (block 1 of item i after
+      // block 0 of item i, block 0 of item i+1 after block 1 of item i), so that one group's pass overlaps the other's
+      // MMA round trips, max pass and epilogue instead of both passes colliding and both waits idling the SM.
+      if (pingpong) {
+        if (g == 1)
+          mbar_wait(bar_p + 0, ph);
+        else if (it > 0)
+          mbar_wait(bar_p + 1, (it - 1) & 1);
       }
       // The first 16 KB of this block's P buffer were the staging slab of the previous item's O store: that store must have
       // finished READING shared memory before P is written again (the PV MMAs that read the old P retired before bar_o).
@@ -191,21 +204,21 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
           w.y = pack_bf16x2(e[2], e[3]);
           w.z = pack_bf16x2(e[4], e[5]);
           w.w = pack_bf16x2(e[6], e[7]);
-          // the row sum must match what the tensor core will see: accumulate the bf16-rounded values
-          sum += bf16_lo(w.x) + bf16_hi(w.x) + bf16_lo(w.y) + bf16_hi(w.y) + bf16_lo(w.z) + bf16_hi(w.z) + bf16_lo(w.w) +
-                 bf16_hi(w.w);
+          // row sum of the unrounded exponentials (attn_fwd_kernel sums the bf16-rounded values the tensor core sees, at
+          // three instructions per element; the two sums differ by ~2^-9 / sqrt(T) relative, far below the bf16 output)
+          sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
           const int col = col0 + q8 * 8;
           const int kb = col >> 6, chunk = (col & 63) >> 3;
           *reinterpret_cast<uint4*>(sPg + kb * 16384 + row * 128 + ((chunk ^ (row & 7)) << 4)) = w;
         }
       };
-      for (int c = 0; c < nfull; ++c) {
+      for (int c = 0; warp_live && c < nfull; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + c * 32, v);
         tmem_ld_wait();
         emit(v, c * 32, 32);
       }
-      if (tail16) {
+      if (warp_live && tail16) {
         uint32_t v[16];
         tmem_ld_32x16(taddr + nfull * 32, v);
         tmem_ld_wait();
@@ -219,16 +232,18 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
       mbar_wait(bar_o + g, ph);
       tc_fence_after();
       uint32_t o0[32], o1[32];
-      tmem_ld_32x32(taddr, o0);
-      tmem_ld_32x32(taddr + 32, o1);
-      tmem_ld_wait();
+      if (warp_live) {
+        tmem_ld_32x32(taddr, o0);
+        tmem_ld_32x32(taddr + 32, o1);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_free + g);
       const float inv = 1.0f / sum;
       uint8_t* stg = sPg;   // P is dead once bar_o has fired
 #pragma unroll
-      for (int q8 = 0; q8 < 4; ++q8) {
+      for (int q8 = 0; warp_live && q8 < 4; ++q8) {
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(o0[q8 * 8 + 0]) * inv, __uint_as_float(o0[q8 * 8 + 1]) * inv);
         w.y = pack_bf16x2(__uint_as_float(o0[q8 * 8 + 2]) * inv, __uint_as_float(o0[q8 * 8 + 3]) * inv);
@@ -237,7 +252,7 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
         *reinterpret_cast<uint4*>(stg + row * 128 + ((q8 ^ (row & 7)) << 4)) = w;
       }
 #pragma unroll
-      for (int q8 = 0; q8 < 4; ++q8) {
+      for (int q8 = 0; warp_live && q8 < 4; ++q8) {
         uint4 w;
         w.x = pack_bf16x2(__uint_as_float(o1[q8 * 8 + 0]) * inv, __uint_as_float(o1[q8 * 8 + 1]) * inv);
         w.y = pack_bf16x2(__uint_as_float(o1[q8 * 8 + 2]) * inv, __uint_as_float(o1[q8 * 8 + 3]) * inv);

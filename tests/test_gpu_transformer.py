@@ -109,7 +109,8 @@ def _attn_ref(qkv, H, scale):
     return (att @ v).transpose(1, 2).reshape(B, T, H * 64)
 
 
-@pytest.mark.parametrize("B,T,H", [(2, 197, 12), (3, 49, 3), (1, 256, 2), (2, 130, 4), (5, 16, 1)])
+# (the last two: several (batch, head) items per SM - buffer reuse / barrier phases of the persistent forward kernel)
+@pytest.mark.parametrize("B,T,H", [(2, 197, 12), (3, 49, 3), (1, 256, 2), (2, 130, 4), (5, 16, 1), (40, 197, 12), (64, 100, 6)])
 def test_attention_fwd_bwd(B, T, H):
     ops = _ops()
     scale = 64 ** -0.5
