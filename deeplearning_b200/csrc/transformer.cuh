@@ -186,6 +186,124 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict
   }
 }
 
+// Second version of the kernel above (the default; B200_LN_BWD=1 selects the first one), same arguments and results:
+//   * every load of a row - x, dy AND the residual gradient `add` - is issued before anything is computed; the first version
+//     fetched `add` only after the two row reductions, a second exposed DRAM round trip per row with nothing else in flight
+//     (24 warps per SM, one row each: 3.9 TB/s at C = 768).  The raw words stay in registers (x fp32 / dy, add bf16 packed:
+//     the same 48 registers the first version spends on xhat and dy*gamma) and xhat, dy*gamma are simply recomputed for the
+//     output phase - two more FMAs per element;
+//   * the per-warp parameter-gradient accumulators are split into a plane of the low and a plane of the high float4 of every
+//     8-channel vector, so that consecutive lanes touch consecutive 16-byte words (the interleaved layout was a 2-way bank
+//     conflict on every read-modify-write).
+template <typename TIn, typename TOut, int MAXV, int LPR = 32>
+__global__ void __launch_bounds__(256, 3)
+layernorm_bwd2_kernel(const __nv_bfloat16* __restrict__ dy, const TIn* __restrict__ x, const float* __restrict__ mean,
+                      const float* __restrict__ rstd, const float* __restrict__ gamma, const TOut* __restrict__ add,
+                      TOut* __restrict__ dx, float* __restrict__ partial, long long rows, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float red[];  // [warps][rows per warp][2][C], each [C] = low float4 plane | high float4 plane
+  constexpr int RPW = 32 / LPR;
+  constexpr bool kEarlyAdd = sizeof(TOut) == 2;   // bf16 residual gradient: 4 registers per vector, fetched up front
+  constexpr int XW = sizeof(TIn) == 4 ? 2 : 1;    // 16-byte words per 8-element vector of x
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int sub = lane % LPR, grp = lane / LPR;
+  const int nvec = C >> 3, half = C >> 1;
+  float* mine = red + (static_cast<long long>(warp) * RPW + grp) * 2 * C;
+  for (int i = sub; i < 2 * C; i += LPR) mine[i] = 0.f;
+  __syncwarp();
+  const long long warp0 = blockIdx.x * static_cast<long long>(nw) + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * nw;
+  auto decode_x = [](const uint4 (&w)[XW], float (&f)[8]) {
+    if constexpr (XW == 2) {
+      f[0] = __uint_as_float(w[0].x); f[1] = __uint_as_float(w[0].y); f[2] = __uint_as_float(w[0].z); f[3] = __uint_as_float(w[0].w);
+      f[4] = __uint_as_float(w[1].x); f[5] = __uint_as_float(w[1].y); f[6] = __uint_as_float(w[1].z); f[7] = __uint_as_float(w[1].w);
+    } else {
+      unpack8(w[0], f);
+    }
+  };
+  for (long long rb = warp0 * RPW; rb < rows; rb += nwarps * RPW) {
+    const long long r = rb + grp;
+    const bool live = r < rows;
+    uint4 xr[MAXV][XW], dr[MAXV], ar[MAXV];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
+        const uint4* xp = reinterpret_cast<const uint4*>(x + r * C + vi * 8);
+#pragma unroll
+        for (int k = 0; k < XW; ++k) xr[i][k] = __ldg(xp + k);
+        dr[i] = __ldg(reinterpret_cast<const uint4*>(dy + r * C + vi * 8));
+        if constexpr (kEarlyAdd) {
+          if (add != nullptr) ar[i] = __ldg(reinterpret_cast<const uint4*>(add + r * C + vi * 8));
+        }
+      }
+    }
+    const float mu = live ? mean[r] : 0.f, rs = live ? rstd[r] : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
+        float xv[8], dv[8], g[8];
+        decode_x(xr[i], xv);
+        unpack8(dr[i], dv);
+        load8f(gamma + vi * 8, g);
+        float4* ab = reinterpret_cast<float4*>(mine) + vi;            // d beta : low plane, high plane at + half floats
+        float4* ag = reinterpret_cast<float4*>(mine + C) + vi;        // d gamma
+        float4 b0 = ab[0], b1 = ab[half >> 2], g0 = ag[0], g1 = ag[half >> 2];
+        float xh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[j] = (xv[j] - mu) * rs;
+          const float dgj = dv[j] * g[j];
+          s1 += dgj;
+          s2 = fmaf(dgj, xh[j], s2);
+        }
+        b0.x += dv[0]; b0.y += dv[1]; b0.z += dv[2]; b0.w += dv[3];
+        b1.x += dv[4]; b1.y += dv[5]; b1.z += dv[6]; b1.w += dv[7];
+        g0.x = fmaf(dv[0], xh[0], g0.x); g0.y = fmaf(dv[1], xh[1], g0.y);
+        g0.z = fmaf(dv[2], xh[2], g0.z); g0.w = fmaf(dv[3], xh[3], g0.w);
+        g1.x = fmaf(dv[4], xh[4], g1.x); g1.y = fmaf(dv[5], xh[5], g1.y);
+        g1.z = fmaf(dv[6], xh[6], g1.z); g1.w = fmaf(dv[7], xh[7], g1.w);
+        ab[0] = b0; ab[half >> 2] = b1; ag[0] = g0; ag[half >> 2] = g1;
+      }
+    }
+    s1 = group_sum<LPR>(s1) / C;
+    s2 = group_sum<LPR>(s2) / C;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = i * LPR + sub;
+      if (live && vi < nvec) {
+        float xv[8], dv[8], g[8], o[8];
+        decode_x(xr[i], xv);
+        unpack8(dr[i], dv);
+        load8f(gamma + vi * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = rs * (dv[j] * g[j] - s1 - (xv[j] - mu) * rs * s2);
+        if (add != nullptr) {
+          float a[8];
+          if constexpr (kEarlyAdd)
+            unpack8(ar[i], a);
+          else
+            load_row8<TOut>(add + r * C + vi * 8, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] += a[j];
+        }
+        store_row8<TOut>(dx + r * C + vi * 8, o);
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) {
+    const int sec = c >= C ? C : 0, cc = c - sec, j = cc & 7;
+    const int pos = sec + (j < 4 ? (cc >> 3) * 4 + j : half + (cc >> 3) * 4 + j - 4);
+    float s = 0.f;
+    for (int w = 0; w < nw * RPW; ++w) s += red[static_cast<long long>(w) * 2 * C + pos];
+    partial[static_cast<long long>(blockIdx.x) * 2 * C + c] = s;
+  }
+}
+
 // Swin PatchMerging front half (classification/swin_transformer/models/swin_transformer.py:333-343): gather the 2x2 neighbourhood
 // [x(0,0), x(1,0), x(0,1), x(1,1)] (row offset first, as the reference concatenates x0,x1,x2,x3) of the fp32 stream
 // [B][H][W][C] into one 4C vector and LayerNorm it -> y bf16 [B*(H/2)*(W/2)][4C].  One warp per output row.
