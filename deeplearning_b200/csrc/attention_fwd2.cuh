@@ -18,6 +18,9 @@
 // O = P V; its first 16 KB double as the O staging slab of the TMA store) = 224 KB.  Warps 0-3 / 4-7: soft-max groups of
 // query block 0 / 1 (thread = query row, TMEM lane = row), warp 8: TMA producer, warps 9 / 10: MMA issuers of block 0 / 1.
 //
+// The single-lane producer / issuer roles wait with a 40 ns back-off (a third of all issued instructions of the first version
+// were their mbarrier polls: profiles/r02_attn_fwd2_ncu.md).
+//
 // Replaces the eager sequence of vit_model.py:95-108 (classification/vision_transformer), as attn_fwd_kernel does.
 #pragma once
 #include "attention.cuh"
@@ -83,11 +86,11 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const int h = item % p.H, b = item / p.H;
-        if (it > 0) mbar_wait(bar_qk_empty, (it - 1) & 1);
+        if (it > 0) mbar_wait_backoff(bar_qk_empty, (it - 1) & 1);
         mbar_expect_tx(bar_qk_full, mblocks * 16384 + p.Tpad * 128);
         for (int g = 0; g < mblocks; ++g) tma_load_3d(sQ + g * 16384, &p.q_map, bar_qk_full, h * 64, g * 128, b);
         tma_load_3d(sK, &p.kv_map, bar_qk_full, HD + h * 64, 0, b);
-        if (it > 0) mbar_wait(bar_v_empty, (it - 1) & 1);
+        if (it > 0) mbar_wait_backoff(bar_v_empty, (it - 1) & 1);
         mbar_expect_tx(bar_v_full, p.Tpad * 128);
         tma_load_3d(sV, &p.kv_map, bar_v_full, 2 * HD + h * 64, 0, b);
       }
@@ -105,8 +108,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
       int it = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x, ++it) {
         const uint32_t ph = it & 1;
-        mbar_wait(bar_qk_full, ph);
-        if (it > 0) mbar_wait(bar_free + g, (it - 1) & 1);   // the previous item's O has left these TMEM columns
+        mbar_wait_backoff(bar_qk_full, ph);
+        if (it > 0) mbar_wait_backoff(bar_free + g, (it - 1) & 1);   // the previous item's O has left these TMEM columns
         tc_fence_after();
         // ---- S = Q K^T : A = Q block (K-major), B = K (K-major, N = Tpad key rows), K = 64 (4 steps)
 #pragma unroll
@@ -116,8 +119,8 @@ __global__ void __launch_bounds__(kAttn2Threads, 1) attn_fwd2_kernel(const __gri
         umma_commit(bar_s + g);
         umma_commit(bar_qk_empty);
         // ---- O = P V : A = P (K-major, key blocks of 64), B = V (MN-major: rows = keys, 64 contiguous d), K = Tpad keys
-        mbar_wait(bar_v_full, ph);
-        mbar_wait(bar_p + g, ph);
+        mbar_wait_backoff(bar_v_full, ph);
+        mbar_wait_backoff(bar_p + g, ph);
         tc_fence_after();
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t da = make_smem_desc_sw128(p_addr + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);

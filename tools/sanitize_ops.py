@@ -12,7 +12,7 @@ from deeplearning_b200 import ops
 
 dev = torch.device("cuda")
 BF = torch.bfloat16
-fam = set(sys.argv[1:]) or {"conv", "stream", "wgrad", "attn", "wattn", "algebra"}
+fam = set(sys.argv[1:]) or {"conv", "stream", "wgrad", "attn", "attn2", "ln", "wattn", "algebra"}
 
 
 def r(*shape, scale=1.0):
@@ -75,5 +75,22 @@ if "wattn" in fam:
     o, lse = ops.window_attention_fwd(qkv, nH, bias, 0, 32 ** -0.5)
     dqkv, dbias = ops.window_attention_bwd(qkv, o, r(B, H, W, C), bias, lse, nH, 0, 32 ** -0.5)
     print("wattn ok", float(o.float().abs().mean()), float(dqkv.float().abs().mean()))
+if "attn2" in fam:
+    # persistent attention forward (attention_fwd2.cuh): 300 (batch, head) items on 148 CTAs, i.e. two or three items per CTA
+    # (buffer reuse, barrier phases, the ping-pong of the two soft-max groups), checked against the per-block kernel's math
+    qkv = r(100, 197, 3 * 3 * 64, scale=0.5)
+    o, lse = ops.attention_fwd(qkv, 3, 0.125)
+    q, k, v = qkv[:2].float().view(2, 197, 3, 3, 64).permute(2, 0, 3, 1, 4)
+    ref = torch.softmax(q @ k.transpose(-1, -2) * 0.125, -1) @ v
+    err = (o[:2].float().view(2, 197, 3, 64).permute(0, 2, 1, 3) - ref).abs().max()
+    print("attn2 ok", float(o.float().abs().mean()), "max|err|", float(err))
+if "ln" in fam:
+    # LayerNorm backward v2 (transformer.cuh): fp32 / bf16 rows with and without the residual-gradient operand
+    for rows, C, dt in ((3000, 768, torch.float32), (5000, 96, torch.float32), (2000, 384, BF)):
+        x = torch.randn(rows, C, device=dev).to(dt)
+        g = torch.rand(C, device=dev) + 0.5
+        y, mean, rstd = ops.layernorm_fwd(x, g, torch.zeros(C, device=dev), 1e-6)
+        dx, dg, db = ops.layernorm_bwd(r(rows, C, scale=0.1), x, mean, rstd, g, add=r(rows, C, scale=0.1) if dt != BF else None)
+        print("ln ok", rows, C, float(dx.float().abs().mean()), float(dg.abs().mean()))
 torch.cuda.synchronize()
 print("done")
