@@ -113,7 +113,7 @@ def res_l3_conv2():   # ResNet layer3 conv2: 3x3 256 -> 256 at 14x14
     return lambda: ops.conv2d_fwd(x, wp, 3, 1, want_stats=True)
 
 
-def vit_fc1():        # ViT-B/16 fc1: [50432, 768] x [3072, 768]^T + bias, GELU, keeps the pre-activation
+def vit_fc1():        # ViT-B/16 fc1: [50432, 768] x [3072, 768]^T + bias, GELU, second output GELU'(pre) for the backward
     a = rnd(256 * 197, 768, scale=0.5)
     wp = ops.pack_weight(torch.randn(3072, 768, device=dev) * 0.03)
     b = torch.randn(3072, device=dev) * 0.1
@@ -127,11 +127,19 @@ def vit_qkv():
     return lambda: ops.gemm(a, wp, bias=b)
 
 
-def vit_fc2_dgrad():  # d_pre = (g W2) * GELU'(pre) with column sums (fc1 bias gradient)
+def vit_fc2_dgrad():  # d_pre = (g W2) * saved GELU'(pre) with column sums (fc1 bias gradient)
     g = rnd(256 * 197, 768, scale=0.1)
     wd = ops.pack_weight(torch.randn(768, 3072, device=dev) * 0.03, mode=1)
     pre = rnd(256 * 197, 3072)
     return lambda: ops.gemm(g, wd, act=3, aux_in=pre, want_stats=True)
+
+
+def vit_ln_bwd():      # ViT-B/16 LayerNorm backward: x fp32 [50432, 768], dy / residual gradient bf16 (layernorm_bwd2_kernel)
+    x = rnd(256 * 197, 768, dtype=torch.float32)
+    g = torch.rand(768, device=dev) + 0.5
+    y, mean, rstd = ops.layernorm_fwd(x, g, torch.zeros(768, device=dev), 1e-6)
+    dy, add = rnd(256 * 197, 768, scale=0.1), rnd(256 * 197, 768, scale=0.1)
+    return lambda: ops.layernorm_bwd(dy, x, mean, rstd, g, add=add)
 
 
 def vit_fc1_wgrad():
