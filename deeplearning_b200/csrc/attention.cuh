@@ -9,6 +9,9 @@
 // (used in place as an MN-major operand - no transpose) into TMEM columns that S has vacated. S / P never touch HBM; only
 // the per-row log-sum-exp is kept for the backward pass.
 //
+// (Since late round 2 the product's forward is the persistent attn_fwd2_kernel of attention_fwd2.cuh - same parameters, math and
+// outputs, 148 -> 101 us per ViT-B/16 layer; this kernel is selected with B200_ATTN_FWD=1 and is the op's A/B reference.)
+//
 // Replaces the eager sequence of vit_model.py:95-108 (classification/vision_transformer): qkv split, (q@k^T)*scale, softmax,
 // attn@v, transpose/reshape, which materialises the [B,12,197,197] score tensor three times in HBM.
 #pragma once
